@@ -1,0 +1,57 @@
+"""ctypes binding of libb200sat.so (the C ABI declared in include/b200sat.h).
+
+No torch types cross the boundary: tensors are passed as raw device pointers + sizes + a cudaStream_t.
+There is no fallback: if the library is missing or a call fails, a Python exception is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200sat.so")
+
+c_void_p, c_int, c_float, c_char_p = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_char_p
+c_ull = ctypes.c_ulonglong
+c_fp = ctypes.c_void_p  # const float*
+
+# name -> (restype, argtypes); kept in sync with include/b200sat.h (tests/test_abi.py checks every symbol).
+SIGNATURES = {
+    "b200sat_last_error": (c_char_p, []),
+    "b200sat_version": (c_int, []),
+    "b200sat_num_sms": (c_int, []),
+    "b200sat_launch_count": (c_ull, []),
+    "b200sat_gemm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                  c_fp, c_void_p, c_int, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                  c_fp, c_int, c_void_p]),
+}
+
+_lib = None
+
+
+class B200SatError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200SatError(
+                f"{LIB_PATH} not found: build it with `python __graft_entry__.py` (no CPU/PyTorch fallback exists)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc == 0:
+        return
+    msg = lib().b200sat_last_error().decode(errors="replace")
+    if rc == -2:
+        raise NotImplementedError(f"b200sat {what}: unsupported: {msg}")
+    if rc < 0:
+        raise ValueError(f"b200sat {what}: invalid argument: {msg}")
+    raise B200SatError(f"b200sat {what}: CUDA error {rc}: {msg}")
