@@ -42,6 +42,48 @@ int b200sat_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* D, i
                       int rope_seq, int rope_dmodel, int rope_dh, int n_half, int seg_in, int seg_out, int seg_off,
                       const float* gate, int force_bn, void* stream);
 
+/* Flash attention forward (tcgen05; non-causal; head_dim 64; Hq % Hkv == 0 grouped-query).  q/k/v/o are bf16 views
+ * [B, N, heads, 64] addressed by element strides (batch, sequence, head); lse (optional, fp32 [B,Hq,Nq]) is the natural-log
+ * row normaliser kept for the backward pass.  Replaces models/transformer.py:406-441 (flash_attn_func / SDPA dispatch,
+ * GQA repeat_interleave :408-411) and the head rearranges of :469-482, :526. */
+int b200sat_attention_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Hq, int Hkv, int Nq,
+                          int Nk, long q_bs, long q_ss, long q_hs, long k_bs, long k_ss, long k_hs, long v_bs, long v_ss,
+                          long v_hs, long o_bs, long o_ss, long o_hs, int head_dim, float scale, void* stream);
+
+/* LayerNorm over the last dim, bf16 in/out, fp32 statistics; gamma (and optional beta) fp32 [D].  With scale/shift
+ * (fp32 [B, ld_mod] rows, rows_per_batch rows of x per batch entry) applies the adaLN modulate y*(1+scale)+shift.
+ * Replaces models/transformer.py:236-241 (LayerNorm.forward) and :680-682, :695-697. */
+int b200sat_layernorm_fwd(const void* x, long ldx, const float* gamma, const float* beta, const float* scale,
+                          const float* shift, long ld_mod, int rows_per_batch, void* y, long ldy, int rows, int D, float eps,
+                          void* stream);
+
+/* y[M,N] = act(x[M,K] w[N,K]^T + bias) (+ add), 1 <= M <= 8: the conditioning MLPs whose M is the batch size.
+ * Replaces models/dit.py:41-76,:140-168 (to_timestep_embed / to_global_embed) and models/transformer.py:767-773,:677-684. */
+int b200sat_small_linear(const void* x, long ldx, const void* w, long ldw, const float* bias, const void* add, long ldadd,
+                         void* y, long ldy, int M, int N, int K, int act_silu, int out_f32, int act_sigmoid_1m, void* stream);
+
+/* out[B, 2*half] = [cos(2 pi t w) | sin(2 pi t w)] (bf16).  t is read at t[*step * t_stride + b] when step != NULL so a
+ * captured CUDA graph can walk a per-step table.  Replaces models/blocks.py:85-94 (FourierFeatures.forward). */
+int b200sat_fourier_features(const float* t, const void* w, void* out, int B, int half, const int* step, int t_stride,
+                             void* stream);
+
+/* DiT input stage: bf16(x*c_in) -> 1x1 conv + residual -> [reps*B*T, C] bf16 rows (token-major).
+ * Replaces models/dit.py:193-195 (+ the CFG batch duplication :330-331 via reps).  x fp32 [B,C,T]; c_in = cin_table[*step]. */
+int b200sat_dit_pre(const float* x, const void* wconv, void* out, int B, int C, int T, int reps, const float* cin_table,
+                    const int* step, void* stream);
+
+/* DiT output stage: drop `prepend` tokens, transpose to [B,C,T], 1x1 conv + residual, optional classifier-free guidance
+ * over the (cond|uncond) batch halves with std-rescale.  Replaces models/dit.py:219-224 and :398-408.  out fp32 [B,C,T]. */
+int b200sat_dit_post(const void* h, long ld_batch, int prepend, const void* wconv, float* out, int B, int C, int T, int cfg,
+                     float cfg_scale, float scale_phi, void* stream);
+
+/* Sampler state update for one step s = *step: den = v*c0 + x*c1; x = c2*x + c3*den + c4*d1 + c5*d2 + c6*noise[s];
+ * coef is fp32 [steps, 8]; hist is a ring of 3 denoised tensors.  Covers k-diffusion's VDenoiser + sample_dpmpp_3m_sde
+ * (called from inference/sampling.py:351-387) and the in-repo v-DDIM update (inference/sampling.py:281-300). */
+int b200sat_sampler_update(float* x, const float* v, float* hist, const float* noise, const float* coef, int* step, long n,
+                           int advance, void* stream);
+int b200sat_step_set(int* step, int value, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

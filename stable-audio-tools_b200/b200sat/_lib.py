@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libb200sat.so")
 c_void_p, c_int, c_float, c_char_p = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_char_p
 c_ull = ctypes.c_ulonglong
 c_fp = ctypes.c_void_p  # const float*
+c_long = ctypes.c_long
 
 # name -> (restype, argtypes); kept in sync with include/b200sat.h (tests/test_abi.py checks every symbol).
 SIGNATURES = {
@@ -22,6 +23,17 @@ SIGNATURES = {
     "b200sat_gemm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_fp, c_void_p, c_int, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                   c_fp, c_int, c_void_p]),
+    "b200sat_attention_fwd": (c_int, [c_void_p] * 4 + [c_fp] + [c_int] * 5 + [c_long] * 12 + [c_int, c_float, c_void_p]),
+    "b200sat_layernorm_fwd": (c_int, [c_void_p, c_long, c_fp, c_fp, c_fp, c_fp, c_long, c_int, c_void_p, c_long, c_int, c_int,
+                                      c_float, c_void_p]),
+    "b200sat_small_linear": (c_int, [c_void_p, c_long, c_void_p, c_long, c_fp, c_void_p, c_long, c_void_p, c_long,
+                                     c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200sat_fourier_features": (c_int, [c_fp, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "b200sat_dit_pre": (c_int, [c_fp, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_fp, c_void_p, c_void_p]),
+    "b200sat_dit_post": (c_int, [c_void_p, c_long, c_int, c_void_p, c_fp, c_int, c_int, c_int, c_int, c_float, c_float,
+                                 c_void_p]),
+    "b200sat_sampler_update": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_void_p, c_long, c_int, c_void_p]),
+    "b200sat_step_set": (c_int, [c_void_p, c_int, c_void_p]),
 }
 
 _lib = None

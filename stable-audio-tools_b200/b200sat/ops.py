@@ -74,3 +74,86 @@ def linear(x, w, bias=None, residual=None, out=None, silu=False, out_f32=False, 
                                  seg_in, seg_out, seg_off, _p(gate), force_bn, _stream())
     check(rc, "gemm_bf16")
     return out
+
+
+def attention(q, k, v, out=None, lse=None, scale=None):
+    """q [B,Nq,Hq,64], k/v [B,Nk,Hkv,64] bf16 views (any batch/seq/head strides, unit stride on the last dim).
+    Returns out [B,Nq,Hq,64] (contiguous unless `out` is given)."""
+    for n, t in (("q", q), ("k", k), ("v", v)):
+        _chk_bf16(t, n)
+        assert t.dim() == 4
+    B, Nq, Hq, D = q.shape
+    _, Nk, Hkv, _ = k.shape
+    if out is None:
+        out = torch.empty((B, Nq, Hq, D), device=q.device, dtype=torch.bfloat16)
+    if scale is None:
+        scale = D ** -0.5
+    rc = lib().b200sat_attention_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), _p(lse), B, Hq, Hkv, Nq, Nk,
+                                     q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2),
+                                     v.stride(0), v.stride(1), v.stride(2), out.stride(0), out.stride(1), out.stride(2),
+                                     D, float(scale), _stream())
+    check(rc, "attention_fwd")
+    return out
+
+
+def layernorm(x, gamma, beta=None, scale=None, shift=None, rows_per_batch=0, out=None, eps=1e-5):
+    """x [rows, D] bf16; gamma/beta fp32 [D]; adaLN scale/shift fp32 [B, >=D] (row stride = stride(0))."""
+    _chk_bf16(x, "x")
+    rows, D = x.shape
+    if out is None:
+        out = torch.empty((rows, D), device=x.device, dtype=torch.bfloat16)
+    ld_mod = scale.stride(0) if scale is not None else 0
+    rc = lib().b200sat_layernorm_fwd(x.data_ptr(), x.stride(0), gamma.data_ptr(), _p(beta), _p(scale), _p(shift), ld_mod,
+                                     rows_per_batch, out.data_ptr(), out.stride(0), rows, D, float(eps), _stream())
+    check(rc, "layernorm_fwd")
+    return out
+
+
+def small_linear(x, w, bias=None, add=None, out=None, silu=False, out_f32=False, sigmoid_1m=False):
+    _chk_bf16(x, "x"); _chk_bf16(w, "w")
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    rc = lib().b200sat_small_linear(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _p(bias), _p(add),
+                                    add.stride(0) if add is not None else 0, out.data_ptr(), out.stride(0), M, N, K,
+                                    int(silu), int(out_f32), int(sigmoid_1m), _stream())
+    check(rc, "small_linear")
+    return out
+
+
+def fourier_features(t, w, out=None, step=None, t_stride=0):
+    B = out.shape[0] if out is not None else t.shape[0]
+    half = w.shape[0]
+    if out is None:
+        out = torch.empty((B, 2 * half), device=w.device, dtype=torch.bfloat16)
+    rc = lib().b200sat_fourier_features(t.data_ptr(), w.data_ptr(), out.data_ptr(), B, half, _p(step), t_stride, _stream())
+    check(rc, "fourier_features")
+    return out
+
+
+def dit_pre(x, wconv, out, reps=1, cin_table=None, step=None):
+    B, C, T = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    rc = lib().b200sat_dit_pre(x.data_ptr(), wconv.data_ptr(), out.data_ptr(), B, C, T, reps, _p(cin_table), _p(step), _stream())
+    check(rc, "dit_pre")
+    return out
+
+
+def dit_post(h, ld_batch, prepend, wconv, out, cfg=False, cfg_scale=1.0, scale_phi=0.0):
+    B, C, T = out.shape
+    rc = lib().b200sat_dit_post(h.data_ptr(), ld_batch, prepend, wconv.data_ptr(), out.data_ptr(), B, C, T, int(cfg),
+                                float(cfg_scale), float(scale_phi), _stream())
+    check(rc, "dit_post")
+    return out
+
+
+def sampler_update(x, v, hist, noise, coef, step, advance=True):
+    rc = lib().b200sat_sampler_update(x.data_ptr(), v.data_ptr(), hist.data_ptr(), _p(noise), coef.data_ptr(), step.data_ptr(),
+                                      x.numel(), int(advance), _stream())
+    check(rc, "sampler_update")
+    return x
+
+
+def step_set(step, value):
+    check(lib().b200sat_step_set(step.data_ptr(), int(value), _stream()), "step_set")

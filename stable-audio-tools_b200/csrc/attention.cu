@@ -1,0 +1,260 @@
+// b200sat — flash attention forward on tcgen05 (non-causal, dh = 64, GQA-aware, ragged sequence tails).
+//
+// Replaces flash_attn_func / F.scaled_dot_product_attention in the reference
+// (stable_audio_tools/models/transformer.py:406-441) for both the self-attention (N = 1025) and the grouped-query
+// cross-attention over the conditioning tokens (Nk = 130, 24 q heads / 12 kv heads, :408-411).  Heads are read in place
+// from the projection outputs ([B, N, heads, 64] views with arbitrary strides), so the 'b n (h d) -> b h n d' rearranges
+// and the repeat_interleave of K/V never touch HBM.
+//
+// One CTA = one 128-query tile of one (batch, head); two CTAs are resident per SM so one CTA's softmax overlaps the
+// other's MMAs.  192 threads:
+//   warp 0 lane 0 : TMA producer (Q once; K,V tiles of 128 keys through a 2-stage ring; 4-D tensor maps, 128B swizzle)
+//   warp 1        : TMEM allocation; lane 0 issues S = Q K^T (128x128x64) and O_j = P V (128x64x128) on tcgen05
+//   warps 2..5    : online softmax — thread == query row (tcgen05.ld 32x32b), P written to smem as the bf16 A operand,
+//                   O accumulated in registers with the running-max rescale.
+#include "common.cuh"
+#include <cstring>
+
+namespace b200sat {
+
+struct AttnParams {
+  CUtensorMap tmQ, tmK, tmV;
+  __nv_bfloat16* O;
+  float* lse;  // optional [B, Hq, Nq]
+  long o_bs, o_ss, o_hs;
+  int B, Hq, Hkv, Nq, Nk;
+  float scale_log2;  // softmax scale * log2(e)
+};
+
+constexpr int AT_BM = 128;   // queries per CTA
+constexpr int AT_BN = 128;   // keys per tile
+constexpr int AT_D = 64;
+constexpr int AT_TILE = AT_BM * AT_D * 2;                       // 16 KB
+constexpr int AT_SMEM = AT_TILE /*Q*/ + 2 * 2 * AT_TILE /*K,V x2*/ + 2 * AT_TILE /*P*/ + 256;
+
+__global__ void __launch_bounds__(192, 2) attention_fwd_tcgen05(const __grid_constant__ AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + AT_TILE;            // stage s: K at sKV + s*2*TILE, V at + TILE
+  uint8_t* sP = smem + 5 * AT_TILE;         // 2 x [128 rows x 64 keys] swizzled blocks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * AT_TILE);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AT_BM;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int hkv = h / (p.Hq / p.Hkv);
+  const int num_kv = (p.Nk + AT_BN - 1) / AT_BN;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();  // the swizzled layouts need a 1024-byte aligned base
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_S = tmem_base;         // 128 fp32 columns
+  const uint32_t tmem_O = tmem_base + 128;   // 64 fp32 columns
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, AT_TILE);
+      tma_load_4d(sQ, &p.tmQ, q_full, 0, h, q0, b);
+      for (int j = 0; j < num_kv; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], 2 * AT_TILE);
+        tma_load_4d(sKV + s * 2 * AT_TILE, &p.tmK, &kv_full[s], 0, hkv, j * AT_BN, b);
+        tma_load_4d(sKV + s * 2 * AT_TILE + AT_TILE, &p.tmV, &kv_full[s], 0, hkv, j * AT_BN, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);  // B = V is MN-major (keys along rows)
+      const uint32_t aQ = smem_u32(sQ);
+      const uint32_t aP = smem_u32(sP);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < num_kv; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&kv_full[s], ph);
+        tc_fence_after();
+        const uint32_t aK = smem_u32(sKV + s * 2 * AT_TILE);
+        const uint32_t aV = aK + AT_TILE;
+#pragma unroll
+        for (int k = 0; k < AT_D / 16; ++k) {
+          umma_bf16(tmem_S, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024), idesc_s, k != 0);
+        }
+        umma_commit(s_full);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < AT_BN / 16; ++k) {
+          const uint32_t pa = aP + (k >> 2) * AT_TILE + (k & 3) * 32;
+          umma_bf16(tmem_O, make_smem_desc_sw128(pa, 16, 1024), make_smem_desc_sw128(aV + k * 2048, 1024, 1024), idesc_o, k != 0);
+        }
+        umma_commit(o_full);
+        umma_commit(&kv_empty[s]);
+      }
+    }
+  } else {
+    // ===================== softmax / output warps =====================
+    const int quarter = warp & 3;  // TMEM lane quarter accessible to this warp
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    float o[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o[i] = 0.f;
+    uint8_t* prow = sP + r * 128;
+    const int sw = r & 7;
+
+    for (int j = 0; j < num_kv; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int kbase = j * AT_BN;
+      const int nvalid = p.Nk - kbase;  // >= 1
+      // pass A: row max
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_S + lane_off + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float sv = (c * 32 + i < nvalid) ? __uint_as_float(raw[i]) : -INFINITY;
+          mx = fmaxf(mx, sv);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      const float alpha = exp2f(m_run - m_new);
+      // pass B: p = exp2(s*scale - m), row sum, bf16 P -> swizzled smem (A operand of the PV MMA)
+      float lsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_S + lane_off + c * 32, raw);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = (c * 32 + i < nvalid) ? exp2f(__uint_as_float(raw[i]) * p.scale_log2 - m_new) : 0.f;
+          const float p1 = (c * 32 + i + 1 < nvalid) ? exp2f(__uint_as_float(raw[i + 1]) * p.scale_log2 - m_new) : 0.f;
+          lsum += p0 + p1;
+          pk[i >> 1] = pack_bf16(p0, p1);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int chunk = c * 4 + t;              // 16-byte chunk index along the 128 keys
+          const int kb = chunk >> 3, cc = chunk & 7;
+          uint4 u = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+          *reinterpret_cast<uint4*>(prow + kb * AT_TILE + ((cc ^ sw) << 4)) = u;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+      l_run = l_run * alpha + lsum;
+      m_run = m_new;
+      // O_j = P V from TMEM, accumulate with rescale
+      mbar_wait(o_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_O + lane_off + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * alpha + __uint_as_float(raw[i]);
+      }
+      tc_fence_before();
+    }
+    const int qrow = q0 + r;
+    if (qrow < p.Nq) {
+      const float inv = 1.0f / l_run;
+      __nv_bfloat16* dst = p.O + static_cast<long>(b) * p.o_bs + static_cast<long>(qrow) * p.o_ss + static_cast<long>(h) * p.o_hs;
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint4 u;
+        u.x = pack_bf16(o[8 * i + 0] * inv, o[8 * i + 1] * inv);
+        u.y = pack_bf16(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
+        u.z = pack_bf16(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
+        u.w = pack_bf16(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
+        d4[i] = u;
+      }
+      if (p.lse) p.lse[(static_cast<long>(b) * p.Hq + h) * p.Nq + qrow] = m_run * 0.6931471805599453f + logf(l_run);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+static int make_head_map(CUtensorMap* tm, const void* base, int B, int H, int N, long bs, long ss, long hs) {
+  uint64_t dims[4] = {AT_D, static_cast<uint64_t>(H), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
+  uint64_t strides[3] = {static_cast<uint64_t>(hs) * 2, static_cast<uint64_t>(ss) * 2, static_cast<uint64_t>(bs) * 2};
+  uint32_t box[4] = {AT_D, 1, AT_BM, 1};
+  return encode_tmap_bf16(tm, base, 4, dims, strides, box, 1);
+}
+
+}  // namespace b200sat
+
+using namespace b200sat;
+
+extern "C" int b200sat_attention_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Hq, int Hkv,
+                                     int Nq, int Nk, long q_bs, long q_ss, long q_hs, long k_bs, long k_ss, long k_hs,
+                                     long v_bs, long v_ss, long v_hs, long o_bs, long o_ss, long o_hs, int head_dim,
+                                     float scale, void* stream) {
+  if (!q || !k || !v || !o || B <= 0 || Hq <= 0 || Hkv <= 0 || Nq <= 0 || Nk <= 0) { set_last_error("attention: bad arguments"); return B200SAT_EINVAL; }
+  if (head_dim != AT_D) { set_last_error("attention: only head_dim 64 is implemented"); return B200SAT_EUNSUPPORTED; }
+  if (Hq % Hkv) { set_last_error("attention: Hq must be a multiple of Hkv"); return B200SAT_EINVAL; }
+  if ((o_ss % 8) || (o_hs % 8) || (o_bs % 8)) { set_last_error("attention: output strides must be multiples of 8 elements"); return B200SAT_EINVAL; }
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = make_head_map(&p.tmQ, q, B, Hq, Nq, q_bs, q_ss, q_hs))) return rc;
+  if ((rc = make_head_map(&p.tmK, k, B, Hkv, Nk, k_bs, k_ss, k_hs))) return rc;
+  if ((rc = make_head_map(&p.tmV, v, B, Hkv, Nk, v_bs, v_ss, v_hs))) return rc;
+  p.O = static_cast<__nv_bfloat16*>(o); p.lse = lse;
+  p.o_bs = o_bs; p.o_ss = o_ss; p.o_hs = o_hs;
+  p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.Nq = Nq; p.Nk = Nk;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200SAT_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    attr_set = true;
+  }
+  dim3 grid((Nq + AT_BM - 1) / AT_BM, Hq, B);
+  attention_fwd_tcgen05<<<grid, 192, AT_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+  B200SAT_CHECK_CUDA(cudaGetLastError());
+  return B200SAT_OK;
+}
