@@ -1,0 +1,77 @@
+"""GPU parity: the DiT engine (libb200sat kernels end to end) vs the CPU oracle on identical seeded weights/inputs.
+
+Tolerance (stated, SURVEY.md section 7 'hard parts'): the engine computes in bf16 with fp32 accumulation, so it is compared with
+the fp32 oracle relative to what the reference's own bf16 path loses:  ||ours - ref32|| <= 1.5 * ||ref_bf16 - ref32|| + 2e-3*||ref32||.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+def _case(embed_dim, depth, heads, cond_dim, T, L, B, gct, cfg_scale, scale_phi, seed=0):
+    from oracle import dit as odit
+    from b200sat.dit_engine import DiTEngine
+    sd = odit.make_state_dict(embed_dim=embed_dim, depth=depth, num_heads=heads, io_channels=64, cond_token_dim=cond_dim,
+                              global_cond_dim=embed_dim, global_cond_type=gct, seed=seed)
+    sd = {k: v.bfloat16().float() for k, v in sd.items()}  # a bf16 checkpoint
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(B, 64, T, generator=g)
+    t = torch.rand(B, generator=g)
+    c = torch.randn(B, L, cond_dim, generator=g)
+    ge = torch.randn(B, embed_dim, generator=g)
+    with torch.no_grad():
+        ref32 = odit.dit_forward(x, t, sd, depth, c, ge, cfg_scale=cfg_scale, scale_phi=scale_phi, global_cond_type=gct)
+        sd16 = {k: v.bfloat16() for k, v in sd.items()}
+        ref16 = odit.dit_forward(x, t, sd16, depth, c, ge, cfg_scale=cfg_scale, scale_phi=scale_phi, global_cond_type=gct).float()
+    eng = DiTEngine(sd)
+    out = eng.forward(x.cuda(), t.cuda(), c.cuda(), ge.cuda(), cfg_scale=cfg_scale, scale_phi=scale_phi)
+    torch.cuda.synchronize()
+    out = out.cpu()
+    assert torch.isfinite(out).all()
+    e_ours, e_ref16 = _rel(out, ref32), _rel(ref16, ref32)
+    print(f"rel err ours {e_ours:.3e}  reference-bf16 {e_ref16:.3e}")
+    assert e_ours <= 1.5 * e_ref16 + 2e-3, (e_ours, e_ref16)
+
+
+@pytest.mark.parametrize("gct", ["prepend", "adaLN"])
+@pytest.mark.parametrize("cfg_scale,scale_phi", [(1.0, 0.0), (6.0, 0.75)])
+def test_dit_small(gct, cfg_scale, scale_phi):
+    _case(embed_dim=256, depth=3, heads=4, cond_dim=128, T=200, L=17, B=2, gct=gct, cfg_scale=cfg_scale, scale_phi=scale_phi)
+
+
+def test_dit_sao_width_4_layers():
+    # Stable-Audio-Open width (d=1536, 24 heads, ctx 130x768, N=1024+1), 4 layers, CFG batch
+    _case(embed_dim=1536, depth=4, heads=24, cond_dim=768, T=1024, L=130, B=1, gct="prepend", cfg_scale=7.0, scale_phi=0.0)
+
+
+def test_dit_sampler_graph_matches_eager_and_oracle():
+    """20-step dpmpp-3m-sde with an injected noise sequence: CUDA-graph loop == eager loop (bitwise), and both track the
+    oracle loop (fp32 CPU) within the bf16 budget on a small DiT."""
+    from oracle import dit as odit, sampling as osamp
+    from b200sat.dit_engine import DiTEngine
+    from b200sat import sampling as bs
+    depth, d = 2, 256
+    sd = odit.make_state_dict(embed_dim=d, depth=depth, num_heads=4, io_channels=64, cond_token_dim=128, global_cond_dim=d, seed=3)
+    sd = {k: v.bfloat16().float() for k, v in sd.items()}
+    g = torch.Generator().manual_seed(5)
+    B, T, L, steps = 1, 128, 9, 20
+    noise = torch.randn(B, 64, T, generator=g)
+    nseq = torch.randn(steps, B, 64, T, generator=g)
+    c = torch.randn(B, L, 128, generator=g); ge = torch.randn(B, d, generator=g)
+    eng = DiTEngine(sd)
+    outs = []
+    for use_graph in (True, False):
+        outs.append(bs.sample_k_dpmpp_3m_sde(eng, noise, steps=steps, cross_attn_cond=c, global_embed=ge, cfg_scale=6.0,
+                                             step_noise=nseq, use_graph=use_graph).cpu())
+    assert torch.equal(outs[0], outs[1])
+    model_fn = lambda x, t, **kw: odit.dit_forward(x, t, sd, depth, c, ge, cfg_scale=6.0)
+    with torch.no_grad():
+        ref = osamp.sample_k_dpmpp_3m_sde(model_fn, noise, steps=steps, noise_seq=nseq)
+    e = _rel(outs[0], ref)
+    print("sampler rel err vs fp32 oracle", e)
+    assert e <= 5e-2, e
