@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json metric on B200: DiT 100-step dpmpp-3m-sde sampling (configs[1]) latent-steps/sec.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                     (the reference's CPU path = the oracle port, on the host cores)
+
+A "step" is one pass of the hot path over one batch: a full 100-step sampling run of the Stable-Audio-Open-1.0 DiT
+(d=1536, 24 layers, 24 heads, 1024 latents + 1 prepended token, cross-attention to 130x768 conditioning, CFG scale 7 =>
+effective batch 2), random-init weights, synthetic conditioning.  Multi-GPU: the sampling loop of one sample is
+sequential, so ranks are independent replicas (different seeds), no data-path collective ("replicas only", weak scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "stable-audio-tools_b200"))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SAMPLE_STEPS = 100
+T_LAT, L_CTX, D_MODEL, DEPTH, HEADS = 1024, 130, 1536, 24, 24
+CFG_SCALE, SIGMA_MIN, SIGMA_MAX, RHO = 7.0, 0.03, 1000.0, 1.0
+BATCH = 1
+# algorithmic work: 2.216 GFLOP per token forward at N=1025
+GFLOP_PER_TOKEN = 2.216
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm=j["hbm_gbs"], bf16=j["bf16_tflops"], bf16_sustained=j.get("bf16_tflops_sustained", j["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], 0.0, set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if "Active" in v and "Not" not in v:
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_cfg_step_seconds(n_steps, threads):
+    """The reference's CPU path for this workload = the oracle port (torch fp32), one CFG denoising step per call."""
+    from oracle import dit as odit
+    torch.set_num_threads(threads)
+    sd = odit.make_state_dict(embed_dim=D_MODEL, depth=DEPTH, num_heads=HEADS, seed=0)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(BATCH, 64, T_LAT, generator=g)
+    c = torch.randn(BATCH, L_CTX, 768, generator=g)
+    ge = torch.randn(BATCH, D_MODEL, generator=g)
+    t = torch.full((BATCH,), 0.7)
+    times = []
+    with torch.no_grad():
+        for _ in range(n_steps):
+            t0 = time.perf_counter()
+            odit.dit_forward(x, t, sd, DEPTH, c, ge, cfg_scale=CFG_SCALE)
+            times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    oracle_cfg_step_seconds(max(1, min(args.warmup, 1)), threads)  # warm-up (bounded: one CFG step)
+    times = oracle_cfg_step_seconds(args.steps, threads)
+    sec = sum(times) / len(times)
+    val = BATCH / sec
+    line = {
+        "impl": "reference", "metric": "dit_sampling_latent_steps_per_sec", "value": val, "unit": "latent-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": "latent-steps/s", "cores": threads, "kind": "port",
+                         "sample": "each step = 1 CFG denoising step (effective batch 2, N=1025) of the 100-step workload, torch fp32 oracle port"},
+        "e2e": {"value": val, "unit": "latent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n):
+    return {"workload": "Stable-Audio-Open-1.0 DiT 100-step dpmpp-3m-sde sampling (BASELINE.json configs[1])",
+            "model": "DiT d=1536 L=24 H=24 ff=6144 ctx=130x768 prepend", "seq_len": T_LAT, "batch_per_gpu": BATCH,
+            "cfg_scale": CFG_SCALE, "sampler": "dpmpp-3m-sde", "sample_steps": SAMPLE_STEPS,
+            "sigma_min": SIGMA_MIN, "sigma_max": SIGMA_MAX, "parallelism": f"replicas x{n} (independent seeds, no collective)",
+            "l2": "no explicit flush: every denoising step streams 2.1 GB of bf16 weights (>> 126 MB L2)"}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from b200sat import init, ops, sampling
+    from b200sat.generation import DiffusionCondModel, generate_diffusion_cond
+    dev = torch.device("cuda", local)
+    sd = init.dit_state_dict(embed_dim=D_MODEL, depth=DEPTH, num_heads=HEADS, seed=0, device=dev)
+    model = DiffusionCondModel.from_state_dict(sd, device=dev)
+    eng = model.engine
+    del sd
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    noise = torch.randn(BATCH, 64, T_LAT, device=dev, generator=g)
+    cross = torch.randn(BATCH, L_CTX, 768, device=dev, generator=g)
+    glob = torch.randn(BATCH, D_MODEL, device=dev, generator=g)
+    smp = model.sampler(BATCH, T_LAT, L_CTX, True, CFG_SCALE, 0.0)
+
+    def one_sample():
+        return sampling.sample_k_dpmpp_3m_sde(eng, noise, SAMPLE_STEPS, SIGMA_MIN, SIGMA_MAX, RHO, cross, glob, CFG_SCALE, 0.0, sampler=smp)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = one_sample()
+    assert torch.isfinite(out).all(), "non-finite latents"
+    # ---------------- device-resident timing (`value`)
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    n0 = ops.LAUNCHES[0]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        one_sample()
+    e1.record()
+    barrier()
+    launches = ops.LAUNCHES[0] - n0
+    clk = clocks.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = ms.item()
+    value = SAMPLE_STEPS * BATCH * world * args.steps / (ms_total * 1e-3)
+
+    # ---------------- end-to-end through the public API with HOST buffers (`e2e`)
+    h_noise = noise.cpu().pin_memory(); h_cross = cross.cpu().pin_memory(); h_glob = glob.cpu().pin_memory()
+    h_out = torch.empty(BATCH, 64, T_LAT).pin_memory()
+
+    def one_e2e():
+        lat = generate_diffusion_cond(model, steps=SAMPLE_STEPS, cfg_scale=CFG_SCALE, batch_size=BATCH,
+                                      conditioning_tensors={"cross_attn_cond": h_cross, "global_cond": h_glob},
+                                      sample_size=T_LAT * 2048, sampler_type="dpmpp-3m-sde", sigma_min=SIGMA_MIN,
+                                      sigma_max=SIGMA_MAX, rho=RHO, noise=h_noise, return_latents=True, device=dev)
+        h_out.copy_(lat, non_blocking=True)
+
+    one_e2e()
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        one_e2e()
+    t1.record()
+    barrier()
+    ms2 = torch.tensor([t0.elapsed_time(t1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_val = SAMPLE_STEPS * BATCH * world * args.steps / (ms2.item() * 1e-3)
+    h2d = h_noise.numel() * 4 + h_cross.numel() * 4 + h_glob.numel() * 4
+    d2h = h_out.numel() * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---------------- roofline of the dominant kernel: the FF1 SwiGLU GEMM (M=2050, N=2x6144, K=1536), timed live
+    pk = peaks()
+    M = 2 * BATCH * (T_LAT + 1)
+    xin = torch.randn(M, D_MODEL, device=dev).bfloat16()
+    outb = torch.empty(M, 4 * D_MODEL, device=dev, dtype=torch.bfloat16)
+    ws = [(eng.w[f"transformer.layers.{i}.ff.ff.0.proj.weight"], eng.w[f"transformer.layers.{i}.ff.ff.0.proj.bias"]) for i in range(DEPTH)]
+    for w_, b_ in ws[:3]:
+        ops.linear(xin, w_, bias=b_, swiglu=True, out=outb)
+    torch.cuda.synchronize()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 4
+    r0.record()
+    for _ in range(reps):
+        for w_, b_ in ws:  # 24 different 37.7 MB weight matrices: inputs larger than L2
+            ops.linear(xin, w_, bias=b_, swiglu=True, out=outb)
+    r1.record()
+    torch.cuda.synchronize()
+    k_ms = r0.elapsed_time(r1) / (reps * DEPTH)
+    k_flop = 2.0 * M * (8 * D_MODEL) * D_MODEL
+    achieved = k_flop / (k_ms * 1e-3) / 1e12
+    roof = {"kernel": "gemm_bf16_tcgen05<256> (FF1 + SwiGLU epilogue, M=2050 N=12288 K=1536)", "bound": "tensor",
+            "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"], "peak_source": pk["src"] + " burst (kernel timed alone)",
+            "avg_launch_ms": k_ms, "traffic": None}
+    step_tflop = SAMPLE_STEPS * 2 * BATCH * (T_LAT + 1) * GFLOP_PER_TOKEN / 1e3
+    whole = {"tflop_per_sample": step_tflop, "achieved_tflops": step_tflop * args.steps * world / (ms_total * 1e-3) / world,
+             "frac_of_sustained_peak": step_tflop * args.steps / (ms_total * 1e-3) / pk["bf16_sustained"]}
+
+    # ---------------- CPU baseline (oracle port) on a bounded sample
+    threads = os.cpu_count() or 1
+    cpu = None
+    if not args.no_cpu_baseline:
+        ts = oracle_cfg_step_seconds(2, threads)
+        cpu_sec = min(ts)
+        cpu = {"value": BATCH / cpu_sec, "unit": "latent-steps/s", "cores": threads, "kind": "port",
+               "sample": "2 CFG denoising steps (of the 100-step workload; effective batch 2, N=1025), torch fp32 oracle port; best of 2"}
+
+    line = {
+        "metric": "dit_sampling_latent_steps_per_sec", "value": value, "unit": "latent-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic (random-init weights, random conditioning)",
+        "config": workload_config(world), "sample_seconds_100_steps": ms_total / args.steps / 1e3,
+        "e2e": {"value": e2e_val, "unit": "latent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "b200sat.generation.generate_diffusion_cond(host pinned noise/conditioning -> host latents)"},
+        "gpu_launches": launches, "clocks": clk, "roofline": roof, "whole_step": whole, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -6,6 +6,9 @@ from ._lib import lib, check
 GEMM_BIAS, GEMM_RESIDUAL, GEMM_SILU, GEMM_SWIGLU, GEMM_ROPE, GEMM_OUT_F32, GEMM_ROW_REMAP, GEMM_GATE = 1, 2, 4, 8, 16, 32, 64, 128
 
 
+LAUNCHES = [0]  # kernel launches issued through this module (bench.py's gpu_launches claim)
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -72,6 +75,7 @@ def linear(x, w, bias=None, residual=None, out=None, silu=False, out_f32=False, 
     rc = lib().b200sat_gemm_bf16(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0),
                                  M, N, K, flags, _p(bias), _p(residual), ldr, _p(rc_), _p(rs_), rseq, rdm, rdh, n_half,
                                  seg_in, seg_out, seg_off, _p(gate), force_bn, _stream())
+    LAUNCHES[0] += 1
     check(rc, "gemm_bf16")
     return out
 
@@ -92,6 +96,7 @@ def attention(q, k, v, out=None, lse=None, scale=None):
                                      q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2),
                                      v.stride(0), v.stride(1), v.stride(2), out.stride(0), out.stride(1), out.stride(2),
                                      D, float(scale), _stream())
+    LAUNCHES[0] += 1
     check(rc, "attention_fwd")
     return out
 
@@ -105,6 +110,7 @@ def layernorm(x, gamma, beta=None, scale=None, shift=None, rows_per_batch=0, out
     ld_mod = scale.stride(0) if scale is not None else 0
     rc = lib().b200sat_layernorm_fwd(x.data_ptr(), x.stride(0), gamma.data_ptr(), _p(beta), _p(scale), _p(shift), ld_mod,
                                      rows_per_batch, out.data_ptr(), out.stride(0), rows, D, float(eps), _stream())
+    LAUNCHES[0] += 1
     check(rc, "layernorm_fwd")
     return out
 
@@ -118,6 +124,7 @@ def small_linear(x, w, bias=None, add=None, out=None, silu=False, out_f32=False,
     rc = lib().b200sat_small_linear(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _p(bias), _p(add),
                                     add.stride(0) if add is not None else 0, out.data_ptr(), out.stride(0), M, N, K,
                                     int(silu), int(out_f32), int(sigmoid_1m), _stream())
+    LAUNCHES[0] += 1
     check(rc, "small_linear")
     return out
 
@@ -128,6 +135,7 @@ def fourier_features(t, w, out=None, step=None, t_stride=0):
     if out is None:
         out = torch.empty((B, 2 * half), device=w.device, dtype=torch.bfloat16)
     rc = lib().b200sat_fourier_features(t.data_ptr(), w.data_ptr(), out.data_ptr(), B, half, _p(step), t_stride, _stream())
+    LAUNCHES[0] += 1
     check(rc, "fourier_features")
     return out
 
@@ -136,6 +144,7 @@ def dit_pre(x, wconv, out, reps=1, cin_table=None, step=None):
     B, C, T = x.shape
     assert x.dtype == torch.float32 and x.is_contiguous()
     rc = lib().b200sat_dit_pre(x.data_ptr(), wconv.data_ptr(), out.data_ptr(), B, C, T, reps, _p(cin_table), _p(step), _stream())
+    LAUNCHES[0] += 1
     check(rc, "dit_pre")
     return out
 
@@ -144,6 +153,7 @@ def dit_post(h, ld_batch, prepend, wconv, out, cfg=False, cfg_scale=1.0, scale_p
     B, C, T = out.shape
     rc = lib().b200sat_dit_post(h.data_ptr(), ld_batch, prepend, wconv.data_ptr(), out.data_ptr(), B, C, T, int(cfg),
                                 float(cfg_scale), float(scale_phi), _stream())
+    LAUNCHES[0] += 1
     check(rc, "dit_post")
     return out
 
@@ -151,9 +161,11 @@ def dit_post(h, ld_batch, prepend, wconv, out, cfg=False, cfg_scale=1.0, scale_p
 def sampler_update(x, v, hist, noise, coef, step, advance=True):
     rc = lib().b200sat_sampler_update(x.data_ptr(), v.data_ptr(), hist.data_ptr(), _p(noise), coef.data_ptr(), step.data_ptr(),
                                       x.numel(), int(advance), _stream())
+    LAUNCHES[0] += 2 if advance else 1
     check(rc, "sampler_update")
     return x
 
 
 def step_set(step, value):
+    LAUNCHES[0] += 1
     check(lib().b200sat_step_set(step.data_ptr(), int(value), _stream()), "step_set")

@@ -104,6 +104,7 @@ class GraphSampler:
         self.graph = None
         self.max_steps = 0
         self.coef = self.cin = self.tt = self.noise = None
+        self.launches_per_step = 0
 
     def _alloc_tables(self, steps):
         if steps > self.max_steps:
@@ -128,7 +129,9 @@ class GraphSampler:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             ops.step_set(self.step, 0)
+            n0 = ops.LAUNCHES[0]
             self._one_step()
+            self.launches_per_step = ops.LAUNCHES[0] - n0
         torch.cuda.current_stream().wait_stream(s)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
@@ -173,6 +176,7 @@ class GraphSampler:
         if self.graph is not None:
             for _ in range(steps):
                 self.graph.replay()
+            ops.LAUNCHES[0] += steps * self.launches_per_step  # kernels replayed from the captured step
         else:
             for _ in range(steps):
                 self._one_step()
