@@ -84,6 +84,47 @@ int b200sat_sampler_update(float* x, const float* v, float* hist, const float* n
                            int advance, void* stream);
 int b200sat_step_set(int* step, int value, void* stream);
 
+/* ---- Oobleck autoencoder (models/autoencoders.py) ------------------------------------------------------------------
+ * Activations are time-major bf16 plane pairs (hi, lo), [B, T, C] each, hi + lo ~ fp32 value; lo pointers may be NULL
+ * when passes == 1 (plain bf16). */
+
+/* Implicit-GEMM Conv1d / ConvTranspose1d on tcgen05 with fused bias, residual add and SnakeBeta epilogue.
+ *   mode 0: stride-1 (dilated) conv, zero padding `pad`        — ResidualUnit convs, autoencoders.py:68-72
+ *   mode 1: strided conv, kernel `taps`, stride `stride`        — EncoderBlock down-sampler, :245-246
+ *   mode 2: transposed conv, kernel 2*stride, stride `stride`   — DecoderBlock up-sampler, :267-269
+ * w_hi/w_lo: packed by b200sat_wn_pack.  out_*: raw result planes (optional); act_*: SnakeBeta(result) planes with the
+ * consumer layer's snake_a = exp(alpha), snake_invb = 1/(exp(beta)+1e-9) (optional).  res_*: residual planes added
+ * before both (ResidualUnit skip, :83).  passes: 1 (bf16) or 3 (hi*hi + hi*lo + lo*hi, fp32-class). */
+int b200sat_conv1d_fwd(const void* in_hi, const void* in_lo, const void* w_hi, const void* w_lo, const float* bias,
+                       const void* res_hi, const void* res_lo, void* out_hi, void* out_lo, void* act_hi, void* act_lo,
+                       const float* snake_a, const float* snake_invb, int B, int T_in, int Cin, int Cout, int taps, int dil,
+                       int pad, int stride, int mode, int passes, void* stream);
+
+/* weight_norm (w = g*v/||v||, norm over all dims but 0; autoencoders.py:23-27) + packing to the GEMM layout as hi/lo bf16
+ * planes.  v fp32 [Cout,Cin,K] (conv) or [Cin,Cout,K] (transposed); g NULL = plain weight. */
+int b200sat_wn_pack(const float* v, const float* g, float* inv_norm_scratch, void* w_hi, void* w_lo, int Cout, int Cin, int K,
+                    int transposed, int stride, void* stream);
+
+/* SnakeBeta parameters (log-scale alpha, beta; blocks.py:321-329) -> exp(alpha), 1/(exp(beta)+1e-9). */
+int b200sat_snake_prep(const float* alpha, const float* beta, float* a, float* invb, int C, void* stream);
+
+/* First conv of the encoder (audio channels -> C; autoencoders.py:303): x fp32 [B,Cin,T] -> planes [B,T,Cout] (+snake). */
+int b200sat_conv_in(const float* x, const float* w, const float* bias, const float* snake_a, const float* snake_invb,
+                    void* out_hi, void* out_lo, void* act_hi, void* act_lo, int B, int Cin, int T, int Cout, int K, int pad,
+                    void* stream);
+
+/* Last conv of the decoder (C -> audio channels; autoencoders.py:355-357): planes [B,T,Cin] -> y fp32 [B,Cout,T]. */
+int b200sat_conv_out(const void* in_hi, const void* in_lo, const float* w, const float* bias, float* y, int B, int Cin, int T,
+                     int Cout, int K, int pad, int tanh_out, void* stream);
+
+/* fp32 [B,C,T] -> hi/lo planes [B,T,C] (decoder input latents). */
+int b200sat_to_planes(const float* x, void* hi, void* lo, int B, int C, int T, void* stream);
+
+/* VAE bottleneck (models/bottleneck.py:105-134): planes [B,T,2L] (mean|scale) -> z = noise*(softplus(scale)+1e-4)+mean
+ * fp32 [B,L,T]; optional fp32 [B,2L,T] copy of (mean|scale); kl_sum += sum(mean^2 + var - log var - 1). */
+int b200sat_vae_sample(const void* hi, const void* lo, const float* noise, float* z, float* mean_scale_out, float* kl_sum,
+                       int B, int L, int T, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

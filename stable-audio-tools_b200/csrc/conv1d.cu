@@ -1,0 +1,576 @@
+// b200sat — Oobleck Conv1d / ConvTranspose1d stacks as im2col-free implicit GEMMs on tcgen05, TMA-staged.
+//
+// Replaces weight_norm + F.conv1d / F.conv_transpose1d (cuDNN) and the eager SnakeBeta kernels of the reference
+// (stable_audio_tools/models/autoencoders.py:23-27, :58-83, :233-283, :285-362; models/blocks.py:291-329).
+//
+// Data layout (DESIGN.md "Oobleck activations"): activations are TIME-MAJOR / channels-last [B, T, C] so that a
+// convolution tap is a row shift: the A operand of tap k is the plain 2-D box rows [t0 + k*dil - pad, +128) x 64 input
+// channels of the SAME tensor, fetched by TMA with out-of-range rows zero-filled (= the conv's zero padding; the batch
+// index is its own tensor-map dimension so padding never leaks between items).  No im2col buffer exists anywhere.
+// Strided (down-sampling) convs view the input as [B, T/s, s, C]; transposed convs are s independent 2-tap convs, one
+// per output phase.  Weights are weight-normalised and packed once per step to [Cout, taps*Cin] (K contiguous).
+//
+// Precision: every activation / weight is a pair of bf16 planes (hi, lo) with hi + lo ~= the fp32 value (2^-17 rel).
+//   passes = 1 : hi x hi only (bf16 GEMM, what autocast training uses)
+//   passes = 3 : hi*hi + hi*lo + lo*hi accumulated in the same fp32 TMEM tile -> fp32-class results on bf16 tensor cores.
+//
+// Epilogue (thread == output time step): + bias, + residual, store raw planes, SnakeBeta with the NEXT layer's
+// (alpha, beta) and store the activated planes — so Snake never makes its own pass over HBM.
+#include "common.cuh"
+#include <cstring>
+
+namespace b200sat {
+
+struct ConvParams {
+  CUtensorMap tmA[2];  // input planes hi, lo: dims {Cin, s_in, T_in/s_in, B}
+  CUtensorMap tmB[2];  // packed weight planes hi, lo: dims {taps*Cin, rows}
+  const float* bias;
+  const float* snake_a;     // exp(alpha) per output channel (of the consumer's SnakeBeta), or null
+  const float* snake_invb;  // 1/(exp(beta)+1e-9)
+  const __nv_bfloat16* res_hi;
+  const __nv_bfloat16* res_lo;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  __nv_bfloat16* act_hi;
+  __nv_bfloat16* act_lo;
+  int B, T_in, T_out, Cin, Cout;
+  int taps, dil, pad, stride;
+  int mode;    // 0 conv (stride 1), 1 strided conv, 2 transposed conv (grid covers `stride` phases)
+  int passes;  // 1 or 3
+  int m_rows;  // GEMM rows per batch item
+  int m_tiles, n_tiles, phases;
+};
+
+constexpr int CV_BM = 128;
+constexpr int CV_BK = 64;
+
+template <int BN>
+struct ConvCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = CV_BM * CV_BK * 2;
+  static constexpr int kBBytes = BN * CV_BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+__device__ __forceinline__ void split_store8(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* v) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a0 = bf16_round(v[2 * i]), a1 = bf16_round(v[2 * i + 1]);
+    h[i] = pack_bf16(a0, a1);
+    l[i] = pack_bf16(v[2 * i] - a0, v[2 * i + 1] - a1);
+  }
+  *reinterpret_cast<uint4*>(hi) = make_uint4(h[0], h[1], h[2], h[3]);
+  if (lo) *reinterpret_cast<uint4*>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1) conv1d_tcgen05(const __grid_constant__ ConvParams p) {
+  using Cfg = ConvCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* tmem_full = bars + 2 * Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_per_phase = p.m_tiles * p.B * p.n_tiles;
+  const int num_tiles = tiles_per_phase * p.phases;
+  const int cin_blocks = p.Cin / CV_BK;
+  const int ksteps_per_pass = p.taps * cin_blocks;
+  const int num_k = p.passes * ksteps_per_pass;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmB[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // tile -> (phase, n_blk, b, m_blk): m fastest so neighbouring CTAs share the weight tile in L2
+  auto decode = [&](int tile, int& ph, int& n_blk, int& b, int& m_blk) {
+    ph = tile / tiles_per_phase;
+    int r = tile % tiles_per_phase;
+    n_blk = r / (p.m_tiles * p.B);
+    r = r % (p.m_tiles * p.B);
+    b = r / p.m_tiles;
+    m_blk = r % p.m_tiles;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int ph, n_blk, b, m_blk;
+        decode(tile, ph, n_blk, b, m_blk);
+        const int m0 = m_blk * CV_BM;
+        for (int ks = 0; ks < num_k; ++ks) {
+          const int pass = ks / ksteps_per_pass;
+          const int rem = ks % ksteps_per_pass;
+          const int tap = rem / cin_blocks;
+          const int cib = rem % cin_blocks;
+          int r = 0, row_off;
+          if (p.mode == 0) {
+            row_off = tap * p.dil - p.pad;
+          } else if (p.mode == 1) {
+            const int d = tap - p.pad;                      // input time = t_out*s + d
+            const int j = (d >= 0) ? d / p.stride : -((-d + p.stride - 1) / p.stride);
+            r = d - j * p.stride;
+            row_off = j;
+          } else {
+            row_off = -tap;                                 // transposed conv phase: x[q - j]
+          }
+          const int a_plane = (pass == 2) ? 1 : 0;          // passes: hi*hi, hi*lo, lo*hi
+          const int b_plane = (pass == 1) ? 1 : 0;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_4d(sa, &p.tmA[a_plane], &full_bar[stage], cib * CV_BK, r, m0 + row_off, b);
+          tma_load_2d(sb, &p.tmB[b_plane], &full_bar[stage], tap * p.Cin + cib * CV_BK, ph * p.Cout + n_blk * BN);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(CV_BM, BN, 0, 0);
+      int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int ks = 0; ks < num_k; ++ks) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+          const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < CV_BK / 16; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (ks | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int ph, n_blk, b, m_blk;
+      decode(tile, ph, n_blk, b, m_blk);
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const int m = m_blk * CV_BM + q * 32 + lane;
+      int t = m;
+      bool ok = m < p.m_rows;
+      if (p.mode == 2) { t = m * p.stride + ph - p.pad; ok = ok && t >= 0 && t < p.T_out; }
+      const size_t row_off = (static_cast<size_t>(b) * p.T_out + (ok ? t : 0)) * p.Cout;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col = n_blk * BN + c * 32;
+        if (col >= p.Cout) break;
+        uint32_t raw[32];
+        float v[32];
+        tmem_ld_32x32(taddr + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + col + i);
+        }
+        if (ok) {
+          const size_t off = row_off + col;
+          if (p.res_hi) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.res_hi + off) + i);
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16(w[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
+            }
+            if (p.res_lo) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.res_lo + off) + i);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16(w[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
+              }
+            }
+          }
+          if (p.out_hi) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_store8(p.out_hi + off + 8 * i, p.out_lo ? p.out_lo + off + 8 * i : nullptr, v + 8 * i);
+          }
+          if (p.act_hi) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float s = sinf(v[i] * __ldg(p.snake_a + col + i));
+              v[i] = v[i] + __ldg(p.snake_invb + col + i) * s * s;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_store8(p.act_hi + off + 8 * i, p.act_lo ? p.act_lo + off + 8 * i : nullptr, v + 8 * i);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::kTmemCols); }
+}
+
+template <int BN>
+static int launch_conv(ConvParams& p, cudaStream_t stream) {
+  using Cfg = ConvCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200SAT_CHECK_CUDA(cudaFuncSetAttribute(conv1d_tcgen05<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  p.m_tiles = (p.m_rows + CV_BM - 1) / CV_BM;
+  p.n_tiles = (p.Cout + BN - 1) / BN;
+  const long tiles = static_cast<long>(p.m_tiles) * p.B * p.n_tiles * p.phases;
+  const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+  conv1d_tcgen05<BN><<<grid, 256, Cfg::kSmemBytes, stream>>>(p);
+  B200SAT_CHECK_CUDA(cudaGetLastError());
+  return B200SAT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// weight_norm (old-style, dim 0: w = g * v / ||v||, autoencoders.py:23-27) + packing into the GEMM layout, hi/lo planes.
+//   conv:        v [Cout, Cin, K]  -> W[co][k*Cin + ci]
+//   transposed:  v [Cin, Cout, K]  -> W[(ph*Cout + co)][j*Cin + ci] = w[ci][co][ph + s*j]     (K = 2s)
+__global__ void wn_norm_kernel(const float* __restrict__ v, float* __restrict__ inv_norm, int inner) {
+  const int r = blockIdx.x;
+  const float* p = v + static_cast<size_t>(r) * inner;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < inner; i += blockDim.x) { const float x = p[i]; s += x * x; }
+  __shared__ float red[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) inv_norm[r] = rsqrtf(s);
+  }
+}
+__global__ void wn_pack_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ inv_norm,
+                               __nv_bfloat16* __restrict__ w_hi, __nv_bfloat16* __restrict__ w_lo, int Cout, int Cin, int K,
+                               int transposed, int stride) {
+  const long n = static_cast<long>(Cout) * Cin * K;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    // i indexes the packed layout (coalesced writes)
+    float w;
+    if (!transposed) {
+      const int co = i / (static_cast<long>(K) * Cin);
+      const int rem = i % (static_cast<long>(K) * Cin);
+      const int k = rem / Cin, ci = rem % Cin;
+      const float vv = v[(static_cast<long>(co) * Cin + ci) * K + k];
+      w = g ? vv * g[co] * inv_norm[co] : vv;
+    } else {
+      const int kp = 2 * Cin;  // packed K per phase row
+      const long row = i / kp;
+      const int rem = i % kp;
+      const int ph = row / Cout, co = row % Cout;
+      const int j = rem / Cin, ci = rem % Cin;
+      const float vv = v[(static_cast<long>(ci) * Cout + co) * K + ph + stride * j];
+      w = g ? vv * g[ci] * inv_norm[ci] : vv;
+    }
+    const float h = bf16_round(w);
+    w_hi[i] = __float2bfloat16_rn(h);
+    if (w_lo) w_lo[i] = __float2bfloat16_rn(w - h);
+  }
+}
+
+// SnakeBeta parameters -> exp(alpha), 1/(exp(beta)+1e-9)   (blocks.py:321-329, :291-292)
+__global__ void snake_prep_kernel(const float* __restrict__ alpha, const float* __restrict__ beta, float* __restrict__ a,
+                                  float* __restrict__ invb, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) { a[i] = expf(alpha[i]); invb[i] = 1.0f / (expf(beta[i]) + 1e-9f); }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Edge layers with 2 audio channels (tensor cores would idle): SIMT kernels.
+// conv_in: x fp32 [B, Cin<=4, T] -> channels-last planes [B, T, Cout] (+ snake planes).  autoencoders.py:303
+__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w /*[Cout,Cin,K]*/,
+                                                      const float* __restrict__ bias, const float* __restrict__ sa,
+                                                      const float* __restrict__ sib, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
+                                                      __nv_bfloat16* act_hi, __nv_bfloat16* act_lo, int B, int Cin, int T, int Cout,
+                                                      int K, int pad) {
+  extern __shared__ float sm[];
+  float* sw = sm;                       // Cout*Cin*K
+  float* sx = sm + Cout * Cin * K;      // Cin * (64 + K - 1)
+  const int b = blockIdx.y, t0 = blockIdx.x * 64;
+  for (int i = threadIdx.x; i < Cout * Cin * K; i += 256) sw[i] = w[i];
+  const int span = 64 + K - 1;
+  for (int i = threadIdx.x; i < Cin * span; i += 256) {
+    const int ci = i / span, tt = i % span;
+    const int t = t0 + tt - pad;
+    sx[i] = (t >= 0 && t < T) ? x[(static_cast<long>(b) * Cin + ci) * T + t] : 0.f;
+  }
+  __syncthreads();
+  // thread -> 8 consecutive output channels of one time step per iteration
+  const int groups = Cout / 8;
+  for (int it = threadIdx.x; it < 64 * groups; it += 256) {
+    const int tt = it / groups, cg = it % groups;
+    const int t = t0 + tt;
+    if (t >= T) continue;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int co = cg * 8 + j;
+      float acc = bias ? bias[co] : 0.f;
+      for (int ci = 0; ci < Cin; ++ci)
+        for (int k = 0; k < K; ++k) acc += sw[(co * Cin + ci) * K + k] * sx[ci * span + tt + k];
+      v[j] = acc;
+    }
+    const size_t off = (static_cast<size_t>(b) * T + t) * Cout + cg * 8;
+    if (out_hi) split_store8(out_hi + off, out_lo ? out_lo + off : nullptr, v);
+    if (act_hi) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float s = sinf(v[j] * sa[cg * 8 + j]); v[j] += sib[cg * 8 + j] * s * s; }
+      split_store8(act_hi + off, act_lo ? act_lo + off : nullptr, v);
+    }
+  }
+}
+
+// conv_out: activated planes [B, T, Cin] -> y fp32 [B, Cout<=4, T], K taps, zero padding, optional tanh.  autoencoders.py:355-357
+__global__ void __launch_bounds__(256) conv_out_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfloat16* __restrict__ in_lo,
+                                                       const float* __restrict__ w /*[Cout,Cin,K]*/, const float* __restrict__ bias,
+                                                       float* __restrict__ y, int B, int Cin, int T, int Cout, int K, int pad, int tanh_out) {
+  extern __shared__ float sm[];
+  float* sw = sm;                         // Cout*K*Cin laid out [co][k][ci]
+  float* sx = sm + Cout * K * Cin;        // (32 + K - 1) * (Cin + 1)
+  const int b = blockIdx.y, t0 = blockIdx.x * 32;
+  for (int i = threadIdx.x; i < Cout * Cin * K; i += 256) {
+    const int co = i / (Cin * K), rem = i % (Cin * K), ci = rem / K, k = rem % K;
+    sw[(co * K + k) * Cin + ci] = w[i];
+  }
+  const int span = 32 + K - 1;
+  for (int i = threadIdx.x; i < span * Cin; i += 256) {
+    const int tt = i / Cin, ci = i % Cin;
+    const int t = t0 + tt - pad;
+    float v = 0.f;
+    if (t >= 0 && t < T) {
+      const size_t off = (static_cast<size_t>(b) * T + t) * Cin + ci;
+      v = __bfloat162float(in_hi[off]) + (in_lo ? __bfloat162float(in_lo[off]) : 0.f);
+    }
+    sx[tt * (Cin + 1) + ci] = v;
+  }
+  __syncthreads();
+  // warp w handles time steps w, w+8, ...; lanes split Cin
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int tt = warp; tt < 32; tt += 8) {
+    const int t = t0 + tt;
+    if (t >= T) break;
+    for (int co = 0; co < Cout; ++co) {
+      float acc = 0.f;
+      for (int k = 0; k < K; ++k)
+        for (int ci = lane; ci < Cin; ci += 32) acc += sw[(co * K + k) * Cin + ci] * sx[(tt + k) * (Cin + 1) + ci];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) {
+        if (bias) acc += bias[co];
+        y[(static_cast<size_t>(b) * Cout + co) * T + t] = tanh_out ? tanhf(acc) : acc;
+      }
+    }
+  }
+}
+
+// fp32 [B, C, T] -> channels-last hi/lo planes [B, T, C] (decoder input latents)
+__global__ void to_planes_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                 int B, int C, int T) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && t < T) ? x[(static_cast<size_t>(b) * C + c) * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    if (t < T && c < C) {
+      const float v = tile[threadIdx.x][i];
+      const float h = bf16_round(v);
+      const size_t off = (static_cast<size_t>(b) * T + t) * C + c;
+      hi[off] = __float2bfloat16_rn(h);
+      if (lo) lo[off] = __float2bfloat16_rn(v - h);
+    }
+  }
+}
+
+// Encoder tail: planes [B, T, 2*L] (mean | scale) -> VAE sample z = noise*(softplus(scale)+1e-4) + mean, fp32 [B, L, T],
+// and KL partial sums (bottleneck.py:105-113).  kl_out accumulates sum over (b, t, c) of (mean^2 + var - log var - 1).
+__global__ void vae_sample_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                  const float* __restrict__ noise, float* __restrict__ z, float* __restrict__ mean_scale_out,
+                                  float* __restrict__ kl_out, int B, int L, int T) {
+  const long n = static_cast<long>(B) * L * T;
+  float klacc = 0.f;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int t = i % T;
+    const int c = (i / T) % L;
+    const int b = i / (static_cast<long>(T) * L);
+    const size_t off = (static_cast<size_t>(b) * T + t) * (2 * L);
+    const float mean = __bfloat162float(hi[off + c]) + (lo ? __bfloat162float(lo[off + c]) : 0.f);
+    const float sc = __bfloat162float(hi[off + L + c]) + (lo ? __bfloat162float(lo[off + L + c]) : 0.f);
+    const float sp = (sc > 20.f) ? sc : log1pf(expf(sc));  // F.softplus (threshold 20)
+    const float stdev = sp + 1e-4f;
+    const float var = stdev * stdev;
+    if (z) z[i] = (noise ? noise[i] : 0.f) * stdev + mean;
+    if (mean_scale_out) {
+      mean_scale_out[(static_cast<size_t>(b) * 2 * L + c) * T + t] = mean;
+      mean_scale_out[(static_cast<size_t>(b) * 2 * L + L + c) * T + t] = sc;
+    }
+    klacc += mean * mean + var - logf(var) - 1.f;
+  }
+  if (kl_out) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) klacc += __shfl_xor_sync(0xffffffffu, klacc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(kl_out, klacc);
+  }
+}
+
+}  // namespace b200sat
+
+using namespace b200sat;
+
+static int make_plane_map(CUtensorMap* tm, const void* base, int B, int T, int C, int s_in) {
+  uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(s_in), static_cast<uint64_t>(T / s_in), static_cast<uint64_t>(B)};
+  uint64_t strides[3] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(C) * s_in * 2, static_cast<uint64_t>(C) * T * 2};
+  uint32_t box[4] = {CV_BK, 1, CV_BM, 1};
+  return encode_tmap_bf16(tm, base, 4, dims, strides, box, 1);
+}
+
+extern "C" int b200sat_conv1d_fwd(const void* in_hi, const void* in_lo, const void* w_hi, const void* w_lo, const float* bias,
+                                  const void* res_hi, const void* res_lo, void* out_hi, void* out_lo, void* act_hi, void* act_lo,
+                                  const float* snake_a, const float* snake_invb, int B, int T_in, int Cin, int Cout, int taps,
+                                  int dil, int pad, int stride, int mode, int passes, void* stream) {
+  if (!in_hi || !w_hi || (!out_hi && !act_hi) || B <= 0 || T_in <= 0) { set_last_error("conv1d: bad arguments"); return B200SAT_EINVAL; }
+  if (Cin % 64 || Cout % 32) { set_last_error("conv1d: Cin must be a multiple of 64 and Cout of 32 (edge layers use conv_in/conv_out)"); return B200SAT_EUNSUPPORTED; }
+  if (passes != 1 && passes != 3) { set_last_error("conv1d: passes must be 1 or 3"); return B200SAT_EINVAL; }
+  if (passes == 3 && (!in_lo || !w_lo)) { set_last_error("conv1d: passes=3 needs lo planes"); return B200SAT_EINVAL; }
+  if (act_hi && (!snake_a || !snake_invb)) { set_last_error("conv1d: activated output needs snake parameters"); return B200SAT_EINVAL; }
+  if (mode < 0 || mode > 2 || stride < 1 || (mode == 1 && T_in % stride)) { set_last_error("conv1d: bad mode/stride"); return B200SAT_EINVAL; }
+  if (mode == 2 && taps != 2 * stride) { set_last_error("conv1d: transposed conv needs kernel_size == 2*stride"); return B200SAT_EUNSUPPORTED; }
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.T_in = T_in; p.Cin = Cin; p.Cout = Cout; p.dil = dil; p.pad = pad; p.stride = stride; p.mode = mode; p.passes = passes;
+  int wrows, wk;
+  if (mode == 0) { p.T_out = T_in + 2 * pad - dil * (taps - 1); p.taps = taps; p.m_rows = p.T_out; p.phases = 1; wrows = Cout; wk = taps * Cin; }
+  else if (mode == 1) { p.T_out = (T_in + 2 * pad - taps) / stride + 1; p.taps = taps; p.m_rows = p.T_out; p.phases = 1; wrows = Cout; wk = taps * Cin; }
+  else { p.T_out = (T_in - 1) * stride - 2 * pad + taps; p.taps = 2; p.m_rows = T_in + 1; p.phases = stride; wrows = stride * Cout; wk = 2 * Cin; }
+  if (p.T_out <= 0) { set_last_error("conv1d: empty output"); return B200SAT_EINVAL; }
+  const int s_in = (mode == 1) ? stride : 1;
+  const int bn = (Cout >= 256) ? 256 : 128;
+  int rc;
+  if ((rc = make_plane_map(&p.tmA[0], in_hi, B, T_in, Cin, s_in))) return rc;
+  if (in_lo && (rc = make_plane_map(&p.tmA[1], in_lo, B, T_in, Cin, s_in))) return rc;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(wk), static_cast<uint64_t>(wrows)};
+    uint64_t strides[1] = {static_cast<uint64_t>(wk) * 2};
+    uint32_t box[2] = {CV_BK, static_cast<uint32_t>(bn)};
+    if ((rc = encode_tmap_bf16(&p.tmB[0], w_hi, 2, dims, strides, box, 1))) return rc;
+    if (w_lo && (rc = encode_tmap_bf16(&p.tmB[1], w_lo, 2, dims, strides, box, 1))) return rc;
+  }
+  p.bias = bias; p.snake_a = snake_a; p.snake_invb = snake_invb;
+  p.res_hi = static_cast<const __nv_bfloat16*>(res_hi); p.res_lo = static_cast<const __nv_bfloat16*>(res_lo);
+  p.out_hi = static_cast<__nv_bfloat16*>(out_hi); p.out_lo = static_cast<__nv_bfloat16*>(out_lo);
+  p.act_hi = static_cast<__nv_bfloat16*>(act_hi); p.act_lo = static_cast<__nv_bfloat16*>(act_lo);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return bn == 256 ? launch_conv<256>(p, s) : launch_conv<128>(p, s);
+}
+
+extern "C" int b200sat_wn_pack(const float* v, const float* g, float* inv_norm_scratch, void* w_hi, void* w_lo, int Cout, int Cin,
+                               int K, int transposed, int stride, void* stream) {
+  if (!v || !w_hi || Cout <= 0 || Cin <= 0 || K <= 0) { set_last_error("wn_pack: bad arguments"); return B200SAT_EINVAL; }
+  if (g && !inv_norm_scratch) { set_last_error("wn_pack: weight-norm needs a scratch buffer of dim-0 floats"); return B200SAT_EINVAL; }
+  if (transposed && K != 2 * stride) { set_last_error("wn_pack: transposed conv needs K == 2*stride"); return B200SAT_EUNSUPPORTED; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int dim0 = transposed ? Cin : Cout;
+  const int inner = (transposed ? Cout : Cin) * K;
+  if (g) wn_norm_kernel<<<dim0, 256, 0, s>>>(v, inv_norm_scratch, inner);
+  const long n = static_cast<long>(Cout) * Cin * K;
+  const int grid = static_cast<int>((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  wn_pack_kernel<<<grid, 256, 0, s>>>(v, g, inv_norm_scratch, static_cast<__nv_bfloat16*>(w_hi), static_cast<__nv_bfloat16*>(w_lo),
+                                      Cout, Cin, K, transposed, stride);
+  B200SAT_CHECK_CUDA(cudaGetLastError());
+  return B200SAT_OK;
+}
+
+extern "C" int b200sat_snake_prep(const float* alpha, const float* beta, float* a, float* invb, int C, void* stream) {
+  if (!alpha || !beta || !a || !invb || C <= 0) { set_last_error("snake_prep: bad arguments"); return B200SAT_EINVAL; }
+  snake_prep_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(alpha, beta, a, invb, C);
+  B200SAT_CHECK_CUDA(cudaGetLastError());
+  return B200SAT_OK;
+}
+
+extern "C" int b200sat_conv_in(const float* x, const float* w, const float* bias, const float* snake_a, const float* snake_invb,
+                               void* out_hi, void* out_lo, void* act_hi, void* act_lo, int B, int Cin, int T, int Cout, int K, int pad,
+                               void* stream) {
+  if (!x || !w || B <= 0 || Cin <= 0 || Cin > 8 || Cout % 8 || K <= 0) { set_last_error("conv_in: bad arguments (Cin <= 8, Cout % 8 == 0)"); return B200SAT_EINVAL; }
+  const int smem = (Cout * Cin * K + Cin * (64 + K - 1)) * 4;
+  if (smem > 48 * 1024) { set_last_error("conv_in: weights do not fit in 48 KB of shared memory"); return B200SAT_EUNSUPPORTED; }
+  dim3 grid((T + 63) / 64, B);
+  conv_in_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      x, w, bias, snake_a, snake_invb, static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo),
+      static_cast<__nv_bfloat16*>(act_hi), static_cast<__nv_bfloat16*>(act_lo), B, Cin, T, Cout, K, pad);
+  B200SAT_CHECK_CUDA(cudaGetLastError());
+  return B200SAT_OK;
+}
+
+extern "C" int b200sat_conv_out(const void* in_hi, const void* in_lo, const float* w, const float* bias, float* y, int B, int Cin,
+                                int T, int Cout, int K, int pad, int tanh_out, void* stream) {
+  if (!in_hi || !w || !y || B <= 0 || Cout <= 0 || Cout > 8) { set_last_error("conv_out: bad arguments (Cout <= 8)"); return B200SAT_EINVAL; }
+  const int smem = (Cout * K * Cin + (32 + K - 1) * (Cin + 1)) * 4;
+  if (smem > 48 * 1024) { set_last_error("conv_out: tile does not fit in 48 KB of shared memory"); return B200SAT_EUNSUPPORTED; }
+  dim3 grid((T + 31) / 32, B);
+  conv_out_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(in_hi), static_cast<const __nv_bfloat16*>(in_lo), w, bias, y, B, Cin, T, Cout, K, pad, tanh_out);
+  B200SAT_CHECK_CUDA(cudaGetLastError());
+  return B200SAT_OK;
+}
+
+extern "C" int b200sat_to_planes(const float* x, void* hi, void* lo, int B, int C, int T, void* stream) {
+  if (!x || !hi || B <= 0 || C <= 0 || T <= 0) { set_last_error("to_planes: bad arguments"); return B200SAT_EINVAL; }
+  dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  to_planes_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), B, C, T);
+  B200SAT_CHECK_CUDA(cudaGetLastError());
+  return B200SAT_OK;
+}
+
+extern "C" int b200sat_vae_sample(const void* hi, const void* lo, const float* noise, float* z, float* mean_scale_out, float* kl_sum,
+                                  int B, int L, int T, void* stream) {
+  if (!hi || B <= 0 || L <= 0 || T <= 0) { set_last_error("vae_sample: bad arguments"); return B200SAT_EINVAL; }
+  const long n = static_cast<long>(B) * L * T;
+  const int grid = static_cast<int>((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+  vae_sample_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(hi), static_cast<const __nv_bfloat16*>(lo),
+                                                                        noise, z, mean_scale_out, kl_sum, B, L, T);
+  B200SAT_CHECK_CUDA(cudaGetLastError());
+  return B200SAT_OK;
+}

@@ -1,0 +1,81 @@
+"""CPU: the oracle restatements reproduce the committed reference outputs (tests/golden, made by oracle/gen_golden.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dit as odit, oobleck as oo, stft_loss as ost, sampling as osamp
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _load(name):
+    z = np.load(os.path.join(G, name), allow_pickle=False)
+    return {k: (torch.from_numpy(z[k]) if k != "meta" else json.loads(str(z[k]))) for k in z.files}
+
+
+@pytest.mark.parametrize("gct", ["prepend", "adaLN"])
+def test_dit_forward_matches_reference(gct):
+    f = _load(f"dit_{gct}.npz")
+    cfg = f["meta"]["cfg"]
+    sd = odit.make_state_dict(global_cond_type=gct, seed=f["meta"]["weights_seed"], **cfg)
+    with torch.no_grad():
+        y = odit.dit_forward(f["x"], f["t"], sd, cfg["depth"], f["cross"], f["glob"], global_cond_type=gct)
+        yc = odit.dit_forward(f["x"], f["t"], sd, cfg["depth"], f["cross"], f["glob"], cfg_scale=6.0, scale_phi=0.75, global_cond_type=gct)
+    assert (y - f["y_plain"]).abs().max() <= 1e-5 * max(1.0, f["y_plain"].abs().max())
+    assert (yc - f["y_cfg"]).abs().max() <= 2e-5 * max(1.0, f["y_cfg"].abs().max())
+
+
+@pytest.mark.parametrize("gct", ["prepend", "adaLN"])
+def test_dit_v_objective_loss_and_grads(gct):
+    f = _load(f"dit_{gct}.npz")
+    cfg = f["meta"]["cfg"]
+    sd = odit.make_state_dict(global_cond_type=gct, seed=f["meta"]["weights_seed"], **cfg)
+    names = [k[5:] for k in f if k.startswith("grad.")]
+    for n in names:
+        sd[n] = sd[n].clone().requires_grad_(True)
+    model = lambda x, t: odit.dit_forward(x, t, sd, cfg["depth"], f["cross"], f["glob"], global_cond_type=gct)
+    loss, _, _ = odit.v_objective_loss(model, f["x"], f["noise"], f["t"])
+    loss.backward()
+    assert abs(loss.item() - f["loss"].item()) <= 1e-5 * max(1.0, abs(f["loss"].item()))
+    for n in names:
+        ref = f["grad." + n]
+        assert (sd[n].grad - ref).abs().max() <= 1e-4 * max(1e-6, ref.abs().max()), n
+
+
+def test_oobleck_matches_reference():
+    f = _load("oobleck_small.npz")
+    sd = oo.make_state_dict(channels=64, c_mults=(1, 2, 4), strides=(2, 4, 4), enc_latent=128, dec_latent=64, seed=f["meta"]["weights_seed"])
+    with torch.no_grad():
+        enc = oo.oobleck_encode(f["x"], sd, (2, 4, 4))
+        lat, kl = oo.vae_sample(enc, f["vae_noise"])
+        dec = oo.oobleck_decode(f["latents"], sd, (2, 4, 4))
+    assert (enc - f["enc"]).abs().max() <= 1e-4 * f["enc"].abs().max()
+    assert (lat - f["latents"]).abs().max() <= 1e-4 * f["latents"].abs().max()
+    assert abs(kl.item() - f["kl"].item()) <= 1e-4 * abs(f["kl"].item())
+    assert (dec - f["dec"]).abs().max() <= 1e-4 * f["dec"].abs().max()
+
+
+def test_mrstft_matches_reference():
+    f = _load("mrstft.npz")
+    ff = [2048, 1024, 512, 256, 128, 64, 32]; hs = [n // 4 for n in ff]
+    taps = ost.a_weighting_fir()
+    assert (taps - f["taps"]).abs().max() <= 1e-7
+    x = f["x"].clone().requires_grad_(True)
+    l_sd = ost.sum_and_difference_loss(x, f["y"], ff, hs, taps)
+    l_sd.backward()
+    assert abs(l_sd.item() - f["loss_sd"].item()) <= 1e-5
+    assert (x.grad - f["grad_sd"]).abs().max() <= 1e-3 * f["grad_sd"].abs().max()
+    assert abs(ost.mrstft_loss(f["x"][:, :1], f["y"][:, :1], ff, hs, taps).item() - f["loss_l"].item()) <= 1e-5
+    assert abs(ost.mrstft_loss(f["x"], f["y"], ff, hs, None).item() - f["loss_plain"].item()) <= 1e-5
+    mag = ost.stft_mag(f["x"].reshape(-1, f["x"].shape[-1]), 256, 64)
+    assert (mag - f["mag256"]).abs().max() <= 1e-4 * f["mag256"].abs().max()
+
+
+def test_vddim_matches_reference():
+    f = _load("vddim_toy.npz")
+    toy = lambda x_, t_, **kw: torch.tanh(x_ * 0.7) * (0.3 + t_.view(-1, 1, 1)) - 0.1 * x_
+    out = osamp.sample_v_ddim(toy, f["noise"], 25)
+    assert (out - f["out"]).abs().max() <= 1e-6
