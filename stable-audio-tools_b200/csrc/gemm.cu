@@ -7,11 +7,14 @@
 // that follow them: bias add, SwiGLU (transformer.py:272-275), residual add (:704-712), the partial NeoX RoPE on
 // q/k (:154-174, :491-507) and SiLU (dit.py:41-76).
 //
-// Structure (one persistent CTA per SM, 256 threads):
+// Structure (one persistent CTA per SM, 384 threads):
 //   warp 0  lane 0 : TMA producer  — cp.async.bulk.tensor tiles of A (128x64) and B (BNx64), 128B swizzle, kStages ring
 //   warp 1  lane 0 : MMA issuer    — tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16, fp32 accumulators in TMEM
 //   warp 2         : TMEM allocator (2 accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1)
-//   warps 4..7     : epilogue      — tcgen05.ld 32x32b (thread == output row), fused math, 16-byte global stores
+//   (CTAS == 2: the same roles in both CTAs of a cluster pair; only the leader CTA issues the 256-row MMAs)
+//   warps 4..11    : epilogue      — tcgen05.ld 32x32b (thread == output row), fused math, 16-byte global stores;
+//                    two warps per SM sub-partition because a lone warp cannot hide its own ALU latency (ncu r1: the
+//                    4-warp epilogue ran at IPC 0.1 and starved the MMA issuer on the tmem_empty barrier)
 #include "common.cuh"
 #include <cstring>
 
@@ -50,12 +53,15 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 
-template <int BN>
+// CTAS == 2: a CTA pair (cluster of 2 on one TPC) computes a 256 x BN tile with tcgen05.mma.cta_group::2 — each CTA
+// stages its own 128 rows of A and HALF of the B tile, so the L2 -> SMEM bytes per MMA flop drop by 1.5x (the 1-CTA kernel
+// is L2-bandwidth bound: 96 B/clk/SM needed vs ~43 B/clk/SM available chip-wide).
+template <int BN, int CTAS>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
-  static constexpr int kBBytes = BN * BLOCK_K * 2;
+  static constexpr int kBBytes = (BN / CTAS) * BLOCK_K * 2;   // per CTA
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (192 * 1024) / kStageBytes > 8 ? 8 : (192 * 1024) / kStageBytes;
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -88,9 +94,12 @@ __device__ __forceinline__ void store_chunk_f32(float* dst, const float (&o)[32]
   }
 }
 
-template <int BN>
-__global__ void __launch_bounds__(256, 1) gemm_bf16_tcgen05(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+template <int BN, int CTAS>
+__global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BN, CTAS>;
+  const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
+  const int unit = (CTAS == 2) ? (blockIdx.x >> 1) : blockIdx.x;          // scheduling unit = CTA or CTA pair
+  const int num_units = (CTAS == 2) ? (gridDim.x >> 1) : gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -119,16 +128,16 @@ __global__ void __launch_bounds__(256, 1) gemm_bf16_tcgen05(const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], 256 * CTAS);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (CTAS == 2) { tmem_alloc_pair(tmem_ptr_smem, Cfg::kTmemCols); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -137,34 +146,44 @@ __global__ void __launch_bounds__(256, 1) gemm_bf16_tcgen05(const __grid_constan
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < num_tiles; tile += num_units) {
         const int m_blk = tile % p.num_m_tiles;
         const int n_blk = tile / p.num_m_tiles;
+        const int m0 = m_blk * (BLOCK_M * CTAS) + cta_rank * BLOCK_M;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(sa, &p.tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
-          if (swiglu) {
-            tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BLOCK_K, n_blk * (BN / 2));
-            tma_load_2d(sb + Cfg::kBBytes / 2, &p.tmB, &full_bar[stage], kb * BLOCK_K, p.n_half + n_blk * (BN / 2));
+          if (CTAS == 1) {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(sa, &p.tmA, &full_bar[stage], kb * BLOCK_K, m0);
+            if (swiglu) {
+              tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BLOCK_K, n_blk * (BN / 2));
+              tma_load_2d(sb + Cfg::kBBytes / 2, &p.tmB, &full_bar[stage], kb * BLOCK_K, p.n_half + n_blk * (BN / 2));
+            } else {
+              tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BN);
+            }
           } else {
-            tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BN);
+            // both CTAs load; all bytes are credited to the leader's barrier, which expects the pair's total
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            tma_load_2d_pair(sa, &p.tmA, &full_bar[stage], kb * BLOCK_K, m0);
+            const int brow = swiglu ? (cta_rank == 0 ? n_blk * (BN / 2) : p.n_half + n_blk * (BN / 2))
+                                    : n_blk * BN + static_cast<int>(cta_rank) * (BN / 2);
+            tma_load_2d_pair(sb, &p.tmB, &full_bar[stage], kb * BLOCK_K, brow);
           }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, 0, 0);
+    if (lane == 0 && cta_rank == 0) {
+      // ===================== MMA issuer (leader CTA only in pair mode) =====================
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M * CTAS, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < num_tiles; tile += num_units) {
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
@@ -178,90 +197,112 @@ __global__ void __launch_bounds__(256, 1) gemm_bf16_tcgen05(const __grid_constan
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance K inside the 128B swizzle row: 16 bf16 = 32 bytes = +2 in the (addr >> 4) field
-            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            if (CTAS == 2) umma_bf16_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);
+          if (CTAS == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[as]);
+        if (CTAS == 2) umma_commit_pair(&tmem_full[as]); else umma_commit(&tmem_full[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int q = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may access
+    // ===================== epilogue (8 warps: 2 per SM sub-partition, each owns half of the tile's columns) ===========
+    const int ew = warp - 4;
+    const int q = ew & 3;      // TMEM lane quarter this warp may access (warp % 4)
+    const int half = ew >> 2;  // column half
+    const int chunks_per_warp = (out_bn / 32 + 1) / 2;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = unit; tile < num_tiles; tile += num_units) {
       const int m_blk = tile % p.num_m_tiles;
       const int n_blk = tile / p.num_m_tiles;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      const int row = m_blk * BLOCK_M + q * 32 + lane;
+      const int row = m_blk * (BLOCK_M * CTAS) + static_cast<int>(cta_rank) * BLOCK_M + q * 32 + lane;
       const bool row_ok = row < p.M;
       int out_row = row;
       if (p.flags & GEMM_ROW_REMAP) out_row = (row / p.seg_in) * p.seg_out + p.seg_off + (row % p.seg_in);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
       const int n0 = n_blk * out_bn;
-      for (int c = 0; c < out_bn / 32; ++c) {
+      for (int cc = 0; cc < chunks_per_warp; ++cc) {
+        const int c = half * chunks_per_warp + cc;
         const int col = n0 + c * 32;
-        if (col >= p.N) break;  // warp-uniform
+        if (c * 32 >= out_bn || col >= p.N) break;  // warp-uniform
         uint32_t raw[32];
         float v[32];
         tmem_ld_32x32(taddr + c * 32, raw);
+        const int ncols = min(32, p.N - col);
+        const bool full = ncols == 32;
+        float bv[32];
+        if (p.flags & GEMM_BIAS) {
+          if (full) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float4 t = __ldg(bp + i); bv[4 * i] = t.x; bv[4 * i + 1] = t.y; bv[4 * i + 2] = t.z; bv[4 * i + 3] = t.w; }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) bv[i] = (i < ncols) ? __ldg(p.bias + col + i) : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) bv[i] = 0.f;
+        }
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-        const int ncols = min(32, p.N - col);
-        if (p.flags & GEMM_BIAS) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += __ldg(p.bias + col + i);
-        }
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) + bv[i];
         if (swiglu) {
-          uint32_t graw[32];
-          tmem_ld_32x32(taddr + BN / 2 + c * 32, graw);
+          // value * silu(gate); the gate half of the tile sits BN/2 accumulator columns further
+          tmem_ld_32x32(taddr + BN / 2 + c * 32, raw);
+          if (p.flags & GEMM_BIAS) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + p.n_half + col);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float4 t = __ldg(bp + i); bv[4 * i] = t.x; bv[4 * i + 1] = t.y; bv[4 * i + 2] = t.z; bv[4 * i + 3] = t.w; }
+          }
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            float g = __uint_as_float(graw[i]);
-            if ((p.flags & GEMM_BIAS) && i < ncols) g += __ldg(p.bias + p.n_half + col + i);
-            // bf16 rounding points follow the reference's bf16 eager path: linear -> silu -> mul
-            g = bf16_round(g);
-            const float a = bf16_round(v[i]);
-            v[i] = a * bf16_round(silu_f(g));
+            const float g = __uint_as_float(raw[i]) + bv[i];
+            v[i] = v[i] * silu_f(g);
           }
         }
         if (p.flags & GEMM_SILU) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = silu_f(bf16_round(v[i]));
+          for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
         }
         if ((p.flags & GEMM_ROPE) && row_ok) {
-          // column -> (which in {q,k,v}, head, dim); rotate dims [0,32) of q and k heads (NeoX half-split, 16 freqs)
+          // column -> (which in {q,k,v}, head, dim); rotate dims [0,32) of q and k heads (NeoX half-split, 16 freqs).
+          // The reference rotates the bf16 projection output in fp32 (transformer.py:491-507): round first.
           const int which = col / p.rope_dmodel;
           const int dim0 = (col % p.rope_dmodel) % p.rope_dh;
           if (which < 2 && dim0 == 0) {
             const int pos = row % p.rope_seq;
-            const float* cs = p.rope_cos + pos * 16;
-            const float* sn = p.rope_sin + pos * 16;
+            const float4* cs = reinterpret_cast<const float4*>(p.rope_cos + pos * 16);
+            const float4* sn = reinterpret_cast<const float4*>(p.rope_sin + pos * 16);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float c_ = __ldg(cs + i), s_ = __ldg(sn + i);
-              const float x1 = bf16_round(v[i]), x2 = bf16_round(v[i + 16]);
-              v[i] = x1 * c_ - x2 * s_;
-              v[i + 16] = x2 * c_ + x1 * s_;
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const float4 c4 = __ldg(cs + i4), s4 = __ldg(sn + i4);
+              const float cc_[4] = {c4.x, c4.y, c4.z, c4.w}, ss_[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int i = 4 * i4 + j;
+                const float x1 = bf16_round(v[i]), x2 = bf16_round(v[i + 16]);
+                v[i] = x1 * cc_[j] - x2 * ss_[j];
+                v[i + 16] = x2 * cc_[j] + x1 * ss_[j];
+              }
             }
           }
         }
         if (row_ok) {
           if (p.flags & GEMM_RESIDUAL) {
             const __nv_bfloat16* r = p.residual + static_cast<size_t>(out_row) * p.ldr + col;
-            float gate[32];
             if (p.flags & GEMM_GATE) {
               const float* gp = p.gate + static_cast<size_t>(row / p.seg_in) * p.N + col;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) gate[i] = (i < ncols) ? __ldg(gp + i) : 0.f;
+              for (int i = 0; i < 32; ++i) if (i < ncols) v[i] = bf16_round(v[i]) * __ldg(gp + i);
             }
-            if (ncols >= 32) {
+            if (full) {
               const uint4* rp = reinterpret_cast<const uint4*>(r);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -270,21 +311,14 @@ __global__ void __launch_bounds__(256, 1) gemm_bf16_tcgen05(const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const float2 f = unpack_bf16(w[j]);
-                  float y0 = bf16_round(v[8 * i + 2 * j]), y1 = bf16_round(v[8 * i + 2 * j + 1]);
-                  if (p.flags & GEMM_GATE) { y0 = bf16_round(y0 * gate[8 * i + 2 * j]); y1 = bf16_round(y1 * gate[8 * i + 2 * j + 1]); }
-                  v[8 * i + 2 * j] = y0 + f.x;
-                  v[8 * i + 2 * j + 1] = y1 + f.y;
+                  // the reference rounds the branch output to bf16 before the residual add (transformer.py:704-712)
+                  v[8 * i + 2 * j] = bf16_round(v[8 * i + 2 * j]) + f.x;
+                  v[8 * i + 2 * j + 1] = bf16_round(v[8 * i + 2 * j + 1]) + f.y;
                 }
               }
             } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                if (i < ncols) {
-                  float y = bf16_round(v[i]);
-                  if (p.flags & GEMM_GATE) y = bf16_round(y * gate[i]);
-                  v[i] = y + __bfloat162float(r[i]);
-                }
-              }
+              for (int i = 0; i < 32; ++i) if (i < ncols) v[i] = bf16_round(v[i]) + __bfloat162float(r[i]);
             }
           }
           if (p.flags & GEMM_OUT_F32) {
@@ -295,34 +329,46 @@ __global__ void __launch_bounds__(256, 1) gemm_bf16_tcgen05(const __grid_constan
         }
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[as]);
+      if (CTAS == 2 && cta_rank != 0) mbar_arrive_remote(&tmem_empty[as], 0);
+      else mbar_arrive(&tmem_empty[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CTAS == 2) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int BN>
+template <int BN, int CTAS>
 static int launch_gemm(GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
-    B200SAT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    B200SAT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   const int out_bn = (p.flags & GEMM_SWIGLU) ? BN / 2 : BN;
-  p.num_m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  p.num_m_tiles = (p.M + BLOCK_M * CTAS - 1) / (BLOCK_M * CTAS);
   p.num_n_tiles = (p.N + out_bn - 1) / out_bn;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_bf16_tcgen05<BN><<<grid, 256, Cfg::kSmemBytes, stream>>>(p);
-  B200SAT_CHECK_CUDA(cudaGetLastError());
+  const int units = num_sms() / CTAS;
+  const int grid = (tiles < units ? tiles : units) * CTAS;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200SAT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05<BN, CTAS>, p));
   return B200SAT_OK;
 }
 
@@ -364,8 +410,16 @@ extern "C" int b200sat_gemm_bf16(const void* A, int lda, const void* B, int ldb,
   GemmParams p;
   memset(&p, 0, sizeof(p));
   const bool swiglu = flags & GEMM_SWIGLU;
-  const int bn = force_bn ? force_bn : pick_bn(M, N, swiglu);
-  if (bn != 64 && bn != 128 && bn != 256) { set_last_error("gemm: force_bn must be 64/128/256"); return B200SAT_EINVAL; }
+  // force_bn: 0 = heuristic; 64/128/256 = 1-CTA tile width; 2128/2256 = CTA-pair (cta_group::2) with BN 128/256
+  int ctas = 1, bn;
+  if (force_bn >= 2000) { ctas = 2; bn = force_bn - 2000; }
+  else if (force_bn) bn = force_bn;
+  else {
+    bn = pick_bn(M, N, swiglu);
+    if (bn == 256 && M > 128) ctas = 2;
+  }
+  if (bn != 64 && bn != 128 && bn != 256) { set_last_error("gemm: force_bn must be 64/128/256/2128/2256"); return B200SAT_EINVAL; }
+  if (ctas == 2 && bn == 64) { set_last_error("gemm: pair mode needs BN >= 128"); return B200SAT_EINVAL; }
   if (swiglu && bn != 256) { set_last_error("gemm: swiglu requires BN=256"); return B200SAT_EINVAL; }
   const int b_rows_total = swiglu ? 2 * N : N;  // value rows [0,N) and gate rows [n_half, n_half+N)
   {
@@ -378,7 +432,7 @@ extern "C" int b200sat_gemm_bf16(const void* A, int lda, const void* B, int ldb,
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(swiglu ? n_half + N : b_rows_total)};
     uint64_t strides[1] = {static_cast<uint64_t>(ldb) * 2};
-    uint32_t box[2] = {BLOCK_K, static_cast<uint32_t>(swiglu ? bn / 2 : bn)};
+    uint32_t box[2] = {BLOCK_K, static_cast<uint32_t>((swiglu || ctas == 2) ? bn / 2 : bn)};
     int rc = encode_tmap_bf16(&p.tmB, B, 2, dims, strides, box, 1);
     if (rc) return rc;
   }
@@ -389,9 +443,10 @@ extern "C" int b200sat_gemm_bf16(const void* A, int lda, const void* B, int ldb,
   p.rope_seq = rope_seq > 0 ? rope_seq : 1; p.rope_dmodel = rope_dmodel > 0 ? rope_dmodel : 1; p.rope_dh = rope_dh > 0 ? rope_dh : 64;
   p.n_half = n_half;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (ctas == 2) return bn == 256 ? launch_gemm<256, 2>(p, s) : launch_gemm<128, 2>(p, s);
   switch (bn) {
-    case 256: return launch_gemm<256>(p, s);
-    case 128: return launch_gemm<128>(p, s);
-    default: return launch_gemm<64>(p, s);
+    case 256: return launch_gemm<256, 1>(p, s);
+    case 128: return launch_gemm<128, 1>(p, s);
+    default: return launch_gemm<64, 1>(p, s);
   }
 }

@@ -14,7 +14,7 @@ def _ref_linear(x, w, bias=None):
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 256), (2050, 4608, 1536), (2050, 1536, 6144), (260, 768, 768),
                                    (2050, 64, 1536), (300, 1536, 64), (77, 200, 136)])
-@pytest.mark.parametrize("bn", [0, 64, 128, 256])
+@pytest.mark.parametrize("bn", [0, 64, 128, 256, 2128, 2256])
 def test_gemm_plain(M, N, K, bn):
     from b200sat import ops
     torch.manual_seed(0)
@@ -44,14 +44,15 @@ def test_gemm_bias_residual_f32():
     assert (out32 - ref32).abs().max().item() <= 2e-3 * ref32.abs().max().item()
 
 
-def test_gemm_swiglu():
+@pytest.mark.parametrize("bn", [256, 2256])
+def test_gemm_swiglu(bn):
     from b200sat import ops
     torch.manual_seed(2)
     M, Nh, K = 2050, 6144, 1536
     x = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
     w = (torch.randn(2 * Nh, K, device="cuda") * 0.03).bfloat16()
     b = torch.randn(2 * Nh, device="cuda") * 0.1
-    out = ops.linear(x, w, bias=b, swiglu=True)
+    out = ops.linear(x, w, bias=b, swiglu=True, force_bn=bn)
     u = _ref_linear(x, w, b)
     ref = u[:, :Nh] * torch.nn.functional.silu(u[:, Nh:])
     assert (out.float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
