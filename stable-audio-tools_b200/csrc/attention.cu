@@ -17,6 +17,12 @@
 
 namespace b200sat {
 
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct AttnParams {
   CUtensorMap tmQ, tmK, tmV;
   __nv_bfloat16* O;
@@ -137,6 +143,7 @@ __global__ void __launch_bounds__(192, 2) attention_fwd_tcgen05(const __grid_con
       tc_fence_after();
       const int kbase = j * AT_BN;
       const int nvalid = p.Nk - kbase;  // >= 1
+      const bool tail = nvalid < AT_BN;  // only the last key tile of a ragged sequence needs the column mask
       // pass A: row max
       float mx = -INFINITY;
 #pragma unroll
@@ -144,14 +151,16 @@ __global__ void __launch_bounds__(192, 2) attention_fwd_tcgen05(const __grid_con
         uint32_t raw[32];
         tmem_ld_32x32(tmem_S + lane_off + c * 32, raw);
         tmem_ld_wait();
+        if (!tail) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float sv = (c * 32 + i < nvalid) ? __uint_as_float(raw[i]) : -INFINITY;
-          mx = fmaxf(mx, sv);
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c * 32 + i < nvalid) ? __uint_as_float(raw[i]) : -INFINITY);
         }
       }
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const float alpha = exp2f(m_run - m_new);
+      const float alpha = fast_exp2(m_run - m_new);
       // pass B: p = exp2(s*scale - m), row sum, bf16 P -> swizzled smem (A operand of the PV MMA)
       float lsum = 0.f;
 #pragma unroll
@@ -160,12 +169,22 @@ __global__ void __launch_bounds__(192, 2) attention_fwd_tcgen05(const __grid_con
         tmem_ld_32x32(tmem_S + lane_off + c * 32, raw);
         tmem_ld_wait();
         uint32_t pk[16];
+        if (!tail) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = (c * 32 + i < nvalid) ? exp2f(__uint_as_float(raw[i]) * p.scale_log2 - m_new) : 0.f;
-          const float p1 = (c * 32 + i + 1 < nvalid) ? exp2f(__uint_as_float(raw[i + 1]) * p.scale_log2 - m_new) : 0.f;
-          lsum += p0 + p1;
-          pk[i >> 1] = pack_bf16(p0, p1);
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(raw[i]), p.scale_log2, -m_new));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(raw[i + 1]), p.scale_log2, -m_new));
+            lsum += p0 + p1;
+            pk[i >> 1] = pack_bf16(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = (c * 32 + i < nvalid) ? fast_exp2(fmaf(__uint_as_float(raw[i]), p.scale_log2, -m_new)) : 0.f;
+            const float p1 = (c * 32 + i + 1 < nvalid) ? fast_exp2(fmaf(__uint_as_float(raw[i + 1]), p.scale_log2, -m_new)) : 0.f;
+            lsum += p0 + p1;
+            pk[i >> 1] = pack_bf16(p0, p1);
+          }
         }
 #pragma unroll
         for (int t = 0; t < 4; ++t) {

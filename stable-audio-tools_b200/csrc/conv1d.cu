@@ -67,7 +67,7 @@ __device__ __forceinline__ void split_store8(__nv_bfloat16* hi, __nv_bfloat16* l
 }
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1) conv1d_tcgen05(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(384, 1) conv1d_tcgen05(const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256, 1) conv1d_tcgen05(const __grid_constant__
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 256); }
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols); tmem_relinquish(); }
@@ -171,7 +171,9 @@ __global__ void __launch_bounds__(256, 1) conv1d_tcgen05(const __grid_constant__
       }
     }
   } else if (warp >= 4) {
-    const int q = warp - 4;
+    const int ew = warp - 4;
+    const int q = ew & 3;       // TMEM lane quarter
+    const int half = ew >> 2;   // column half (two epilogue warps per SM sub-partition)
     int as = 0; uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int ph, n_blk, b, m_blk;
@@ -184,7 +186,8 @@ __global__ void __launch_bounds__(256, 1) conv1d_tcgen05(const __grid_constant__
       if (p.mode == 2) { t = m * p.stride + ph - p.pad; ok = ok && t >= 0 && t < p.T_out; }
       const size_t row_off = (static_cast<size_t>(b) * p.T_out + (ok ? t : 0)) * p.Cout;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int cc = 0; cc < BN / 64; ++cc) {
+        const int c = half * (BN / 64) + cc;
         const int col = n_blk * BN + c * 32;
         if (col >= p.Cout) break;
         uint32_t raw[32];
@@ -194,8 +197,9 @@ __global__ void __launch_bounds__(256, 1) conv1d_tcgen05(const __grid_constant__
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
         if (p.bias) {
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + col + i);
+          for (int i = 0; i < 8; ++i) { const float4 t4 = __ldg(bp + i); v[4 * i] += t4.x; v[4 * i + 1] += t4.y; v[4 * i + 2] += t4.z; v[4 * i + 3] += t4.w; }
         }
         if (ok) {
           const size_t off = row_off + col;
@@ -222,10 +226,17 @@ __global__ void __launch_bounds__(256, 1) conv1d_tcgen05(const __grid_constant__
             for (int i = 0; i < 4; ++i) split_store8(p.out_hi + off + 8 * i, p.out_lo ? p.out_lo + off + 8 * i : nullptr, v + 8 * i);
           }
           if (p.act_hi) {
+            const float4* ap = reinterpret_cast<const float4*>(p.snake_a + col);
+            const float4* ip = reinterpret_cast<const float4*>(p.snake_invb + col);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float s = sinf(v[i] * __ldg(p.snake_a + col + i));
-              v[i] = v[i] + __ldg(p.snake_invb + col + i) * s * s;
+            for (int i = 0; i < 8; ++i) {
+              const float4 a4 = __ldg(ap + i), b4 = __ldg(ip + i);
+              const float aa[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float s = sinf(v[4 * i + j] * aa[j]);
+                v[4 * i + j] += bb[j] * s * s;
+              }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) split_store8(p.act_hi + off + 8 * i, p.act_lo ? p.act_lo + off + 8 * i : nullptr, v + 8 * i);
@@ -254,7 +265,7 @@ static int launch_conv(ConvParams& p, cudaStream_t stream) {
   p.n_tiles = (p.Cout + BN - 1) / BN;
   const long tiles = static_cast<long>(p.m_tiles) * p.B * p.n_tiles * p.phases;
   const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-  conv1d_tcgen05<BN><<<grid, 256, Cfg::kSmemBytes, stream>>>(p);
+  conv1d_tcgen05<BN><<<grid, 384, Cfg::kSmemBytes, stream>>>(p);
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }
