@@ -32,6 +32,10 @@ unsigned long long b200sat_launch_count(void);
 #define B200SAT_GEMM_OUT_F32 32
 #define B200SAT_GEMM_ROW_REMAP 64
 #define B200SAT_GEMM_GATE 128
+#define B200SAT_GEMM_A_MN 256        /* A stored [K,M]: weight-gradient GEMMs (dW = dY^T X) */
+#define B200SAT_GEMM_B_MN 512        /* B stored [K,N]: data-gradient GEMMs (dX = dY W) */
+#define B200SAT_GEMM_ACCUM 1024      /* fp32 D += acc */
+#define B200SAT_GEMM_SWIGLU_BWD 2048 /* D[M,2N] = SwiGLU backward of acc against saved pre-activation aux */
 
 /* D[M,N] = epilogue(A[M,K] x B[N,K]^T), bf16 in, fp32 accumulate (tcgen05 + TMA).
  * Replaces nn.Linear (cuBLASLt) + the eager epilogues of models/transformer.py:263-275 (GLU/SwiGLU), :308 (ff out),
@@ -40,7 +44,7 @@ unsigned long long b200sat_launch_count(void);
 int b200sat_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* D, int ldd, int M, int N, int K, int flags,
                       const float* bias, const void* residual, int ldr, const float* rope_cos, const float* rope_sin,
                       int rope_seq, int rope_dmodel, int rope_dh, int n_half, int seg_in, int seg_out, int seg_off,
-                      const float* gate, int force_bn, void* stream);
+                      const float* gate, void* aux, int ld_aux, int force_bn, void* stream);
 
 /* Flash attention forward (tcgen05; non-causal; head_dim 64; Hq % Hkv == 0 grouped-query).  q/k/v/o are bf16 views
  * [B, N, heads, 64] addressed by element strides (batch, sequence, head); lse (optional, fp32 [B,Hq,Nq]) is the natural-log
@@ -124,6 +128,25 @@ int b200sat_to_planes(const float* x, void* hi, void* lo, int B, int C, int T, v
  * fp32 [B,L,T]; optional fp32 [B,2L,T] copy of (mean|scale); kl_sum += sum(mean^2 + var - log var - 1). */
 int b200sat_vae_sample(const void* hi, const void* lo, const float* noise, float* z, float* mean_scale_out, float* kl_sum,
                        int B, int L, int T, void* stream);
+
+/* ---- backward pass of the DiT blocks --------------------------------------------------------------------------------- */
+
+/* Flash-attention backward (tcgen05): dQ, dK, dV from dO with the forward's O and LSE; optional inverse RoPE on dQ/dK rows
+ * (rope_cos/sin [N,16], position = sequence index) so gradients land in the pre-rotation layout of the qkv projection.
+ * strides: HOST array of 8 x (batch, seq, head) element strides for q, k, v, o, dO, dQ, dK, dV.  delta_scratch: fp32 [B,Hq,Nq].
+ * Backward of models/transformer.py:406-441 (+ :154-174). */
+int b200sat_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                          float* delta_scratch, void* dq, void* dk, void* dv, int B, int Hq, int Hkv, int Nq, int Nk,
+                          const long* strides, int head_dim, float scale, const float* rope_cos, const float* rope_sin,
+                          void* stream);
+
+/* LayerNorm backward: dx_out = dres + dLN(dy; x, gamma); dgamma (fp32 [D], optional) accumulates.  Backward of
+ * models/transformer.py:236-238 fused with the residual-stream gradient add of :703-712. */
+int b200sat_layernorm_bwd(const void* x, long ldx, const void* dy, long lddy, const float* gamma, const void* dres, long ldr,
+                          void* dx_out, long ldo, float* dgamma, int rows, int D, float eps, void* stream);
+
+/* out[n] += sum_m dY[m,n]: bias gradients of nn.Linear. */
+int b200sat_colsum(const void* dy, long ld, float* out, int M, int N, void* stream);
 
 #ifdef __cplusplus
 }

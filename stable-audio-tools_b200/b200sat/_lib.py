@@ -22,7 +22,7 @@ SIGNATURES = {
     "b200sat_launch_count": (c_ull, []),
     "b200sat_gemm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_fp, c_void_p, c_int, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                  c_fp, c_int, c_void_p]),
+                                  c_fp, c_void_p, c_int, c_int, c_void_p]),
     "b200sat_attention_fwd": (c_int, [c_void_p] * 4 + [c_fp] + [c_int] * 5 + [c_long] * 12 + [c_int, c_float, c_void_p]),
     "b200sat_layernorm_fwd": (c_int, [c_void_p, c_long, c_fp, c_fp, c_fp, c_fp, c_long, c_int, c_void_p, c_long, c_int, c_int,
                                       c_float, c_void_p]),
@@ -40,6 +40,11 @@ SIGNATURES = {
     "b200sat_conv_in": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp] + [c_void_p] * 4 + [c_int] * 6 + [c_void_p]),
     "b200sat_conv_out": (c_int, [c_void_p, c_void_p, c_fp, c_fp, c_fp] + [c_int] * 7 + [c_void_p]),
     "b200sat_to_planes": (c_int, [c_fp, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "b200sat_attention_bwd": (c_int, [c_void_p] * 5 + [c_fp, c_fp] + [c_void_p] * 3 + [c_int] * 5 + [ctypes.POINTER(ctypes.c_long), c_int,
+                                      c_float, c_fp, c_fp, c_void_p]),
+    "b200sat_layernorm_bwd": (c_int, [c_void_p, c_long, c_void_p, c_long, c_fp, c_void_p, c_long, c_void_p, c_long, c_fp, c_int, c_int,
+                                      c_float, c_void_p]),
+    "b200sat_colsum": (c_int, [c_void_p, c_long, c_fp, c_int, c_int, c_void_p]),
     "b200sat_vae_sample": (c_int, [c_void_p, c_void_p, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_void_p]),
 }
 

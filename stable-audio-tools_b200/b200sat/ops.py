@@ -4,6 +4,7 @@ import torch
 from ._lib import lib, check
 
 GEMM_BIAS, GEMM_RESIDUAL, GEMM_SILU, GEMM_SWIGLU, GEMM_ROPE, GEMM_OUT_F32, GEMM_ROW_REMAP, GEMM_GATE = 1, 2, 4, 8, 16, 32, 64, 128
+GEMM_A_MN, GEMM_B_MN, GEMM_ACCUM, GEMM_SWIGLU_BWD = 256, 512, 1024, 2048
 
 
 LAUNCHES = [0]  # kernel launches issued through this module (bench.py's gpu_launches claim)
@@ -25,7 +26,7 @@ def _chk_bf16(t, name):
 
 
 def linear(x, w, bias=None, residual=None, out=None, silu=False, out_f32=False, swiglu=False, rope=None,
-           row_remap=None, gate=None, force_bn=0):
+           row_remap=None, gate=None, force_bn=0, save_pre=None):
     """out = epilogue(x @ w.T).  x [M,K] bf16, w [N,K] bf16 (nn.Linear layout), bias fp32 [N].
 
     swiglu: w is the GLU projection [2*Nh, K]; out [M, Nh] = (u[:, :Nh]) * silu(u[:, Nh:]).
@@ -74,7 +75,27 @@ def linear(x, w, bias=None, residual=None, out=None, silu=False, out_f32=False, 
         flags |= GEMM_GATE
     rc = lib().b200sat_gemm_bf16(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0),
                                  M, N, K, flags, _p(bias), _p(residual), ldr, _p(rc_), _p(rs_), rseq, rdm, rdh, n_half,
-                                 seg_in, seg_out, seg_off, _p(gate), force_bn, _stream())
+                                 seg_in, seg_out, seg_off, _p(gate), _p(save_pre), save_pre.stride(0) if save_pre is not None else 0,
+                                 force_bn, _stream())
+    LAUNCHES[0] += 1
+    check(rc, "gemm_bf16")
+    return out
+
+
+def gemm(a, b, out, M, N, K, a_mn=False, b_mn=False, accumulate=False, swiglu_bwd_aux=None, force_bn=0):
+    """General D[M,N] (=|+=) A . B^T for the backward pass.  a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N] if b_mn), bf16.
+    out: bf16 [M,N], or fp32 when accumulate (gradient accumulation), or bf16 [M,2N] with swiglu_bwd_aux = saved u [M,2N]."""
+    _chk_bf16(a, "a"); _chk_bf16(b, "b")
+    flags = (GEMM_A_MN if a_mn else 0) | (GEMM_B_MN if b_mn else 0)
+    n_half = 0
+    if out.dtype == torch.float32:
+        flags |= GEMM_OUT_F32 | (GEMM_ACCUM if accumulate else 0)
+    if swiglu_bwd_aux is not None:
+        flags |= GEMM_SWIGLU_BWD
+        n_half = N
+    rc = lib().b200sat_gemm_bf16(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(), out.stride(0), M, N, K, flags,
+                                 0, 0, 0, 0, 0, 0, 0, 0, n_half, 0, 0, 0, 0, _p(swiglu_bwd_aux),
+                                 swiglu_bwd_aux.stride(0) if swiglu_bwd_aux is not None else 0, force_bn, _stream())
     LAUNCHES[0] += 1
     check(rc, "gemm_bf16")
     return out
@@ -169,3 +190,44 @@ def sampler_update(x, v, hist, noise, coef, step, advance=True):
 def step_set(step, value):
     LAUNCHES[0] += 1
     check(lib().b200sat_step_set(step.data_ptr(), int(value), _stream()), "step_set")
+
+
+def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, scale=None, rope=None):
+    """All tensors bf16 [B, N, H, 64] views (arbitrary batch/seq/head strides); lse fp32 [B, Hq, Nq] from the forward.
+    rope = (cos, sin) fp32 [N,16]: inverse rotation applied to dq, dk (self-attention)."""
+    import ctypes
+    B, Nq, Hq, D = q.shape
+    _, Nk, Hkv, _ = k.shape
+    if scale is None:
+        scale = D ** -0.5
+    st = []
+    for t in (q, k, v, o, d_o, dq, dk, dv):
+        _chk_bf16(t, "attention_bwd operand")
+        st += [t.stride(0), t.stride(1), t.stride(2)]
+    arr = (ctypes.c_long * 24)(*st)
+    delta = torch.empty(B, Hq, Nq, device=q.device, dtype=torch.float32)
+    rc = lib().b200sat_attention_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr(), lse.data_ptr(),
+                                     delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, Hq, Hkv, Nq, Nk, arr, D,
+                                     float(scale), _p(rope[0]) if rope else 0, _p(rope[1]) if rope else 0, _stream())
+    LAUNCHES[0] += 3
+    check(rc, "attention_bwd")
+
+
+def layernorm_bwd(x, dy, gamma, dres=None, out=None, dgamma=None, eps=1e-5):
+    rows, D = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    rc = lib().b200sat_layernorm_bwd(x.data_ptr(), x.stride(0), dy.data_ptr(), dy.stride(0), gamma.data_ptr(), _p(dres),
+                                     dres.stride(0) if dres is not None else 0, out.data_ptr(), out.stride(0), _p(dgamma), rows, D,
+                                     float(eps), _stream())
+    LAUNCHES[0] += 1
+    check(rc, "layernorm_bwd")
+    return out
+
+
+def colsum(dy, out):
+    M, N = dy.shape
+    rc = lib().b200sat_colsum(dy.data_ptr(), dy.stride(0), out.data_ptr(), M, N, _stream())
+    LAUNCHES[0] += 1
+    check(rc, "colsum")
+    return out

@@ -1,0 +1,471 @@
+// b200sat — flash attention backward on tcgen05 (non-causal, dh = 64, GQA-aware, ragged tails, optional inverse RoPE).
+//
+// Backward of the attention the reference reaches through flash_attn_func / F.scaled_dot_product_attention
+// (stable_audio_tools/models/transformer.py:406-441) together with the backward of apply_rotary_pos_emb (:154-174) on
+// dQ / dK, so that the gradient buffers land directly in the layout of the fused qkv projection.
+//
+//   delta[q]  = sum_d O[q,d] dO[q,d]
+//   P = exp(S*scale - lse),  dP = dO V^T,  dS = P o (dP - delta)
+//   dV = P^T dO,   dK = scale * dS^T Q,   dQ = scale * dS K
+//
+// Two kernels, each the forward kernel's structure (TMA producer warp, one MMA-issuing thread, four softmax warps whose
+// threads own one row of the score tile in TMEM):
+//   attention_bwd_dkv : CTA = (128 keys, kv head, batch); loops over the q heads of the GQA group x q tiles; S^T and dP^T are
+//                       produced transposed (A = K / V) so P^T, dS^T are written row-wise as A operands; dV, dK accumulate
+//                       in TMEM across the whole loop.  Q and dO tiles are consumed twice from the same shared-memory bytes:
+//                       as K-major B operands (S^T, dP^T) and as MN-major B operands (dV += P^T dO, dK += dS^T Q).
+//   attention_bwd_dq  : CTA = (128 queries, head, batch); loops over key tiles; dQ accumulates in TMEM.
+#include "common.cuh"
+#include <cstring>
+
+namespace b200sat {
+
+__device__ __forceinline__ float bw_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+constexpr int BW_T = 128 * 64 * 2;  // one 128 x 64 bf16 tile = 16 KB
+
+struct AttnBwdParams {
+  CUtensorMap tmQ, tmK, tmV, tmdO;
+  const float* lse;    // [B, Hq, Nq]
+  const float* delta;  // [B, Hq, Nq]
+  __nv_bfloat16* dQ;
+  __nv_bfloat16* dK;
+  __nv_bfloat16* dV;
+  long dq_bs, dq_ss, dq_hs, dk_bs, dk_ss, dk_hs, dv_bs, dv_ss, dv_hs;
+  const float* rope_cos;  // [N, 16] or null: inverse rotation applied to dQ / dK rows (position = sequence index)
+  const float* rope_sin;
+  int B, Hq, Hkv, Nq, Nk;
+  float scale, scale_log2;
+};
+
+// write 32 fp32 values (already scaled) as bf16 into the swizzled 128-column A-operand tile: row r, columns [c*32, c*32+32)
+__device__ __forceinline__ void store_operand_chunk(uint8_t* tile_row, int sw, int c, const float (&v)[32]) {
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int chunk = c * 4 + t;
+    const int kb = chunk >> 3, cc = chunk & 7;
+    uint4 u;
+    u.x = pack_bf16(v[8 * t + 0], v[8 * t + 1]);
+    u.y = pack_bf16(v[8 * t + 2], v[8 * t + 3]);
+    u.z = pack_bf16(v[8 * t + 4], v[8 * t + 5]);
+    u.w = pack_bf16(v[8 * t + 6], v[8 * t + 7]);
+    *reinterpret_cast<uint4*>(tile_row + kb * BW_T + ((cc ^ sw) << 4)) = u;
+  }
+}
+
+// rows of a [*, 64] gradient: optional inverse RoPE on dims [0,32), scale, bf16 store (128 bytes)
+__device__ __forceinline__ void store_grad_row(__nv_bfloat16* dst, float (&g)[64], float scale, const float* cs, const float* sn) {
+#pragma unroll
+  for (int i = 0; i < 64; ++i) g[i] *= scale;
+  if (cs) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float c_ = __ldg(cs + i), s_ = __ldg(sn + i);
+      const float a = g[i], b = g[i + 16];
+      g[i] = a * c_ + b * s_;
+      g[i + 16] = b * c_ - a * s_;
+    }
+  }
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint4 u;
+    u.x = pack_bf16(g[8 * i + 0], g[8 * i + 1]);
+    u.y = pack_bf16(g[8 * i + 2], g[8 * i + 3]);
+    u.z = pack_bf16(g[8 * i + 4], g[8 * i + 5]);
+    u.w = pack_bf16(g[8 * i + 6], g[8 * i + 7]);
+    d4[i] = u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, float* __restrict__ delta,
+                                  int B, int H, int N, long o_bs, long o_ss, long o_hs, long d_bs, long d_ss, long d_hs) {
+  const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<long>(B) * H * N) return;
+  const int n = i % N;
+  const int h = (i / N) % H;
+  const int b = i / (static_cast<long>(N) * H);
+  const uint4* po = reinterpret_cast<const uint4*>(o + b * o_bs + n * o_ss + h * o_hs);
+  const uint4* pd = reinterpret_cast<const uint4*>(d_o + b * d_bs + n * d_ss + h * d_hs);
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const uint4 a = __ldg(po + k), c = __ldg(pd + k);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 x = unpack_bf16(aw[j]), y = unpack_bf16(cw[j]);
+      acc += x.x * y.x + x.y * y.y;
+    }
+  }
+  delta[i] = acc;  // layout [B, H, N]
+}
+
+// ------------------------------------------------------------------------------------------------------------
+constexpr int DKV_SMEM = 2 * BW_T /*K,V*/ + 4 * BW_T /*ring of (Q,dO) x2*/ + 2 * BW_T /*P^T*/ + 2 * BW_T /*dS^T*/ + 4 * 128 * 4 + 256;
+
+__global__ void __launch_bounds__(192, 1) attention_bwd_dkv_tcgen05(const __grid_constant__ AttnBwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + BW_T;
+  uint8_t* sRing = smem + 2 * BW_T;     // stage s: Q at + s*2*BW_T, dO at + BW_T
+  uint8_t* sPT = smem + 6 * BW_T;
+  uint8_t* sdST = smem + 8 * BW_T;
+  float* s_lse = reinterpret_cast<float*>(smem + 10 * BW_T);   // [2][128] (pre-multiplied by log2 e)
+  float* s_delta = s_lse + 256;                                 // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + 256);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* qdo_full = bars + 1;   // [2]
+  uint64_t* qdo_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* acc_done = bars + 7;   // MMA3/4 of an iteration retired: P^T / dS^T buffers reusable, accumulators up to date
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * 128;
+  const int hk = blockIdx.y;
+  const int b = blockIdx.z;
+  const int G = p.Hq / p.Hkv;
+  const int nq = (p.Nq + 127) / 128;
+  const int iters = G * nq;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tm_ST = tmem_base, tm_dPT = tmem_base + 128, tm_dV = tmem_base + 256, tm_dK = tmem_base + 320;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(kv_full, 2 * BW_T);
+      tma_load_4d(sK, &p.tmK, kv_full, 0, hk, k0, b);
+      tma_load_4d(sV, &p.tmV, kv_full, 0, hk, k0, b);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it & 1;
+        const int h = hk * G + it / nq, qt = it % nq;
+        mbar_wait(&qdo_empty[s], ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&qdo_full[s], 2 * BW_T);
+        tma_load_4d(sRing + s * 2 * BW_T, &p.tmQ, &qdo_full[s], 0, h, qt * 128, b);
+        tma_load_4d(sRing + s * 2 * BW_T + BW_T, &p.tmdO, &qdo_full[s], 0, h, qt * 128, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t id_acc = make_idesc_bf16(128, 64, 0, 1);
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aPT = smem_u32(sPT), adST = smem_u32(sdST);
+      mbar_wait(kv_full, 0);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it & 1;
+        mbar_wait(&qdo_full[s], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t aQ = smem_u32(sRing + s * 2 * BW_T), adO = aQ + BW_T;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // S^T[kv, q] = K Q^T
+          umma_bf16(tm_ST, make_smem_desc_sw128(aK + k * 32, 16, 1024), make_smem_desc_sw128(aQ + k * 32, 16, 1024), id_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // dP^T[kv, q] = V dO^T
+          umma_bf16(tm_dPT, make_smem_desc_sw128(aV + k * 32, 16, 1024), make_smem_desc_sw128(adO + k * 32, 16, 1024), id_s, k != 0);
+        umma_commit(s_full);
+        mbar_wait(p_full, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // dV[kv, d] += P^T dO   (dO tile re-read as an MN-major operand: rows = q = MMA K)
+          const uint32_t pa = aPT + (k >> 2) * BW_T + (k & 3) * 32;
+          umma_bf16(tm_dV, make_smem_desc_sw128(pa, 16, 1024), make_smem_desc_sw128(adO + k * 2048, 1024, 1024), id_acc, (it | k) != 0);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // dK[kv, d] += dS^T Q
+          const uint32_t pa = adST + (k >> 2) * BW_T + (k & 3) * 32;
+          umma_bf16(tm_dK, make_smem_desc_sw128(pa, 16, 1024), make_smem_desc_sw128(aQ + k * 2048, 1024, 1024), id_acc, (it | k) != 0);
+        }
+        umma_commit(&qdo_empty[s]);
+        umma_commit(acc_done);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;          // key row of this thread
+    const int tid = (warp - 2) * 32 + lane;     // 0..127 among the softmax threads
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const bool key_ok = (k0 + r) < p.Nk;
+    uint8_t* pt_row = sPT + r * 128;
+    uint8_t* ds_row = sdST + r * 128;
+    const int sw = r & 7;
+    for (int it = 0; it < iters; ++it) {
+      const int h = hk * G + it / nq, qt = it % nq;
+      const int buf = it & 1;
+      {  // stage lse / delta of this q tile (column statistics) for all 128 softmax threads
+        const int q = qt * 128 + tid;
+        const long idx = (static_cast<long>(b) * p.Hq + h) * p.Nq + q;
+        s_lse[buf * 128 + tid] = (q < p.Nq) ? p.lse[idx] * 1.4426950408889634f : INFINITY;  // out-of-range query => P = 0
+        s_delta[buf * 128 + tid] = (q < p.Nq) ? p.delta[idx] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+      if (it > 0) mbar_wait(acc_done, (it - 1) & 1);  // previous P^T / dS^T consumed
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rs[32], rp[32];
+        tmem_ld_32x32(tm_ST + lane_off + c * 32, rs);
+        tmem_ld_32x32(tm_dPT + lane_off + c * 32, rp);
+        tmem_ld_wait();
+        float pv[32], dsv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float l2 = s_lse[buf * 128 + c * 32 + i];
+          const float pr = key_ok ? bw_exp2(fmaf(__uint_as_float(rs[i]), p.scale_log2, -l2)) : 0.f;
+          pv[i] = pr;
+          dsv[i] = pr * (__uint_as_float(rp[i]) - s_delta[buf * 128 + c * 32 + i]);
+        }
+        store_operand_chunk(pt_row, sw, c, pv);
+        store_operand_chunk(ds_row, sw, c, dsv);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    mbar_wait(acc_done, (iters - 1) & 1);
+    tc_fence_after();
+    float g[64];
+    const int krow = k0 + r;
+    // dV
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t raw[32];
+      tmem_ld_32x32(tm_dV + lane_off + c * 32, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) g[c * 32 + i] = __uint_as_float(raw[i]);
+    }
+    if (key_ok) store_grad_row(p.dV + b * p.dv_bs + krow * p.dv_ss + hk * p.dv_hs, g, 1.0f, nullptr, nullptr);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t raw[32];
+      tmem_ld_32x32(tm_dK + lane_off + c * 32, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) g[c * 32 + i] = __uint_as_float(raw[i]);
+    }
+    if (key_ok) {
+      const float* cs = p.rope_cos ? p.rope_cos + krow * 16 : nullptr;
+      const float* sn = p.rope_cos ? p.rope_sin + krow * 16 : nullptr;
+      store_grad_row(p.dK + b * p.dk_bs + krow * p.dk_ss + hk * p.dk_hs, g, p.scale, cs, sn);
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+constexpr int DQ_SMEM = 2 * BW_T /*Q,dO*/ + 4 * BW_T /*ring of (K,V) x2*/ + 2 * BW_T /*dS*/ + 256;
+
+__global__ void __launch_bounds__(192, 1) attention_bwd_dq_tcgen05(const __grid_constant__ AttnBwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sdO = smem + BW_T;
+  uint8_t* sRing = smem + 2 * BW_T;  // stage s: K at + s*2*BW_T, V at + BW_T
+  uint8_t* sdS = smem + 6 * BW_T;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 8 * BW_T);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* acc_done = bars + 7;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int hk = h / (p.Hq / p.Hkv);
+  const int nkv = (p.Nk + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 128, tm_dQ = tmem_base + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * BW_T);
+      tma_load_4d(sQ, &p.tmQ, q_full, 0, h, q0, b);
+      tma_load_4d(sdO, &p.tmdO, q_full, 0, h, q0, b);
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j & 1;
+        mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], 2 * BW_T);
+        tma_load_4d(sRing + s * 2 * BW_T, &p.tmK, &kv_full[s], 0, hk, j * 128, b);
+        tma_load_4d(sRing + s * 2 * BW_T + BW_T, &p.tmV, &kv_full[s], 0, hk, j * 128, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t id_acc = make_idesc_bf16(128, 64, 0, 1);
+      const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), adS = smem_u32(sdS);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j & 1;
+        mbar_wait(&kv_full[s], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t aK = smem_u32(sRing + s * 2 * BW_T), aV = aK + BW_T;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // S[q, kv] = Q K^T
+          umma_bf16(tm_S, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024), id_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // dP[q, kv] = dO V^T
+          umma_bf16(tm_dP, make_smem_desc_sw128(adO + k * 32, 16, 1024), make_smem_desc_sw128(aV + k * 32, 16, 1024), id_s, k != 0);
+        umma_commit(s_full);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // dQ[q, d] += dS K   (K tile re-read MN-major: rows = keys = MMA K)
+          const uint32_t pa = adS + (k >> 2) * BW_T + (k & 3) * 32;
+          umma_bf16(tm_dQ, make_smem_desc_sw128(pa, 16, 1024), make_smem_desc_sw128(aK + k * 2048, 1024, 1024), id_acc, (j | k) != 0);
+        }
+        umma_commit(&kv_empty[s]);
+        umma_commit(acc_done);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const int qrow = q0 + r;
+    const bool q_ok = qrow < p.Nq;
+    const long sidx = (static_cast<long>(b) * p.Hq + h) * p.Nq + qrow;
+    const float lse2 = q_ok ? p.lse[sidx] * 1.4426950408889634f : INFINITY;
+    const float dl = q_ok ? p.delta[sidx] : 0.f;
+    uint8_t* ds_row = sdS + r * 128;
+    const int sw = r & 7;
+    for (int j = 0; j < nkv; ++j) {
+      const int nvalid = p.Nk - j * 128;
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      if (j > 0) mbar_wait(acc_done, (j - 1) & 1);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rs[32], rp[32];
+        tmem_ld_32x32(tm_S + lane_off + c * 32, rs);
+        tmem_ld_32x32(tm_dP + lane_off + c * 32, rp);
+        tmem_ld_wait();
+        float dsv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float pr = (c * 32 + i < nvalid) ? bw_exp2(fmaf(__uint_as_float(rs[i]), p.scale_log2, -lse2)) : 0.f;
+          dsv[i] = pr * (__uint_as_float(rp[i]) - dl);
+        }
+        store_operand_chunk(ds_row, sw, c, dsv);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    mbar_wait(acc_done, (nkv - 1) & 1);
+    tc_fence_after();
+    float g[64];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t raw[32];
+      tmem_ld_32x32(tm_dQ + lane_off + c * 32, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) g[c * 32 + i] = __uint_as_float(raw[i]);
+    }
+    if (q_ok) {
+      const float* cs = p.rope_cos ? p.rope_cos + qrow * 16 : nullptr;
+      const float* sn = p.rope_cos ? p.rope_sin + qrow * 16 : nullptr;
+      store_grad_row(p.dQ + b * p.dq_bs + qrow * p.dq_ss + h * p.dq_hs, g, p.scale, cs, sn);
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+static int bw_head_map(CUtensorMap* tm, const void* base, int B, int H, int N, long bs, long ss, long hs) {
+  uint64_t dims[4] = {64, static_cast<uint64_t>(H), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
+  uint64_t strides[3] = {static_cast<uint64_t>(hs) * 2, static_cast<uint64_t>(ss) * 2, static_cast<uint64_t>(bs) * 2};
+  uint32_t box[4] = {64, 1, 128, 1};
+  return encode_tmap_bf16(tm, base, 4, dims, strides, box, 1);
+}
+
+}  // namespace b200sat
+
+using namespace b200sat;
+
+extern "C" int b200sat_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                                     float* delta_scratch, void* dq, void* dk, void* dv, int B, int Hq, int Hkv, int Nq, int Nk,
+                                     const long* strides /* 8 x (batch, seq, head): q k v o do dq dk dv */, int head_dim, float scale,
+                                     const float* rope_cos, const float* rope_sin, void* stream) {
+  if (!q || !k || !v || !o || !d_o || !lse || !delta_scratch || !dq || !dk || !dv || !strides) { set_last_error("attention_bwd: null argument"); return B200SAT_EINVAL; }
+  if (head_dim != 64) { set_last_error("attention_bwd: only head_dim 64 is implemented"); return B200SAT_EUNSUPPORTED; }
+  if (B <= 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv || Nq <= 0 || Nk <= 0) { set_last_error("attention_bwd: bad shape"); return B200SAT_EINVAL; }
+  if ((rope_cos == nullptr) != (rope_sin == nullptr)) { set_last_error("attention_bwd: rope tables go together"); return B200SAT_EINVAL; }
+  const long* sq = strides, *sk = strides + 3, *sv = strides + 6, *so = strides + 9, *sdo = strides + 12, *sdq = strides + 15,
+              *sdk = strides + 18, *sdv = strides + 21;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  {
+    const long n = static_cast<long>(B) * Hq * Nq;
+    attn_delta_kernel<<<static_cast<int>((n + 127) / 128), 128, 0, s>>>(static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o),
+                                                                        delta_scratch, B, Hq, Nq, so[0], so[1], so[2], sdo[0], sdo[1], sdo[2]);
+  }
+  AttnBwdParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = bw_head_map(&p.tmQ, q, B, Hq, Nq, sq[0], sq[1], sq[2]))) return rc;
+  if ((rc = bw_head_map(&p.tmK, k, B, Hkv, Nk, sk[0], sk[1], sk[2]))) return rc;
+  if ((rc = bw_head_map(&p.tmV, v, B, Hkv, Nk, sv[0], sv[1], sv[2]))) return rc;
+  if ((rc = bw_head_map(&p.tmdO, d_o, B, Hq, Nq, sdo[0], sdo[1], sdo[2]))) return rc;
+  p.lse = lse; p.delta = delta_scratch;
+  p.dQ = static_cast<__nv_bfloat16*>(dq); p.dK = static_cast<__nv_bfloat16*>(dk); p.dV = static_cast<__nv_bfloat16*>(dv);
+  p.dq_bs = sdq[0]; p.dq_ss = sdq[1]; p.dq_hs = sdq[2];
+  p.dk_bs = sdk[0]; p.dk_ss = sdk[1]; p.dk_hs = sdk[2];
+  p.dv_bs = sdv[0]; p.dv_ss = sdv[1]; p.dv_hs = sdv[2];
+  p.rope_cos = rope_cos; p.rope_sin = rope_sin;
+  p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.Nq = Nq; p.Nk = Nk;
+  p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200SAT_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_dkv_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    B200SAT_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_dq_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+    attr_set = true;
+  }
+  attention_bwd_dkv_tcgen05<<<dim3((Nk + 127) / 128, Hkv, B), 192, DKV_SMEM, s>>>(p);
+  attention_bwd_dq_tcgen05<<<dim3((Nq + 127) / 128, Hq, B), 192, DQ_SMEM, s>>>(p);
+  B200SAT_CHECK_CUDA(cudaGetLastError());
+  return B200SAT_OK;
+}

@@ -29,6 +29,10 @@ enum GemmFlags : int {
   GEMM_OUT_F32 = 32,    // fp32 output instead of bf16
   GEMM_ROW_REMAP = 64,  // out_row = (r / seg_in) * seg_out + seg_off + r % seg_in
   GEMM_GATE = 128,      // out = residual + bf16(acc+bias) * gate[b, n]   (adaLN: gate = sigmoid(1 - g), fp32 [B, N])
+  GEMM_A_MN = 256,      // A is stored [K, M] (M contiguous): the transposed operand of a weight-gradient GEMM
+  GEMM_B_MN = 512,      // B is stored [K, N] (N contiguous): data-gradient GEMM through an nn.Linear weight [N_out=K, N]
+  GEMM_ACCUM = 1024,    // fp32 output accumulates: D += acc (gradient accumulation into .grad)
+  GEMM_SWIGLU_BWD = 2048,  // D[M, 2*N]: [dact*silu(g) | dact*a*silu'(g)] with (a|g) read from aux [M, 2*N] (n_half = N)
 };
 
 struct GemmParams {
@@ -40,6 +44,8 @@ struct GemmParams {
   const float* rope_cos;  // [rope_seq, 16]
   const float* rope_sin;
   const float* gate;      // [B, N] fp32 (adaLN)
+  __nv_bfloat16* aux;     // SwiGLU fwd: optional copy of the pre-activation u [M, 2*n_half]; SwiGLU bwd: the saved u
+  int ld_aux;
   int M, N, K;
   int ldd, ldr;
   int flags;
@@ -62,7 +68,8 @@ struct GemmCfg {
   static constexpr int kBBytes = (BN / CTAS) * BLOCK_K * 2;   // per CTA
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (192 * 1024) / kStageBytes > 8 ? 8 : (192 * 1024) / kStageBytes;
-  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
+  static constexpr int kAccStride = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns per accumulator stage
+  static constexpr int kTmemCols = 2 * kAccStride;                            // two stages, power of two
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -114,6 +121,8 @@ __global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constan
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
   const bool swiglu = (p.flags & GEMM_SWIGLU) != 0;
+  const bool a_mn = (p.flags & GEMM_A_MN) != 0;
+  const bool b_mn = (p.flags & GEMM_B_MN) != 0;
   // Output columns handled per tile (SwiGLU folds value|gate halves of the tile into BN/2 outputs).
   const int out_bn = swiglu ? BN / 2 : BN;
 
@@ -154,7 +163,31 @@ __global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constan
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          if (CTAS == 1) {
+          if (a_mn || b_mn) {
+            // MN-major operands: 64(mn) x 64(k) boxes, one per 64-wide block of the M / N extent (8 KB each)
+            if (CTAS == 1 || cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], CTAS * Cfg::kStageBytes);
+            if (a_mn) {
+#pragma unroll
+              for (int i = 0; i < BLOCK_M / 64; ++i) {
+                if (CTAS == 2) tma_load_2d_pair(sa + i * 8192, &p.tmA, &full_bar[stage], m0 + 64 * i, kb * BLOCK_K);
+                else tma_load_2d(sa + i * 8192, &p.tmA, &full_bar[stage], m0 + 64 * i, kb * BLOCK_K);
+              }
+            } else {
+              if (CTAS == 2) tma_load_2d_pair(sa, &p.tmA, &full_bar[stage], kb * BLOCK_K, m0);
+              else tma_load_2d(sa, &p.tmA, &full_bar[stage], kb * BLOCK_K, m0);
+            }
+            const int nb0 = n_blk * BN + static_cast<int>(cta_rank) * (BN / CTAS);
+            if (b_mn) {
+#pragma unroll
+              for (int i = 0; i < BN / CTAS / 64; ++i) {
+                if (CTAS == 2) tma_load_2d_pair(sb + i * 8192, &p.tmB, &full_bar[stage], nb0 + 64 * i, kb * BLOCK_K);
+                else tma_load_2d(sb + i * 8192, &p.tmB, &full_bar[stage], nb0 + 64 * i, kb * BLOCK_K);
+              }
+            } else {
+              if (CTAS == 2) tma_load_2d_pair(sb, &p.tmB, &full_bar[stage], kb * BLOCK_K, nb0);
+              else tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BLOCK_K, nb0);
+            }
+          } else if (CTAS == 1) {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
             tma_load_2d(sa, &p.tmA, &full_bar[stage], kb * BLOCK_K, m0);
             if (swiglu) {
@@ -178,7 +211,10 @@ __global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constan
   } else if (warp == 1) {
     if (lane == 0 && cta_rank == 0) {
       // ===================== MMA issuer (leader CTA only in pair mode) =====================
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M * CTAS, BN, 0, 0);
+      const uint32_t idesc = make_idesc_bf16(BLOCK_M * CTAS, BN, a_mn ? 1u : 0u, b_mn ? 1u : 0u);
+      // per UMMA_K step: K-major advances 32 B inside the swizzle row; MN-major advances 16 k-rows = 2048 B
+      const uint32_t a_step = a_mn ? (2048u >> 4) : 2u, b_step = b_mn ? (2048u >> 4) : 2u;
+      const uint32_t a_lbo = a_mn ? 8192u : 16u, b_lbo = b_mn ? 8192u : 16u;
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -186,19 +222,18 @@ __global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constan
       for (int tile = unit; tile < num_tiles; tile += num_units) {
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BN;
+        const uint32_t tmem_d = tmem_base + as * Cfg::kAccStride;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
-          const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
+          const uint64_t da = make_smem_desc_sw128(sa, a_lbo, 1024);
+          const uint64_t db = make_smem_desc_sw128(sb, b_lbo, 1024);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance K inside the 128B swizzle row: 16 bf16 = 32 bytes = +2 in the (addr >> 4) field
-            if (CTAS == 2) umma_bf16_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-            else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            if (CTAS == 2) umma_bf16_pair(tmem_d, da + a_step * k, db + b_step * k, idesc, (kb | k) != 0);
+            else umma_bf16(tmem_d, da + a_step * k, db + b_step * k, idesc, (kb | k) != 0);
           }
           if (CTAS == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -224,7 +259,7 @@ __global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constan
       const bool row_ok = row < p.M;
       int out_row = row;
       if (p.flags & GEMM_ROW_REMAP) out_row = (row / p.seg_in) * p.seg_out + p.seg_off + (row % p.seg_in);
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::kAccStride;
       const int n0 = n_blk * out_bn;
       for (int cc = 0; cc < chunks_per_warp; ++cc) {
         const int c = half * chunks_per_warp + cc;
@@ -261,11 +296,43 @@ __global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constan
             for (int i = 0; i < 8; ++i) { const float4 t = __ldg(bp + i); bv[4 * i] = t.x; bv[4 * i + 1] = t.y; bv[4 * i + 2] = t.z; bv[4 * i + 3] = t.w; }
           }
           tmem_ld_wait();
+          float gv[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float g = __uint_as_float(raw[i]) + bv[i];
-            v[i] = v[i] * silu_f(g);
+          for (int i = 0; i < 32; ++i) gv[i] = __uint_as_float(raw[i]) + bv[i];
+          if (p.aux && row_ok) {  // training forward: keep the pre-activation (value | gate) for the backward
+            __nv_bfloat16* ua = p.aux + static_cast<size_t>(row) * p.ld_aux + col;
+            store_chunk_bf16(ua, v, 32);
+            store_chunk_bf16(ua + p.n_half, gv, 32);
           }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = v[i] * silu_f(gv[i]);
+        }
+        if ((p.flags & GEMM_SWIGLU_BWD) && row_ok && full) {
+          // v = d(act); saved u = (a | g):  d a = v*silu(g),  d g = v*a*sigmoid(g)*(1 + g*(1 - sigmoid(g)))
+          const __nv_bfloat16* ua = p.aux + static_cast<size_t>(row) * p.ld_aux + col;
+          float da[32], dg[32];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 au = __ldg(reinterpret_cast<const uint4*>(ua) + i);
+            const uint4 gu = __ldg(reinterpret_cast<const uint4*>(ua + p.n_half) + i);
+            const uint32_t aw[4] = {au.x, au.y, au.z, au.w}, gw[4] = {gu.x, gu.y, gu.z, gu.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 af = unpack_bf16(aw[j]), gf = unpack_bf16(gw[j]);
+              const float a2[2] = {af.x, af.y}, g2[2] = {gf.x, gf.y};
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int idx = 8 * i + 2 * j + e;
+                const float sg = __fdividef(1.0f, 1.0f + __expf(-g2[e]));
+                da[idx] = v[idx] * g2[e] * sg;
+                dg[idx] = v[idx] * a2[e] * sg * (1.0f + g2[e] * (1.0f - sg));
+              }
+            }
+          }
+          __nv_bfloat16* dd = reinterpret_cast<__nv_bfloat16*>(p.D) + static_cast<size_t>(out_row) * p.ldd + col;
+          store_chunk_bf16(dd, da, 32);
+          store_chunk_bf16(dd + p.n_half, dg, 32);
+          continue;
         }
         if (p.flags & GEMM_SILU) {
 #pragma unroll
@@ -322,7 +389,12 @@ __global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constan
             }
           }
           if (p.flags & GEMM_OUT_F32) {
-            store_chunk_f32(reinterpret_cast<float*>(p.D) + static_cast<size_t>(out_row) * p.ldd + col, v, ncols);
+            float* dp = reinterpret_cast<float*>(p.D) + static_cast<size_t>(out_row) * p.ldd + col;
+            if (p.flags & GEMM_ACCUM) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += dp[i];
+            }
+            store_chunk_f32(dp, v, ncols);
           } else {
             store_chunk_bf16(reinterpret_cast<__nv_bfloat16*>(p.D) + static_cast<size_t>(out_row) * p.ldd + col, v, ncols);
           }
@@ -372,24 +444,27 @@ static int launch_gemm(GemmParams& p, cudaStream_t stream) {
   return B200SAT_OK;
 }
 
-static int pick_bn(int M, int N, bool swiglu) {
-  if (swiglu) return 256;
+// Tile-shape heuristic: minimise waves x per-tile time over {CTA-pair 256/192/128, single-CTA 128/64}.
+// Efficiencies are relative MMA-pipe rates measured with tools/gemm_sweep.py on B200 (profiles/).
+static void pick_config(int M, int N, bool swiglu, bool mn_major, int* bn_out, int* ctas_out) {
+  if (swiglu) { *bn_out = 256; *ctas_out = M > 128 ? 2 : 1; return; }
   const int sms = num_sms();
-  const int mt = (M + BLOCK_M - 1) / BLOCK_M;
-  int best = 256;
-  double best_cost = 1e30;
-  const int cands[3] = {256, 128, 64};
-  // cost model: waves x per-tile time; narrow tiles re-read A from shared memory more often (lower MMA efficiency)
-  const double eff[3] = {1.0, 0.92, 0.62};
-  for (int i = 0; i < 3; ++i) {
-    const int bn = cands[i];
-    const int nt = (N + bn - 1) / bn;
-    const long tiles = static_cast<long>(mt) * nt;
-    const long waves = (tiles + sms - 1) / sms;
-    const double cost = waves * (bn / eff[i]);
-    if (cost < best_cost) { best_cost = cost; best = bn; }
+  struct Cand { int bn, ctas; double eff; };
+  const Cand cands[5] = {{256, 2, 1.00}, {192, 2, 0.97}, {128, 2, 0.85}, {128, 1, 0.70}, {64, 1, 0.45}};
+  double best = 1e30;
+  *bn_out = 128; *ctas_out = 1;
+  for (int i = 0; i < 5; ++i) {
+    const Cand& c = cands[i];
+    if (c.ctas == 2 && M <= 128) continue;
+    if (c.bn == 192 && mn_major) continue;  // 96-column halves are not a whole number of 64-wide MN-major boxes
+    if (c.bn > 64 && N <= c.bn / 2) continue;
+    const long mt = (M + 128 * c.ctas - 1) / (128 * c.ctas);
+    const long nt = (N + c.bn - 1) / c.bn;
+    const long units = sms / c.ctas;
+    const long waves = (mt * nt + units - 1) / units;
+    const double cost = waves * (c.bn / c.eff);
+    if (cost < best) { best = cost; *bn_out = c.bn; *ctas_out = c.ctas; }
   }
-  return best;
 }
 
 }  // namespace b200sat
@@ -400,9 +475,13 @@ using namespace b200sat;
 extern "C" int b200sat_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* D, int ldd, int M, int N, int K,
                                  int flags, const float* bias, const void* residual, int ldr, const float* rope_cos,
                                  const float* rope_sin, int rope_seq, int rope_dmodel, int rope_dh, int n_half, int seg_in,
-                                 int seg_out, int seg_off, const float* gate, int force_bn, void* stream) {
+                                 int seg_out, int seg_off, const float* gate, void* aux, int ld_aux, int force_bn,
+                                 void* stream) {
   if (!A || !B || !D || M <= 0 || N <= 0 || K <= 0) { set_last_error("gemm: null pointer or empty shape"); return B200SAT_EINVAL; }
-  if ((lda % 8) || (ldb % 8) || (K % 8)) { set_last_error("gemm: lda/ldb/K must be multiples of 8 (16-byte TMA strides)"); return B200SAT_EINVAL; }
+  if ((lda % 8) || (ldb % 8)) { set_last_error("gemm: lda/ldb must be multiples of 8 (16-byte TMA strides)"); return B200SAT_EINVAL; }
+  if ((K % 8) && !(flags & (GEMM_A_MN | GEMM_B_MN))) { set_last_error("gemm: K must be a multiple of 8"); return B200SAT_EINVAL; }
+  if ((flags & GEMM_SWIGLU_BWD) && (!aux || n_half != N || (N % 32))) { set_last_error("gemm: swiglu_bwd needs aux and n_half == N"); return B200SAT_EINVAL; }
+  if ((flags & (GEMM_A_MN | GEMM_B_MN)) && (flags & GEMM_SWIGLU)) { set_last_error("gemm: swiglu with MN-major operands"); return B200SAT_EUNSUPPORTED; }
   if ((ldd % 8) || ((flags & GEMM_RESIDUAL) && (ldr % 8))) { set_last_error("gemm: ldd/ldr must be multiples of 8"); return B200SAT_EINVAL; }
   if ((flags & GEMM_SWIGLU) && (N % 128 || n_half <= 0)) { set_last_error("gemm: swiglu needs N % 128 == 0 and n_half"); return B200SAT_EINVAL; }
   if ((flags & GEMM_ROPE) && (!rope_cos || !rope_sin || rope_dh != 64 || rope_seq <= 0)) { set_last_error("gemm: rope needs tables, dh == 64"); return B200SAT_EINVAL; }
@@ -414,22 +493,32 @@ extern "C" int b200sat_gemm_bf16(const void* A, int lda, const void* B, int ldb,
   int ctas = 1, bn;
   if (force_bn >= 2000) { ctas = 2; bn = force_bn - 2000; }
   else if (force_bn) bn = force_bn;
-  else {
-    bn = pick_bn(M, N, swiglu);
-    if (bn == 256 && M > 128) ctas = 2;
-  }
-  if (bn != 64 && bn != 128 && bn != 256) { set_last_error("gemm: force_bn must be 64/128/256/2128/2256"); return B200SAT_EINVAL; }
+  else pick_config(M, N, swiglu, (flags & (GEMM_A_MN | GEMM_B_MN)) != 0, &bn, &ctas);
+  if (bn != 64 && bn != 128 && bn != 256 && !(bn == 192 && ctas == 2)) { set_last_error("gemm: force_bn must be 64/128/256/2128/2192/2256"); return B200SAT_EINVAL; }
   if (ctas == 2 && bn == 64) { set_last_error("gemm: pair mode needs BN >= 128"); return B200SAT_EINVAL; }
+  if (bn == 192 && (flags & (GEMM_A_MN | GEMM_B_MN))) { set_last_error("gemm: BN=192 is K-major only"); return B200SAT_EUNSUPPORTED; }
   if (swiglu && bn != 256) { set_last_error("gemm: swiglu requires BN=256"); return B200SAT_EINVAL; }
   const int b_rows_total = swiglu ? 2 * N : N;  // value rows [0,N) and gate rows [n_half, n_half+N)
-  {
+  if (flags & GEMM_A_MN) {  // A stored [K, M]
+    uint64_t dims[2] = {static_cast<uint64_t>(M), static_cast<uint64_t>(K)};
+    uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
+    uint32_t box[2] = {64, BLOCK_K};
+    int rc = encode_tmap_bf16(&p.tmA, A, 2, dims, strides, box, 1);
+    if (rc) return rc;
+  } else {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
     uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
     uint32_t box[2] = {BLOCK_K, BLOCK_M};
     int rc = encode_tmap_bf16(&p.tmA, A, 2, dims, strides, box, 1);
     if (rc) return rc;
   }
-  {
+  if (flags & GEMM_B_MN) {  // B stored [K, N]
+    uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(K)};
+    uint64_t strides[1] = {static_cast<uint64_t>(ldb) * 2};
+    uint32_t box[2] = {64, BLOCK_K};
+    int rc = encode_tmap_bf16(&p.tmB, B, 2, dims, strides, box, 1);
+    if (rc) return rc;
+  } else {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(swiglu ? n_half + N : b_rows_total)};
     uint64_t strides[1] = {static_cast<uint64_t>(ldb) * 2};
     uint32_t box[2] = {BLOCK_K, static_cast<uint32_t>((swiglu || ctas == 2) ? bn / 2 : bn)};
@@ -438,12 +527,13 @@ extern "C" int b200sat_gemm_bf16(const void* A, int lda, const void* B, int ldb,
   }
   p.D = D; p.bias = bias; p.residual = static_cast<const __nv_bfloat16*>(residual);
   p.rope_cos = rope_cos; p.rope_sin = rope_sin; p.gate = gate;
+  p.aux = static_cast<__nv_bfloat16*>(aux); p.ld_aux = ld_aux;
   p.M = M; p.N = N; p.K = K; p.ldd = ldd; p.ldr = ldr; p.flags = flags;
   p.seg_in = seg_in > 0 ? seg_in : 1; p.seg_out = seg_out; p.seg_off = seg_off;
   p.rope_seq = rope_seq > 0 ? rope_seq : 1; p.rope_dmodel = rope_dmodel > 0 ? rope_dmodel : 1; p.rope_dh = rope_dh > 0 ? rope_dh : 64;
   p.n_half = n_half;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (ctas == 2) return bn == 256 ? launch_gemm<256, 2>(p, s) : launch_gemm<128, 2>(p, s);
+  if (ctas == 2) return bn == 256 ? launch_gemm<256, 2>(p, s) : (bn == 192 ? launch_gemm<192, 2>(p, s) : launch_gemm<128, 2>(p, s));
   switch (bn) {
     case 256: return launch_gemm<256, 1>(p, s);
     case 128: return launch_gemm<128, 1>(p, s);

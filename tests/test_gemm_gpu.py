@@ -14,7 +14,7 @@ def _ref_linear(x, w, bias=None):
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 256), (2050, 4608, 1536), (2050, 1536, 6144), (260, 768, 768),
                                    (2050, 64, 1536), (300, 1536, 64), (77, 200, 136)])
-@pytest.mark.parametrize("bn", [0, 64, 128, 256, 2128, 2256])
+@pytest.mark.parametrize("bn", [0, 64, 128, 256, 2128, 2192, 2256])
 def test_gemm_plain(M, N, K, bn):
     from b200sat import ops
     torch.manual_seed(0)
@@ -94,3 +94,53 @@ def test_gemm_row_remap_silu():
     o2 = ops.linear(x, w, silu=True)
     r2 = torch.nn.functional.silu(_ref_linear(x, w))
     assert (o2.float() - r2).abs().max().item() <= 2e-2 * r2.abs().max().item()
+
+
+@pytest.mark.parametrize("bn", [0, 128, 256, 2128, 2256])
+@pytest.mark.parametrize("M,N,K", [(2050, 1536, 6144), (1000, 768, 1536), (300, 200, 136)])
+def test_gemm_dgrad_b_mn_major(M, N, K, bn):
+    """dX[M,N] = dY[M,K] @ W[K,N]  (W = nn.Linear weight [out=K, in=N], read in place as an MN-major B operand)."""
+    from b200sat import ops
+    torch.manual_seed(5)
+    dy = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(K, N, device="cuda") * 0.05).bfloat16()
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(dy, w, out, M, N, K, b_mn=True, force_bn=bn)
+    ref = dy.float() @ w.float()
+    assert (out.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("bn", [0, 128, 256, 2128, 2256])
+@pytest.mark.parametrize("M,N,K", [(1536, 1536, 2050), (12288, 1536, 8200), (200, 136, 300)])
+def test_gemm_wgrad_both_mn_major_accumulate(M, N, K, bn):
+    """dW[M=out, N=in] += dY[K=tokens, M]^T @ X[K, N]  (both operands token-major => MN-major), fp32 accumulation."""
+    from b200sat import ops
+    torch.manual_seed(6)
+    dy = (torch.randn(K, M, device="cuda") * 0.5).bfloat16()
+    x = (torch.randn(K, N, device="cuda") * 0.5).bfloat16()
+    acc = torch.randn(M, N, device="cuda")
+    ref = acc + dy.float().t() @ x.float()
+    ops.gemm(dy, x, acc, M, N, K, a_mn=True, b_mn=True, accumulate=True, force_bn=bn)
+    assert (acc - ref).abs().max().item() <= 1e-2 * ref.abs().max().item() + 1e-3
+
+
+def test_gemm_swiglu_save_and_backward():
+    from b200sat import ops
+    torch.manual_seed(7)
+    M, Nh, K = 1000, 6144, 1536
+    x = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    w1 = (torch.randn(2 * Nh, K, device="cuda") * 0.03).bfloat16()
+    b1 = torch.randn(2 * Nh, device="cuda") * 0.1
+    u = torch.empty(M, 2 * Nh, device="cuda", dtype=torch.bfloat16)
+    act = ops.linear(x, w1, bias=b1, swiglu=True, save_pre=u)
+    uref = x.float() @ w1.float().t() + b1
+    assert (u.float() - uref).abs().max().item() <= 2e-2 * uref.abs().max().item()
+    # backward through act = a*silu(g) fused into the dgrad GEMM of the second linear: dact = dY @ W2
+    w2 = (torch.randn(1536, Nh, device="cuda") * 0.03).bfloat16()
+    dy = torch.randn(M, 1536, device="cuda").bfloat16()
+    du = torch.empty(M, 2 * Nh, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(dy, w2, du, M, Nh, 1536, b_mn=True, swiglu_bwd_aux=u)
+    uf = u.float().requires_grad_(True)
+    a, g = uf[:, :Nh], uf[:, Nh:]
+    (a * torch.nn.functional.silu(g)).backward(dy.float() @ w2.float())
+    assert (du.float() - uf.grad).abs().max().item() <= 2e-2 * uf.grad.abs().max().item()
