@@ -1,0 +1,264 @@
+"""Training path of the DiT denoiser: forward + backward of the ContinuousTransformer stack on libb200sat kernels, wrapped
+as ONE autograd node, behind an nn.Module with the reference's parameter names (so reference checkpoints load by key and
+the v-objective training step of training/diffusion.py:381-449 runs on it unchanged).
+
+What runs where
+  * the 24 TransformerBlocks (transformer.py:703-712: LN -> self-attn (+RoPE) -> +res -> LN -> GQA cross-attn -> +res -> LN ->
+    SwiGLU FF -> +res): forward AND backward on the tcgen05 / TMA kernels, activations saved (no recompute: the reference's
+    per-layer `checkpoint` (:842-843) is a memory workaround, not semantics; 0.6 GB/layer at batch 8 fits 180 GB easily);
+  * weight gradients accumulate in fp32 directly into a flat .grad buffer (GEMM epilogue `+=`), ordered by layer so the
+    DDP hook can all-reduce one contiguous slice per finished layer (see b200sat/ddp.py);
+  * the O(d) prologue/epilogue around the stack (1x1 convs, project_in/out, timestep/global/cond MLPs; < 0.2 % of the
+    FLOPs) is plain PyTorch autograd in bf16 — host plumbing, not a hot op.
+"""
+import math
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .dit_engine import DiTConfig
+
+
+class _StackFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h0, cemb, model):
+        ctx.model = model
+        return model._stack_forward(h0, cemb)
+
+    @staticmethod
+    def backward(ctx, dout):
+        dh0, dcemb = ctx.model._stack_backward(dout.contiguous())
+        return dh0, dcemb, None
+
+
+_LAYER_PARAMS = [  # (suffix, shape fn(d, ck)) in flat-buffer order
+    ("pre_norm.gamma", lambda d, ck: (d,)), ("self_attn.to_qkv.weight", lambda d, ck: (3 * d, d)), ("self_attn.to_out.weight", lambda d, ck: (d, d)),
+    ("cross_attend_norm.gamma", lambda d, ck: (d,)), ("cross_attn.to_q.weight", lambda d, ck: (d, d)), ("cross_attn.to_kv.weight", lambda d, ck: (2 * ck, ck)),
+    ("cross_attn.to_out.weight", lambda d, ck: (d, d)), ("ff_norm.gamma", lambda d, ck: (d,)), ("ff.ff.0.proj.weight", lambda d, ck: (8 * d, d)),
+    ("ff.ff.0.proj.bias", lambda d, ck: (8 * d,)), ("ff.ff.2.weight", lambda d, ck: (d, 4 * d)), ("ff.ff.2.bias", lambda d, ck: (d,)),
+]
+
+
+class DiTTrainModel(nn.Module):
+    """`DiffusionTransformer` (models/dit.py) for training, `global_cond_type='prepend'`, continuous transformer."""
+
+    def __init__(self, state_dict, device="cuda"):
+        super().__init__()
+        cfg = DiTConfig.from_state_dict(state_dict)
+        if cfg.global_cond_type != "prepend":
+            raise NotImplementedError("b200sat training path: only global_cond_type='prepend' is implemented")
+        self.cfg = cfg
+        dev = torch.device(device)
+        d, ck, L = cfg.embed_dim, cfg.cond_embed_dim, cfg.depth
+        # ---- flat fp32 master / grad buffers, layer-major
+        names, shapes = [], []
+        for i in range(L):
+            for suf, fn in _LAYER_PARAMS:
+                names.append(f"transformer.layers.{i}.{suf}"); shapes.append(fn(d, ck))
+        self._layer_numel = sum(math.prod(s) for s in shapes[: len(_LAYER_PARAMS)])
+        misc = [k for k in state_dict if k not in names and torch.is_tensor(state_dict[k]) and not k.endswith(".beta") and not k.endswith("inv_freq")]
+        for k in misc:
+            names.append(k); shapes.append(tuple(state_dict[k].shape))
+        total = sum(math.prod(s) for s in shapes)
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        self._p = {}
+        off = 0
+        for n, s in zip(names, shapes):
+            k = math.prod(s)
+            view = self.flat[off:off + k].view(s)
+            view.copy_(state_dict[n].to(dev, torch.float32))
+            p = nn.Parameter(view)
+            p.grad = self.flat_grad[off:off + k].view(s)
+            self.register_parameter(n.replace(".", "__"), p)
+            self._p[n] = p
+            off += k
+        self.register_buffer("inv_freq", state_dict["transformer.rotary_pos_emb.inv_freq"].to(dev, torch.float32))
+        self._names = names
+        self.stack_numel = L * self._layer_numel
+        self._bf = torch.empty(self.stack_numel, device=dev, dtype=torch.bfloat16)   # bf16 working copy of the stack weights
+        self._ws = {}
+        self._rope = {}
+        self.grad_ready_hook = None   # callable(layer_index, flat_grad_slice) fired when a layer's gradients are final
+
+    # ------------------------------------------------------------------ parameter plumbing
+    def state_dict_reference(self):
+        sd = {n: p.detach().clone() for n, p in self._p.items()}
+        sd["transformer.rotary_pos_emb.inv_freq"] = self.inv_freq.clone()
+        return sd
+
+    def zero_grad(self, set_to_none=False):
+        self.flat_grad.zero_()
+
+    def layer_grad_slice(self, i):
+        return self.flat_grad[i * self._layer_numel:(i + 1) * self._layer_numel]
+
+    def misc_grad_slice(self):
+        return self.flat_grad[self.stack_numel:]
+
+    def _w(self, i, suf):
+        """bf16 view of a stack weight inside the working copy (refreshed once per forward)."""
+        off = i * self._layer_numel
+        d, ck = self.cfg.embed_dim, self.cfg.cond_embed_dim
+        for s, fn in _LAYER_PARAMS:
+            shp = fn(d, ck)
+            k = math.prod(shp)
+            if s == suf:
+                return self._bf[off:off + k].view(shp)
+            off += k
+        raise KeyError(suf)
+
+    def _g(self, i, suf):
+        return self._p[f"transformer.layers.{i}.{suf}"].grad
+
+    def _f32(self, i, suf):
+        return self._p[f"transformer.layers.{i}.{suf}"].detach()
+
+    def rope_tables(self, n):
+        if n not in self._rope:
+            fr = torch.outer(torch.arange(n, device=self.flat.device, dtype=torch.float32), self.inv_freq)
+            self._rope[n] = (fr.cos().contiguous(), fr.sin().contiguous())
+        return self._rope[n]
+
+    # ------------------------------------------------------------------ workspace (saved activations + scratch)
+    def _workspace(self, B, N, Lc):
+        key = (B, N, Lc)
+        if key in self._ws:
+            return self._ws[key]
+        c = self.cfg
+        d, H, ck, L = c.embed_dim, c.num_heads, c.cond_embed_dim, c.depth
+        M = B * N
+        dev = self.flat.device
+        bf = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)
+        ws = dict(
+            h=bf(L + 1, M, d), n1=bf(L, M, d), qkv=bf(L, M, 3 * d), a1=bf(L, M, d), lse1=torch.empty(L, B, H, N, device=dev),
+            h1=bf(L, M, d), n2=bf(L, M, d), q2=bf(L, M, d), kv2=bf(L, B * Lc, 2 * ck), a2=bf(L, M, d), lse2=torch.empty(L, B, H, N, device=dev),
+            h2=bf(L, M, d), n3=bf(L, M, d), u=bf(L, M, 8 * d), act=bf(L, M, 4 * d),
+            dh_a=bf(M, d), dh_b=bf(M, d), dn=bf(M, d), du=bf(M, 8 * d), da=bf(M, d), dqkv=bf(M, 3 * d), dq2=bf(M, d),
+            dkv2=bf(B * Lc, 2 * ck), dcemb=bf(B * Lc, ck),
+        )
+        self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ stack forward / backward on the CUDA kernels
+    def _stack_forward(self, h0, cemb):
+        c = self.cfg
+        d, H, ck, L = c.embed_dim, c.num_heads, c.cond_embed_dim, c.depth
+        B, N, Lc = self._shape
+        M = B * N
+        ws = self._workspace(B, N, Lc)
+        self._bf.copy_(self.flat[: self.stack_numel])     # refresh bf16 working weights from the fp32 masters
+        self._cemb = cemb.contiguous()
+        rope = (*self.rope_tables(N), N, d, 64)
+        ws["h"][0].copy_(h0)
+        kvh = ck // 64
+        for i in range(L):
+            h = ws["h"][i]
+            ops.layernorm(h, self._f32(i, "pre_norm.gamma"), out=ws["n1"][i])
+            ops.linear(ws["n1"][i], self._w(i, "self_attn.to_qkv.weight"), out=ws["qkv"][i], rope=rope)
+            qkv = ws["qkv"][i].view(B, N, 3, H, 64)
+            ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], out=ws["a1"][i].view(B, N, H, 64), lse=ws["lse1"][i])
+            ops.linear(ws["a1"][i], self._w(i, "self_attn.to_out.weight"), residual=h, out=ws["h1"][i])
+            ops.layernorm(ws["h1"][i], self._f32(i, "cross_attend_norm.gamma"), out=ws["n2"][i])
+            ops.linear(ws["n2"][i], self._w(i, "cross_attn.to_q.weight"), out=ws["q2"][i])
+            ops.linear(self._cemb, self._w(i, "cross_attn.to_kv.weight"), out=ws["kv2"][i])
+            kv = ws["kv2"][i].view(B, Lc, 2, kvh, 64)
+            ops.attention(ws["q2"][i].view(B, N, H, 64), kv[:, :, 0], kv[:, :, 1], out=ws["a2"][i].view(B, N, H, 64), lse=ws["lse2"][i])
+            ops.linear(ws["a2"][i], self._w(i, "cross_attn.to_out.weight"), residual=ws["h1"][i], out=ws["h2"][i])
+            ops.layernorm(ws["h2"][i], self._f32(i, "ff_norm.gamma"), out=ws["n3"][i])
+            ops.linear(ws["n3"][i], self._w(i, "ff.ff.0.proj.weight"), bias=self._f32(i, "ff.ff.0.proj.bias"), swiglu=True,
+                       out=ws["act"][i], save_pre=ws["u"][i])
+            ops.linear(ws["act"][i], self._w(i, "ff.ff.2.weight"), bias=self._f32(i, "ff.ff.2.bias"), residual=ws["h2"][i], out=ws["h"][i + 1])
+        return ws["h"][L].clone()
+
+    def _stack_backward(self, dout):
+        c = self.cfg
+        d, H, ck, L = c.embed_dim, c.num_heads, c.cond_embed_dim, c.depth
+        B, N, Lc = self._shape
+        M = B * N
+        ws = self._workspace(B, N, Lc)
+        cos, sin = self.rope_tables(N)
+        kvh = ck // 64
+        dh, dh_alt = ws["dh_a"], ws["dh_b"]
+        dh.copy_(dout)
+        ws["dcemb"].zero_()
+        W, G = self._w, self._g
+        for i in reversed(range(L)):
+            # ---- feed-forward branch: h_out = h2 + W2 (a * silu(g)) + b2,  (a|g) = W1 n3 + b1
+            ops.colsum(dh, G(i, "ff.ff.2.bias"))
+            ops.gemm(dh, ws["act"][i], G(i, "ff.ff.2.weight"), d, 4 * d, M, a_mn=True, b_mn=True, accumulate=True)
+            ops.gemm(dh, W(i, "ff.ff.2.weight"), ws["du"], M, 4 * d, d, b_mn=True, swiglu_bwd_aux=ws["u"][i])
+            ops.colsum(ws["du"], G(i, "ff.ff.0.proj.bias"))
+            ops.gemm(ws["du"], ws["n3"][i], G(i, "ff.ff.0.proj.weight"), 8 * d, d, M, a_mn=True, b_mn=True, accumulate=True)
+            ops.gemm(ws["du"], W(i, "ff.ff.0.proj.weight"), ws["dn"], M, d, 8 * d, b_mn=True)
+            ops.layernorm_bwd(ws["h2"][i], ws["dn"], self._f32(i, "ff_norm.gamma"), dres=dh, out=dh_alt, dgamma=G(i, "ff_norm.gamma"))
+            dh, dh_alt = dh_alt, dh
+            # ---- cross-attention branch
+            ops.gemm(dh, ws["a2"][i], G(i, "cross_attn.to_out.weight"), d, d, M, a_mn=True, b_mn=True, accumulate=True)
+            ops.gemm(dh, W(i, "cross_attn.to_out.weight"), ws["da"], M, d, d, b_mn=True)
+            kv = ws["kv2"][i].view(B, Lc, 2, kvh, 64)
+            dkv = ws["dkv2"].view(B, Lc, 2, kvh, 64)
+            ops.attention_bwd(ws["q2"][i].view(B, N, H, 64), kv[:, :, 0], kv[:, :, 1], ws["a2"][i].view(B, N, H, 64),
+                              ws["da"].view(B, N, H, 64), ws["lse2"][i], ws["dq2"].view(B, N, H, 64), dkv[:, :, 0], dkv[:, :, 1])
+            ops.gemm(ws["dq2"], ws["n2"][i], G(i, "cross_attn.to_q.weight"), d, d, M, a_mn=True, b_mn=True, accumulate=True)
+            ops.gemm(ws["dq2"], W(i, "cross_attn.to_q.weight"), ws["dn"], M, d, d, b_mn=True)
+            ops.gemm(ws["dkv2"], self._cemb, G(i, "cross_attn.to_kv.weight"), 2 * ck, ck, B * Lc, a_mn=True, b_mn=True, accumulate=True)
+            ops.gemm(ws["dkv2"], W(i, "cross_attn.to_kv.weight"), ws["dcemb"], B * Lc, ck, 2 * ck, b_mn=True, residual=ws["dcemb"])
+            ops.layernorm_bwd(ws["h1"][i], ws["dn"], self._f32(i, "cross_attend_norm.gamma"), dres=dh, out=dh_alt, dgamma=G(i, "cross_attend_norm.gamma"))
+            dh, dh_alt = dh_alt, dh
+            # ---- self-attention branch
+            ops.gemm(dh, ws["a1"][i], G(i, "self_attn.to_out.weight"), d, d, M, a_mn=True, b_mn=True, accumulate=True)
+            ops.gemm(dh, W(i, "self_attn.to_out.weight"), ws["da"], M, d, d, b_mn=True)
+            qkv = ws["qkv"][i].view(B, N, 3, H, 64)
+            dqkv = ws["dqkv"].view(B, N, 3, H, 64)
+            ops.attention_bwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], ws["a1"][i].view(B, N, H, 64), ws["da"].view(B, N, H, 64),
+                              ws["lse1"][i], dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], rope=(cos, sin))
+            ops.gemm(ws["dqkv"], ws["n1"][i], G(i, "self_attn.to_qkv.weight"), 3 * d, d, M, a_mn=True, b_mn=True, accumulate=True)
+            ops.gemm(ws["dqkv"], W(i, "self_attn.to_qkv.weight"), ws["dn"], M, d, 3 * d, b_mn=True)
+            ops.layernorm_bwd(ws["h"][i], ws["dn"], self._f32(i, "pre_norm.gamma"), dres=dh, out=dh_alt, dgamma=G(i, "pre_norm.gamma"))
+            dh, dh_alt = dh_alt, dh
+            if self.grad_ready_hook is not None:
+                self.grad_ready_hook(i, self.layer_grad_slice(i))
+        return dh.clone(), ws["dcemb"].clone()
+
+    # ------------------------------------------------------------------ full model forward (training branch of dit.py:231-431)
+    def forward(self, x, t, cross_attn_cond=None, global_embed=None, cfg_dropout_prob=0.0):
+        c, P = self.cfg, self._p
+        bf = torch.bfloat16
+        B, C, T = x.shape
+        x, t = x.to(bf), t.to(bf)
+        lin = lambda inp, w, b=None: F.linear(inp, P[w].to(bf), None if b is None else P[b].to(bf))
+        if cross_attn_cond is not None:
+            cc = cross_attn_cond.to(bf)
+            if cfg_dropout_prob > 0.0:  # dit.py:306-310
+                mask = torch.bernoulli(torch.full((B, 1, 1), cfg_dropout_prob, device=x.device)).to(torch.bool)
+                cc = torch.where(mask, torch.zeros_like(cc), cc)
+            cemb = lin(F.silu(lin(cc, "to_cond_embed.0.weight")), "to_cond_embed.2.weight")
+        else:
+            raise NotImplementedError("b200sat training path expects cross-attention conditioning")
+        f = 2 * math.pi * t[:, None] @ P["timestep_features.weight"].to(bf).T
+        te = torch.cat([f.cos(), f.sin()], dim=-1)
+        te = lin(F.silu(lin(te, "to_timestep_embed.0.weight", "to_timestep_embed.0.bias")), "to_timestep_embed.2.weight", "to_timestep_embed.2.bias")
+        if global_embed is not None:
+            ge = lin(F.silu(lin(global_embed.to(bf), "to_global_embed.0.weight")), "to_global_embed.2.weight")
+            te = ge + te
+        xin = F.conv1d(x, P["preprocess_conv.weight"].to(bf)) + x
+        h0 = torch.cat([te.unsqueeze(1), lin(xin.transpose(1, 2), "transformer.project_in.weight")], dim=1)   # [B, N, d]
+        N = T + 1
+        Lc = cemb.shape[1]
+        self._shape = (B, N, Lc)
+        hL = _StackFn.apply(h0.reshape(B * N, c.embed_dim).contiguous(), cemb.reshape(B * Lc, -1).contiguous(), self)
+        out = lin(hL.view(B, N, c.embed_dim), "transformer.project_out.weight").transpose(1, 2)[:, :, 1:]
+        out = F.conv1d(out, P["postprocess_conv.weight"].to(bf)) + out
+        return out
+
+
+def v_objective_loss(model, x0, noise, t, cross_attn_cond, global_embed, cfg_dropout_prob=0.0):
+    """training/diffusion.py:405-449: alpha/sigma from t, noised input, v target, MSE."""
+    alpha = torch.cos(t * math.pi / 2)[:, None, None]
+    sigma = torch.sin(t * math.pi / 2)[:, None, None]
+    noised = x0 * alpha + noise * sigma
+    target = noise * alpha - x0 * sigma
+    out = model(noised, t, cross_attn_cond=cross_attn_cond, global_embed=global_embed, cfg_dropout_prob=cfg_dropout_prob)
+    return F.mse_loss(out.float(), target)

@@ -82,7 +82,7 @@ def linear(x, w, bias=None, residual=None, out=None, silu=False, out_f32=False, 
     return out
 
 
-def gemm(a, b, out, M, N, K, a_mn=False, b_mn=False, accumulate=False, swiglu_bwd_aux=None, force_bn=0):
+def gemm(a, b, out, M, N, K, a_mn=False, b_mn=False, accumulate=False, swiglu_bwd_aux=None, residual=None, force_bn=0):
     """General D[M,N] (=|+=) A . B^T for the backward pass.  a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N] if b_mn), bf16.
     out: bf16 [M,N], or fp32 when accumulate (gradient accumulation), or bf16 [M,2N] with swiglu_bwd_aux = saved u [M,2N]."""
     _chk_bf16(a, "a"); _chk_bf16(b, "b")
@@ -93,8 +93,11 @@ def gemm(a, b, out, M, N, K, a_mn=False, b_mn=False, accumulate=False, swiglu_bw
     if swiglu_bwd_aux is not None:
         flags |= GEMM_SWIGLU_BWD
         n_half = N
+    if residual is not None:
+        flags |= GEMM_RESIDUAL
     rc = lib().b200sat_gemm_bf16(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(), out.stride(0), M, N, K, flags,
-                                 0, 0, 0, 0, 0, 0, 0, 0, n_half, 0, 0, 0, 0, _p(swiglu_bwd_aux),
+                                 0, _p(residual), residual.stride(0) if residual is not None else 0, 0, 0, 0, 0, 0, n_half, 0, 0, 0, 0,
+                                 _p(swiglu_bwd_aux),
                                  swiglu_bwd_aux.stride(0) if swiglu_bwd_aux is not None else 0, force_bn, _stream())
     LAUNCHES[0] += 1
     check(rc, "gemm_bf16")
