@@ -82,6 +82,21 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(int(q) / int(per))))
+    except Exception:
+        pass
+    return n
+
+
 def oracle_cfg_step_seconds(n_steps, threads):
     """The reference's CPU path for this workload = the oracle port (torch fp32), one CFG denoising step per call."""
     from oracle import dit as odit
@@ -105,7 +120,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     oracle_cfg_step_seconds(max(1, min(args.warmup, 1)), threads)  # warm-up (bounded: one CFG step)
     times = oracle_cfg_step_seconds(args.steps, threads)
     sec = sum(times) / len(times)
@@ -128,6 +143,66 @@ def workload_config(n):
             "cfg_scale": CFG_SCALE, "sampler": "dpmpp-3m-sde", "sample_steps": SAMPLE_STEPS,
             "sigma_min": SIGMA_MIN, "sigma_max": SIGMA_MAX, "parallelism": f"replicas x{n} (independent seeds, no collective)",
             "l2": "no explicit flush: every denoising step streams 2.1 GB of bf16 weights (>> 126 MB L2)"}
+
+
+def measure_train(args, dev, rank, world, dist):
+    """BASELINE.json configs[2] (DiT part): v-objective training step, batch 8 x 1024 latents per GPU (pre-encoded latents,
+    random T5-shaped conditioning), bf16 compute / fp32 master weights, AdamW, layer-bucketed NCCL all-reduce when N > 1."""
+    from b200sat import init
+    from b200sat.dit_train import DiTTrainModel, v_objective_loss
+    from b200sat.ddp import GradAllReducer
+    B = 8
+    sd = init.dit_state_dict(embed_dim=D_MODEL, depth=DEPTH, num_heads=HEADS, seed=0, device=dev, dtype=torch.float32)
+    model = DiTTrainModel(sd, device=dev)
+    del sd
+    opt = torch.optim.AdamW(model.parameters(), lr=5e-5, betas=(0.9, 0.999), weight_decay=1e-3, fused=True)
+    red = GradAllReducer(model)
+    g = torch.Generator().manual_seed(42 + rank)
+    h_lat = torch.randn(B, 64, T_LAT, generator=g).pin_memory()
+    h_cross = torch.randn(B, L_CTX, 768, generator=g).pin_memory()
+    h_glob = torch.randn(B, D_MODEL, generator=g).pin_memory()
+    h_loss = torch.zeros(1).pin_memory()
+    gd = torch.Generator(device=dev).manual_seed(7 + rank)
+
+    def step():
+        lat = h_lat.to(dev, non_blocking=True); cross = h_cross.to(dev, non_blocking=True); glob = h_glob.to(dev, non_blocking=True)
+        noise = torch.randn(lat.shape, device=dev, generator=gd)
+        t = torch.rand(B, device=dev, generator=gd)
+        model.zero_grad()
+        loss = v_objective_loss(model, lat, noise, t, cross, glob, cfg_dropout_prob=0.1)
+        (loss * red.loss_scale).backward()
+        red.finish()
+        opt.step()
+        h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+
+    for _ in range(3):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    k = max(3, min(args.steps * 2, 10))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(k):
+        step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = ms.item() / k
+    tokens = B * T_LAT * world
+    flop = 3 * GFLOP_PER_TOKEN * 1e9 * B * (T_LAT + 1)
+    pk = peaks()
+    out = {"metric": "dit_training_latent_tokens_per_sec", "value": tokens / (ms_step * 1e-3), "unit": "latent-tokens/s", "ms_per_step": ms_step,
+           "steps": k, "batch_per_gpu": B, "seq_len": T_LAT, "loss": float(h_loss.item()), "optimizer": "AdamW(fused) fp32 masters",
+           "pre_encoded": True, "includes": "H2D of latents+conditioning, fwd, bwd, layer-bucketed all-reduce, optimizer step, D2H loss",
+           "tflops_per_gpu": flop / (ms_step * 1e-3) / 1e12, "frac_of_sustained_peak": flop / (ms_step * 1e-3) / 1e12 / pk["bf16_sustained"]}
+    del model, opt
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(args):
@@ -210,6 +285,12 @@ def run_ours(args):
     h2d = h_noise.numel() * 4 + h_cross.numel() * 4 + h_glob.numel() * 4
     d2h = h_out.numel() * 4
 
+    train = None
+    if not args.no_train:
+        del smp
+        model._samplers.clear()
+        torch.cuda.empty_cache()
+        train = measure_train(args, dev, rank, world, dist)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -242,7 +323,7 @@ def run_ours(args):
              "frac_of_sustained_peak": step_tflop * args.steps / (ms_total * 1e-3) / pk["bf16_sustained"]}
 
     # ---------------- CPU baseline (oracle port) on a bounded sample
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     cpu = None
     if not args.no_cpu_baseline:
         ts = oracle_cfg_step_seconds(2, threads)
@@ -257,7 +338,7 @@ def run_ours(args):
         "config": workload_config(world), "sample_seconds_100_steps": ms_total / args.steps / 1e3,
         "e2e": {"value": e2e_val, "unit": "latent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "b200sat.generation.generate_diffusion_cond(host pinned noise/conditioning -> host latents)"},
-        "gpu_launches": launches, "clocks": clk, "roofline": roof, "whole_step": whole, "cpu_baseline": cpu,
+        "gpu_launches": launches, "clocks": clk, "roofline": roof, "whole_step": whole, "cpu_baseline": cpu, "train": train,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -271,6 +352,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
