@@ -148,6 +148,21 @@ int b200sat_layernorm_bwd(const void* x, long ldx, const void* dy, long lddy, co
 /* out[n] += sum_m dY[m,n]: bias gradients of nn.Linear. */
 int b200sat_colsum(const void* dy, long ld, float* out, int M, int N, void* stream);
 
+/* ---- multi-resolution STFT loss (training/losses/auraloss.py) -------------------------------------------------------- */
+
+/* out[b,r,t] = FIR_taps( sum_c mix[r,c] x[b,c,t] ), zero padded: FIRFilter.forward (A-weighting, auraloss.py:155-169) fused with
+ * SumAndDifference (:44-73) / channel selection via the R x C mixing matrix.  x fp32 [B,C,T] -> out fp32 [B,R,T], R <= 4. */
+int b200sat_stft_prefilter(const float* x, float* out, const float* mix, const float* taps, int B, int C, int T, int R, int ntaps,
+                           void* stream);
+
+/* One STFT resolution over `rows` mono signal pairs (input xf, target yf; fp32 [rows, T]): per row acc[row] += { sum (|Y|-|X|)^2,
+ * sum |Y|^2, sum |log|X| - log|Y|| } over all frames and bins, |.| = sqrt(max(re^2+im^2, eps)); torch.stft semantics
+ * (center, reflect pad, periodic hann `window` [n_fft], onesided).  twiddle: fp32 pairs exp(-2 pi i k / n_fft), k < n_fft/2.
+ * Replaces STFTLoss.stft + SpectralConvergenceLoss + STFTMagnitudeLoss (auraloss.py:171-223, :368-449); nothing but the three
+ * sums leaves the SM. */
+int b200sat_stft_loss_accumulate(const float* xf, const float* yf, double* acc, const float* window, const float* twiddle, int rows,
+                                 int T, int n_fft, int hop, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

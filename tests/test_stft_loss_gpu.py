@@ -1,0 +1,41 @@
+"""GPU parity: fused multi-resolution STFT loss kernels vs the committed reference outputs (auraloss) and the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+FFT = [2048, 1024, 512, 256, 128, 64, 32]
+HOP = [n // 4 for n in FFT]
+
+
+def test_mrstft_golden():
+    from b200sat.stft_loss import MultiResolutionSTFTLoss, SumAndDifferenceSTFTLoss
+    z = np.load(os.path.join(G, "mrstft.npz"))
+    x, y = torch.from_numpy(z["x"]).cuda(), torch.from_numpy(z["y"]).cuda()
+    sd = SumAndDifferenceSTFTLoss(FFT, HOP, FFT, perceptual_weighting=True, sample_rate=44100)
+    mr = MultiResolutionSTFTLoss(FFT, HOP, FFT, perceptual_weighting=True, sample_rate=44100)
+    plain = MultiResolutionSTFTLoss(FFT, HOP, FFT)
+    assert abs(sd(x, y).item() - float(z["loss_sd"])) <= 2e-5
+    assert abs(mr(x[:, :1], y[:, :1]).item() - float(z["loss_l"])) <= 2e-5
+    assert abs(plain(x, y).item() - float(z["loss_plain"])) <= 2e-5
+
+
+def test_mrstft_config4_shape_vs_oracle():
+    """4 x 2 x 65536 (the autoencoder training clip length): all four generator-loss STFT terms in one pass."""
+    from oracle import stft_loss as ost
+    from b200sat.stft_loss import SumAndDifferenceSTFTLoss, autoencoder_mrstft_terms
+    g = torch.Generator().manual_seed(0)
+    reals = torch.randn(4, 2, 65536, generator=g) * 0.3
+    dec = reals + 0.05 * torch.randn(4, 2, 65536, generator=g)
+    taps = ost.a_weighting_fir()
+    ref_sd = ost.sum_and_difference_loss(reals, dec, FFT, HOP, taps).item()
+    ref_l = ost.mrstft_loss(reals[:, :1], dec[:, :1], FFT, HOP, taps).item()
+    ref_r = ost.mrstft_loss(reals[:, 1:], dec[:, 1:], FFT, HOP, taps).item()
+    loss = SumAndDifferenceSTFTLoss(FFT, HOP, FFT, perceptual_weighting=True, sample_rate=44100)
+    sd, l, r = autoencoder_mrstft_terms(loss, dec.cuda(), reals.cuda())
+    for got, ref in ((sd, ref_sd), (l, ref_l), (r, ref_r)):
+        assert abs(got.item() - ref) <= 2e-5 * max(1.0, abs(ref)), (got.item(), ref)
