@@ -7,11 +7,12 @@
 // and the repeat_interleave of K/V never touch HBM.
 //
 // One CTA = one 128-query tile of one (batch, head); two CTAs are resident per SM so one CTA's softmax overlaps the
-// other's MMAs.  192 threads:
+// other's MMAs.  320 threads:
 //   warp 0 lane 0 : TMA producer (Q once; K,V tiles of 128 keys through a 2-stage ring; 4-D tensor maps, 128B swizzle)
 //   warp 1        : TMEM allocation; lane 0 issues S = Q K^T (128x128x64) and O_j = P V (128x64x128) on tcgen05
-//   warps 2..5    : online softmax — thread == query row (tcgen05.ld 32x32b), P written to smem as the bf16 A operand,
-//                   O accumulated in registers with the running-max rescale.
+//   warps 2..9    : online softmax — two threads per query row (64 keys each; tcgen05.ld 32x32b), P written to smem as the
+//                   bf16 A operand, O (32 dims per thread) accumulated in registers with the running-max rescale.
+//                   (ncu r1: with 4 softmax warps the kernel was latency-bound: issue-active 31 %, tensor pipe 17 %.)
 #include "common.cuh"
 #include <cstring>
 
@@ -36,9 +37,9 @@ constexpr int AT_BM = 128;   // queries per CTA
 constexpr int AT_BN = 128;   // keys per tile
 constexpr int AT_D = 64;
 constexpr int AT_TILE = AT_BM * AT_D * 2;                       // 16 KB
-constexpr int AT_SMEM = AT_TILE /*Q*/ + 2 * 2 * AT_TILE /*K,V x2*/ + 2 * AT_TILE /*P*/ + 256;
+constexpr int AT_SMEM = AT_TILE /*Q*/ + 2 * 2 * AT_TILE /*K,V x2*/ + 2 * AT_TILE /*P*/ + 256 /*barriers*/ + 512 /*row-max exchange*/;
 
-__global__ void __launch_bounds__(192, 2) attention_fwd_tcgen05(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sKV = smem + AT_TILE;            // stage s: K at sKV + s*2*TILE, V at + TILE
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(192, 2) attention_fwd_tcgen05(const __grid_con
   uint64_t* p_full = bars + 6;
   uint64_t* o_full = bars + 7;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+  __nv_bfloat16* s_max = reinterpret_cast<__nv_bfloat16*>(smem + 7 * AT_TILE + 256);  // [2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(192, 2) attention_fwd_tcgen05(const __grid_con
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 256);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -128,43 +130,52 @@ __global__ void __launch_bounds__(192, 2) attention_fwd_tcgen05(const __grid_con
     }
   } else {
     // ===================== softmax / output warps =====================
-    const int quarter = warp & 3;  // TMEM lane quarter accessible to this warp
+    // 8 warps: two threads per query row (same TMEM lane quarter, different 64-key halves).  They only have to agree on the
+    // running max of the row: each publishes its half's max rounded UP to bf16 (any common upper bound is a valid softmax
+    // shift) through 512 B of shared memory and a 64-thread named barrier; row sums stay per-thread until the end.
+    const int quarter = warp & 3;          // TMEM lane quarter accessible to this warp
+    const int half = (warp - 2) >> 2;      // which 64 keys of the 128-key tile / which 32 output dims
     const int r = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     float m_run = -INFINITY, l_run = 0.f;
-    float o[64];
+    float o[32];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.f;
+    for (int i = 0; i < 32; ++i) o[i] = 0.f;
     uint8_t* prow = sP + r * 128;
     const int sw = r & 7;
+    __nv_bfloat16* my_max = s_max + half * 128 + r;
+    const __nv_bfloat16* other_max = s_max + (half ^ 1) * 128 + r;
 
     for (int j = 0; j < num_kv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      const int kbase = j * AT_BN;
-      const int nvalid = p.Nk - kbase;  // >= 1
-      const bool tail = nvalid < AT_BN;  // only the last key tile of a ragged sequence needs the column mask
-      // pass A: row max
+      const int nvalid = p.Nk - j * AT_BN - half * 64;   // valid keys among this thread's 64 columns (may be <= 0)
+      const bool tail = nvalid < 64;
+      // pass A: max over this thread's 64 columns
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
         uint32_t raw[32];
-        tmem_ld_32x32(tmem_S + lane_off + c * 32, raw);
+        tmem_ld_32x32(tmem_S + lane_off + (half * 2 + cc) * 32, raw);
         tmem_ld_wait();
         if (!tail) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c * 32 + i < nvalid) ? __uint_as_float(raw[i]) : -INFINITY);
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (cc * 32 + i < nvalid) ? __uint_as_float(raw[i]) : -INFINITY);
         }
       }
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      *my_max = __float2bfloat16_ru(mx * p.scale_log2);
+      asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
+      const float m_pair = fmaxf(__bfloat162float(*my_max), __bfloat162float(*other_max));
+      const float m_new = fmaxf(m_run, m_pair);
       const float alpha = fast_exp2(m_run - m_new);
-      // pass B: p = exp2(s*scale - m), row sum, bf16 P -> swizzled smem (A operand of the PV MMA)
+      // pass B: p = exp2(s*scale - m), partial row sum, bf16 P -> swizzled smem (A operand of the PV MMA)
       float lsum = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
         uint32_t raw[32];
         tmem_ld_32x32(tmem_S + lane_off + c * 32, raw);
         tmem_ld_wait();
@@ -180,8 +191,8 @@ __global__ void __launch_bounds__(192, 2) attention_fwd_tcgen05(const __grid_con
         } else {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float p0 = (c * 32 + i < nvalid) ? fast_exp2(fmaf(__uint_as_float(raw[i]), p.scale_log2, -m_new)) : 0.f;
-            const float p1 = (c * 32 + i + 1 < nvalid) ? fast_exp2(fmaf(__uint_as_float(raw[i + 1]), p.scale_log2, -m_new)) : 0.f;
+            const float p0 = (cc * 32 + i < nvalid) ? fast_exp2(fmaf(__uint_as_float(raw[i]), p.scale_log2, -m_new)) : 0.f;
+            const float p1 = (cc * 32 + i + 1 < nvalid) ? fast_exp2(fmaf(__uint_as_float(raw[i + 1]), p.scale_log2, -m_new)) : 0.f;
             lsum += p0 + p1;
             pk[i >> 1] = pack_bf16(p0, p1);
           }
@@ -189,9 +200,9 @@ __global__ void __launch_bounds__(192, 2) attention_fwd_tcgen05(const __grid_con
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int chunk = c * 4 + t;              // 16-byte chunk index along the 128 keys
-          const int kb = chunk >> 3, cc = chunk & 7;
+          const int kb = chunk >> 3, ch = chunk & 7;
           uint4 u = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
-          *reinterpret_cast<uint4*>(prow + kb * AT_TILE + ((cc ^ sw) << 4)) = u;
+          *reinterpret_cast<uint4*>(prow + kb * AT_TILE + ((ch ^ sw) << 4)) = u;
         }
       }
       fence_proxy_async_smem();
@@ -199,26 +210,30 @@ __global__ void __launch_bounds__(192, 2) attention_fwd_tcgen05(const __grid_con
       mbar_arrive(p_full);
       l_run = l_run * alpha + lsum;
       m_run = m_new;
-      // O_j = P V from TMEM, accumulate with rescale
+      // O_j = P V from TMEM: this thread accumulates output dims [half*32, half*32+32) with the rescale
       mbar_wait(o_full, j & 1);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      {
         uint32_t raw[32];
-        tmem_ld_32x32(tmem_O + lane_off + c * 32, raw);
+        tmem_ld_32x32(tmem_O + lane_off + half * 32, raw);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * alpha + __uint_as_float(raw[i]);
+        for (int i = 0; i < 32; ++i) o[i] = o[i] * alpha + __uint_as_float(raw[i]);
       }
       tc_fence_before();
     }
+    // combine the two partial row sums (P buffer is free now: reuse its first KB as fp32 scratch)
+    float* s_l = reinterpret_cast<float*>(sP);
+    s_l[half * 128 + r] = l_run;
+    asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
+    const float l_tot = l_run + s_l[(half ^ 1) * 128 + r];
     const int qrow = q0 + r;
     if (qrow < p.Nq) {
-      const float inv = 1.0f / l_run;
-      __nv_bfloat16* dst = p.O + static_cast<long>(b) * p.o_bs + static_cast<long>(qrow) * p.o_ss + static_cast<long>(h) * p.o_hs;
+      const float inv = 1.0f / l_tot;
+      __nv_bfloat16* dst = p.O + static_cast<long>(b) * p.o_bs + static_cast<long>(qrow) * p.o_ss + static_cast<long>(h) * p.o_hs + half * 32;
       uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         uint4 u;
         u.x = pack_bf16(o[8 * i + 0] * inv, o[8 * i + 1] * inv);
         u.y = pack_bf16(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
@@ -226,7 +241,7 @@ __global__ void __launch_bounds__(192, 2) attention_fwd_tcgen05(const __grid_con
         u.w = pack_bf16(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
         d4[i] = u;
       }
-      if (p.lse) p.lse[(static_cast<long>(b) * p.Hq + h) * p.Nq + qrow] = m_run * 0.6931471805599453f + logf(l_run);
+      if (p.lse && half == 0) p.lse[(static_cast<long>(b) * p.Hq + h) * p.Nq + qrow] = m_run * 0.6931471805599453f + logf(l_tot);
     }
   }
 
@@ -273,7 +288,7 @@ extern "C" int b200sat_attention_fwd(const void* q, const void* k, const void* v
     attr_set = true;
   }
   dim3 grid((Nq + AT_BM - 1) / AT_BM, Hq, B);
-  attention_fwd_tcgen05<<<grid, 192, AT_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+  attention_fwd_tcgen05<<<grid, 320, AT_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }

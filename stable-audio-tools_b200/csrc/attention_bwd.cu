@@ -82,6 +82,31 @@ __device__ __forceinline__ void store_grad_row(__nv_bfloat16* dst, float (&g)[64
   }
 }
 
+// 32 consecutive dims of a gradient row (dims [0,32) carry the rotary pairs (i, i+16) when cs != null)
+__device__ __forceinline__ void store_grad_half(__nv_bfloat16* dst, float (&g)[32], float scale, const float* cs, const float* sn) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) g[i] *= scale;
+  if (cs) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float c_ = __ldg(cs + i), s_ = __ldg(sn + i);
+      const float a = g[i], b = g[i + 16];
+      g[i] = a * c_ + b * s_;
+      g[i + 16] = b * c_ - a * s_;
+    }
+  }
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u;
+    u.x = pack_bf16(g[8 * i + 0], g[8 * i + 1]);
+    u.y = pack_bf16(g[8 * i + 2], g[8 * i + 3]);
+    u.z = pack_bf16(g[8 * i + 4], g[8 * i + 5]);
+    u.w = pack_bf16(g[8 * i + 6], g[8 * i + 7]);
+    d4[i] = u;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, float* __restrict__ delta,
                                   int B, int H, int N, long o_bs, long o_ss, long o_hs, long d_bs, long d_ss, long d_hs) {
@@ -109,7 +134,7 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
 // ------------------------------------------------------------------------------------------------------------
 constexpr int DKV_SMEM = 2 * BW_T /*K,V*/ + 4 * BW_T /*ring of (Q,dO) x2*/ + 2 * BW_T /*P^T*/ + 2 * BW_T /*dS^T*/ + 4 * 128 * 4 + 256;
 
-__global__ void __launch_bounds__(192, 1) attention_bwd_dkv_tcgen05(const __grid_constant__ AttnBwdParams p) {
+__global__ void __launch_bounds__(320, 1) attention_bwd_dkv_tcgen05(const __grid_constant__ AttnBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sK = smem;
   uint8_t* sV = smem + BW_T;
@@ -140,7 +165,7 @@ __global__ void __launch_bounds__(192, 1) attention_bwd_dkv_tcgen05(const __grid
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 256);
     mbar_init(acc_done, 1);
     fence_barrier_init();
   }
@@ -200,9 +225,12 @@ __global__ void __launch_bounds__(192, 1) attention_bwd_dkv_tcgen05(const __grid
       }
     }
   } else {
+    // 8 warps: two threads per key row, each owning 64 of the 128 query columns (no cross-thread reduction is needed in the
+    // backward: lse and delta are per-column inputs).
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;          // key row of this thread
-    const int tid = (warp - 2) * 32 + lane;     // 0..127 among the softmax threads
+    const int tid = (warp - 2) * 32 + lane;     // 0..255 among the softmax threads
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const bool key_ok = (k0 + r) < p.Nk;
     uint8_t* pt_row = sPT + r * 128;
@@ -211,18 +239,20 @@ __global__ void __launch_bounds__(192, 1) attention_bwd_dkv_tcgen05(const __grid
     for (int it = 0; it < iters; ++it) {
       const int h = hk * G + it / nq, qt = it % nq;
       const int buf = it & 1;
-      {  // stage lse / delta of this q tile (column statistics) for all 128 softmax threads
-        const int q = qt * 128 + tid;
+      {  // stage lse / delta of this q tile (column statistics): threads 0..127 lse, 128..255 delta
+        const int qi = tid & 127;
+        const int q = qt * 128 + qi;
         const long idx = (static_cast<long>(b) * p.Hq + h) * p.Nq + q;
-        s_lse[buf * 128 + tid] = (q < p.Nq) ? p.lse[idx] * 1.4426950408889634f : INFINITY;  // out-of-range query => P = 0
-        s_delta[buf * 128 + tid] = (q < p.Nq) ? p.delta[idx] : 0.f;
+        if (tid < 128) s_lse[buf * 128 + qi] = (q < p.Nq) ? p.lse[idx] * 1.4426950408889634f : INFINITY;  // out-of-range query => P = 0
+        else s_delta[buf * 128 + qi] = (q < p.Nq) ? p.delta[idx] : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(s_full, it & 1);
       tc_fence_after();
       if (it > 0) mbar_wait(acc_done, (it - 1) & 1);  // previous P^T / dS^T consumed
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
         uint32_t rs[32], rp[32];
         tmem_ld_32x32(tm_ST + lane_off + c * 32, rs);
         tmem_ld_32x32(tm_dPT + lane_off + c * 32, rp);
@@ -244,30 +274,27 @@ __global__ void __launch_bounds__(192, 1) attention_bwd_dkv_tcgen05(const __grid
     }
     mbar_wait(acc_done, (iters - 1) & 1);
     tc_fence_after();
-    float g[64];
+    float g[32];
     const int krow = k0 + r;
-    // dV
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    {
       uint32_t raw[32];
-      tmem_ld_32x32(tm_dV + lane_off + c * 32, raw);
+      tmem_ld_32x32(tm_dV + lane_off + half * 32, raw);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) g[c * 32 + i] = __uint_as_float(raw[i]);
+      for (int i = 0; i < 32; ++i) g[i] = __uint_as_float(raw[i]);
     }
-    if (key_ok) store_grad_row(p.dV + b * p.dv_bs + krow * p.dv_ss + hk * p.dv_hs, g, 1.0f, nullptr, nullptr);
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    if (key_ok) store_grad_half(p.dV + b * p.dv_bs + krow * p.dv_ss + hk * p.dv_hs + half * 32, g, 1.0f, nullptr, nullptr);
+    {
       uint32_t raw[32];
-      tmem_ld_32x32(tm_dK + lane_off + c * 32, raw);
+      tmem_ld_32x32(tm_dK + lane_off + half * 32, raw);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) g[c * 32 + i] = __uint_as_float(raw[i]);
+      for (int i = 0; i < 32; ++i) g[i] = __uint_as_float(raw[i]);
     }
     if (key_ok) {
-      const float* cs = p.rope_cos ? p.rope_cos + krow * 16 : nullptr;
-      const float* sn = p.rope_cos ? p.rope_sin + krow * 16 : nullptr;
-      store_grad_row(p.dK + b * p.dk_bs + krow * p.dk_ss + hk * p.dk_hs, g, p.scale, cs, sn);
+      const bool rot = p.rope_cos != nullptr && half == 0;
+      store_grad_half(p.dK + b * p.dk_bs + krow * p.dk_ss + hk * p.dk_hs + half * 32, g, p.scale,
+                      rot ? p.rope_cos + krow * 16 : nullptr, rot ? p.rope_sin + krow * 16 : nullptr);
     }
     tc_fence_before();
   }
@@ -279,7 +306,7 @@ __global__ void __launch_bounds__(192, 1) attention_bwd_dkv_tcgen05(const __grid
 // ------------------------------------------------------------------------------------------------------------
 constexpr int DQ_SMEM = 2 * BW_T /*Q,dO*/ + 4 * BW_T /*ring of (K,V) x2*/ + 2 * BW_T /*dS*/ + 256;
 
-__global__ void __launch_bounds__(192, 1) attention_bwd_dq_tcgen05(const __grid_constant__ AttnBwdParams p) {
+__global__ void __launch_bounds__(320, 1) attention_bwd_dq_tcgen05(const __grid_constant__ AttnBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sdO = smem + BW_T;
@@ -306,7 +333,7 @@ __global__ void __launch_bounds__(192, 1) attention_bwd_dq_tcgen05(const __grid_
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 256);
     mbar_init(acc_done, 1);
     fence_barrier_init();
   }
@@ -361,6 +388,7 @@ __global__ void __launch_bounds__(192, 1) attention_bwd_dq_tcgen05(const __grid_
     }
   } else {
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const int qrow = q0 + r;
@@ -376,7 +404,8 @@ __global__ void __launch_bounds__(192, 1) attention_bwd_dq_tcgen05(const __grid_
       tc_fence_after();
       if (j > 0) mbar_wait(acc_done, (j - 1) & 1);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
         uint32_t rs[32], rp[32];
         tmem_ld_32x32(tm_S + lane_off + c * 32, rs);
         tmem_ld_32x32(tm_dP + lane_off + c * 32, rp);
@@ -395,19 +424,18 @@ __global__ void __launch_bounds__(192, 1) attention_bwd_dq_tcgen05(const __grid_
     }
     mbar_wait(acc_done, (nkv - 1) & 1);
     tc_fence_after();
-    float g[64];
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    float g[32];
+    {
       uint32_t raw[32];
-      tmem_ld_32x32(tm_dQ + lane_off + c * 32, raw);
+      tmem_ld_32x32(tm_dQ + lane_off + half * 32, raw);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) g[c * 32 + i] = __uint_as_float(raw[i]);
+      for (int i = 0; i < 32; ++i) g[i] = __uint_as_float(raw[i]);
     }
     if (q_ok) {
-      const float* cs = p.rope_cos ? p.rope_cos + qrow * 16 : nullptr;
-      const float* sn = p.rope_cos ? p.rope_sin + qrow * 16 : nullptr;
-      store_grad_row(p.dQ + b * p.dq_bs + qrow * p.dq_ss + h * p.dq_hs, g, p.scale, cs, sn);
+      const bool rot = p.rope_cos != nullptr && half == 0;
+      store_grad_half(p.dQ + b * p.dq_bs + qrow * p.dq_ss + h * p.dq_hs + half * 32, g, p.scale,
+                      rot ? p.rope_cos + qrow * 16 : nullptr, rot ? p.rope_sin + qrow * 16 : nullptr);
     }
     tc_fence_before();
   }
@@ -464,8 +492,8 @@ extern "C" int b200sat_attention_bwd(const void* q, const void* k, const void* v
     B200SAT_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_dq_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
     attr_set = true;
   }
-  attention_bwd_dkv_tcgen05<<<dim3((Nk + 127) / 128, Hkv, B), 192, DKV_SMEM, s>>>(p);
-  attention_bwd_dq_tcgen05<<<dim3((Nq + 127) / 128, Hq, B), 192, DQ_SMEM, s>>>(p);
+  attention_bwd_dkv_tcgen05<<<dim3((Nk + 127) / 128, Hkv, B), 320, DKV_SMEM, s>>>(p);
+  attention_bwd_dq_tcgen05<<<dim3((Nq + 127) / 128, Hq, B), 320, DQ_SMEM, s>>>(p);
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }

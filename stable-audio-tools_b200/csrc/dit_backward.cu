@@ -9,10 +9,10 @@ namespace b200sat {
 // dx_out = dres + dx fuses the residual-stream gradient add of the pre-norm block (transformer.py:703-712).
 // Persistent grid: each warp walks rows, keeps its dgamma partials in registers; one atomicAdd per column per block.
 template <int MAXC>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
-                                                            const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dres,
-                                                            __nv_bfloat16* __restrict__ dx_out, float* __restrict__ dgamma, int rows,
-                                                            int D, long ldx, long lddy, long ldr, long ldo, float eps) {
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                               const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dres,
+                                                               __nv_bfloat16* __restrict__ dx_out, float* __restrict__ dgamma, int rows,
+                                                               int D, long ldx, long lddy, long ldr, long ldo, float eps) {
   extern __shared__ float s_dg[];  // [D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunk = D / 8;
@@ -27,22 +27,19 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
   for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
     const __nv_bfloat16* xr = x + static_cast<long>(row) * ldx;
     const __nv_bfloat16* dr = dy + static_cast<long>(row) * lddy;
-    float xv[MAXC][8], gv[MAXC][8];
+    // x and dy stay packed (bf16x2) in registers: 2 x MAXC x 4 words instead of 2 x MAXC x 8 floats (ncu r1: the fp32 version
+    // needed 238 registers => 8 warps/SM => 1.3 TB/s)
+    uint4 xp[MAXC], dp[MAXC];
     float sum = 0.f;
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
       const int ch = lane + c * 32;
       if (ch < nchunk) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr) + ch);
-        const uint4 w = __ldg(reinterpret_cast<const uint4*>(dr) + ch);
-        const uint32_t uw[4] = {u.x, u.y, u.z, u.w}, ww[4] = {w.x, w.y, w.z, w.w};
+        xp[c] = __ldg(reinterpret_cast<const uint4*>(xr) + ch);
+        dp[c] = __ldg(reinterpret_cast<const uint4*>(dr) + ch);
+        const uint32_t uw[4] = {xp[c].x, xp[c].y, xp[c].z, xp[c].w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = unpack_bf16(uw[j]), d = unpack_bf16(ww[j]);
-          xv[c][2 * j] = f.x; xv[c][2 * j + 1] = f.y;
-          gv[c][2 * j] = d.x; gv[c][2 * j + 1] = d.y;   // dy for now
-          sum += f.x + f.y;
-        }
+        for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16(uw[j]); sum += f.x + f.y; }
       }
     }
 #pragma unroll
@@ -50,10 +47,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
     const float mean = sum / D;
     float sq = 0.f;
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c)
-      if (lane + c * 32 < nchunk)
+    for (int c = 0; c < MAXC; ++c) {
+      if (lane + c * 32 < nchunk) {
+        const uint32_t uw[4] = {xp[c].x, xp[c].y, xp[c].z, xp[c].w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { const float d = xv[c][j] - mean; sq += d * d; }
+        for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16(uw[j]); const float d0 = f.x - mean, d1 = f.y - mean; sq += d0 * d0 + d1 * d1; }
+      }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     const float rstd = rsqrtf(sq / D + eps);
@@ -62,14 +62,16 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
     for (int c = 0; c < MAXC; ++c) {
       const int ch = lane + c * 32;
       if (ch < nchunk) {
+        const uint32_t uw[4] = {xp[c].x, xp[c].y, xp[c].z, xp[c].w}, ww[4] = {dp[c].x, dp[c].y, dp[c].z, dp[c].w};
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + ch * 2), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + ch * 2 + 1);
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xh = (xv[c][j] - mean) * rstd;
-          const float dyv = gv[c][j];
-          dg[c][j] += dyv * xh;
-          const float g = dyv * __ldg(gamma + ch * 8 + j);
-          xv[c][j] = xh; gv[c][j] = g;
-          sg += g; sgx += g * xh;
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16(uw[j]), d = unpack_bf16(ww[j]);
+          const float xh0 = (f.x - mean) * rstd, xh1 = (f.y - mean) * rstd;
+          dg[c][2 * j] += d.x * xh0; dg[c][2 * j + 1] += d.y * xh1;
+          const float q0 = d.x * gm[2 * j], q1 = d.y * gm[2 * j + 1];
+          sg += q0 + q1; sgx += q0 * xh0 + q1 * xh1;
         }
       }
     }
@@ -82,18 +84,22 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
     for (int c = 0; c < MAXC; ++c) {
       const int ch = lane + c * 32;
       if (ch < nchunk) {
-        float o[8];
+        const uint32_t uw[4] = {xp[c].x, xp[c].y, xp[c].z, xp[c].w}, ww[4] = {dp[c].x, dp[c].y, dp[c].z, dp[c].w};
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + ch * 2), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + ch * 2 + 1);
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        uint4 ru = make_uint4(0, 0, 0, 0);
+        if (rr) ru = __ldg(reinterpret_cast<const uint4*>(rr) + ch);
+        const uint32_t rw[4] = {ru.x, ru.y, ru.z, ru.w};
+        uint32_t ow[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rstd * (gv[c][j] - mg - xv[c][j] * mgx);
-        if (rr) {
-          const uint4 u = __ldg(reinterpret_cast<const uint4*>(rr) + ch);
-          const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16(uw[j]); o[2 * j] += f.x; o[2 * j + 1] += f.y; }
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16(uw[j]), d = unpack_bf16(ww[j]), rs = unpack_bf16(rw[j]);
+          const float xh0 = (f.x - mean) * rstd, xh1 = (f.y - mean) * rstd;
+          const float o0 = rstd * (d.x * gm[2 * j] - mg - xh0 * mgx) + rs.x;
+          const float o1 = rstd * (d.y * gm[2 * j + 1] - mg - xh1 * mgx) + rs.y;
+          ow[j] = pack_bf16(o0, o1);
         }
-        uint4 u;
-        u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
-        reinterpret_cast<uint4*>(orow)[ch] = u;
+        reinterpret_cast<uint4*>(orow)[ch] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
       }
     }
   }
@@ -139,16 +145,23 @@ extern "C" int b200sat_layernorm_bwd(const void* x, long ldx, const void* dy, lo
   int grid = (rows + 7) / 8;
   const int cap = 2 * num_sms();
   if (grid > cap) grid = cap;
-  layernorm_bwd_kernel<8><<<grid, 256, D * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), gamma, static_cast<const __nv_bfloat16*>(dres),
-      static_cast<__nv_bfloat16*>(dx_out), dgamma, rows, D, ldx, lddy, ldr, ldo, eps);
+  if (D <= 1536)
+    layernorm_bwd_kernel<6><<<grid, 256, D * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), gamma, static_cast<const __nv_bfloat16*>(dres),
+        static_cast<__nv_bfloat16*>(dx_out), dgamma, rows, D, ldx, lddy, ldr, ldo, eps);
+  else
+    layernorm_bwd_kernel<8><<<grid, 256, D * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), gamma, static_cast<const __nv_bfloat16*>(dres),
+        static_cast<__nv_bfloat16*>(dx_out), dgamma, rows, D, ldx, lddy, ldr, ldo, eps);
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }
 
 extern "C" int b200sat_colsum(const void* dy, long ld, float* out, int M, int N, void* stream) {
   if (!dy || !out || M <= 0 || N <= 0 || (N % 2) || (ld % 2)) { set_last_error("colsum: bad arguments (N, ld even)"); return B200SAT_EINVAL; }
-  const int rpb = 256;
+  // enough row chunks to fill the machine even for narrow matrices
+  int rpb = 256;
+  while (rpb > 32 && static_cast<long>((N + 511) / 512) * ((M + rpb - 1) / rpb) < 2L * num_sms()) rpb >>= 1;
   dim3 grid((N + 511) / 512, (M + rpb - 1) / rpb);
   colsum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(dy), ld, out, M, N, rpb);
   B200SAT_CHECK_CUDA(cudaGetLastError());
