@@ -33,6 +33,7 @@ enum GemmFlags : int {
   GEMM_B_MN = 512,      // B is stored [K, N] (N contiguous): data-gradient GEMM through an nn.Linear weight [N_out=K, N]
   GEMM_ACCUM = 1024,    // fp32 output accumulates: D += acc (gradient accumulation into .grad)
   GEMM_SWIGLU_BWD = 2048,  // D[M, 2*N]: [dact*silu(g) | dact*a*silu'(g)] with (a|g) read from aux [M, 2*N] (n_half = N)
+  GEMM_ATOMIC = 4096,      // fp32 D += acc with red.global.add (split-K weight gradients: several CTAs own one output tile)
 };
 
 struct GemmParams {
@@ -53,6 +54,7 @@ struct GemmParams {
   int rope_seq, rope_dmodel, rope_dh;
   int n_half;
   int num_m_tiles, num_n_tiles;
+  int ksplit, kb_per_split;  // split-K: tile index -> (k-slice, n, m); each slice covers kb_per_split k-blocks
 };
 
 constexpr int BLOCK_M = 128;
@@ -118,8 +120,9 @@ __global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int mn_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_tiles = mn_tiles * p.ksplit;
+  const int total_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
   const bool swiglu = (p.flags & GEMM_SWIGLU) != 0;
   const bool a_mn = (p.flags & GEMM_A_MN) != 0;
   const bool b_mn = (p.flags & GEMM_B_MN) != 0;
@@ -156,10 +159,12 @@ __global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = unit; tile < num_tiles; tile += num_units) {
-        const int m_blk = tile % p.num_m_tiles;
-        const int n_blk = tile / p.num_m_tiles;
+        const int mn = tile % mn_tiles, ks = tile / mn_tiles;
+        const int m_blk = mn % p.num_m_tiles;
+        const int n_blk = mn / p.num_m_tiles;
         const int m0 = m_blk * (BLOCK_M * CTAS) + cta_rank * BLOCK_M;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb_begin = ks * p.kb_per_split, kb_end = min(total_kb, kb_begin + p.kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
@@ -223,7 +228,9 @@ __global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constan
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * Cfg::kAccStride;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int ks = tile / mn_tiles;
+        const int kb_begin = ks * p.kb_per_split, kb_end = min(total_kb, kb_begin + p.kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -232,8 +239,8 @@ __global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constan
           const uint64_t db = make_smem_desc_sw128(sb, b_lbo, 1024);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            if (CTAS == 2) umma_bf16_pair(tmem_d, da + a_step * k, db + b_step * k, idesc, (kb | k) != 0);
-            else umma_bf16(tmem_d, da + a_step * k, db + b_step * k, idesc, (kb | k) != 0);
+            if (CTAS == 2) umma_bf16_pair(tmem_d, da + a_step * k, db + b_step * k, idesc, (kb != kb_begin) || (k != 0));
+            else umma_bf16(tmem_d, da + a_step * k, db + b_step * k, idesc, (kb != kb_begin) || (k != 0));
           }
           if (CTAS == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -251,8 +258,9 @@ __global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constan
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = unit; tile < num_tiles; tile += num_units) {
-      const int m_blk = tile % p.num_m_tiles;
-      const int n_blk = tile / p.num_m_tiles;
+      const int mn = tile % mn_tiles;
+      const int m_blk = mn % p.num_m_tiles;
+      const int n_blk = mn / p.num_m_tiles;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const int row = m_blk * (BLOCK_M * CTAS) + static_cast<int>(cta_rank) * BLOCK_M + q * 32 + lane;
@@ -390,6 +398,17 @@ __global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constan
           }
           if (p.flags & GEMM_OUT_F32) {
             float* dp = reinterpret_cast<float*>(p.D) + static_cast<size_t>(out_row) * p.ldd + col;
+            if (p.flags & GEMM_ATOMIC) {
+              if (full) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp + 4 * i), "f"(v[4 * i]), "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3]) : "memory");
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (i < ncols) atomicAdd(dp + i, v[i]);
+              }
+              continue;
+            }
             if (p.flags & GEMM_ACCUM) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += dp[i];
@@ -426,8 +445,19 @@ static int launch_gemm(GemmParams& p, cudaStream_t stream) {
   const int out_bn = (p.flags & GEMM_SWIGLU) ? BN / 2 : BN;
   p.num_m_tiles = (p.M + BLOCK_M * CTAS - 1) / (BLOCK_M * CTAS);
   p.num_n_tiles = (p.N + out_bn - 1) / out_bn;
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int units = num_sms() / CTAS;
+  const int total_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  p.ksplit = 1;
+  if ((p.flags & GEMM_ACCUM) && (p.flags & GEMM_OUT_F32)) {
+    // gradient accumulation with few output tiles and a long K (tokens): split K across idle SMs, combine with fp32 reds
+    const int mn = p.num_m_tiles * p.num_n_tiles;
+    int ks = units / mn;
+    if (ks > 8) ks = 8;
+    while (ks > 1 && total_kb / ks < 16) --ks;
+    if (ks > 1) { p.ksplit = ks; p.flags = (p.flags & ~GEMM_ACCUM) | GEMM_ATOMIC; }
+  }
+  p.kb_per_split = (total_kb + p.ksplit - 1) / p.ksplit;
+  const int tiles = p.num_m_tiles * p.num_n_tiles * p.ksplit;
   const int grid = (tiles < units ? tiles : units) * CTAS;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -450,7 +480,7 @@ static void pick_config(int M, int N, bool swiglu, bool mn_major, int* bn_out, i
   if (swiglu) { *bn_out = 256; *ctas_out = M > 128 ? 2 : 1; return; }
   const int sms = num_sms();
   struct Cand { int bn, ctas; double eff; };
-  const Cand cands[5] = {{256, 2, 1.00}, {192, 2, 0.97}, {128, 2, 0.85}, {128, 1, 0.70}, {64, 1, 0.45}};
+  const Cand cands[5] = {{256, 2, 1.00}, {192, 2, 0.85}, {128, 2, 0.62}, {128, 1, 0.55}, {64, 1, 0.32}};
   double best = 1e30;
   *bn_out = 128; *ctas_out = 1;
   for (int i = 0; i < 5; ++i) {
