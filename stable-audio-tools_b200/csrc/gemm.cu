@@ -478,6 +478,9 @@ static int launch_gemm(GemmParams& p, cudaStream_t stream) {
 // Efficiencies are relative MMA-pipe rates measured with tools/gemm_sweep.py on B200 (profiles/).
 static void pick_config(int M, int N, bool swiglu, bool mn_major, int* bn_out, int* ctas_out) {
   if (swiglu) { *bn_out = 256; *ctas_out = M > 128 ? 2 : 1; return; }
+  // transposed-operand (gradient) GEMMs: the 256x256 pair tile is the only shape that stays MMA-bound with MN-major boxes
+  // (measured: 256x128 pair tiles reach 0.6 PF, 256x256 1.24 PF); low tile counts are handled by split-K instead
+  if (mn_major && M > 128 && N > 128) { *bn_out = 256; *ctas_out = 2; return; }
   const int sms = num_sms();
   struct Cand { int bn, ctas; double eff; };
   const Cand cands[5] = {{256, 2, 1.00}, {192, 2, 0.85}, {128, 2, 0.62}, {128, 1, 0.55}, {64, 1, 0.32}};
