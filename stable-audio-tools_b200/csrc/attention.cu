@@ -34,25 +34,35 @@ struct AttnParams {
 };
 
 constexpr int AT_BM = 128;   // queries per CTA
-constexpr int AT_BN = 128;   // keys per tile
+constexpr int AT_BN = 64;    // keys per tile
 constexpr int AT_D = 64;
-constexpr int AT_TILE = AT_BM * AT_D * 2;                       // 16 KB
-constexpr int AT_SMEM = AT_TILE /*Q*/ + 2 * 2 * AT_TILE /*K,V x2*/ + 2 * AT_TILE /*P*/ + 256 /*barriers*/ + 512 /*row-max exchange*/;
+constexpr int AT_QT = AT_BM * AT_D * 2;   // 16 KB: Q tile, P tile (128 x 64 bf16)
+constexpr int AT_KT = AT_BN * AT_D * 2;   //  8 KB: K tile, V tile
+constexpr int AT_KV_STAGES = 3;
+constexpr int AT_SMEM = AT_QT /*Q*/ + AT_KV_STAGES * 2 * AT_KT /*K,V ring*/ + 2 * AT_QT /*P x2*/ + 256 /*barriers*/ + 512 /*row-max exchange*/;
+constexpr float AT_RESCALE_THRESHOLD = 8.0f;  // log2 units: O/l are only rescaled when the row max grows by more than 2^8
 
+// Pipeline (round-1 redesign after the ncu capture of the first version: tensor pipe 17 %, issue slots 31 %, every tile paid
+// four serial barrier hops S -> softmax -> P -> PV -> O read):
+//   * 64-key tiles, the score tile S double-buffered in TMEM: the MMA thread keeps S(j+1), S(j+2) ahead of the softmax warps;
+//   * O accumulates in TMEM across tiles (PV issued with accumulate) — the softmax warps never wait for PV on the common path;
+//   * lazy rescale: the running max only moves when it grows by more than 2^8 (any upper bound is a valid softmax shift), and
+//     only then a thread waits for the previous PV and rescales its half row of O in TMEM (tcgen05.ld -> scale -> tcgen05.st);
+//   * P double-buffered in shared memory so the softmax of tile j+1 overlaps the PV MMA of tile j.
 __global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
-  uint8_t* sKV = smem + AT_TILE;            // stage s: K at sKV + s*2*TILE, V at + TILE
-  uint8_t* sP = smem + 5 * AT_TILE;         // 2 x [128 rows x 64 keys] swizzled blocks
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * AT_TILE);
+  uint8_t* sKV = smem + AT_QT;                                   // stage s: K at + s*2*AT_KT, V at + AT_KT
+  uint8_t* sP = sKV + AT_KV_STAGES * 2 * AT_KT;                  // 2 x [128 rows x 64 keys]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * AT_QT);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
-  __nv_bfloat16* s_max = reinterpret_cast<__nv_bfloat16*>(smem + 7 * AT_TILE + 256);  // [2 halves][128 rows]
+  uint64_t* kv_full = bars + 1;    // [3]
+  uint64_t* kv_empty = bars + 4;   // [3]
+  uint64_t* s_full = bars + 7;     // [2]
+  uint64_t* p_full = bars + 9;     // [2]
+  uint64_t* pv_done = bars + 11;   // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
+  __nv_bfloat16* s_max = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -68,10 +78,8 @@ __global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_con
     tma_prefetch_desc(&p.tmK);
     tma_prefetch_desc(&p.tmV);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 256);
-    mbar_init(o_full, 1);
+    for (int i = 0; i < AT_KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 256); mbar_init(&pv_done[i], 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -82,148 +90,142 @@ __global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tmem_S = tmem_base;         // 128 fp32 columns
-  const uint32_t tmem_O = tmem_base + 128;   // 64 fp32 columns
+  const uint32_t tmem_O = tmem_base + 128;   // 64 fp32 columns; S buffers at +0 and +64
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, AT_TILE);
+      mbar_arrive_expect_tx(q_full, AT_QT);
       tma_load_4d(sQ, &p.tmQ, q_full, 0, h, q0, b);
       for (int j = 0; j < num_kv; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
+        const int s = j % AT_KV_STAGES;
+        const uint32_t ph = (j / AT_KV_STAGES) & 1;
         mbar_wait(&kv_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], 2 * AT_TILE);
-        tma_load_4d(sKV + s * 2 * AT_TILE, &p.tmK, &kv_full[s], 0, hkv, j * AT_BN, b);
-        tma_load_4d(sKV + s * 2 * AT_TILE + AT_TILE, &p.tmV, &kv_full[s], 0, hkv, j * AT_BN, b);
+        mbar_arrive_expect_tx(&kv_full[s], 2 * AT_KT);
+        tma_load_4d(sKV + s * 2 * AT_KT, &p.tmK, &kv_full[s], 0, hkv, j * AT_BN, b);
+        tma_load_4d(sKV + s * 2 * AT_KT + AT_KT, &p.tmV, &kv_full[s], 0, hkv, j * AT_BN, b);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);  // B = V is MN-major (keys along rows)
       const uint32_t aQ = smem_u32(sQ);
-      const uint32_t aP = smem_u32(sP);
+      auto issue_s = [&](int j) {
+        const int s = j % AT_KV_STAGES;
+        mbar_wait(&kv_full[s], (j / AT_KV_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t aK = smem_u32(sKV + s * 2 * AT_KT);
+        const uint32_t tS = tmem_base + (j & 1) * 64;
+#pragma unroll
+        for (int k = 0; k < AT_D / 16; ++k)
+          umma_bf16(tS, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024), idesc_s, k != 0);
+        umma_commit(&s_full[j & 1]);
+      };
       mbar_wait(q_full, 0);
+      issue_s(0);
+      if (num_kv > 1) issue_s(1);
       for (int j = 0; j < num_kv; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&kv_full[s], ph);
+        const int s = j % AT_KV_STAGES;
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t aK = smem_u32(sKV + s * 2 * AT_TILE);
-        const uint32_t aV = aK + AT_TILE;
+        const uint32_t aP = smem_u32(sP + (j & 1) * AT_QT);
+        const uint32_t aV = smem_u32(sKV + s * 2 * AT_KT + AT_KT);
 #pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k) {
-          umma_bf16(tmem_S, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024), idesc_s, k != 0);
-        }
-        umma_commit(s_full);
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < AT_BN / 16; ++k) {
-          const uint32_t pa = aP + (k >> 2) * AT_TILE + (k & 3) * 32;
-          umma_bf16(tmem_O, make_smem_desc_sw128(pa, 16, 1024), make_smem_desc_sw128(aV + k * 2048, 1024, 1024), idesc_o, k != 0);
-        }
-        umma_commit(o_full);
+        for (int k = 0; k < AT_BN / 16; ++k)
+          umma_bf16(tmem_O, make_smem_desc_sw128(aP + k * 32, 16, 1024), make_smem_desc_sw128(aV + k * 2048, 1024, 1024), idesc_o, (j | k) != 0);
+        umma_commit(&pv_done[j & 1]);
         umma_commit(&kv_empty[s]);
+        if (j + 2 < num_kv) issue_s(j + 2);   // its S buffer was consumed before p_full(j) completed
       }
     }
   } else {
-    // ===================== softmax / output warps =====================
-    // 8 warps: two threads per query row (same TMEM lane quarter, different 64-key halves).  They only have to agree on the
-    // running max of the row: each publishes its half's max rounded UP to bf16 (any common upper bound is a valid softmax
-    // shift) through 512 B of shared memory and a 64-thread named barrier; row sums stay per-thread until the end.
+    // ===================== softmax / output warps: two threads per query row, 32 keys each per tile =====================
     const int quarter = warp & 3;          // TMEM lane quarter accessible to this warp
-    const int half = (warp - 2) >> 2;      // which 64 keys of the 128-key tile / which 32 output dims
+    const int half = (warp - 2) >> 2;      // which 32 keys of the 64-key tile / which 32 output dims
     const int r = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     float m_run = -INFINITY, l_run = 0.f;
-    float o[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) o[i] = 0.f;
-    uint8_t* prow = sP + r * 128;
     const int sw = r & 7;
     __nv_bfloat16* my_max = s_max + half * 128 + r;
     const __nv_bfloat16* other_max = s_max + (half ^ 1) * 128 + r;
 
     for (int j = 0; j < num_kv; ++j) {
-      mbar_wait(s_full, j & 1);
+      const int buf = j & 1;
+      mbar_wait(&s_full[buf], (j >> 1) & 1);
       tc_fence_after();
-      const int nvalid = p.Nk - j * AT_BN - half * 64;   // valid keys among this thread's 64 columns (may be <= 0)
-      const bool tail = nvalid < 64;
-      // pass A: max over this thread's 64 columns
+      const int nvalid = p.Nk - j * AT_BN - half * 32;   // valid keys among this thread's 32 columns (may be <= 0)
+      uint32_t raw[32];
+      tmem_ld_32x32(tmem_base + lane_off + buf * 64 + half * 32, raw);
+      tmem_ld_wait();
       float mx = -INFINITY;
+      if (nvalid >= 32) {
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        uint32_t raw[32];
-        tmem_ld_32x32(tmem_S + lane_off + (half * 2 + cc) * 32, raw);
-        tmem_ld_wait();
-        if (!tail) {
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
+      } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (cc * 32 + i < nvalid) ? __uint_as_float(raw[i]) : -INFINITY);
-        }
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (i < nvalid) ? __uint_as_float(raw[i]) : -INFINITY);
       }
+      // the two threads of a row agree on a shift: max of the two half-row maxima, rounded UP to bf16
       *my_max = __float2bfloat16_ru(mx * p.scale_log2);
       asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
       const float m_pair = fmaxf(__bfloat162float(*my_max), __bfloat162float(*other_max));
-      const float m_new = fmaxf(m_run, m_pair);
-      const float alpha = fast_exp2(m_run - m_new);
-      // pass B: p = exp2(s*scale - m), partial row sum, bf16 P -> swizzled smem (A operand of the PV MMA)
+      asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");   // partner has read my slot before I overwrite it next tile
+      if (m_pair > m_run + AT_RESCALE_THRESHOLD) {
+        // rare path: move the shift.  l and the TMEM-resident O row are rescaled; all earlier PV MMAs must have retired.
+        const float alpha = fast_exp2(m_run - m_pair);
+        if (j > 0) {
+          mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+          tc_fence_after();
+          uint32_t ov[32];
+          tmem_ld_32x32(tmem_O + lane_off + half * 32, ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+          tmem_st_32x32(tmem_O + lane_off + half * 32, ov);
+          tmem_st_wait();
+        }
+        l_run *= alpha;
+        m_run = m_pair;
+      }
+      // p = exp2(s*scale - m), partial row sum, bf16 P -> swizzled smem (A operand of the PV MMA)
       float lsum = 0.f;
+      uint32_t pk[16];
+      if (nvalid >= 32) {
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = half * 2 + cc;
-        uint32_t raw[32];
-        tmem_ld_32x32(tmem_S + lane_off + c * 32, raw);
-        tmem_ld_wait();
-        uint32_t pk[16];
-        if (!tail) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(raw[i]), p.scale_log2, -m_new));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(raw[i + 1]), p.scale_log2, -m_new));
-            lsum += p0 + p1;
-            pk[i >> 1] = pack_bf16(p0, p1);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = (cc * 32 + i < nvalid) ? fast_exp2(fmaf(__uint_as_float(raw[i]), p.scale_log2, -m_new)) : 0.f;
-            const float p1 = (cc * 32 + i + 1 < nvalid) ? fast_exp2(fmaf(__uint_as_float(raw[i + 1]), p.scale_log2, -m_new)) : 0.f;
-            lsum += p0 + p1;
-            pk[i >> 1] = pack_bf16(p0, p1);
-          }
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(raw[i]), p.scale_log2, -m_run));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(raw[i + 1]), p.scale_log2, -m_run));
+          lsum += p0 + p1;
+          pk[i >> 1] = pack_bf16(p0, p1);
         }
+      } else {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int chunk = c * 4 + t;              // 16-byte chunk index along the 128 keys
-          const int kb = chunk >> 3, ch = chunk & 7;
-          uint4 u = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
-          *reinterpret_cast<uint4*>(prow + kb * AT_TILE + ((ch ^ sw) << 4)) = u;
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = (i < nvalid) ? fast_exp2(fmaf(__uint_as_float(raw[i]), p.scale_log2, -m_run)) : 0.f;
+          const float p1 = (i + 1 < nvalid) ? fast_exp2(fmaf(__uint_as_float(raw[i + 1]), p.scale_log2, -m_run)) : 0.f;
+          lsum += p0 + p1;
+          pk[i >> 1] = pack_bf16(p0, p1);
         }
+      }
+      l_run += lsum;
+      if (j >= 2) mbar_wait(&pv_done[buf], ((j >> 1) - 1) & 1);   // PV(j-2) has finished reading this P buffer
+      uint8_t* prow = sP + buf * AT_QT + r * 128;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int ch = half * 4 + t;              // 16-byte chunk index along the 64 keys
+        *reinterpret_cast<uint4*>(prow + ((ch ^ sw) << 4)) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(p_full);
-      l_run = l_run * alpha + lsum;
-      m_run = m_new;
-      // O_j = P V from TMEM: this thread accumulates output dims [half*32, half*32+32) with the rescale
-      mbar_wait(o_full, j & 1);
-      tc_fence_after();
-      {
-        uint32_t raw[32];
-        tmem_ld_32x32(tmem_O + lane_off + half * 32, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = o[i] * alpha + __uint_as_float(raw[i]);
-      }
-      tc_fence_before();
+      mbar_arrive(&p_full[buf]);
     }
-    // combine the two partial row sums (P buffer is free now: reuse its first KB as fp32 scratch)
-    float* s_l = reinterpret_cast<float*>(sP);
+    // epilogue: all PV MMAs retired -> read this thread's 32 output dims, combine the two partial row sums, normalise
+    mbar_wait(&pv_done[(num_kv - 1) & 1], ((num_kv - 1) >> 1) & 1);
+    tc_fence_after();
+    uint32_t ov[32];
+    tmem_ld_32x32(tmem_O + lane_off + half * 32, ov);
+    tmem_ld_wait();
+    float* s_l = reinterpret_cast<float*>(sP);   // P buffers are free now
     s_l[half * 128 + r] = l_run;
     asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
     const float l_tot = l_run + s_l[(half ^ 1) * 128 + r];
@@ -235,14 +237,15 @@ __global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_con
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         uint4 u;
-        u.x = pack_bf16(o[8 * i + 0] * inv, o[8 * i + 1] * inv);
-        u.y = pack_bf16(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
-        u.z = pack_bf16(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
-        u.w = pack_bf16(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
+        u.x = pack_bf16(__uint_as_float(ov[8 * i + 0]) * inv, __uint_as_float(ov[8 * i + 1]) * inv);
+        u.y = pack_bf16(__uint_as_float(ov[8 * i + 2]) * inv, __uint_as_float(ov[8 * i + 3]) * inv);
+        u.z = pack_bf16(__uint_as_float(ov[8 * i + 4]) * inv, __uint_as_float(ov[8 * i + 5]) * inv);
+        u.w = pack_bf16(__uint_as_float(ov[8 * i + 6]) * inv, __uint_as_float(ov[8 * i + 7]) * inv);
         d4[i] = u;
       }
       if (p.lse && half == 0) p.lse[(static_cast<long>(b) * p.Hq + h) * p.Nq + qrow] = m_run * 0.6931471805599453f + logf(l_tot);
     }
+    tc_fence_before();
   }
 
   tc_fence_before();
@@ -253,10 +256,10 @@ __global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_con
   }
 }
 
-static int make_head_map(CUtensorMap* tm, const void* base, int B, int H, int N, long bs, long ss, long hs) {
+static int make_head_map(CUtensorMap* tm, const void* base, int B, int H, int N, long bs, long ss, long hs, int box_rows) {
   uint64_t dims[4] = {AT_D, static_cast<uint64_t>(H), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
   uint64_t strides[3] = {static_cast<uint64_t>(hs) * 2, static_cast<uint64_t>(ss) * 2, static_cast<uint64_t>(bs) * 2};
-  uint32_t box[4] = {AT_D, 1, AT_BM, 1};
+  uint32_t box[4] = {AT_D, 1, static_cast<uint32_t>(box_rows), 1};
   return encode_tmap_bf16(tm, base, 4, dims, strides, box, 1);
 }
 
@@ -275,9 +278,9 @@ extern "C" int b200sat_attention_fwd(const void* q, const void* k, const void* v
   AttnParams p;
   memset(&p, 0, sizeof(p));
   int rc;
-  if ((rc = make_head_map(&p.tmQ, q, B, Hq, Nq, q_bs, q_ss, q_hs))) return rc;
-  if ((rc = make_head_map(&p.tmK, k, B, Hkv, Nk, k_bs, k_ss, k_hs))) return rc;
-  if ((rc = make_head_map(&p.tmV, v, B, Hkv, Nk, v_bs, v_ss, v_hs))) return rc;
+  if ((rc = make_head_map(&p.tmQ, q, B, Hq, Nq, q_bs, q_ss, q_hs, AT_BM))) return rc;
+  if ((rc = make_head_map(&p.tmK, k, B, Hkv, Nk, k_bs, k_ss, k_hs, AT_BN))) return rc;
+  if ((rc = make_head_map(&p.tmV, v, B, Hkv, Nk, v_bs, v_ss, v_hs, AT_BN))) return rc;
   p.O = static_cast<__nv_bfloat16*>(o); p.lse = lse;
   p.o_bs = o_bs; p.o_ss = o_ss; p.o_hs = o_hs;
   p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.Nq = Nq; p.Nk = Nk;

@@ -48,3 +48,20 @@ def test_attention_strided_qkv():
     ops.attention(q, k, v, out=out)
     ro, _ = _ref(q, k, v)
     assert (out.float() - ro).abs().max().item() <= 2e-2
+
+
+def test_attention_lazy_rescale_path():
+    """Large-magnitude, growing scores: the running max moves by > 2^8 many times, exercising the TMEM rescale of O."""
+    from b200sat import ops
+    torch.manual_seed(2)
+    B, N, H = 1, 777, 2
+    q = (torch.randn(B, N, H, 64, device="cuda") * 4).bfloat16()
+    k = torch.randn(B, N, H, 64, device="cuda")
+    k = (k * torch.linspace(0.2, 6.0, N, device="cuda")[None, :, None, None]).bfloat16()   # later keys score higher
+    v = torch.randn(B, N, H, 64, device="cuda").bfloat16()
+    lse = torch.zeros(B, H, N, device="cuda")
+    o = ops.attention(q, k, v, lse=lse)
+    ro, rl = _ref(q, k, v)
+    assert torch.isfinite(o.float()).all()
+    assert (o.float() - ro).abs().max().item() <= 3e-2
+    assert (lse - rl).abs().max().item() <= 2e-2 * rl.abs().max().item()
