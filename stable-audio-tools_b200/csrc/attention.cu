@@ -170,9 +170,12 @@ __global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_con
       asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
       const float m_pair = fmaxf(__bfloat162float(*my_max), __bfloat162float(*other_max));
       asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");   // partner has read my slot before I overwrite it next tile
-      if (m_pair > m_run + AT_RESCALE_THRESHOLD) {
-        // rare path: move the shift.  l and the TMEM-resident O row are rescaled; all earlier PV MMAs must have retired.
-        const float alpha = fast_exp2(m_run - m_pair);
+      // rare path: move the shift.  l and the TMEM-resident O row are rescaled; all earlier PV MMAs must have retired.
+      // tcgen05.ld/st are warp-collective, so the branch is taken by the whole warp when ANY of its rows needs it (rows
+      // that do not move use alpha = 1); the partner warp owns the same rows and takes the same decision.
+      const bool need = m_pair > m_run + AT_RESCALE_THRESHOLD;
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = need ? fast_exp2(m_run - m_pair) : 1.0f;
         if (j > 0) {
           mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
           tc_fence_after();
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_con
           tmem_st_wait();
         }
         l_run *= alpha;
-        m_run = m_pair;
+        if (need) m_run = m_pair;
       }
       // p = exp2(s*scale - m), partial row sum, bf16 P -> swizzled smem (A operand of the PV MMA)
       float lsum = 0.f;
