@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 
 namespace b200sat {
@@ -10,6 +11,12 @@ static thread_local char g_err[512] = "";
 void set_last_error(const char* msg) {
   strncpy(g_err, msg ? msg : "", sizeof(g_err) - 1);
   g_err[sizeof(g_err) - 1] = 0;
+}
+
+int pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200SAT_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v;
 }
 
 int num_sms() {

@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_con
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 256); mbar_init(&pv_done[i], 1); }
     fence_barrier_init();
   }
+  griddep_launch();
   if (warp == 1) {
     tmem_alloc(tmem_ptr_smem, 256);
     tmem_relinquish();
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_wait();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t tmem_O = tmem_base + 128;   // 64 fp32 columns; S buffers at +0 and +64
 
@@ -294,7 +296,7 @@ extern "C" int b200sat_attention_fwd(const void* q, const void* k, const void* v
     attr_set = true;
   }
   dim3 grid((Nq + AT_BM - 1) / AT_BM, Hq, B);
-  attention_fwd_tcgen05<<<grid, 320, AT_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+  B200SAT_CHECK_CUDA(launch_k(attention_fwd_tcgen05, dim3(grid), dim3(320), AT_SMEM, static_cast<cudaStream_t>(stream), 1, p));
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }

@@ -110,6 +110,8 @@ __device__ __forceinline__ void store_grad_half(__nv_bfloat16* dst, float (&g)[3
 // ------------------------------------------------------------------------------------------------------------
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, float* __restrict__ delta,
                                   int B, int H, int N, long o_bs, long o_ss, long o_hs, long d_bs, long d_ss, long d_hs) {
+  griddep_launch();
+  griddep_wait();
   const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<long>(B) * H * N) return;
   const int n = i % N;
@@ -169,10 +171,12 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dkv_tcgen05(const __grid
     mbar_init(acc_done, 1);
     fence_barrier_init();
   }
+  griddep_launch();
   if (warp == 1) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_wait();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t tm_ST = tmem_base, tm_dPT = tmem_base + 128, tm_dV = tmem_base + 256, tm_dK = tmem_base + 320;
 
@@ -337,10 +341,12 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dq_tcgen05(const __grid_
     mbar_init(acc_done, 1);
     fence_barrier_init();
   }
+  griddep_launch();
   if (warp == 1) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_wait();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 128, tm_dQ = tmem_base + 256;
 
@@ -468,8 +474,8 @@ extern "C" int b200sat_attention_bwd(const void* q, const void* k, const void* v
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   {
     const long n = static_cast<long>(B) * Hq * Nq;
-    attn_delta_kernel<<<static_cast<int>((n + 127) / 128), 128, 0, s>>>(static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o),
-                                                                        delta_scratch, B, Hq, Nq, so[0], so[1], so[2], sdo[0], sdo[1], sdo[2]);
+    B200SAT_CHECK_CUDA(launch_k(attn_delta_kernel, dim3(static_cast<int>((n + 127) / 128)), dim3(128), 0, s, 1, static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o),
+                                                                        delta_scratch, B, Hq, Nq, so[0], so[1], so[2], sdo[0], sdo[1], sdo[2]));
   }
   AttnBwdParams p;
   memset(&p, 0, sizeof(p));
@@ -492,8 +498,8 @@ extern "C" int b200sat_attention_bwd(const void* q, const void* k, const void* v
     B200SAT_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_dq_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
     attr_set = true;
   }
-  attention_bwd_dkv_tcgen05<<<dim3((Nk + 127) / 128, Hkv, B), 320, DKV_SMEM, s>>>(p);
-  attention_bwd_dq_tcgen05<<<dim3((Nq + 127) / 128, Hq, B), 320, DQ_SMEM, s>>>(p);
+  B200SAT_CHECK_CUDA(launch_k(attention_bwd_dkv_tcgen05, dim3((Nk + 127) / 128, Hkv, B), dim3(320), DKV_SMEM, s, 1, p));
+  B200SAT_CHECK_CUDA(launch_k(attention_bwd_dq_tcgen05, dim3((Nq + 127) / 128, Hq, B), dim3(320), DQ_SMEM, s, 1, p));
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }

@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #define B200SAT_OK 0
 #define B200SAT_EINVAL (-1)
@@ -238,6 +239,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, u
 }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel lets its successor start launching immediately (`griddep_launch`) and blocks
+// before its first dependent global-memory access (`griddep_wait`) until the predecessor grid has completed and flushed.
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // small numeric helpers
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -260,6 +267,29 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
                      const uint32_t* box, int swizzle128);
 int num_sms();
 void set_last_error(const char* msg);
+}  // namespace b200sat
+
+namespace b200sat {
+int pdl_enabled();  // api.cu: B200SAT_PDL=0 disables programmatic dependent launch
+// Launch with the programmatic-stream-serialization attribute (+ optional cluster width).
+template <typename K, typename... Args>
+inline cudaError_t launch_k(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[n].val.programmaticStreamSerializationAllowed = pdl_enabled();
+  ++n;
+  if (cluster > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = cluster; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = at; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 }  // namespace b200sat
 
 #define B200SAT_CHECK_CUDA(expr)                                   \

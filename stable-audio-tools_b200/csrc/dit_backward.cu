@@ -14,6 +14,8 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
                                                                __nv_bfloat16* __restrict__ dx_out, float* __restrict__ dgamma, int rows,
                                                                int D, long ldx, long lddy, long ldr, long ldo, float eps) {
   extern __shared__ float s_dg[];  // [D]
+  griddep_launch();
+  griddep_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunk = D / 8;
   for (int i = threadIdx.x; i < D; i += blockDim.x) s_dg[i] = 0.f;
@@ -119,6 +121,8 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
 // out[n] += sum_m dY[m, n]  (bias gradients).  grid (ceil(N/512), row chunks); thread = 2 adjacent columns.
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ dy, long ld, float* __restrict__ out, int M, int N,
                                                      int rows_per_block) {
+  griddep_launch();
+  griddep_wait();
   const int col = (blockIdx.x * 256 + threadIdx.x) * 2;
   if (col >= N) return;
   const int r0 = blockIdx.y * rows_per_block;
@@ -146,13 +150,13 @@ extern "C" int b200sat_layernorm_bwd(const void* x, long ldx, const void* dy, lo
   const int cap = 2 * num_sms();
   if (grid > cap) grid = cap;
   if (D <= 1536)
-    layernorm_bwd_kernel<6><<<grid, 256, D * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+    B200SAT_CHECK_CUDA(launch_k(layernorm_bwd_kernel<6>, dim3(grid), dim3(256), D * sizeof(float), static_cast<cudaStream_t>(stream), 1, 
         static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), gamma, static_cast<const __nv_bfloat16*>(dres),
-        static_cast<__nv_bfloat16*>(dx_out), dgamma, rows, D, ldx, lddy, ldr, ldo, eps);
+        static_cast<__nv_bfloat16*>(dx_out), dgamma, rows, D, ldx, lddy, ldr, ldo, eps));
   else
-    layernorm_bwd_kernel<8><<<grid, 256, D * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+    B200SAT_CHECK_CUDA(launch_k(layernorm_bwd_kernel<8>, dim3(grid), dim3(256), D * sizeof(float), static_cast<cudaStream_t>(stream), 1, 
         static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), gamma, static_cast<const __nv_bfloat16*>(dres),
-        static_cast<__nv_bfloat16*>(dx_out), dgamma, rows, D, ldx, lddy, ldr, ldo, eps);
+        static_cast<__nv_bfloat16*>(dx_out), dgamma, rows, D, ldx, lddy, ldr, ldo, eps));
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }
@@ -163,7 +167,7 @@ extern "C" int b200sat_colsum(const void* dy, long ld, float* out, int M, int N,
   int rpb = 256;
   while (rpb > 32 && static_cast<long>((N + 511) / 512) * ((M + rpb - 1) / rpb) < 2L * num_sms()) rpb >>= 1;
   dim3 grid((N + 511) / 512, (M + rpb - 1) / rpb);
-  colsum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(dy), ld, out, M, N, rpb);
+  B200SAT_CHECK_CUDA(launch_k(colsum_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, static_cast<const __nv_bfloat16*>(dy), ld, out, M, N, rpb));
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }

@@ -15,6 +15,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
                                                         const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
                                                         int rows, int D, long ldx, long ldy, int rows_per_batch, long ld_mod,
                                                         float eps) {
+  griddep_launch();
+  griddep_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -86,6 +88,8 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const __nv_bfloat16* 
                                                            const float* __restrict__ bias, const __nv_bfloat16* __restrict__ add,
                                                            long ldadd, void* __restrict__ y, long ldy, int M, int N, int K,
                                                            int act_silu, int out_f32, int act_sigmoid_1m) {
+  griddep_launch();
+  griddep_wait();
   const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (n >= N) return;
   const int lane = threadIdx.x & 31;
@@ -132,6 +136,8 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const __nv_bfloat16* 
 __global__ void fourier_features_kernel(const float* __restrict__ t, const __nv_bfloat16* __restrict__ w,
                                         __nv_bfloat16* __restrict__ out, int B, int half, const int* __restrict__ step,
                                         int t_stride) {
+  griddep_launch();
+  griddep_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * half) return;
   const int b = i / half, j = i % half;
@@ -151,6 +157,8 @@ __global__ void __launch_bounds__(256) dit_pre_kernel(const float* __restrict__ 
                                                       const float* __restrict__ cin_table, const int* __restrict__ step) {
   __shared__ float sx[C][65];
   __shared__ float sw[C][C + 1];
+  griddep_launch();
+  griddep_wait();
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * 64;
   const float c_in = cin_table ? cin_table[step ? *step : 0] : 1.0f;
@@ -194,6 +202,8 @@ __global__ void __launch_bounds__(256) dit_post_kernel(const __nv_bfloat16* __re
   __shared__ float so[2][C][TT + 1];
   __shared__ float sy[2][C][TT + 1];
   __shared__ __nv_bfloat16 sw[C][C];
+  griddep_launch();
+  griddep_wait();
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * TT;
   const int nb = cfg ? 2 : 1;
@@ -272,6 +282,8 @@ __global__ void __launch_bounds__(256) dit_post_kernel(const __nv_bfloat16* __re
 __global__ void sampler_update_kernel(float* __restrict__ x, const float* __restrict__ v, float* __restrict__ hist,
                                       const float* __restrict__ noise, const float* __restrict__ coef, const int* __restrict__ step,
                                       long n) {
+  griddep_launch();
+  griddep_wait();
   const int s = *step;
   const float* c = coef + s * 8;
   const float c_out = c[0], c_skip = c[1], A = c[2], Bd = c[3], C1 = c[4], C2 = c[5], NZ = c[6];
@@ -290,8 +302,8 @@ __global__ void sampler_update_kernel(float* __restrict__ x, const float* __rest
     x[i] = xn;
   }
 }
-__global__ void step_advance_kernel(int* step) { *step += 1; }
-__global__ void step_set_kernel(int* step, int v) { *step = v; }
+__global__ void step_advance_kernel(int* step) { griddep_launch(); griddep_wait(); *step += 1; }
+__global__ void step_set_kernel(int* step, int v) { griddep_launch(); griddep_wait(); *step = v; }
 
 }  // namespace b200sat
 
@@ -308,11 +320,11 @@ extern "C" int b200sat_layernorm_fwd(const void* x, long ldx, const float* gamma
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int rpb = rows_per_batch > 0 ? rows_per_batch : rows;
   if (D <= 2048)
-    layernorm_kernel<8><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), gamma, beta, scale, shift,
-                                             static_cast<__nv_bfloat16*>(y), rows, D, ldx, ldy, rpb, ld_mod, eps);
+    B200SAT_CHECK_CUDA(launch_k(layernorm_kernel<8>, dim3(grid), dim3(256), 0, s, 1, static_cast<const __nv_bfloat16*>(x), gamma, beta, scale, shift,
+                                             static_cast<__nv_bfloat16*>(y), rows, D, ldx, ldy, rpb, ld_mod, eps));
   else
-    layernorm_kernel<16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), gamma, beta, scale, shift,
-                                              static_cast<__nv_bfloat16*>(y), rows, D, ldx, ldy, rpb, ld_mod, eps);
+    B200SAT_CHECK_CUDA(launch_k(layernorm_kernel<16>, dim3(grid), dim3(256), 0, s, 1, static_cast<const __nv_bfloat16*>(x), gamma, beta, scale, shift,
+                                              static_cast<__nv_bfloat16*>(y), rows, D, ldx, ldy, rpb, ld_mod, eps));
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }
@@ -322,9 +334,9 @@ extern "C" int b200sat_small_linear(const void* x, long ldx, const void* w, long
                                     int act_sigmoid_1m, void* stream) {
   if (!x || !w || !y || M <= 0 || M > 8 || N <= 0 || K <= 0) { set_last_error("small_linear: bad arguments (1 <= M <= 8)"); return B200SAT_EINVAL; }
   if (K % 8 || ldx % 8 || ldw % 8) { set_last_error("small_linear: K, ldx, ldw must be multiples of 8"); return B200SAT_EINVAL; }
-  small_linear_kernel<<<(N + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  B200SAT_CHECK_CUDA(launch_k(small_linear_kernel, dim3((N + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, 
       static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(w), ldw, bias,
-      static_cast<const __nv_bfloat16*>(add), ldadd, y, ldy, M, N, K, act_silu, out_f32, act_sigmoid_1m);
+      static_cast<const __nv_bfloat16*>(add), ldadd, y, ldy, M, N, K, act_silu, out_f32, act_sigmoid_1m));
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }
@@ -333,8 +345,8 @@ extern "C" int b200sat_fourier_features(const float* t, const void* w, void* out
                                         int t_stride, void* stream) {
   if (!t || !w || !out || B <= 0 || half <= 0) { set_last_error("fourier_features: bad arguments"); return B200SAT_EINVAL; }
   const int n = B * half;
-  fourier_features_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      t, static_cast<const __nv_bfloat16*>(w), static_cast<__nv_bfloat16*>(out), B, half, step, t_stride);
+  B200SAT_CHECK_CUDA(launch_k(fourier_features_kernel, dim3((n + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), 1, 
+      t, static_cast<const __nv_bfloat16*>(w), static_cast<__nv_bfloat16*>(out), B, half, step, t_stride));
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }
@@ -344,9 +356,9 @@ extern "C" int b200sat_dit_pre(const float* x, const void* wconv, void* out, int
   if (!x || !wconv || !out || B <= 0 || T <= 0 || reps <= 0) { set_last_error("dit_pre: bad arguments"); return B200SAT_EINVAL; }
   if (C != 64) { set_last_error("dit_pre: only io_channels == 64 is implemented"); return B200SAT_EUNSUPPORTED; }
   dim3 grid((T + 63) / 64, B);
-  dit_pre_kernel<64><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<const __nv_bfloat16*>(wconv),
+  B200SAT_CHECK_CUDA(launch_k(dit_pre_kernel<64>, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, x, static_cast<const __nv_bfloat16*>(wconv),
                                                                          static_cast<__nv_bfloat16*>(out), B, T, reps,
-                                                                         cin_table, step);
+                                                                         cin_table, step));
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }
@@ -356,9 +368,9 @@ extern "C" int b200sat_dit_post(const void* h, long ld_batch, int prepend, const
   if (!h || !wconv || !out || B <= 0 || T <= 0) { set_last_error("dit_post: bad arguments"); return B200SAT_EINVAL; }
   if (C != 64) { set_last_error("dit_post: only io_channels == 64 is implemented"); return B200SAT_EUNSUPPORTED; }
   dim3 grid((T + 31) / 32, B);
-  dit_post_kernel<64><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(h), ld_batch,
+  B200SAT_CHECK_CUDA(launch_k(dit_post_kernel<64>, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, static_cast<const __nv_bfloat16*>(h), ld_batch,
                                                                           prepend, static_cast<const __nv_bfloat16*>(wconv),
-                                                                          out, B, T, cfg, cfg_scale, scale_phi);
+                                                                          out, B, T, cfg, cfg_scale, scale_phi));
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }
@@ -368,15 +380,15 @@ extern "C" int b200sat_sampler_update(float* x, const float* v, float* hist, con
   if (!x || !v || !hist || !coef || !step || n <= 0) { set_last_error("sampler_update: bad arguments"); return B200SAT_EINVAL; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int grid = static_cast<int>((n + 1023) / 1024 < 1184 ? (n + 1023) / 1024 : 1184);
-  sampler_update_kernel<<<grid, 256, 0, s>>>(x, v, hist, noise, coef, step, n);
-  if (advance) step_advance_kernel<<<1, 1, 0, s>>>(step);
+  B200SAT_CHECK_CUDA(launch_k(sampler_update_kernel, dim3(grid), dim3(256), 0, s, 1, x, v, hist, noise, coef, step, n));
+  if (advance) B200SAT_CHECK_CUDA(launch_k(step_advance_kernel, dim3(1), dim3(1), 0, s, 1, step));
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }
 
 extern "C" int b200sat_step_set(int* step, int value, void* stream) {
   if (!step) { set_last_error("step_set: null"); return B200SAT_EINVAL; }
-  step_set_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(step, value);
+  B200SAT_CHECK_CUDA(launch_k(step_set_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), 1, step, value));
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }

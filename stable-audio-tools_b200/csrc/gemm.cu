@@ -148,9 +148,11 @@ __global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constan
     if (CTAS == 2) { tmem_alloc_pair(tmem_ptr_smem, Cfg::kTmemCols); tmem_relinquish_pair(); }
     else { tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols); tmem_relinquish(); }
   }
+  griddep_launch();
   tc_fence_before();
   if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
+  griddep_wait();   // everything above overlapped the previous kernel's tail; global memory is touched only below
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
@@ -459,18 +461,7 @@ static int launch_gemm(GemmParams& p, cudaStream_t stream) {
   p.kb_per_split = (total_kb + p.ksplit - 1) / p.ksplit;
   const int tiles = p.num_m_tiles * p.num_n_tiles * p.ksplit;
   const int grid = (tiles < units ? tiles : units) * CTAS;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(384);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  B200SAT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05<BN, CTAS>, p));
+  B200SAT_CHECK_CUDA(launch_k(gemm_bf16_tcgen05<BN, CTAS>, dim3(grid), dim3(384), Cfg::kSmemBytes, stream, CTAS, p));
   return B200SAT_OK;
 }
 
