@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(384, 1) conv1d_tcgen05(const __grid_constant__
               const float aa[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float s = sinf(v[4 * i + j] * aa[j]);
+                const float s = fast_sin(v[4 * i + j] * aa[j]);
                 v[4 * i + j] += bb[j] * s * s;
               }
             }
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
     if (out_hi) split_store8(out_hi + off, out_lo ? out_lo + off : nullptr, v);
     if (act_hi) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { const float s = sinf(v[j] * sa[cg * 8 + j]); v[j] += sib[cg * 8 + j] * s * s; }
+      for (int j = 0; j < 8; ++j) { const float s = fast_sin(v[j] * sa[cg * 8 + j]); v[j] += sib[cg * 8 + j] * s * s; }
       split_store8(act_hi + off, act_lo ? act_lo + off : nullptr, v);
     }
   }
