@@ -205,6 +205,117 @@ def measure_train(args, dev, rank, world, dist):
     return out
 
 
+def _graph_time_us(fn, reps=10, iters=3):
+    """Kernel time with host launch overhead removed: capture `reps` calls in a CUDA graph, replay, CUDA events."""
+    fn(); torch.cuda.synchronize()
+    side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        g.replay()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (reps * iters)
+
+
+def other_kernels(dev, pk):
+    """Roofline rows for the other named kernels of the hot path (attention, Oobleck convs, MRSTFT, LayerNorm), timed live."""
+    from b200sat import ops
+    from b200sat.autoencoder import OobleckEngine
+    from b200sat.stft_loss import SumAndDifferenceSTFTLoss, autoencoder_mrstft_terms
+    out = []
+    B, N, H = 2, T_LAT + 1, HEADS
+    qkv = torch.randn(B, N, 3, H, 64, device=dev).bfloat16()
+    o = torch.empty(B, N, H, 64, device=dev, dtype=torch.bfloat16)
+    us = _graph_time_us(lambda: ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], out=o), reps=20)
+    fl = 4.0 * B * H * N * N * 64
+    out.append({"kernel": "attention_fwd_tcgen05 (self-attention B=2 H=24 N=1025 dh=64)", "bound": "tensor", "achieved": fl / us / 1e6,
+                "peak": pk["bf16"], "unit": "TFLOP/s", "frac": fl / us / 1e6 / pk["bf16"], "avg_launch_ms": us / 1e3})
+    x = torch.randn(2050, D_MODEL, device=dev).bfloat16(); gm = torch.ones(D_MODEL, device=dev); y = torch.empty_like(x)
+    us = _graph_time_us(lambda: ops.layernorm(x, gm, out=y), reps=20)
+    by = 2.0 * x.numel() * 2
+    out.append({"kernel": "layernorm_kernel (2050 x 1536 bf16)", "bound": "hbm", "achieved": by / us / 1e3, "peak": pk["hbm"], "unit": "GB/s",
+                "frac": by / us / 1e3 / pk["hbm"], "avg_launch_ms": us / 1e3, "note": "12.6 MB working set is L2-resident: latency-, not HBM-bound"})
+    # Oobleck: random-init weights of the stable_audio_2_0_vae architecture, 47 s stereo clip (1024 latents)
+    g = torch.Generator(device=dev).manual_seed(0)
+    sd = _oobleck_state_dict(dev, g)
+    for prec in ("bf16", "fp32x3"):
+        eng = OobleckEngine(sd, precision=prec, device=dev)
+        a = torch.randn(1, 2, T_LAT * 2048, device=dev) * 0.3
+        z = eng.encode(a); torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(); z = eng.encode(a); e1.record(); w = eng.decode(z); e2.record(); torch.cuda.synchronize()
+        fl = 5.163e12
+        for name, ms in (("OobleckEncoder fwd", e0.elapsed_time(e1)), ("OobleckDecoder fwd", e1.elapsed_time(e2))):
+            out.append({"kernel": f"conv1d_tcgen05 stack: {name}, 47 s stereo clip, precision={prec}", "bound": "tensor", "achieved": fl / ms / 1e9,
+                        "peak": pk["bf16_sustained"], "unit": "TFLOP/s (algorithmic; fp32x3 executes 3x the MMAs)", "frac": fl / ms / 1e9 / pk["bf16_sustained"], "ms": ms})
+        del eng, a, z, w
+        torch.cuda.empty_cache()
+    FFT = [2048, 1024, 512, 256, 128, 64, 32]
+    loss = SumAndDifferenceSTFTLoss(FFT, [n // 4 for n in FFT], FFT, perceptual_weighting=True, sample_rate=44100)
+    reals = torch.randn(8, 2, 65536, device=dev) * 0.3; dec = reals + 0.05 * torch.randn_like(reals)
+    autoencoder_mrstft_terms(loss, dec, reals); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        autoencoder_mrstft_terms(loss, dec, reals)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    gf = 0.55 * 8  # BASELINE.md: ~0.55 GFLOP fp32 per item per generator step
+    out.append({"kernel": "MRSTFT (FIR + 7-resolution Stockham STFT + loss sums), 8 x 2 x 65536, all four generator-loss terms", "bound": "hbm",
+                "achieved": 8 * 2 * 2 * 65536 * 4 / ms / 1e6, "peak": pk["hbm"], "unit": "GB/s", "frac": 8 * 2 * 2 * 65536 * 4 / ms / 1e6 / pk["hbm"], "ms": ms,
+                "gflops_fp32": gf / ms, "note": "fused: 8.4 MB of waveforms in, 84 scalars out; bound by fp32 SIMT/shared memory, not HBM"})
+    return out
+
+
+def _oobleck_state_dict(dev, g):
+    """Random weights with the reference names/shapes of stable_audio_2_0_vae.json (autoencoders.py:285-362)."""
+    import math
+    sd = {}
+    ch, cm, strides = 128, [1, 1, 2, 4, 8, 16], [2, 4, 4, 8, 8]
+
+    def conv(p, cout, cin, k, bias=True, transpose=False):
+        shape = (cin, cout, k) if transpose else (cout, cin, k)
+        v = torch.randn(*shape, device=dev, generator=g) / math.sqrt(cin * k)
+        sd[p + "weight_v"] = v
+        sd[p + "weight_g"] = v.flatten(1).norm(dim=1).view(shape[0], 1, 1) * 0.7
+        if bias:
+            sd[p + "bias"] = 0.05 * torch.randn(cout, device=dev, generator=g)
+
+    def snake(p, c):
+        sd[p + "alpha"] = 0.3 * torch.randn(c, device=dev, generator=g); sd[p + "beta"] = 0.3 * torch.randn(c, device=dev, generator=g)
+
+    def ru(p, c):
+        snake(p + "layers.0.", c); conv(p + "layers.1.", c, c, 7); snake(p + "layers.2.", c); conv(p + "layers.3.", c, c, 1)
+
+    n = len(strides)
+    p = "encoder.layers."
+    conv(p + "0.", cm[0] * ch, 2, 7)
+    for i in range(n):
+        ci, co = cm[i] * ch, cm[i + 1] * ch
+        for j in range(3):
+            ru(f"{p}{i + 1}.layers.{j}.", ci)
+        snake(f"{p}{i + 1}.layers.3.", ci); conv(f"{p}{i + 1}.layers.4.", co, ci, 2 * strides[i])
+    snake(f"{p}{n + 1}.", cm[-1] * ch); conv(f"{p}{n + 2}.", 128, cm[-1] * ch, 3)
+    p = "decoder.layers."
+    conv(p + "0.", cm[-1] * ch, 64, 7)
+    for idx, i in enumerate(range(n, 0, -1)):
+        ci, co = cm[i] * ch, cm[i - 1] * ch
+        q = f"{p}{idx + 1}."
+        snake(q + "layers.0.", ci); conv(q + "layers.1.", co, ci, 2 * strides[i - 1], transpose=True)
+        for j in range(3):
+            ru(f"{q}layers.{2 + j}.", co)
+    snake(f"{p}{n + 1}.", cm[0] * ch); conv(f"{p}{n + 2}.", 2, cm[0] * ch, 7, bias=False)
+    return sd
+
+
 def run_ours(args):
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -317,7 +428,9 @@ def run_ours(args):
     achieved = k_flop / (k_ms * 1e-3) / 1e12
     roof = {"kernel": "gemm_bf16_tcgen05<256> (FF1 + SwiGLU epilogue, M=2050 N=12288 K=1536)", "bound": "tensor",
             "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"], "peak_source": pk["src"] + " burst (kernel timed alone)",
-            "avg_launch_ms": k_ms, "traffic": None}
+            "avg_launch_ms": k_ms, "traffic": 47.5e6,
+            "traffic_source": "profiles/r1_ncu_full_summary.txt: dram read 44.2 MB + write 3.3 MB per launch (ncu --set full); algorithmic 69 MB"}
+    other = other_kernels(dev, pk) if not args.no_train else None
     step_tflop = SAMPLE_STEPS * 2 * BATCH * (T_LAT + 1) * GFLOP_PER_TOKEN / 1e3
     whole = {"tflop_per_sample": step_tflop, "achieved_tflops": step_tflop * args.steps * world / (ms_total * 1e-3) / world,
              "frac_of_sustained_peak": step_tflop * args.steps / (ms_total * 1e-3) / pk["bf16_sustained"]}
@@ -338,7 +451,7 @@ def run_ours(args):
         "config": workload_config(world), "sample_seconds_100_steps": ms_total / args.steps / 1e3,
         "e2e": {"value": e2e_val, "unit": "latent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "b200sat.generation.generate_diffusion_cond(host pinned noise/conditioning -> host latents)"},
-        "gpu_launches": launches, "clocks": clk, "roofline": roof, "whole_step": whole, "cpu_baseline": cpu, "train": train,
+        "gpu_launches": launches, "clocks": clk, "roofline": roof, "whole_step": whole, "cpu_baseline": cpu, "train": train, "other_kernels": other,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
