@@ -134,41 +134,45 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
 }
 
 // ------------------------------------------------------------------------------------------------------------
-constexpr int DKV_SMEM = 2 * BW_T /*K,V*/ + 4 * BW_T /*ring of (Q,dO) x2*/ + 2 * BW_T /*P^T*/ + 2 * BW_T /*dS^T*/ + 4 * 128 * 4 + 256;
+// Pipelined v2 of both kernels (after the ncu/launch-list pass on v1: one score tile in flight per CTA left the tensor pipe and
+// the softmax warps waiting on each other; 327 + 258 us for the B=8 self-attention backward): 64-wide inner tiles, score tiles
+// (S, dP) DOUBLE-BUFFERED in TMEM so the MMA thread runs two tiles ahead, operand tiles (P^T / dS^T / dS) double-buffered in
+// shared memory so the accumulate MMAs of tile j overlap the softmax math of tile j+1.  Accumulators never leave TMEM.
+constexpr int BW_HT = 64 * 64 * 2;  // a 64 x 64 bf16 tile = 8 KB
+constexpr int BW_STAGES = 3;
+constexpr int DKV_SMEM = 2 * BW_T /*K,V*/ + BW_STAGES * 2 * BW_HT /*(Q,dO) ring*/ + 2 * BW_T /*P^T x2*/ + 2 * BW_T /*dS^T x2*/ + 4 * 64 * 4 + 256;
 
 __global__ void __launch_bounds__(320, 1) attention_bwd_dkv_tcgen05(const __grid_constant__ AttnBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sK = smem;
   uint8_t* sV = smem + BW_T;
-  uint8_t* sRing = smem + 2 * BW_T;     // stage s: Q at + s*2*BW_T, dO at + BW_T
-  uint8_t* sPT = smem + 6 * BW_T;
-  uint8_t* sdST = smem + 8 * BW_T;
-  float* s_lse = reinterpret_cast<float*>(smem + 10 * BW_T);   // [2][128] (pre-multiplied by log2 e)
-  float* s_delta = s_lse + 256;                                 // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + 256);
+  uint8_t* sRing = smem + 2 * BW_T;                         // stage s: Q tile (64 rows) at + s*2*BW_HT, dO tile at + BW_HT
+  uint8_t* sPT = sRing + BW_STAGES * 2 * BW_HT;             // 2 buffers of [128 keys x 64 queries]
+  uint8_t* sdST = sPT + 2 * BW_T;
+  float* s_lse = reinterpret_cast<float*>(sdST + 2 * BW_T); // [2][64] (pre-multiplied by log2 e)
+  float* s_delta = s_lse + 128;                             // [2][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + 128);
   uint64_t* kv_full = bars + 0;
-  uint64_t* qdo_full = bars + 1;   // [2]
-  uint64_t* qdo_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* acc_done = bars + 7;   // MMA3/4 of an iteration retired: P^T / dS^T buffers reusable, accumulators up to date
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* qdo_full = bars + 1;    // [3]
+  uint64_t* qdo_empty = bars + 4;   // [3]
+  uint64_t* s_full = bars + 7;      // [2]
+  uint64_t* p_full = bars + 9;      // [2]
+  uint64_t* acc_free = bars + 11;   // [2] accumulate MMAs of a tile retired: its P^T / dS^T buffer is reusable
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * 128;
   const int hk = blockIdx.y;
   const int b = blockIdx.z;
   const int G = p.Hq / p.Hkv;
-  const int nq = (p.Nq + 127) / 128;
+  const int nq = (p.Nq + 63) / 64;
   const int iters = G * nq;
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
     mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 256);
-    mbar_init(acc_done, 1);
+    for (int i = 0; i < BW_STAGES; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 256); mbar_init(&acc_free[i], 1); }
     fence_barrier_init();
   }
   griddep_launch();
@@ -178,7 +182,8 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dkv_tcgen05(const __grid
   tc_fence_after();
   griddep_wait();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tm_ST = tmem_base, tm_dPT = tmem_base + 128, tm_dV = tmem_base + 256, tm_dK = tmem_base + 320;
+  // columns: S^T buffers [0,64) [64,128); dP^T buffers [128,192) [192,256); dV [256,320); dK [320,384)
+  const uint32_t tm_dV = tmem_base + 256, tm_dK = tmem_base + 320;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -186,97 +191,103 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dkv_tcgen05(const __grid
       tma_load_4d(sK, &p.tmK, kv_full, 0, hk, k0, b);
       tma_load_4d(sV, &p.tmV, kv_full, 0, hk, k0, b);
       for (int it = 0; it < iters; ++it) {
-        const int s = it & 1;
+        const int s = it % BW_STAGES;
         const int h = hk * G + it / nq, qt = it % nq;
-        mbar_wait(&qdo_empty[s], ((it >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&qdo_full[s], 2 * BW_T);
-        tma_load_4d(sRing + s * 2 * BW_T, &p.tmQ, &qdo_full[s], 0, h, qt * 128, b);
-        tma_load_4d(sRing + s * 2 * BW_T + BW_T, &p.tmdO, &qdo_full[s], 0, h, qt * 128, b);
+        mbar_wait(&qdo_empty[s], ((it / BW_STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&qdo_full[s], 2 * BW_HT);
+        tma_load_4d(sRing + s * 2 * BW_HT, &p.tmQ, &qdo_full[s], 0, h, qt * 64, b);
+        tma_load_4d(sRing + s * 2 * BW_HT + BW_HT, &p.tmdO, &qdo_full[s], 0, h, qt * 64, b);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t id_s = make_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t id_acc = make_idesc_bf16(128, 64, 0, 1);
-      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aPT = smem_u32(sPT), adST = smem_u32(sdST);
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
+      auto issue_scores = [&](int it) {
+        const int s = it % BW_STAGES;
+        mbar_wait(&qdo_full[s], (it / BW_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t aQ = smem_u32(sRing + s * 2 * BW_HT), adO = aQ + BW_HT;
+        const uint32_t tS = tmem_base + (it & 1) * 64, tP = tmem_base + 128 + (it & 1) * 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // S^T[keys, q] = K Q^T
+          umma_bf16(tS, make_smem_desc_sw128(aK + k * 32, 16, 1024), make_smem_desc_sw128(aQ + k * 32, 16, 1024), id_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // dP^T[keys, q] = V dO^T
+          umma_bf16(tP, make_smem_desc_sw128(aV + k * 32, 16, 1024), make_smem_desc_sw128(adO + k * 32, 16, 1024), id_s, k != 0);
+        umma_commit(&s_full[it & 1]);
+      };
       mbar_wait(kv_full, 0);
+      issue_scores(0);
+      if (iters > 1) issue_scores(1);
       for (int it = 0; it < iters; ++it) {
-        const int s = it & 1;
-        mbar_wait(&qdo_full[s], (it >> 1) & 1);
+        const int s = it % BW_STAGES;
+        mbar_wait(&p_full[it & 1], (it >> 1) & 1);
         tc_fence_after();
-        const uint32_t aQ = smem_u32(sRing + s * 2 * BW_T), adO = aQ + BW_T;
+        const uint32_t aQ = smem_u32(sRing + s * 2 * BW_HT), adO = aQ + BW_HT;
+        const uint32_t aPT = smem_u32(sPT + (it & 1) * BW_T), adST = smem_u32(sdST + (it & 1) * BW_T);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // S^T[kv, q] = K Q^T
-          umma_bf16(tm_ST, make_smem_desc_sw128(aK + k * 32, 16, 1024), make_smem_desc_sw128(aQ + k * 32, 16, 1024), id_s, k != 0);
+        for (int k = 0; k < 4; ++k)   // dV[keys, d] += P^T dO   (dO tile re-read MN-major: rows = queries = MMA K)
+          umma_bf16(tm_dV, make_smem_desc_sw128(aPT + k * 32, 16, 1024), make_smem_desc_sw128(adO + k * 2048, 1024, 1024), id_acc, (it | k) != 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // dP^T[kv, q] = V dO^T
-          umma_bf16(tm_dPT, make_smem_desc_sw128(aV + k * 32, 16, 1024), make_smem_desc_sw128(adO + k * 32, 16, 1024), id_s, k != 0);
-        umma_commit(s_full);
-        mbar_wait(p_full, it & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {  // dV[kv, d] += P^T dO   (dO tile re-read as an MN-major operand: rows = q = MMA K)
-          const uint32_t pa = aPT + (k >> 2) * BW_T + (k & 3) * 32;
-          umma_bf16(tm_dV, make_smem_desc_sw128(pa, 16, 1024), make_smem_desc_sw128(adO + k * 2048, 1024, 1024), id_acc, (it | k) != 0);
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {  // dK[kv, d] += dS^T Q
-          const uint32_t pa = adST + (k >> 2) * BW_T + (k & 3) * 32;
-          umma_bf16(tm_dK, make_smem_desc_sw128(pa, 16, 1024), make_smem_desc_sw128(aQ + k * 2048, 1024, 1024), id_acc, (it | k) != 0);
-        }
+        for (int k = 0; k < 4; ++k)   // dK[keys, d] += dS^T Q
+          umma_bf16(tm_dK, make_smem_desc_sw128(adST + k * 32, 16, 1024), make_smem_desc_sw128(aQ + k * 2048, 1024, 1024), id_acc, (it | k) != 0);
         umma_commit(&qdo_empty[s]);
-        umma_commit(acc_done);
+        umma_commit(&acc_free[it & 1]);
+        if (it + 2 < iters) issue_scores(it + 2);   // its TMEM buffers were drained before p_full(it) completed
       }
     }
   } else {
-    // 8 warps: two threads per key row, each owning 64 of the 128 query columns (no cross-thread reduction is needed in the
-    // backward: lse and delta are per-column inputs).
+    // 8 warps: two threads per key row, each owning 32 of the 64 query columns of a tile
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;          // key row of this thread
     const int tid = (warp - 2) * 32 + lane;     // 0..255 among the softmax threads
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const bool key_ok = (k0 + r) < p.Nk;
-    uint8_t* pt_row = sPT + r * 128;
-    uint8_t* ds_row = sdST + r * 128;
     const int sw = r & 7;
     for (int it = 0; it < iters; ++it) {
       const int h = hk * G + it / nq, qt = it % nq;
       const int buf = it & 1;
-      {  // stage lse / delta of this q tile (column statistics): threads 0..127 lse, 128..255 delta
-        const int qi = tid & 127;
-        const int q = qt * 128 + qi;
+      if (tid < 128) {  // stage the column statistics of this q tile: threads 0..63 lse, 64..127 delta
+        const int qi = tid & 63;
+        const int q = qt * 64 + qi;
         const long idx = (static_cast<long>(b) * p.Hq + h) * p.Nq + q;
-        if (tid < 128) s_lse[buf * 128 + qi] = (q < p.Nq) ? p.lse[idx] * 1.4426950408889634f : INFINITY;  // out-of-range query => P = 0
-        else s_delta[buf * 128 + qi] = (q < p.Nq) ? p.delta[idx] : 0.f;
+        if (tid < 64) s_lse[buf * 64 + qi] = (q < p.Nq) ? p.lse[idx] * 1.4426950408889634f : INFINITY;  // out-of-range query => P = 0
+        else s_delta[buf * 64 + qi] = (q < p.Nq) ? p.delta[idx] : 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      mbar_wait(s_full, it & 1);
+      mbar_wait(&s_full[buf], (it >> 1) & 1);
       tc_fence_after();
-      if (it > 0) mbar_wait(acc_done, (it - 1) & 1);  // previous P^T / dS^T consumed
+      uint32_t rs[32], rp[32];
+      tmem_ld_32x32(tmem_base + lane_off + buf * 64 + half * 32, rs);
+      tmem_ld_32x32(tmem_base + 128 + lane_off + buf * 64 + half * 32, rp);
+      tmem_ld_wait();
+      uint32_t pk[16], dk_[16];
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = half * 2 + cc;
-        uint32_t rs[32], rp[32];
-        tmem_ld_32x32(tm_ST + lane_off + c * 32, rs);
-        tmem_ld_32x32(tm_dPT + lane_off + c * 32, rp);
-        tmem_ld_wait();
-        float pv[32], dsv[32];
+      for (int i = 0; i < 32; i += 2) {
+        const float l0 = s_lse[buf * 64 + half * 32 + i], l1 = s_lse[buf * 64 + half * 32 + i + 1];
+        const float p0 = key_ok ? bw_exp2(fmaf(__uint_as_float(rs[i]), p.scale_log2, -l0)) : 0.f;
+        const float p1 = key_ok ? bw_exp2(fmaf(__uint_as_float(rs[i + 1]), p.scale_log2, -l1)) : 0.f;
+        pk[i >> 1] = pack_bf16(p0, p1);
+        dk_[i >> 1] = pack_bf16(p0 * (__uint_as_float(rp[i]) - s_delta[buf * 64 + half * 32 + i]),
+                                p1 * (__uint_as_float(rp[i + 1]) - s_delta[buf * 64 + half * 32 + i + 1]));
+      }
+      if (it >= 2) mbar_wait(&acc_free[buf], ((it >> 1) - 1) & 1);   // accumulate MMAs of tile it-2 have finished reading this buffer
+      uint8_t* pt_row = sPT + buf * BW_T + r * 128;
+      uint8_t* ds_row = sdST + buf * BW_T + r * 128;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float l2 = s_lse[buf * 128 + c * 32 + i];
-          const float pr = key_ok ? bw_exp2(fmaf(__uint_as_float(rs[i]), p.scale_log2, -l2)) : 0.f;
-          pv[i] = pr;
-          dsv[i] = pr * (__uint_as_float(rp[i]) - s_delta[buf * 128 + c * 32 + i]);
-        }
-        store_operand_chunk(pt_row, sw, c, pv);
-        store_operand_chunk(ds_row, sw, c, dsv);
+      for (int t = 0; t < 4; ++t) {
+        const int ch = half * 4 + t;
+        *reinterpret_cast<uint4*>(pt_row + ((ch ^ sw) << 4)) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+        *reinterpret_cast<uint4*>(ds_row + ((ch ^ sw) << 4)) = make_uint4(dk_[4 * t], dk_[4 * t + 1], dk_[4 * t + 2], dk_[4 * t + 3]);
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[buf]);
     }
-    mbar_wait(acc_done, (iters - 1) & 1);
+    mbar_wait(&acc_free[(iters - 1) & 1], ((iters - 1) >> 1) & 1);
     tc_fence_after();
     float g[32];
     const int krow = k0 + r;
@@ -308,37 +319,35 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dkv_tcgen05(const __grid
 }
 
 // ------------------------------------------------------------------------------------------------------------
-constexpr int DQ_SMEM = 2 * BW_T /*Q,dO*/ + 4 * BW_T /*ring of (K,V) x2*/ + 2 * BW_T /*dS*/ + 256;
+constexpr int DQ_SMEM = 2 * BW_T /*Q,dO*/ + BW_STAGES * 2 * BW_HT /*(K,V) ring*/ + 2 * BW_T /*dS x2*/ + 256;
 
 __global__ void __launch_bounds__(320, 1) attention_bwd_dq_tcgen05(const __grid_constant__ AttnBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sdO = smem + BW_T;
-  uint8_t* sRing = smem + 2 * BW_T;  // stage s: K at + s*2*BW_T, V at + BW_T
-  uint8_t* sdS = smem + 6 * BW_T;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 8 * BW_T);
+  uint8_t* sRing = smem + 2 * BW_T;                       // stage s: K tile (64 keys) at + s*2*BW_HT, V tile at + BW_HT
+  uint8_t* sdS = sRing + BW_STAGES * 2 * BW_HT;           // 2 buffers of [128 queries x 64 keys]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 2 * BW_T);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* acc_done = bars + 7;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* kv_full = bars + 1;    // [3]
+  uint64_t* kv_empty = bars + 4;   // [3]
+  uint64_t* s_full = bars + 7;     // [2]
+  uint64_t* p_full = bars + 9;     // [2]
+  uint64_t* acc_free = bars + 11;  // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int hk = h / (p.Hq / p.Hkv);
-  const int nkv = (p.Nk + 127) / 128;
+  const int nkv = (p.Nk + 63) / 64;
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 256);
-    mbar_init(acc_done, 1);
+    for (int i = 0; i < BW_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 256); mbar_init(&acc_free[i], 1); }
     fence_barrier_init();
   }
   griddep_launch();
@@ -348,7 +357,8 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dq_tcgen05(const __grid_
   tc_fence_after();
   griddep_wait();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tm_S = tmem_base, tm_dP = tmem_base + 128, tm_dQ = tmem_base + 256;
+  // columns: S buffers [0,64) [64,128); dP buffers [128,192) [192,256); dQ [256,320)
+  const uint32_t tm_dQ = tmem_base + 256;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -356,40 +366,47 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dq_tcgen05(const __grid_
       tma_load_4d(sQ, &p.tmQ, q_full, 0, h, q0, b);
       tma_load_4d(sdO, &p.tmdO, q_full, 0, h, q0, b);
       for (int j = 0; j < nkv; ++j) {
-        const int s = j & 1;
-        mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], 2 * BW_T);
-        tma_load_4d(sRing + s * 2 * BW_T, &p.tmK, &kv_full[s], 0, hk, j * 128, b);
-        tma_load_4d(sRing + s * 2 * BW_T + BW_T, &p.tmV, &kv_full[s], 0, hk, j * 128, b);
+        const int s = j % BW_STAGES;
+        mbar_wait(&kv_empty[s], ((j / BW_STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], 2 * BW_HT);
+        tma_load_4d(sRing + s * 2 * BW_HT, &p.tmK, &kv_full[s], 0, hk, j * 64, b);
+        tma_load_4d(sRing + s * 2 * BW_HT + BW_HT, &p.tmV, &kv_full[s], 0, hk, j * 64, b);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t id_s = make_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t id_acc = make_idesc_bf16(128, 64, 0, 1);
-      const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), adS = smem_u32(sdS);
+      const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO);
+      auto issue_scores = [&](int j) {
+        const int s = j % BW_STAGES;
+        mbar_wait(&kv_full[s], (j / BW_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t aK = smem_u32(sRing + s * 2 * BW_HT), aV = aK + BW_HT;
+        const uint32_t tS = tmem_base + (j & 1) * 64, tP = tmem_base + 128 + (j & 1) * 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // S[q, keys] = Q K^T
+          umma_bf16(tS, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024), id_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // dP[q, keys] = dO V^T
+          umma_bf16(tP, make_smem_desc_sw128(adO + k * 32, 16, 1024), make_smem_desc_sw128(aV + k * 32, 16, 1024), id_s, k != 0);
+        umma_commit(&s_full[j & 1]);
+      };
       mbar_wait(q_full, 0);
+      issue_scores(0);
+      if (nkv > 1) issue_scores(1);
       for (int j = 0; j < nkv; ++j) {
-        const int s = j & 1;
-        mbar_wait(&kv_full[s], (j >> 1) & 1);
+        const int s = j % BW_STAGES;
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t aK = smem_u32(sRing + s * 2 * BW_T), aV = aK + BW_T;
+        const uint32_t aK = smem_u32(sRing + s * 2 * BW_HT);
+        const uint32_t adS = smem_u32(sdS + (j & 1) * BW_T);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // S[q, kv] = Q K^T
-          umma_bf16(tm_S, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024), id_s, k != 0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)   // dP[q, kv] = dO V^T
-          umma_bf16(tm_dP, make_smem_desc_sw128(adO + k * 32, 16, 1024), make_smem_desc_sw128(aV + k * 32, 16, 1024), id_s, k != 0);
-        umma_commit(s_full);
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {  // dQ[q, d] += dS K   (K tile re-read MN-major: rows = keys = MMA K)
-          const uint32_t pa = adS + (k >> 2) * BW_T + (k & 3) * 32;
-          umma_bf16(tm_dQ, make_smem_desc_sw128(pa, 16, 1024), make_smem_desc_sw128(aK + k * 2048, 1024, 1024), id_acc, (j | k) != 0);
-        }
+        for (int k = 0; k < 4; ++k)   // dQ[q, d] += dS K   (K tile re-read MN-major: rows = keys = MMA K)
+          umma_bf16(tm_dQ, make_smem_desc_sw128(adS + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 2048, 1024, 1024), id_acc, (j | k) != 0);
         umma_commit(&kv_empty[s]);
-        umma_commit(acc_done);
+        umma_commit(&acc_free[j & 1]);
+        if (j + 2 < nkv) issue_scores(j + 2);
       }
     }
   } else {
@@ -402,33 +419,35 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dq_tcgen05(const __grid_
     const long sidx = (static_cast<long>(b) * p.Hq + h) * p.Nq + qrow;
     const float lse2 = q_ok ? p.lse[sidx] * 1.4426950408889634f : INFINITY;
     const float dl = q_ok ? p.delta[sidx] : 0.f;
-    uint8_t* ds_row = sdS + r * 128;
     const int sw = r & 7;
     for (int j = 0; j < nkv; ++j) {
-      const int nvalid = p.Nk - j * 128;
-      mbar_wait(s_full, j & 1);
+      const int buf = j & 1;
+      const int nvalid = p.Nk - j * 64 - half * 32;
+      mbar_wait(&s_full[buf], (j >> 1) & 1);
       tc_fence_after();
-      if (j > 0) mbar_wait(acc_done, (j - 1) & 1);
+      uint32_t rs[32], rp[32];
+      tmem_ld_32x32(tmem_base + lane_off + buf * 64 + half * 32, rs);
+      tmem_ld_32x32(tmem_base + 128 + lane_off + buf * 64 + half * 32, rp);
+      tmem_ld_wait();
+      uint32_t dk_[16];
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = half * 2 + cc;
-        uint32_t rs[32], rp[32];
-        tmem_ld_32x32(tm_S + lane_off + c * 32, rs);
-        tmem_ld_32x32(tm_dP + lane_off + c * 32, rp);
-        tmem_ld_wait();
-        float dsv[32];
+      for (int i = 0; i < 32; i += 2) {
+        const float p0 = (i < nvalid) ? bw_exp2(fmaf(__uint_as_float(rs[i]), p.scale_log2, -lse2)) : 0.f;
+        const float p1 = (i + 1 < nvalid) ? bw_exp2(fmaf(__uint_as_float(rs[i + 1]), p.scale_log2, -lse2)) : 0.f;
+        dk_[i >> 1] = pack_bf16(p0 * (__uint_as_float(rp[i]) - dl), p1 * (__uint_as_float(rp[i + 1]) - dl));
+      }
+      if (j >= 2) mbar_wait(&acc_free[buf], ((j >> 1) - 1) & 1);
+      uint8_t* ds_row = sdS + buf * BW_T + r * 128;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float pr = (c * 32 + i < nvalid) ? bw_exp2(fmaf(__uint_as_float(rs[i]), p.scale_log2, -lse2)) : 0.f;
-          dsv[i] = pr * (__uint_as_float(rp[i]) - dl);
-        }
-        store_operand_chunk(ds_row, sw, c, dsv);
+      for (int t = 0; t < 4; ++t) {
+        const int ch = half * 4 + t;
+        *reinterpret_cast<uint4*>(ds_row + ((ch ^ sw) << 4)) = make_uint4(dk_[4 * t], dk_[4 * t + 1], dk_[4 * t + 2], dk_[4 * t + 3]);
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[buf]);
     }
-    mbar_wait(acc_done, (nkv - 1) & 1);
+    mbar_wait(&acc_free[(nkv - 1) & 1], ((nkv - 1) >> 1) & 1);
     tc_fence_after();
     float g[32];
     {
@@ -450,10 +469,10 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dq_tcgen05(const __grid_
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-static int bw_head_map(CUtensorMap* tm, const void* base, int B, int H, int N, long bs, long ss, long hs) {
+static int bw_head_map(CUtensorMap* tm, const void* base, int B, int H, int N, long bs, long ss, long hs, int rows) {
   uint64_t dims[4] = {64, static_cast<uint64_t>(H), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
   uint64_t strides[3] = {static_cast<uint64_t>(hs) * 2, static_cast<uint64_t>(ss) * 2, static_cast<uint64_t>(bs) * 2};
-  uint32_t box[4] = {64, 1, 128, 1};
+  uint32_t box[4] = {64, 1, static_cast<uint32_t>(rows), 1};
   return encode_tmap_bf16(tm, base, 4, dims, strides, box, 1);
 }
 
@@ -477,13 +496,13 @@ extern "C" int b200sat_attention_bwd(const void* q, const void* k, const void* v
     B200SAT_CHECK_CUDA(launch_k(attn_delta_kernel, dim3(static_cast<int>((n + 127) / 128)), dim3(128), 0, s, 1, static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o),
                                                                         delta_scratch, B, Hq, Nq, so[0], so[1], so[2], sdo[0], sdo[1], sdo[2]));
   }
-  AttnBwdParams p;
+  AttnBwdParams p, pq;   // p: dK/dV kernel (128-key rows, 64-query inner tiles); pq: dQ kernel (128-query rows, 64-key inner tiles)
   memset(&p, 0, sizeof(p));
   int rc;
-  if ((rc = bw_head_map(&p.tmQ, q, B, Hq, Nq, sq[0], sq[1], sq[2]))) return rc;
-  if ((rc = bw_head_map(&p.tmK, k, B, Hkv, Nk, sk[0], sk[1], sk[2]))) return rc;
-  if ((rc = bw_head_map(&p.tmV, v, B, Hkv, Nk, sv[0], sv[1], sv[2]))) return rc;
-  if ((rc = bw_head_map(&p.tmdO, d_o, B, Hq, Nq, sdo[0], sdo[1], sdo[2]))) return rc;
+  if ((rc = bw_head_map(&p.tmQ, q, B, Hq, Nq, sq[0], sq[1], sq[2], 64))) return rc;
+  if ((rc = bw_head_map(&p.tmK, k, B, Hkv, Nk, sk[0], sk[1], sk[2], 128))) return rc;
+  if ((rc = bw_head_map(&p.tmV, v, B, Hkv, Nk, sv[0], sv[1], sv[2], 128))) return rc;
+  if ((rc = bw_head_map(&p.tmdO, d_o, B, Hq, Nq, sdo[0], sdo[1], sdo[2], 64))) return rc;
   p.lse = lse; p.delta = delta_scratch;
   p.dQ = static_cast<__nv_bfloat16*>(dq); p.dK = static_cast<__nv_bfloat16*>(dk); p.dV = static_cast<__nv_bfloat16*>(dv);
   p.dq_bs = sdq[0]; p.dq_ss = sdq[1]; p.dq_hs = sdq[2];
@@ -498,8 +517,13 @@ extern "C" int b200sat_attention_bwd(const void* q, const void* k, const void* v
     B200SAT_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_dq_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
     attr_set = true;
   }
+  pq = p;
+  if ((rc = bw_head_map(&pq.tmQ, q, B, Hq, Nq, sq[0], sq[1], sq[2], 128))) return rc;
+  if ((rc = bw_head_map(&pq.tmK, k, B, Hkv, Nk, sk[0], sk[1], sk[2], 64))) return rc;
+  if ((rc = bw_head_map(&pq.tmV, v, B, Hkv, Nk, sv[0], sv[1], sv[2], 64))) return rc;
+  if ((rc = bw_head_map(&pq.tmdO, d_o, B, Hq, Nq, sdo[0], sdo[1], sdo[2], 128))) return rc;
   B200SAT_CHECK_CUDA(launch_k(attention_bwd_dkv_tcgen05, dim3((Nk + 127) / 128, Hkv, B), dim3(320), DKV_SMEM, s, 1, p));
-  B200SAT_CHECK_CUDA(launch_k(attention_bwd_dq_tcgen05, dim3((Nq + 127) / 128, Hq, B), dim3(320), DQ_SMEM, s, 1, p));
+  B200SAT_CHECK_CUDA(launch_k(attention_bwd_dq_tcgen05, dim3((Nq + 127) / 128, Hq, B), dim3(320), DQ_SMEM, s, 1, pq));
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }
