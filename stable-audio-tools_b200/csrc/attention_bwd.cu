@@ -139,26 +139,27 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
 // (S, dP) DOUBLE-BUFFERED in TMEM so the MMA thread runs two tiles ahead, operand tiles (P^T / dS^T / dS) double-buffered in
 // shared memory so the accumulate MMAs of tile j overlap the softmax math of tile j+1.  Accumulators never leave TMEM.
 constexpr int BW_HT = 64 * 64 * 2;  // a 64 x 64 bf16 tile = 8 KB
-constexpr int BW_STAGES = 3;
-constexpr int DKV_SMEM = 2 * BW_T /*K,V*/ + BW_STAGES * 2 * BW_HT /*(Q,dO) ring*/ + 2 * BW_T /*P^T x2*/ + 2 * BW_T /*dS^T x2*/ + 4 * 64 * 4 + 256;
+constexpr int BW_STAGES = 4;    // inner-tile ring: the scores of tile j+3 are issued while tiles j+1, j+2 still wait for their accumulate MMAs
+constexpr int BW_NB = 3;       // score-tile buffers in TMEM and operand-tile buffers in shared memory (MMA thread runs BW_NB tiles ahead)
+constexpr int DKV_SMEM = 2 * BW_T /*K,V*/ + BW_STAGES * 2 * BW_HT /*(Q,dO) ring*/ + BW_NB * BW_T /*P^T*/ + BW_NB * BW_T /*dS^T*/ + 2 * BW_NB * 64 * 4 + 256;
 
 __global__ void __launch_bounds__(320, 1) attention_bwd_dkv_tcgen05(const __grid_constant__ AttnBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sK = smem;
   uint8_t* sV = smem + BW_T;
   uint8_t* sRing = smem + 2 * BW_T;                         // stage s: Q tile (64 rows) at + s*2*BW_HT, dO tile at + BW_HT
-  uint8_t* sPT = sRing + BW_STAGES * 2 * BW_HT;             // 2 buffers of [128 keys x 64 queries]
-  uint8_t* sdST = sPT + 2 * BW_T;
-  float* s_lse = reinterpret_cast<float*>(sdST + 2 * BW_T); // [2][64] (pre-multiplied by log2 e)
-  float* s_delta = s_lse + 128;                             // [2][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + 128);
+  uint8_t* sPT = sRing + BW_STAGES * 2 * BW_HT;             // BW_NB buffers of [128 keys x 64 queries]
+  uint8_t* sdST = sPT + BW_NB * BW_T;
+  float* s_lse = reinterpret_cast<float*>(sdST + BW_NB * BW_T); // [BW_NB][64] (pre-multiplied by log2 e)
+  float* s_delta = s_lse + BW_NB * 64;                          // [BW_NB][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + BW_NB * 64);
   uint64_t* kv_full = bars + 0;
-  uint64_t* qdo_full = bars + 1;    // [3]
-  uint64_t* qdo_empty = bars + 4;   // [3]
-  uint64_t* s_full = bars + 7;      // [2]
-  uint64_t* p_full = bars + 9;      // [2]
-  uint64_t* acc_free = bars + 11;   // [2] accumulate MMAs of a tile retired: its P^T / dS^T buffer is reusable
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* qdo_full = bars + 1;    // [BW_STAGES]
+  uint64_t* qdo_empty = bars + 5;   // [BW_STAGES]
+  uint64_t* s_full = bars + 9;      // [BW_NB]
+  uint64_t* p_full = bars + 12;     // [BW_NB]
+  uint64_t* acc_free = bars + 15;   // [BW_NB] accumulate MMAs of a tile retired: its P^T / dS^T buffer is reusable
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * 128;
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dkv_tcgen05(const __grid
     if (smem_u32(smem) & 1023u) __trap();
     mbar_init(kv_full, 1);
     for (int i = 0; i < BW_STAGES; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 256); mbar_init(&acc_free[i], 1); }
+    for (int i = 0; i < BW_NB; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 256); mbar_init(&acc_free[i], 1); }
     fence_barrier_init();
   }
   griddep_launch();
@@ -182,8 +183,8 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dkv_tcgen05(const __grid
   tc_fence_after();
   griddep_wait();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  // columns: S^T buffers [0,64) [64,128); dP^T buffers [128,192) [192,256); dV [256,320); dK [320,384)
-  const uint32_t tm_dV = tmem_base + 256, tm_dK = tmem_base + 320;
+  // columns: 3 S^T buffers [0,192); 3 dP^T buffers [192,384); dV [384,448); dK [448,512)
+  const uint32_t tm_dV = tmem_base + 384, tm_dK = tmem_base + 448;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -209,24 +210,23 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dkv_tcgen05(const __grid
         mbar_wait(&qdo_full[s], (it / BW_STAGES) & 1);
         tc_fence_after();
         const uint32_t aQ = smem_u32(sRing + s * 2 * BW_HT), adO = aQ + BW_HT;
-        const uint32_t tS = tmem_base + (it & 1) * 64, tP = tmem_base + 128 + (it & 1) * 64;
+        const uint32_t tS = tmem_base + (it % BW_NB) * 64, tP = tmem_base + 192 + (it % BW_NB) * 64;
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // S^T[keys, q] = K Q^T
           umma_bf16(tS, make_smem_desc_sw128(aK + k * 32, 16, 1024), make_smem_desc_sw128(aQ + k * 32, 16, 1024), id_s, k != 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // dP^T[keys, q] = V dO^T
           umma_bf16(tP, make_smem_desc_sw128(aV + k * 32, 16, 1024), make_smem_desc_sw128(adO + k * 32, 16, 1024), id_s, k != 0);
-        umma_commit(&s_full[it & 1]);
+        umma_commit(&s_full[it % BW_NB]);
       };
       mbar_wait(kv_full, 0);
-      issue_scores(0);
-      if (iters > 1) issue_scores(1);
+      for (int i = 0; i < BW_NB && i < iters; ++i) issue_scores(i);
       for (int it = 0; it < iters; ++it) {
         const int s = it % BW_STAGES;
-        mbar_wait(&p_full[it & 1], (it >> 1) & 1);
+        mbar_wait(&p_full[it % BW_NB], (it / BW_NB) & 1);
         tc_fence_after();
         const uint32_t aQ = smem_u32(sRing + s * 2 * BW_HT), adO = aQ + BW_HT;
-        const uint32_t aPT = smem_u32(sPT + (it & 1) * BW_T), adST = smem_u32(sdST + (it & 1) * BW_T);
+        const uint32_t aPT = smem_u32(sPT + (it % BW_NB) * BW_T), adST = smem_u32(sdST + (it % BW_NB) * BW_T);
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // dV[keys, d] += P^T dO   (dO tile re-read MN-major: rows = queries = MMA K)
           umma_bf16(tm_dV, make_smem_desc_sw128(aPT + k * 32, 16, 1024), make_smem_desc_sw128(adO + k * 2048, 1024, 1024), id_acc, (it | k) != 0);
@@ -234,8 +234,8 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dkv_tcgen05(const __grid
         for (int k = 0; k < 4; ++k)   // dK[keys, d] += dS^T Q
           umma_bf16(tm_dK, make_smem_desc_sw128(adST + k * 32, 16, 1024), make_smem_desc_sw128(aQ + k * 2048, 1024, 1024), id_acc, (it | k) != 0);
         umma_commit(&qdo_empty[s]);
-        umma_commit(&acc_free[it & 1]);
-        if (it + 2 < iters) issue_scores(it + 2);   // its TMEM buffers were drained before p_full(it) completed
+        umma_commit(&acc_free[it % BW_NB]);
+        if (it + BW_NB < iters) issue_scores(it + BW_NB);   // its TMEM buffers were drained before p_full(it) completed
       }
     }
   } else {
@@ -247,22 +247,27 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dkv_tcgen05(const __grid
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const bool key_ok = (k0 + r) < p.Nk;
     const int sw = r & 7;
+    // column statistics (lse, delta) of the NEXT q tile are fetched one iteration ahead so their global-memory latency is off the
+    // critical path (ncu v2: the whole CTA sat at the staging barrier waiting for this load)
+    auto fetch_stat = [&](int it) -> float {
+      if (tid >= 128 || it >= iters) return 0.f;
+      const int hh = hk * G + it / nq, qq = (it % nq) * 64 + (tid & 63);
+      const long idx = (static_cast<long>(b) * p.Hq + hh) * p.Nq + qq;
+      if (tid < 64) return (qq < p.Nq) ? p.lse[idx] * 1.4426950408889634f : INFINITY;   // out-of-range query => P = 0
+      return (qq < p.Nq) ? p.delta[idx] : 0.f;
+    };
+    float stat_next = fetch_stat(0);
     for (int it = 0; it < iters; ++it) {
-      const int h = hk * G + it / nq, qt = it % nq;
-      const int buf = it & 1;
-      if (tid < 128) {  // stage the column statistics of this q tile: threads 0..63 lse, 64..127 delta
-        const int qi = tid & 63;
-        const int q = qt * 64 + qi;
-        const long idx = (static_cast<long>(b) * p.Hq + h) * p.Nq + q;
-        if (tid < 64) s_lse[buf * 64 + qi] = (q < p.Nq) ? p.lse[idx] * 1.4426950408889634f : INFINITY;  // out-of-range query => P = 0
-        else s_delta[buf * 64 + qi] = (q < p.Nq) ? p.delta[idx] : 0.f;
-      }
+      const int buf = it % BW_NB;
+      if (tid < 64) s_lse[buf * 64 + tid] = stat_next;
+      else if (tid < 128) s_delta[buf * 64 + (tid & 63)] = stat_next;
+      stat_next = fetch_stat(it + 1);
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      mbar_wait(&s_full[buf], (it >> 1) & 1);
+      mbar_wait(&s_full[buf], (it / BW_NB) & 1);
       tc_fence_after();
       uint32_t rs[32], rp[32];
       tmem_ld_32x32(tmem_base + lane_off + buf * 64 + half * 32, rs);
-      tmem_ld_32x32(tmem_base + 128 + lane_off + buf * 64 + half * 32, rp);
+      tmem_ld_32x32(tmem_base + 192 + lane_off + buf * 64 + half * 32, rp);
       tmem_ld_wait();
       uint32_t pk[16], dk_[16];
 #pragma unroll
@@ -274,7 +279,7 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dkv_tcgen05(const __grid
         dk_[i >> 1] = pack_bf16(p0 * (__uint_as_float(rp[i]) - s_delta[buf * 64 + half * 32 + i]),
                                 p1 * (__uint_as_float(rp[i + 1]) - s_delta[buf * 64 + half * 32 + i + 1]));
       }
-      if (it >= 2) mbar_wait(&acc_free[buf], ((it >> 1) - 1) & 1);   // accumulate MMAs of tile it-2 have finished reading this buffer
+      if (it >= BW_NB) mbar_wait(&acc_free[buf], ((it / BW_NB) - 1) & 1);   // accumulate MMAs of tile it-BW_NB finished reading this buffer
       uint8_t* pt_row = sPT + buf * BW_T + r * 128;
       uint8_t* ds_row = sdST + buf * BW_T + r * 128;
 #pragma unroll
@@ -287,7 +292,7 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dkv_tcgen05(const __grid
       tc_fence_before();
       mbar_arrive(&p_full[buf]);
     }
-    mbar_wait(&acc_free[(iters - 1) & 1], ((iters - 1) >> 1) & 1);
+    mbar_wait(&acc_free[(iters - 1) % BW_NB], ((iters - 1) / BW_NB) & 1);
     tc_fence_after();
     float g[32];
     const int krow = k0 + r;
@@ -319,7 +324,7 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dkv_tcgen05(const __grid
 }
 
 // ------------------------------------------------------------------------------------------------------------
-constexpr int DQ_SMEM = 2 * BW_T /*Q,dO*/ + BW_STAGES * 2 * BW_HT /*(K,V) ring*/ + 2 * BW_T /*dS x2*/ + 256;
+constexpr int DQ_SMEM = 2 * BW_T /*Q,dO*/ + BW_STAGES * 2 * BW_HT /*(K,V) ring*/ + BW_NB * BW_T /*dS*/ + 256;
 
 __global__ void __launch_bounds__(320, 1) attention_bwd_dq_tcgen05(const __grid_constant__ AttnBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -327,14 +332,14 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dq_tcgen05(const __grid_
   uint8_t* sdO = smem + BW_T;
   uint8_t* sRing = smem + 2 * BW_T;                       // stage s: K tile (64 keys) at + s*2*BW_HT, V tile at + BW_HT
   uint8_t* sdS = sRing + BW_STAGES * 2 * BW_HT;           // 2 buffers of [128 queries x 64 keys]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 2 * BW_T);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + BW_NB * BW_T);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;    // [3]
-  uint64_t* kv_empty = bars + 4;   // [3]
-  uint64_t* s_full = bars + 7;     // [2]
-  uint64_t* p_full = bars + 9;     // [2]
-  uint64_t* acc_free = bars + 11;  // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* kv_full = bars + 1;    // [BW_STAGES]
+  uint64_t* kv_empty = bars + 5;   // [BW_STAGES]
+  uint64_t* s_full = bars + 9;     // [BW_NB]
+  uint64_t* p_full = bars + 12;    // [BW_NB]
+  uint64_t* acc_free = bars + 15;  // [BW_NB]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128;
@@ -347,7 +352,7 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dq_tcgen05(const __grid_
     if (smem_u32(smem) & 1023u) __trap();
     mbar_init(q_full, 1);
     for (int i = 0; i < BW_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 256); mbar_init(&acc_free[i], 1); }
+    for (int i = 0; i < BW_NB; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 256); mbar_init(&acc_free[i], 1); }
     fence_barrier_init();
   }
   griddep_launch();
@@ -357,8 +362,8 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dq_tcgen05(const __grid_
   tc_fence_after();
   griddep_wait();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  // columns: S buffers [0,64) [64,128); dP buffers [128,192) [192,256); dQ [256,320)
-  const uint32_t tm_dQ = tmem_base + 256;
+  // columns: 3 S buffers [0,192); 3 dP buffers [192,384); dQ [384,448)
+  const uint32_t tm_dQ = tmem_base + 384;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -383,30 +388,29 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dq_tcgen05(const __grid_
         mbar_wait(&kv_full[s], (j / BW_STAGES) & 1);
         tc_fence_after();
         const uint32_t aK = smem_u32(sRing + s * 2 * BW_HT), aV = aK + BW_HT;
-        const uint32_t tS = tmem_base + (j & 1) * 64, tP = tmem_base + 128 + (j & 1) * 64;
+        const uint32_t tS = tmem_base + (j % BW_NB) * 64, tP = tmem_base + 192 + (j % BW_NB) * 64;
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // S[q, keys] = Q K^T
           umma_bf16(tS, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024), id_s, k != 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // dP[q, keys] = dO V^T
           umma_bf16(tP, make_smem_desc_sw128(adO + k * 32, 16, 1024), make_smem_desc_sw128(aV + k * 32, 16, 1024), id_s, k != 0);
-        umma_commit(&s_full[j & 1]);
+        umma_commit(&s_full[j % BW_NB]);
       };
       mbar_wait(q_full, 0);
-      issue_scores(0);
-      if (nkv > 1) issue_scores(1);
+      for (int i = 0; i < BW_NB && i < nkv; ++i) issue_scores(i);
       for (int j = 0; j < nkv; ++j) {
         const int s = j % BW_STAGES;
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        mbar_wait(&p_full[j % BW_NB], (j / BW_NB) & 1);
         tc_fence_after();
         const uint32_t aK = smem_u32(sRing + s * 2 * BW_HT);
-        const uint32_t adS = smem_u32(sdS + (j & 1) * BW_T);
+        const uint32_t adS = smem_u32(sdS + (j % BW_NB) * BW_T);
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // dQ[q, d] += dS K   (K tile re-read MN-major: rows = keys = MMA K)
           umma_bf16(tm_dQ, make_smem_desc_sw128(adS + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 2048, 1024, 1024), id_acc, (j | k) != 0);
         umma_commit(&kv_empty[s]);
-        umma_commit(&acc_free[j & 1]);
-        if (j + 2 < nkv) issue_scores(j + 2);
+        umma_commit(&acc_free[j % BW_NB]);
+        if (j + BW_NB < nkv) issue_scores(j + BW_NB);
       }
     }
   } else {
@@ -421,13 +425,13 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dq_tcgen05(const __grid_
     const float dl = q_ok ? p.delta[sidx] : 0.f;
     const int sw = r & 7;
     for (int j = 0; j < nkv; ++j) {
-      const int buf = j & 1;
+      const int buf = j % BW_NB;
       const int nvalid = p.Nk - j * 64 - half * 32;
-      mbar_wait(&s_full[buf], (j >> 1) & 1);
+      mbar_wait(&s_full[buf], (j / BW_NB) & 1);
       tc_fence_after();
       uint32_t rs[32], rp[32];
       tmem_ld_32x32(tmem_base + lane_off + buf * 64 + half * 32, rs);
-      tmem_ld_32x32(tmem_base + 128 + lane_off + buf * 64 + half * 32, rp);
+      tmem_ld_32x32(tmem_base + 192 + lane_off + buf * 64 + half * 32, rp);
       tmem_ld_wait();
       uint32_t dk_[16];
 #pragma unroll
@@ -436,7 +440,7 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dq_tcgen05(const __grid_
         const float p1 = (i + 1 < nvalid) ? bw_exp2(fmaf(__uint_as_float(rs[i + 1]), p.scale_log2, -lse2)) : 0.f;
         dk_[i >> 1] = pack_bf16(p0 * (__uint_as_float(rp[i]) - dl), p1 * (__uint_as_float(rp[i + 1]) - dl));
       }
-      if (j >= 2) mbar_wait(&acc_free[buf], ((j >> 1) - 1) & 1);
+      if (j >= BW_NB) mbar_wait(&acc_free[buf], ((j / BW_NB) - 1) & 1);
       uint8_t* ds_row = sdS + buf * BW_T + r * 128;
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
@@ -447,7 +451,7 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dq_tcgen05(const __grid_
       tc_fence_before();
       mbar_arrive(&p_full[buf]);
     }
-    mbar_wait(&acc_free[(nkv - 1) & 1], ((nkv - 1) >> 1) & 1);
+    mbar_wait(&acc_free[(nkv - 1) % BW_NB], ((nkv - 1) / BW_NB) & 1);
     tc_fence_after();
     float g[32];
     {
