@@ -64,6 +64,10 @@ class DiTEngine:
         for k in list(w):
             if k.endswith("bias"):
                 w[k] = w[k].bfloat16().float().contiguous()
+        # all layers' cross-attention K/V projections stacked: one GEMM per forward instead of `depth` small ones
+        kvs = [w[f"transformer.layers.{i}.cross_attn.to_kv.weight"] for i in range(self.cfg.depth) if f"transformer.layers.{i}.cross_attn.to_kv.weight" in w]
+        if len(kvs) == self.cfg.depth and self.cfg.depth > 0:
+            w["_all_to_kv.weight"] = torch.cat(kvs, dim=0).contiguous()
         self.w = w
 
     def rope_tables(self, seq):
@@ -94,7 +98,7 @@ class DiTEngine:
         )
         if L > 0:
             ws.update(ctx_in=bf(Bx * L, c.cond_token_dim), ctx1=bf(Bx * L, c.cond_embed_dim), ctx=bf(Bx * L, c.cond_embed_dim),
-                      kv=bf(Bx * L, 2 * c.cond_embed_dim))
+                      kv=bf(Bx * L, 2 * c.cond_embed_dim), kv_all=bf(Bx * L, c.depth * 2 * c.cond_embed_dim))
         if c.global_cond_type == "adaLN":
             ws.update(g1=bf(Bx, d), g6=bf(Bx, 6 * d))
         self._ws[key] = ws
@@ -117,6 +121,8 @@ class DiTEngine:
         if ctx_in is not None:
             ops.linear(ctx_in, w["to_cond_embed.0.weight"], silu=True, out=ws["ctx1"])
             ctx = ops.linear(ws["ctx1"], w["to_cond_embed.2.weight"], out=ws["ctx"])
+            if "_all_to_kv.weight" in w:   # K/V of the conditioning tokens for every layer (transformer.py:469-472), one launch
+                ops.linear(ctx, w["_all_to_kv.weight"], out=ws["kv_all"])
         ops.fourier_features(t, w["timestep_features.weight"], out=ws["ff_feat"], step=step,
                              t_stride=Bx if step is not None else 0)
         self._lin_small(ws["ff_feat"], w["to_timestep_embed.0.weight"], w["to_timestep_embed.0.bias"], ws["te1"], silu=True)
@@ -161,9 +167,12 @@ class DiTEngine:
             if ctx is not None and (p + "cross_attn.to_q.weight") in w:
                 ops.layernorm(h, w[p + "cross_attend_norm.gamma"], out=ws["n"])
                 ops.linear(ws["n"], w[p + "cross_attn.to_q.weight"], out=ws["q"])
-                ops.linear(ctx, w[p + "cross_attn.to_kv.weight"], out=ws["kv"])
                 kvh = c.cond_embed_dim // 64
-                kv = ws["kv"].view(Bx, L, 2, kvh, 64)
+                if "_all_to_kv.weight" in w:
+                    kv = ws["kv_all"].view(Bx, L, c.depth, 2, kvh, 64)[:, :, i]
+                else:
+                    ops.linear(ctx, w[p + "cross_attn.to_kv.weight"], out=ws["kv"])
+                    kv = ws["kv"].view(Bx, L, 2, kvh, 64)
                 ops.attention(ws["q"].view(Bx, N, H, 64), kv[:, :, 0], kv[:, :, 1], out=ws["a"].view(Bx, N, H, 64))
                 ops.linear(ws["a"], w[p + "cross_attn.to_out.weight"], residual=h, out=h)
             # feed-forward (transformer.py:712 / :693-701)
