@@ -35,6 +35,8 @@ unsigned long long b200sat_launch_count(void);
 #define B200SAT_GEMM_A_MN 256        /* A stored [K,M]: weight-gradient GEMMs (dW = dY^T X) */
 #define B200SAT_GEMM_B_MN 512        /* B stored [K,N]: data-gradient GEMMs (dX = dY W) */
 #define B200SAT_GEMM_ACCUM 1024      /* fp32 D += acc */
+#define B200SAT_GEMM_LN_A 8192       /* A = raw LayerNorm input, gamma folded into B: out = rstd*(acc - mean*colsum) (transformer.py:236-238 fused) */
+#define B200SAT_GEMM_ROWSTATS 16384  /* accumulate (sum, sumsq) of each output row into out_stats for the next fused LayerNorm */
 #define B200SAT_GEMM_SWIGLU_BWD 2048 /* D[M,2N] = SwiGLU backward of acc against saved pre-activation aux */
 
 /* D[M,N] = epilogue(A[M,K] x B[N,K]^T), bf16 in, fp32 accumulate (tcgen05 + TMA).
@@ -44,7 +46,8 @@ unsigned long long b200sat_launch_count(void);
 int b200sat_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* D, int ldd, int M, int N, int K, int flags,
                       const float* bias, const void* residual, int ldr, const float* rope_cos, const float* rope_sin,
                       int rope_seq, int rope_dmodel, int rope_dh, int n_half, int seg_in, int seg_out, int seg_off,
-                      const float* gate, void* aux, int ld_aux, int force_bn, void* stream);
+                      const float* gate, void* aux, int ld_aux, const float* ln_stats, const float* ln_colsum, float ln_eps,
+                      float* out_stats, int force_bn, void* stream);
 
 /* Flash attention forward (tcgen05; non-causal; head_dim 64; Hq % Hkv == 0 grouped-query).  q/k/v/o are bf16 views
  * [B, N, heads, 64] addressed by element strides (batch, sequence, head); lse (optional, fp32 [B,Hq,Nq]) is the natural-log
@@ -64,7 +67,8 @@ int b200sat_layernorm_fwd(const void* x, long ldx, const float* gamma, const flo
 /* y[M,N] = act(x[M,K] w[N,K]^T + bias) (+ add), 1 <= M <= 8: the conditioning MLPs whose M is the batch size.
  * Replaces models/dit.py:41-76,:140-168 (to_timestep_embed / to_global_embed) and models/transformer.py:767-773,:677-684. */
 int b200sat_small_linear(const void* x, long ldx, const void* w, long ldw, const float* bias, const void* add, long ldadd,
-                         void* y, long ldy, int M, int N, int K, int act_silu, int out_f32, int act_sigmoid_1m, void* stream);
+                         void* y, long ldy, int M, int N, int K, int act_silu, int out_f32, int act_sigmoid_1m, float* stats,
+                         long stats_stride, void* stream);
 
 /* out[B, 2*half] = [cos(2 pi t w) | sin(2 pi t w)] (bf16).  t is read at t[*step * t_stride + b] when step != NULL so a
  * captured CUDA graph can walk a per-step table.  Replaces models/blocks.py:85-94 (FourierFeatures.forward). */

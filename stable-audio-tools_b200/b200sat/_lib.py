@@ -22,12 +22,12 @@ SIGNATURES = {
     "b200sat_launch_count": (c_ull, []),
     "b200sat_gemm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_fp, c_void_p, c_int, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                  c_fp, c_void_p, c_int, c_int, c_void_p]),
+                                  c_fp, c_void_p, c_int, c_fp, c_fp, c_float, c_fp, c_int, c_void_p]),
     "b200sat_attention_fwd": (c_int, [c_void_p] * 4 + [c_fp] + [c_int] * 5 + [c_long] * 12 + [c_int, c_float, c_void_p]),
     "b200sat_layernorm_fwd": (c_int, [c_void_p, c_long, c_fp, c_fp, c_fp, c_fp, c_long, c_int, c_void_p, c_long, c_int, c_int,
                                       c_float, c_void_p]),
     "b200sat_small_linear": (c_int, [c_void_p, c_long, c_void_p, c_long, c_fp, c_void_p, c_long, c_void_p, c_long,
-                                     c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+                                     c_int, c_int, c_int, c_int, c_int, c_int, c_fp, c_long, c_void_p]),
     "b200sat_fourier_features": (c_int, [c_fp, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "b200sat_dit_pre": (c_int, [c_fp, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_fp, c_void_p, c_void_p]),
     "b200sat_dit_post": (c_int, [c_void_p, c_long, c_int, c_void_p, c_fp, c_int, c_int, c_int, c_int, c_float, c_float,

@@ -36,9 +36,12 @@ class DiTConfig:
 
 
 class DiTEngine:
-    def __init__(self, state_dict, config=None, device="cuda"):
+    def __init__(self, state_dict, config=None, device="cuda", fuse_layernorm=True):
         self.cfg = config or DiTConfig.from_state_dict(state_dict)
         self.device = torch.device(device)
+        # prepend path: LayerNorm is folded into the consumer GEMM (gamma into the weights, mean/rstd correction in the epilogue,
+        # row statistics produced by the previous residual GEMM's epilogue) — no LayerNorm pass over HBM at all
+        self.fuse_ln = bool(fuse_layernorm) and self.cfg.global_cond_type == "prepend"
         self.w = {}
         self.load_state_dict(state_dict)
         self._ws = {}
@@ -68,6 +71,16 @@ class DiTEngine:
         kvs = [w[f"transformer.layers.{i}.cross_attn.to_kv.weight"] for i in range(self.cfg.depth) if f"transformer.layers.{i}.cross_attn.to_kv.weight" in w]
         if len(kvs) == self.cfg.depth and self.cfg.depth > 0:
             w["_all_to_kv.weight"] = torch.cat(kvs, dim=0).contiguous()
+        self.ln_fold = {}
+        if getattr(self, "fuse_ln", False):
+            for i in range(self.cfg.depth):
+                p = f"transformer.layers.{i}."
+                for norm, lin in (("pre_norm", "self_attn.to_qkv"), ("cross_attend_norm", "cross_attn.to_q"), ("ff_norm", "ff.ff.0.proj")):
+                    if (p + lin + ".weight") not in w or (p + norm + ".gamma") not in w:
+                        self.fuse_ln = False
+                        break
+                    wf = (w[p + lin + ".weight"].float() * w[p + norm + ".gamma"][None, :]).to(torch.bfloat16).contiguous()
+                    self.ln_fold[p + lin] = (wf, wf.float().sum(dim=1).contiguous())
         self.w = w
 
     def rope_tables(self, seq):
@@ -101,6 +114,8 @@ class DiTEngine:
                       kv=bf(Bx * L, 2 * c.cond_embed_dim), kv_all=bf(Bx * L, c.depth * 2 * c.cond_embed_dim))
         if c.global_cond_type == "adaLN":
             ws.update(g1=bf(Bx, d), g6=bf(Bx, 6 * d))
+        if self.fuse_ln:
+            ws["stats"] = torch.zeros(3 * c.depth + 1, M, 2, device=dev, dtype=torch.float32)
         self._ws[key] = ws
         return ws
 
@@ -127,15 +142,20 @@ class DiTEngine:
                              t_stride=Bx if step is not None else 0)
         self._lin_small(ws["ff_feat"], w["to_timestep_embed.0.weight"], w["to_timestep_embed.0.bias"], ws["te1"], silu=True)
         gdst = h.view(Bx, N, d)[:, 0, :] if P else ws["gl"]
+        fuse = self.fuse_ln and P == 1 and Bx <= 8
+        st = ws["stats"] if fuse else None
+        if fuse:
+            st.zero_()
+        st0 = dict(stats=st[0], stats_stride=2 * N) if fuse else {}
         if global_in is not None:
             self._lin_small(global_in, w["to_global_embed.0.weight"], None, ws["ge1"], silu=True)
             self._lin_small(ws["ge1"], w["to_global_embed.2.weight"], None, ws["ge"])
-            self._lin_small(ws["te1"], w["to_timestep_embed.2.weight"], w["to_timestep_embed.2.bias"], gdst, add=ws["ge"])
+            self._lin_small(ws["te1"], w["to_timestep_embed.2.weight"], w["to_timestep_embed.2.bias"], gdst, add=ws["ge"], **st0)
         else:
-            self._lin_small(ws["te1"], w["to_timestep_embed.2.weight"], w["to_timestep_embed.2.bias"], gdst)
+            self._lin_small(ws["te1"], w["to_timestep_embed.2.weight"], w["to_timestep_embed.2.bias"], gdst, **st0)
         # --- input stage (dit.py:193-195, transformer.py:811-819)
         ops.dit_pre(x, w["preprocess_conv.weight"], ws["xin"], reps=reps, cin_table=cin_table, step=step)
-        ops.linear(ws["xin"], w["transformer.project_in.weight"], out=h, row_remap=(T, N, P))
+        ops.linear(ws["xin"], w["transformer.project_in.weight"], out=h, row_remap=(T, N, P), out_stats=st[0] if fuse else None)
         cos, sin = self.rope_tables(N)
         # --- adaLN modulation tables (transformer.py:836-837, :677)
         mods = None
@@ -156,6 +176,27 @@ class DiTEngine:
                 m6, gt = mods[i]
                 sc_s, sh_s, g_s = m6[:, 0:d], m6[:, d:2 * d], gt[:, 2 * d:3 * d].contiguous()
                 sc_f, sh_f, g_f = m6[:, 3 * d:4 * d], m6[:, 4 * d:5 * d], gt[:, 5 * d:6 * d].contiguous()
+            if fuse:
+                # LayerNorm-free block: raw residual stream in, statistics travel through the GEMM epilogues
+                wq, cq = self.ln_fold[p + "self_attn.to_qkv"]
+                ops.linear(h, wq, out=ws["qkv"], rope=rope, ln=(st[3 * i], cq, 1e-5))
+                qkv = ws["qkv"].view(Bx, N, 3, H, 64)
+                ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], out=ws["a"].view(Bx, N, H, 64))
+                ops.linear(ws["a"], w[p + "self_attn.to_out.weight"], residual=h, out=h, out_stats=st[3 * i + 1])
+                if ctx is not None and (p + "cross_attn.to_q.weight") in w:
+                    wq2, cq2 = self.ln_fold[p + "cross_attn.to_q"]
+                    ops.linear(h, wq2, out=ws["q"], ln=(st[3 * i + 1], cq2, 1e-5))
+                    kvh = c.cond_embed_dim // 64
+                    kv = ws["kv_all"].view(Bx, L, c.depth, 2, kvh, 64)[:, :, i]
+                    ops.attention(ws["q"].view(Bx, N, H, 64), kv[:, :, 0], kv[:, :, 1], out=ws["a"].view(Bx, N, H, 64))
+                    ops.linear(ws["a"], w[p + "cross_attn.to_out.weight"], residual=h, out=h, out_stats=st[3 * i + 2])
+                    ff_stats = st[3 * i + 2]
+                else:
+                    ff_stats = st[3 * i + 1]
+                wf, cf = self.ln_fold[p + "ff.ff.0.proj"]
+                ops.linear(h, wf, bias=w[p + "ff.ff.0.proj.bias"], swiglu=True, out=ws["ff"], ln=(ff_stats, cf, 1e-5))
+                ops.linear(ws["ff"], w[p + "ff.ff.2.weight"], bias=w[p + "ff.ff.2.bias"], residual=h, out=h, out_stats=st[3 * i + 3])
+                continue
             # self-attention (transformer.py:704 / :678-686)
             ops.layernorm(h, w[p + "pre_norm.gamma"], scale=sc_s, shift=sh_s, rows_per_batch=N, out=ws["n"])
             ops.linear(ws["n"], w[p + "self_attn.to_qkv.weight"], out=ws["qkv"], rope=rope)
@@ -186,9 +227,9 @@ class DiTEngine:
                      scale_phi=scale_phi)
         return out
 
-    def _lin_small(self, x, wt, bias, out, silu=False, add=None):
+    def _lin_small(self, x, wt, bias, out, silu=False, add=None, stats=None, stats_stride=0):
         if x.shape[0] <= 8:
-            ops.small_linear(x, wt, bias=bias, add=add, out=out, silu=silu)
+            ops.small_linear(x, wt, bias=bias, add=add, out=out, silu=silu, stats=stats, stats_stride=stats_stride)
         else:
             if out.stride(0) != out.shape[1] or add is not None and silu:
                 raise NotImplementedError("conditioning MLP with batch > 8 into a strided destination")

@@ -4,7 +4,7 @@ import torch
 from ._lib import lib, check
 
 GEMM_BIAS, GEMM_RESIDUAL, GEMM_SILU, GEMM_SWIGLU, GEMM_ROPE, GEMM_OUT_F32, GEMM_ROW_REMAP, GEMM_GATE = 1, 2, 4, 8, 16, 32, 64, 128
-GEMM_A_MN, GEMM_B_MN, GEMM_ACCUM, GEMM_SWIGLU_BWD = 256, 512, 1024, 2048
+GEMM_A_MN, GEMM_B_MN, GEMM_ACCUM, GEMM_SWIGLU_BWD, GEMM_LN_A, GEMM_ROWSTATS = 256, 512, 1024, 2048, 8192, 16384
 
 
 LAUNCHES = [0]  # kernel launches issued through this module (bench.py's gpu_launches claim)
@@ -26,7 +26,7 @@ def _chk_bf16(t, name):
 
 
 def linear(x, w, bias=None, residual=None, out=None, silu=False, out_f32=False, swiglu=False, rope=None,
-           row_remap=None, gate=None, force_bn=0, save_pre=None):
+           row_remap=None, gate=None, force_bn=0, save_pre=None, ln=None, out_stats=None):
     """out = epilogue(x @ w.T).  x [M,K] bf16, w [N,K] bf16 (nn.Linear layout), bias fp32 [N].
 
     swiglu: w is the GLU projection [2*Nh, K]; out [M, Nh] = (u[:, :Nh]) * silu(u[:, Nh:]).
@@ -73,10 +73,17 @@ def linear(x, w, bias=None, residual=None, out=None, silu=False, out_f32=False, 
     if gate is not None:
         assert gate.dtype == torch.float32 and gate.is_contiguous()
         flags |= GEMM_GATE
+    ln_stats = ln_colsum = None
+    ln_eps = 0.0
+    if ln is not None:      # (row stats [M,2] fp32, colsum [N] fp32, eps): LayerNorm folded into this GEMM
+        ln_stats, ln_colsum, ln_eps = ln
+        flags |= GEMM_LN_A
+    if out_stats is not None:
+        flags |= GEMM_ROWSTATS
     rc = lib().b200sat_gemm_bf16(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0),
                                  M, N, K, flags, _p(bias), _p(residual), ldr, _p(rc_), _p(rs_), rseq, rdm, rdh, n_half,
                                  seg_in, seg_out, seg_off, _p(gate), _p(save_pre), save_pre.stride(0) if save_pre is not None else 0,
-                                 force_bn, _stream())
+                                 _p(ln_stats), _p(ln_colsum), float(ln_eps), _p(out_stats), force_bn, _stream())
     LAUNCHES[0] += 1
     check(rc, "gemm_bf16")
     return out
@@ -98,7 +105,7 @@ def gemm(a, b, out, M, N, K, a_mn=False, b_mn=False, accumulate=False, swiglu_bw
     rc = lib().b200sat_gemm_bf16(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(), out.stride(0), M, N, K, flags,
                                  0, _p(residual), residual.stride(0) if residual is not None else 0, 0, 0, 0, 0, 0, n_half, 0, 0, 0, 0,
                                  _p(swiglu_bwd_aux),
-                                 swiglu_bwd_aux.stride(0) if swiglu_bwd_aux is not None else 0, force_bn, _stream())
+                                 swiglu_bwd_aux.stride(0) if swiglu_bwd_aux is not None else 0, 0, 0, 0.0, 0, force_bn, _stream())
     LAUNCHES[0] += 1
     check(rc, "gemm_bf16")
     return out
@@ -139,7 +146,7 @@ def layernorm(x, gamma, beta=None, scale=None, shift=None, rows_per_batch=0, out
     return out
 
 
-def small_linear(x, w, bias=None, add=None, out=None, silu=False, out_f32=False, sigmoid_1m=False):
+def small_linear(x, w, bias=None, add=None, out=None, silu=False, out_f32=False, sigmoid_1m=False, stats=None, stats_stride=0):
     _chk_bf16(x, "x"); _chk_bf16(w, "w")
     M, K = x.shape
     N = w.shape[0]
@@ -147,7 +154,7 @@ def small_linear(x, w, bias=None, add=None, out=None, silu=False, out_f32=False,
         out = torch.empty((M, N), device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
     rc = lib().b200sat_small_linear(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _p(bias), _p(add),
                                     add.stride(0) if add is not None else 0, out.data_ptr(), out.stride(0), M, N, K,
-                                    int(silu), int(out_f32), int(sigmoid_1m), _stream())
+                                    int(silu), int(out_f32), int(sigmoid_1m), _p(stats), stats_stride, _stream())
     LAUNCHES[0] += 1
     check(rc, "small_linear")
     return out

@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const __nv_bfloat16* 
                                                            const __nv_bfloat16* __restrict__ w, long ldw,
                                                            const float* __restrict__ bias, const __nv_bfloat16* __restrict__ add,
                                                            long ldadd, void* __restrict__ y, long ldy, int M, int N, int K,
-                                                           int act_silu, int out_f32, int act_sigmoid_1m) {
+                                                           int act_silu, int out_f32, int act_sigmoid_1m, float* __restrict__ stats,
+                                                           long stats_stride) {
   griddep_launch();
   griddep_wait();
   const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -127,6 +128,11 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const __nv_bfloat16* 
       if (act_sigmoid_1m) t = 1.0f / (1.0f + __expf(-(bf16_round(1.0f - t))));  // sigmoid(1 - g), transformer.py:684
       if (out_f32) reinterpret_cast<float*>(y)[m * ldy + n] = t;
       else reinterpret_cast<__nv_bfloat16*>(y)[m * ldy + n] = __float2bfloat16_rn(t);
+      if (stats) {  // (sum, sum of squares) of the bf16 output row, for a LayerNorm folded into the consumer GEMM
+        const float r_ = bf16_round(t);
+        atomicAdd(stats + m * stats_stride, r_);
+        atomicAdd(stats + m * stats_stride + 1, r_ * r_);
+      }
     }
   }
 }
@@ -331,12 +337,12 @@ extern "C" int b200sat_layernorm_fwd(const void* x, long ldx, const float* gamma
 
 extern "C" int b200sat_small_linear(const void* x, long ldx, const void* w, long ldw, const float* bias, const void* add,
                                     long ldadd, void* y, long ldy, int M, int N, int K, int act_silu, int out_f32,
-                                    int act_sigmoid_1m, void* stream) {
+                                    int act_sigmoid_1m, float* stats, long stats_stride, void* stream) {
   if (!x || !w || !y || M <= 0 || M > 8 || N <= 0 || K <= 0) { set_last_error("small_linear: bad arguments (1 <= M <= 8)"); return B200SAT_EINVAL; }
   if (K % 8 || ldx % 8 || ldw % 8) { set_last_error("small_linear: K, ldx, ldw must be multiples of 8"); return B200SAT_EINVAL; }
   B200SAT_CHECK_CUDA(launch_k(small_linear_kernel, dim3((N + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, 
       static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(w), ldw, bias,
-      static_cast<const __nv_bfloat16*>(add), ldadd, y, ldy, M, N, K, act_silu, out_f32, act_sigmoid_1m));
+      static_cast<const __nv_bfloat16*>(add), ldadd, y, ldy, M, N, K, act_silu, out_f32, act_sigmoid_1m, stats, stats_stride));
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }

@@ -33,7 +33,9 @@ enum GemmFlags : int {
   GEMM_B_MN = 512,      // B is stored [K, N] (N contiguous): data-gradient GEMM through an nn.Linear weight [N_out=K, N]
   GEMM_ACCUM = 1024,    // fp32 output accumulates: D += acc (gradient accumulation into .grad)
   GEMM_SWIGLU_BWD = 2048,  // D[M, 2*N]: [dact*silu(g) | dact*a*silu'(g)] with (a|g) read from aux [M, 2*N] (n_half = N)
-  GEMM_ATOMIC = 4096,      // fp32 D += acc with red.global.add (split-K weight gradients: several CTAs own one output tile)
+  GEMM_ATOMIC = 4096,
+  GEMM_LN_A = 8192,        // A is the RAW LayerNorm input and B has gamma folded in: out = rstd_m*(acc - mean_m*colsum_n) (+bias ...)
+  GEMM_ROWSTATS = 16384,   // also accumulate per-row (sum, sum of squares) of the bf16 output into out_stats (next LayerNorm)      // fp32 D += acc with red.global.add (split-K weight gradients: several CTAs own one output tile)
 };
 
 struct GemmParams {
@@ -45,6 +47,10 @@ struct GemmParams {
   const float* rope_cos;  // [rope_seq, 16]
   const float* rope_sin;
   const float* gate;      // [B, N] fp32 (adaLN)
+  const float* ln_stats;   // [M, 2] (sum x, sum x^2) over the K features of each A row
+  const float* ln_colsum;  // [N] (SwiGLU: [n_half + N]) sum_k B[n, k] of the gamma-folded weight
+  float* out_stats;        // [rows, 2]
+  float ln_eps;
   __nv_bfloat16* aux;     // SwiGLU fwd: optional copy of the pre-activation u [M, 2*n_half]; SwiGLU bwd: the saved u
   int ld_aux;
   int M, N, K;
@@ -271,6 +277,12 @@ __global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constan
       if (p.flags & GEMM_ROW_REMAP) out_row = (row / p.seg_in) * p.seg_out + p.seg_off + (row % p.seg_in);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::kAccStride;
       const int n0 = n_blk * out_bn;
+      float ln_mean = 0.f, ln_rstd = 1.f, st1 = 0.f, st2 = 0.f;
+      if ((p.flags & GEMM_LN_A) && row_ok) {
+        const float2 st = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + row);
+        ln_mean = st.x / p.K;
+        ln_rstd = rsqrtf(fmaxf(st.y / p.K - ln_mean * ln_mean, 0.f) + p.ln_eps);
+      }
       for (int cc = 0; cc < chunks_per_warp; ++cc) {
         const int c = half * chunks_per_warp + cc;
         const int col = n0 + c * 32;
@@ -295,6 +307,18 @@ __global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constan
           for (int i = 0; i < 32; ++i) bv[i] = 0.f;
         }
         tmem_ld_wait();
+        if (p.flags & GEMM_LN_A) {
+          // LayerNorm folded into the GEMM: acc = x_raw . (gamma o W)^T  =>  LN(x).W^T = rstd*(acc - mean*colsum)
+          const float4* cp = reinterpret_cast<const float4*>(p.ln_colsum + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 c4 = full ? __ldg(cp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            raw[4 * i + 0] = __float_as_uint(ln_rstd * (__uint_as_float(raw[4 * i + 0]) - ln_mean * c4.x));
+            raw[4 * i + 1] = __float_as_uint(ln_rstd * (__uint_as_float(raw[4 * i + 1]) - ln_mean * c4.y));
+            raw[4 * i + 2] = __float_as_uint(ln_rstd * (__uint_as_float(raw[4 * i + 2]) - ln_mean * c4.z));
+            raw[4 * i + 3] = __float_as_uint(ln_rstd * (__uint_as_float(raw[4 * i + 3]) - ln_mean * c4.w));
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) + bv[i];
         if (swiglu) {
@@ -306,6 +330,17 @@ __global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constan
             for (int i = 0; i < 8; ++i) { const float4 t = __ldg(bp + i); bv[4 * i] = t.x; bv[4 * i + 1] = t.y; bv[4 * i + 2] = t.z; bv[4 * i + 3] = t.w; }
           }
           tmem_ld_wait();
+          if (p.flags & GEMM_LN_A) {
+            const float4* cp = reinterpret_cast<const float4*>(p.ln_colsum + p.n_half + col);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 c4 = __ldg(cp + i);
+              raw[4 * i + 0] = __float_as_uint(ln_rstd * (__uint_as_float(raw[4 * i + 0]) - ln_mean * c4.x));
+              raw[4 * i + 1] = __float_as_uint(ln_rstd * (__uint_as_float(raw[4 * i + 1]) - ln_mean * c4.y));
+              raw[4 * i + 2] = __float_as_uint(ln_rstd * (__uint_as_float(raw[4 * i + 2]) - ln_mean * c4.z));
+              raw[4 * i + 3] = __float_as_uint(ln_rstd * (__uint_as_float(raw[4 * i + 3]) - ln_mean * c4.w));
+            }
+          }
           float gv[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) gv[i] = __uint_as_float(raw[i]) + bv[i];
@@ -398,6 +433,10 @@ __global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constan
               for (int i = 0; i < 32; ++i) if (i < ncols) v[i] = bf16_round(v[i]) + __bfloat162float(r[i]);
             }
           }
+          if (p.flags & GEMM_ROWSTATS) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (i < ncols) { const float r_ = bf16_round(v[i]); st1 += r_; st2 += r_ * r_; }
+          }
           if (p.flags & GEMM_OUT_F32) {
             float* dp = reinterpret_cast<float*>(p.D) + static_cast<size_t>(out_row) * p.ldd + col;
             if (p.flags & GEMM_ATOMIC) {
@@ -420,6 +459,10 @@ __global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constan
             store_chunk_bf16(reinterpret_cast<__nv_bfloat16*>(p.D) + static_cast<size_t>(out_row) * p.ldd + col, v, ncols);
           }
         }
+      }
+      if ((p.flags & GEMM_ROWSTATS) && row_ok) {
+        atomicAdd(p.out_stats + 2 * static_cast<size_t>(out_row), st1);
+        atomicAdd(p.out_stats + 2 * static_cast<size_t>(out_row) + 1, st2);
       }
       tc_fence_before();
       if (CTAS == 2 && cta_rank != 0) mbar_arrive_remote(&tmem_empty[as], 0);
@@ -499,11 +542,13 @@ using namespace b200sat;
 extern "C" int b200sat_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* D, int ldd, int M, int N, int K,
                                  int flags, const float* bias, const void* residual, int ldr, const float* rope_cos,
                                  const float* rope_sin, int rope_seq, int rope_dmodel, int rope_dh, int n_half, int seg_in,
-                                 int seg_out, int seg_off, const float* gate, void* aux, int ld_aux, int force_bn,
-                                 void* stream) {
+                                 int seg_out, int seg_off, const float* gate, void* aux, int ld_aux, const float* ln_stats,
+                                 const float* ln_colsum, float ln_eps, float* out_stats, int force_bn, void* stream) {
   if (!A || !B || !D || M <= 0 || N <= 0 || K <= 0) { set_last_error("gemm: null pointer or empty shape"); return B200SAT_EINVAL; }
   if ((lda % 8) || (ldb % 8)) { set_last_error("gemm: lda/ldb must be multiples of 8 (16-byte TMA strides)"); return B200SAT_EINVAL; }
   if ((K % 8) && !(flags & (GEMM_A_MN | GEMM_B_MN))) { set_last_error("gemm: K must be a multiple of 8"); return B200SAT_EINVAL; }
+  if ((flags & GEMM_LN_A) && (!ln_stats || !ln_colsum || (N % 32))) { set_last_error("gemm: LN_A needs row statistics, column sums and N % 32 == 0"); return B200SAT_EINVAL; }
+  if ((flags & GEMM_ROWSTATS) && !out_stats) { set_last_error("gemm: ROWSTATS needs out_stats"); return B200SAT_EINVAL; }
   if ((flags & GEMM_SWIGLU_BWD) && (!aux || n_half != N || (N % 32))) { set_last_error("gemm: swiglu_bwd needs aux and n_half == N"); return B200SAT_EINVAL; }
   if ((flags & (GEMM_A_MN | GEMM_B_MN)) && (flags & GEMM_SWIGLU)) { set_last_error("gemm: swiglu with MN-major operands"); return B200SAT_EUNSUPPORTED; }
   if ((ldd % 8) || ((flags & GEMM_RESIDUAL) && (ldr % 8))) { set_last_error("gemm: ldd/ldr must be multiples of 8"); return B200SAT_EINVAL; }
@@ -552,6 +597,7 @@ extern "C" int b200sat_gemm_bf16(const void* A, int lda, const void* B, int ldb,
   p.D = D; p.bias = bias; p.residual = static_cast<const __nv_bfloat16*>(residual);
   p.rope_cos = rope_cos; p.rope_sin = rope_sin; p.gate = gate;
   p.aux = static_cast<__nv_bfloat16*>(aux); p.ld_aux = ld_aux;
+  p.ln_stats = ln_stats; p.ln_colsum = ln_colsum; p.ln_eps = ln_eps; p.out_stats = out_stats;
   p.M = M; p.N = N; p.K = K; p.ldd = ldd; p.ldr = ldr; p.flags = flags;
   p.seg_in = seg_in > 0 ? seg_in : 1; p.seg_out = seg_out; p.seg_off = seg_off;
   p.rope_seq = rope_seq > 0 ? rope_seq : 1; p.rope_dmodel = rope_dmodel > 0 ? rope_dmodel : 1; p.rope_dh = rope_dh > 0 ? rope_dh : 64;

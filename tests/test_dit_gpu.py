@@ -13,7 +13,7 @@ def _rel(a, b):
     return ((a - b).norm() / b.norm()).item()
 
 
-def _case(embed_dim, depth, heads, cond_dim, T, L, B, gct, cfg_scale, scale_phi, seed=0):
+def _case(embed_dim, depth, heads, cond_dim, T, L, B, gct, cfg_scale, scale_phi, seed=0, fuse_ln=True):
     from oracle import dit as odit
     from b200sat.dit_engine import DiTEngine
     sd = odit.make_state_dict(embed_dim=embed_dim, depth=depth, num_heads=heads, io_channels=64, cond_token_dim=cond_dim,
@@ -28,7 +28,7 @@ def _case(embed_dim, depth, heads, cond_dim, T, L, B, gct, cfg_scale, scale_phi,
         ref32 = odit.dit_forward(x, t, sd, depth, c, ge, cfg_scale=cfg_scale, scale_phi=scale_phi, global_cond_type=gct)
         sd16 = {k: v.bfloat16() for k, v in sd.items()}
         ref16 = odit.dit_forward(x, t, sd16, depth, c, ge, cfg_scale=cfg_scale, scale_phi=scale_phi, global_cond_type=gct).float()
-    eng = DiTEngine(sd)
+    eng = DiTEngine(sd, fuse_layernorm=fuse_ln)
     out = eng.forward(x.cuda(), t.cuda(), c.cuda(), ge.cuda(), cfg_scale=cfg_scale, scale_phi=scale_phi)
     torch.cuda.synchronize()
     out = out.cpu()
@@ -42,6 +42,11 @@ def _case(embed_dim, depth, heads, cond_dim, T, L, B, gct, cfg_scale, scale_phi,
 @pytest.mark.parametrize("cfg_scale,scale_phi", [(1.0, 0.0), (6.0, 0.75)])
 def test_dit_small(gct, cfg_scale, scale_phi):
     _case(embed_dim=256, depth=3, heads=4, cond_dim=128, T=200, L=17, B=2, gct=gct, cfg_scale=cfg_scale, scale_phi=scale_phi)
+
+
+def test_dit_small_unfused_layernorm_path():
+    """The explicit LayerNorm kernel path (what adaLN and training use) on the prepend model."""
+    _case(embed_dim=256, depth=3, heads=4, cond_dim=128, T=200, L=17, B=2, gct="prepend", cfg_scale=6.0, scale_phi=0.75, fuse_ln=False)
 
 
 def test_dit_sao_width_4_layers():
