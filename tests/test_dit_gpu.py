@@ -68,12 +68,16 @@ def test_dit_sampler_graph_matches_eager_and_oracle():
     noise = torch.randn(B, 64, T, generator=g)
     nseq = torch.randn(steps, B, 64, T, generator=g)
     c = torch.randn(B, L, 128, generator=g); ge = torch.randn(B, d, generator=g)
-    eng = DiTEngine(sd)
+    # bitwise graph == eager on the deterministic (explicit LayerNorm) path; the LN-fused path sums row statistics with fp32
+    # atomics (order-dependent in the last bit), so it is compared with a tolerance instead
+    eng = DiTEngine(sd, fuse_layernorm=False)
     outs = []
     for use_graph in (True, False):
         outs.append(bs.sample_k_dpmpp_3m_sde(eng, noise, steps=steps, cross_attn_cond=c, global_embed=ge, cfg_scale=6.0,
                                              step_noise=nseq, use_graph=use_graph).cpu())
     assert torch.equal(outs[0], outs[1])
+    fused = bs.sample_k_dpmpp_3m_sde(DiTEngine(sd), noise, steps=steps, cross_attn_cond=c, global_embed=ge, cfg_scale=6.0, step_noise=nseq).cpu()
+    assert _rel(fused, outs[0]) <= 2e-2
     model_fn = lambda x, t, **kw: odit.dit_forward(x, t, sd, depth, c, ge, cfg_scale=6.0)
     with torch.no_grad():
         ref = osamp.sample_k_dpmpp_3m_sde(model_fn, noise, steps=steps, noise_seq=nseq)
