@@ -200,6 +200,35 @@ def measure_train(args, dev, rank, world, dist):
            "steps": k, "batch_per_gpu": B, "seq_len": T_LAT, "loss": float(h_loss.item()), "optimizer": "AdamW(fused) fp32 masters",
            "pre_encoded": True, "includes": "H2D of latents+conditioning, fwd, bwd, layer-bucketed all-reduce, optimizer step, D2H loss",
            "tflops_per_gpu": flop / (ms_step * 1e-3) / 1e12, "frac_of_sustained_peak": flop / (ms_step * 1e-3) / 1e12 / pk["bf16_sustained"]}
+    # same step with the frozen Oobleck encoder inside it (pre_encoded = False, training/diffusion.py:364-375): 8 x 47 s stereo
+    # clips encoded one at a time (iterate_batch) in bf16, then the DiT step on the fresh latents
+    try:
+        from b200sat.autoencoder import OobleckEngine
+        ae = OobleckEngine(_oobleck_state_dict(dev, torch.Generator(device=dev).manual_seed(3)), precision="bf16", device=dev)
+        audio = (torch.randn(B, 2, T_LAT * 2048, device=dev, generator=gd).clamp(-1, 1) * 0.5)
+
+        def step_enc():
+            lat = ae.encode_audio(audio, noise=None, iterate_batch=True)
+            cross = h_cross.to(dev, non_blocking=True); glob = h_glob.to(dev, non_blocking=True)
+            noise = torch.randn(lat.shape, device=dev, generator=gd)
+            t = torch.rand(B, device=dev, generator=gd)
+            model.zero_grad()
+            loss = v_objective_loss(model, lat, noise, t, cross, glob, cfg_dropout_prob=0.1)
+            (loss * red.loss_scale).backward()
+            red.finish()
+            opt.step()
+
+        step_enc(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            step_enc()
+        e1.record(); torch.cuda.synchronize()
+        ms_enc = e0.elapsed_time(e1) / 3
+        out["with_frozen_encoder"] = {"ms_per_step": ms_enc, "value": tokens / world / (ms_enc * 1e-3) * world, "unit": "latent-tokens/s",
+                                      "note": "per-rank time (not max-reduced); encoder = 8 x 5.16 TFLOP forward, bf16 single-pass convs"}
+        del ae, audio
+    except Exception as ex:  # keep the headline numbers if the secondary measurement fails
+        out["with_frozen_encoder"] = {"error": repr(ex)[:200]}
     del model, opt
     torch.cuda.empty_cache()
     return out

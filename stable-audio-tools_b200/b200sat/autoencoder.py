@@ -232,3 +232,41 @@ class OobleckEngine:
         ops.LAUNCHES[0] += 1
         check(rc, "conv_out")
         return y
+
+
+    # ------------------------------------------------------------------ orchestration of AudioAutoencoder (autoencoders.py:446-534, 601-732)
+    @torch.no_grad()
+    def encode_audio(self, audio, noise=None, iterate_batch=False):
+        """`AudioAutoencoder.encode` + VAE bottleneck: optionally one item at a time (`iterate_batch`, autoencoders.py:470-474),
+        which bounds the live activation set to one clip (1 GB planes per tensor for a 47 s clip)."""
+        if not iterate_batch or audio.shape[0] == 1:
+            return self.encode(audio, noise=noise)
+        outs = []
+        for i in range(audio.shape[0]):
+            outs.append(self.encode(audio[i:i + 1], noise=None if noise is None else noise[i:i + 1]))
+        return torch.cat(outs, dim=0)
+
+    @torch.no_grad()
+    def decode_audio(self, latents, chunked=False, overlap=32, chunk_size=128):
+        """`AudioAutoencoder.decode_audio` (autoencoders.py:671-732): full decode, or overlap-discard chunked decode for long
+        latents: chunks of `chunk_size` latents hopping by chunk_size - overlap; each chunk contributes its interior (half an
+        overlap trimmed at every internal edge) so the zero-padded conv edges never reach the output."""
+        if not chunked or latents.shape[-1] <= chunk_size:
+            return self.decode(latents)
+        ratio = 1
+        for s_ in self.strides:
+            ratio *= s_
+        B, L, total = latents.shape
+        hop = chunk_size - overlap
+        starts = list(range(0, total - chunk_size + 1, hop))
+        if starts[-1] != total - chunk_size:
+            starts.append(total - chunk_size)
+        out = None
+        for ci, st in enumerate(starts):
+            y = self.decode(latents[:, :, st:st + chunk_size])
+            if out is None:
+                out = torch.zeros(B, y.shape[1], total * ratio, device=y.device, dtype=y.dtype)
+            lo = 0 if ci == 0 else (overlap // 2) * ratio
+            hi = chunk_size * ratio if ci == len(starts) - 1 else (chunk_size - overlap // 2) * ratio
+            out[:, :, st * ratio + lo: st * ratio + hi] = y[:, :, lo:hi]
+        return out
