@@ -167,6 +167,17 @@ int b200sat_stft_prefilter(const float* x, float* out, const float* mix, const f
 int b200sat_stft_loss_accumulate(const float* xf, const float* yf, double* acc, const float* window, const float* twiddle, int rows,
                                  int T, int n_fft, int hop, float eps, void* stream);
 
+/* Backward of b200sat_stft_loss_accumulate for one resolution: recomputes each frame's transform, forms the magnitude gradients from
+ * the per-row coefficients coef[row] = {a1, a2, a3} (a1 = c_sc/sqrt(S1 S2), a2 = c_sc sqrt(S1)/S2^1.5, a3 = c_log), runs ONE
+ * inverse-direction complex FFT per frame for both signals and scatter-adds d loss / d xf, d yf (fp32 [rows,T], accumulated).
+ * Backward of auraloss.py:368-449. */
+int b200sat_stft_loss_backward(const float* xf, const float* yf, float* dxf, float* dyf, const float* coef, const float* window,
+                               const float* twiddle, int rows, int T, int n_fft, int hop, float eps, void* stream);
+
+/* Backward of b200sat_stft_prefilter: dx[B,C,T] = mix^T . FIR^T(dout[B,R,T]). */
+int b200sat_stft_prefilter_backward(const float* dout, float* dx, const float* mix, const float* taps, int B, int C, int T, int R,
+                                    int ntaps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

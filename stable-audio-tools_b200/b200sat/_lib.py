@@ -47,6 +47,8 @@ SIGNATURES = {
     "b200sat_colsum": (c_int, [c_void_p, c_long, c_fp, c_int, c_int, c_void_p]),
     "b200sat_stft_prefilter": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200sat_stft_loss_accumulate": (c_int, [c_fp, c_fp, c_void_p, c_fp, c_fp, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "b200sat_stft_loss_backward": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "b200sat_stft_prefilter_backward": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200sat_vae_sample": (c_int, [c_void_p, c_void_p, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_void_p]),
 }
 

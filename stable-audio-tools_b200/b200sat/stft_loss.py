@@ -3,7 +3,8 @@ auraloss (`MultiResolutionSTFTLoss`, `SumAndDifferenceSTFTLoss`; training/losses
 the shipped configs use: hann window, win_length == fft_size, w_sc = w_log_mag = 1, w_lin_mag = w_phs = 0, optional
 A-weighting (`perceptual_weighting=True`), reduction 'mean', output 'loss'.
 
-Round-1 status: forward (loss value) only; the backward (gradient w.r.t. the decoded audio) is the next kernel.
+Forward and backward (gradients w.r.t. both arguments) run on the fused kernels; nothing but the waveforms, their filtered copies
+and 3 sums per (row, resolution) ever exists in HBM.
 """
 import math
 import numpy as np
@@ -52,23 +53,21 @@ class _STFTLossBase:
             self._dev[key] = (self.taps.to(device).contiguous(), tabs)
         return self._dev[key]
 
-    def _accumulate(self, x, y, mix):
-        """x, y fp32 [B, C, T]; mix [R, C].  Returns acc [n_res, B*R, 3] (float64) and the per-resolution bin counts."""
-        if x.shape != y.shape or x.dim() != 3:
-            raise ValueError("input and target must be [B, channels, T] with identical shapes")
-        if x.requires_grad or y.requires_grad:
-            raise NotImplementedError("b200sat STFT loss: backward not implemented yet (forward value only)")
-        dev = x.device
+    def _prefilter(self, x, mixd, taps):
         B, C, T = x.shape
-        R = mix.shape[0]
-        taps, tabs = self._tables(dev)
+        R = mixd.shape[0]
+        out = torch.empty(B, R, T, device=x.device)
+        check(lib().b200sat_stft_prefilter(x.data_ptr(), out.data_ptr(), mixd.data_ptr(), taps.data_ptr(), B, C, T, R, taps.numel(),
+                                           torch.cuda.current_stream().cuda_stream), "stft_prefilter")
+        ops.LAUNCHES[0] += 1
+        return out
+
+    def _accumulate_filtered(self, xf, yf):
+        """xf, yf fp32 [B, R, T] -> acc [n_res, B*R, 3] float64 and per-resolution bin counts."""
+        dev = xf.device
+        B, R, T = xf.shape
+        _, tabs = self._tables(dev)
         st = torch.cuda.current_stream().cuda_stream
-        x = x.float().contiguous(); y = y.float().contiguous()
-        mixd = mix.to(dev, torch.float32).contiguous()
-        xf = torch.empty(B, R, T, device=dev); yf = torch.empty(B, R, T, device=dev)
-        for src, dst in ((x, xf), (y, yf)):
-            check(lib().b200sat_stft_prefilter(src.data_ptr(), dst.data_ptr(), mixd.data_ptr(), taps.data_ptr(), B, C, T, R, taps.numel(), st), "stft_prefilter")
-            ops.LAUNCHES[0] += 1
         acc = torch.zeros(len(self.fft_sizes), B * R, 3, device=dev, dtype=torch.float64)
         counts = []
         for i, (n, hop) in enumerate(zip(self.fft_sizes, self.hop_sizes)):
@@ -77,22 +76,78 @@ class _STFTLossBase:
                                                      hop, self.eps, st), "stft_loss_accumulate")
             ops.LAUNCHES[0] += 1
             counts.append((n // 2 + 1) * (T // hop + 1))
-        return acc.view(len(self.fft_sizes), B, R, 3), counts
+        return acc, counts
+
+    def group_losses(self, input, target, mix, groups):
+        """Differentiable per-group losses.  mix [R, C]: rows of the mixing matrix = mono signals derived from the channels;
+        groups: list of lists of row indices r; every group is one MultiResolutionSTFTLoss evaluation over (batch x its rows)."""
+        if input.shape != target.shape or input.dim() != 3:
+            raise ValueError("input and target must be [B, channels, T] with identical shapes")
+        return _MRSTFTFn.apply(input, target, self, mix, groups)
+
+
+class _MRSTFTFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, obj, mix, groups):
+        dev = x.device
+        B, C, T = x.shape
+        R = mix.shape[0]
+        taps, tabs = obj._tables(dev)
+        mixd = mix.to(dev, torch.float32).contiguous()
+        xf = obj._prefilter(x.detach().float().contiguous(), mixd, taps)
+        yf = obj._prefilter(y.detach().float().contiguous(), mixd, taps)
+        acc, counts = obj._accumulate_filtered(xf, yf)
+        acc4 = acc.view(len(obj.fft_sizes), B, R, 3)
+        cnt = torch.tensor(counts, device=dev, dtype=torch.float64)
+        out = []
+        for rows in groups:
+            a = acc4[:, :, rows, :].reshape(len(obj.fft_sizes), B * len(rows), 3)
+            sc = torch.sqrt(a[..., 0]) / torch.sqrt(a[..., 1])          # per row ||Y-X||_F / ||Y||_F   (auraloss.py:181)
+            lm = a[..., 2].sum(dim=1) / (cnt * a.shape[1])              # mean |log X - log Y|         (auraloss.py:219-223)
+            out.append((sc.mean(dim=1) + lm).mean())                   # per resolution, then mean over resolutions (:437-443, :534)
+        ctx.obj, ctx.groups, ctx.mixd, ctx.shape = obj, groups, mixd, (B, C, T, R)
+        ctx.save_for_backward(xf, yf, acc4, cnt)
+        return torch.stack(out).float()
 
     @staticmethod
-    def _group_loss(acc_g, counts):
-        """acc_g [n_res, rows, 3] for ONE MultiResolutionSTFTLoss evaluation -> scalar (auraloss.py:437-443, :534)."""
-        sc = torch.sqrt(acc_g[..., 0]) / torch.sqrt(acc_g[..., 1])                       # per row ||Y-X||_F / ||Y||_F
-        cnt = torch.tensor(counts, device=acc_g.device, dtype=torch.float64)
-        lm = acc_g[..., 2].sum(dim=1) / (cnt * acc_g.shape[1])                           # mean |log X - log Y|
-        return (sc.mean(dim=1) + lm).mean().float()
+    def backward(ctx, g):
+        obj, groups, mixd = ctx.obj, ctx.groups, ctx.mixd
+        B, C, T, R = ctx.shape
+        xf, yf, acc4, cnt = ctx.saved_tensors
+        dev = xf.device
+        taps, tabs = obj._tables(dev)
+        n_res = len(obj.fft_sizes)
+        st = torch.cuda.current_stream().cuda_stream
+        # per-row weights: d total / d L_group, divided by (n_res * rows in the group)
+        wrow = torch.zeros(R, device=dev, dtype=torch.float64)
+        for gi, rows in enumerate(groups):
+            wrow[rows] = g[gi].double() / (n_res * B * len(rows))
+        dxf = torch.zeros_like(xf); dyf = torch.zeros_like(yf)
+        for i, (n, hop) in enumerate(zip(obj.fft_sizes, obj.hop_sizes)):
+            S1, S2 = acc4[i, :, :, 0], acc4[i, :, :, 1]                  # [B, R]
+            cs = wrow[None, :].expand(B, R)
+            coef = torch.stack([cs / torch.sqrt(S1 * S2), cs * torch.sqrt(S1) / S2.pow(1.5), cs / cnt[i]], dim=-1).float().contiguous()
+            win, tw = tabs[i]
+            check(lib().b200sat_stft_loss_backward(xf.data_ptr(), yf.data_ptr(), dxf.data_ptr(), dyf.data_ptr(), coef.data_ptr(), win.data_ptr(),
+                                                   tw.data_ptr(), B * R, T, n, hop, obj.eps, st), "stft_loss_backward")
+            ops.LAUNCHES[0] += 1
+        grads = []
+        for need, d in ((ctx.needs_input_grad[0], dxf), (ctx.needs_input_grad[1], dyf)):
+            if not need:
+                grads.append(None)
+                continue
+            dx = torch.empty(B, C, T, device=dev)
+            check(lib().b200sat_stft_prefilter_backward(d.data_ptr(), dx.data_ptr(), mixd.data_ptr(), taps.data_ptr(), B, C, T, R, taps.numel(), st),
+                  "stft_prefilter_backward")
+            ops.LAUNCHES[0] += 1
+            grads.append(dx)
+        return grads[0], grads[1], None, None, None
 
 
 class MultiResolutionSTFTLoss(_STFTLossBase):
     def __call__(self, input, target):
-        B, C, T = input.shape
-        acc, counts = self._accumulate(input, target, torch.eye(C))
-        return self._group_loss(acc.reshape(len(self.fft_sizes), B * C, 3), counts)
+        C = input.shape[1]
+        return self.group_losses(input, target, torch.eye(C), [list(range(C))])[0]
 
     forward = __call__
 
@@ -107,18 +162,15 @@ class SumAndDifferenceSTFTLoss(_STFTLossBase):
     def __call__(self, input, target):
         if input.shape[1] != 2:
             raise ValueError(f"Input must be stereo: {input.shape[1]} channel(s).")
-        acc, counts = self._accumulate(input, target, torch.tensor([[1.0, 1.0], [1.0, -1.0]]))
-        ls = self._group_loss(acc[:, :, 0], counts)
-        ld = self._group_loss(acc[:, :, 1], counts)
-        return (self.w_sum * ls + self.w_diff * ld) / 2
+        l = self.group_losses(input, target, torch.tensor([[1.0, 1.0], [1.0, -1.0]]), [[0], [1]])
+        return (self.w_sum * l[0] + self.w_diff * l[1]) / 2
 
     forward = __call__
 
 
 def autoencoder_mrstft_terms(loss_sd, decoded, reals):
     """The four STFT terms of the autoencoder generator loss in ONE pass over the waveforms (training/autoencoders.py:185-194,
-    training/losses/losses.py:107-113 argument swap: input = reals, target = decoded): returns (sum/difference, left, right)."""
-    acc, counts = loss_sd._accumulate(reals, decoded, torch.tensor([[1.0, 1.0], [1.0, -1.0], [1.0, 0.0], [0.0, 1.0]]))
-    g = loss_sd._group_loss
-    sd = (loss_sd.w_sum * g(acc[:, :, 0], counts) + loss_sd.w_diff * g(acc[:, :, 1], counts)) / 2
-    return sd, g(acc[:, :, 2], counts), g(acc[:, :, 3], counts)
+    training/losses/losses.py:107-113 argument swap: input = reals, target = decoded): returns (sum/difference, left, right),
+    differentiable w.r.t. `decoded`."""
+    l = loss_sd.group_losses(reals, decoded, torch.tensor([[1.0, 1.0], [1.0, -1.0], [1.0, 0.0], [0.0, 1.0]]), [[0], [1], [2], [3]])
+    return (loss_sd.w_sum * l[0] + loss_sd.w_diff * l[1]) / 2, l[2], l[3]

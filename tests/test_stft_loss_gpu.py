@@ -39,3 +39,36 @@ def test_mrstft_config4_shape_vs_oracle():
     sd, l, r = autoencoder_mrstft_terms(loss, dec.cuda(), reals.cuda())
     for got, ref in ((sd, ref_sd), (l, ref_l), (r, ref_r)):
         assert abs(got.item() - ref) <= 2e-5 * max(1.0, abs(ref)), (got.item(), ref)
+
+
+def test_mrstft_backward_golden_and_oracle():
+    """Gradient w.r.t. the input against the reference-generated golden (auraloss autograd), and gradients w.r.t. the decoded
+    audio of the 4-term autoencoder loss against oracle autograd."""
+    from oracle import stft_loss as ost
+    from b200sat.stft_loss import SumAndDifferenceSTFTLoss, autoencoder_mrstft_terms
+    z = np.load(os.path.join(G, "mrstft.npz"))
+    x = torch.from_numpy(z["x"]).cuda().requires_grad_(True)
+    y = torch.from_numpy(z["y"]).cuda()
+    sd = SumAndDifferenceSTFTLoss(FFT, HOP, FFT, perceptual_weighting=True, sample_rate=44100)
+    loss = sd(x, y)
+    loss.backward()
+    ref = torch.from_numpy(z["grad_sd"]).cuda()
+    rel = ((x.grad - ref).norm() / ref.norm()).item()
+    print("grad vs auraloss golden: rel", rel)
+    assert abs(loss.item() - float(z["loss_sd"])) <= 2e-5 and rel <= 2e-3
+    # gradient through the target argument (what the autoencoder training uses: input = reals, target = decoded)
+    g = torch.Generator().manual_seed(3)
+    reals = torch.randn(2, 2, 16384, generator=g) * 0.3
+    dec = (reals + 0.05 * torch.randn(2, 2, 16384, generator=g))
+    taps = ost.a_weighting_fir()
+    dref = dec.clone().requires_grad_(True)
+    tot_ref = (1.0 * ost.sum_and_difference_loss(reals, dref, FFT, HOP, taps) + 0.5 * ost.mrstft_loss(reals[:, :1], dref[:, :1], FFT, HOP, taps)
+               + 0.5 * ost.mrstft_loss(reals[:, 1:], dref[:, 1:], FFT, HOP, taps))
+    tot_ref.backward()
+    dgpu = dec.cuda().requires_grad_(True)
+    l_sd, l_l, l_r = autoencoder_mrstft_terms(sd, dgpu, reals.cuda())
+    tot = 1.0 * l_sd + 0.5 * l_l + 0.5 * l_r
+    tot.backward()
+    rel = ((dgpu.grad.cpu() - dref.grad).norm() / dref.grad.norm()).item()
+    print("4-term generator STFT loss: value", tot.item(), tot_ref.item(), "grad rel", rel)
+    assert abs(tot.item() - tot_ref.item()) <= 5e-5 and rel <= 2e-3
