@@ -178,6 +178,41 @@ int b200sat_stft_loss_backward(const float* xf, const float* yf, float* dxf, flo
 int b200sat_stft_prefilter_backward(const float* dout, float* dx, const float* mix, const float* taps, int B, int C, int T, int R,
                                     int ntaps, void* stream);
 
+/* ---- backward of the Oobleck convolutions -------------------------------------------------------------------------------- */
+
+/* One tap of a conv weight gradient: dW[Ca,Cb] (fp32, +=) = sum_{b, t < T_iter} A[b,(t+offA)*sA+rA,:]^T (x) B[b,(t+offB)*sB+rB,:],
+ * A/B = time-major bf16 planes [B,T,C] read in place (out-of-range rows = zero padding).  tcgen05 GEMM with both operands
+ * MN-major, split-K over time.  Backward (dW = dY (*) X) of models/autoencoders.py:58-83, :233-283. */
+int b200sat_conv_wgrad(const void* a_plane, int Ca, int Ta, int sA, int rA, int offA, const void* b_plane, int Cb, int Tb, int sB,
+                       int rB, int offB, float* dW, int B, int T_iter, void* stream);
+
+/* SnakeBeta backward fused with the skip-connection add and the parameter reductions (models/blocks.py:291-329 under autograd):
+ * d_raw = d_skip + d_act * (1 + invb*a*sin(2 a x)); dalpha/dbeta [C] (log-scale parameters) and dbias [C] (= column sums of d_raw, the
+ * bias gradient of the conv that produced x; optional) are accumulated with fp32 atomics.  Planes are bf16 [rows, C]. */
+int b200sat_snake_bwd(const void* d_act, const void* x_raw, const void* d_skip, const float* snake_a, const float* snake_invb, void* d_raw,
+                      float* dalpha, float* dbeta, float* dbias, long rows, int C, void* stream);
+
+/* Weight-normalised weights packed for the data-gradient convolution (run through b200sat_conv1d_fwd on the output gradient):
+ * mode 0 -> flipped taps, run as mode 0 with pad' = dil*(K-1)-pad; mode 1 (strided) -> run as mode 2; mode 2 (transposed) -> run
+ * as mode 1; channels swap roles.  inv_norm = the 1/||v|| rows b200sat_wn_pack left in its scratch.  autoencoders.py:23-27. */
+int b200sat_wn_pack_dgrad(const float* v, const float* g, const float* inv_norm, void* out, int Cout, int Cin, int K, int mode, int stride,
+                          void* stream);
+
+/* weight_norm backward: dw_taps fp32 [K][R][Cc] (filled by b200sat_conv_wgrad, one tap per launch) -> dv [R][Cc][K], dg [R]
+ * (g NULL: plain weight, dv = dw re-laid out).  torch.nn.utils.weight_norm under autograd, autoencoders.py:23-27. */
+int b200sat_wn_bwd(const float* dw_taps, const float* v, const float* g, const float* inv_norm, float* dv, float* dg, int R, int Cc, int K,
+                   void* stream);
+
+/* Weight gradient of the audio-channel edge convs: dW[c*stride_c + a*stride_a + k] += sum_{b,t} plane[b,t,c]*sig[b,a,t+sign*(k-pad)];
+ * plane bf16 [B,T,C], sig fp32 [B,A,T].  Encoder conv_in (autoencoders.py:303): sign +1; decoder conv_out (:355-357): sign -1. */
+int b200sat_edge_wgrad(const void* plane, const float* sig, float* dW, int B, int T, int C, int A, int K, int pad, int sign, long stride_c,
+                       long stride_a, void* stream);
+
+/* VAE bottleneck backward (bottleneck.py:105-113): dz bf16 plane [B,T,L] (NULL = 0), ms forward plane [B,T,2L], noise fp32 [B,L,T];
+ * the KL term contributes kl_scale * (*kl_grad) * d(sum_c(mean^2 + var - log var - 1)); d_ms bf16 plane [B,T,2L]. */
+int b200sat_vae_sample_bwd(const void* dz, const void* ms, const float* noise, const float* kl_grad, float kl_scale, void* d_ms, int B,
+                           int L, int T, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

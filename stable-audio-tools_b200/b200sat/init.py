@@ -49,3 +49,44 @@ def dit_state_dict(embed_dim=1536, depth=24, num_heads=24, io_channels=64, cond_
         if global_cond_type == "adaLN":
             sd[p + "to_scale_shift_gate"] = (torch.randn(6 * d, generator=g, device=device) / d ** 0.5).to(dtype)
     return sd
+
+
+def oobleck_state_dict(dev, g, ch=128):
+    """Random weights with the reference names/shapes of stable_audio_2_0_vae.json (autoencoders.py:285-362)."""
+    import math
+    sd = {}
+    cm, strides = [1, 1, 2, 4, 8, 16], [2, 4, 4, 8, 8]
+
+    def conv(p, cout, cin, k, bias=True, transpose=False):
+        shape = (cin, cout, k) if transpose else (cout, cin, k)
+        v = torch.randn(*shape, device=dev, generator=g) / math.sqrt(cin * k)
+        sd[p + "weight_v"] = v
+        sd[p + "weight_g"] = v.flatten(1).norm(dim=1).view(shape[0], 1, 1) * 0.7
+        if bias:
+            sd[p + "bias"] = 0.05 * torch.randn(cout, device=dev, generator=g)
+
+    def snake(p, c):
+        sd[p + "alpha"] = 0.3 * torch.randn(c, device=dev, generator=g); sd[p + "beta"] = 0.3 * torch.randn(c, device=dev, generator=g)
+
+    def ru(p, c):
+        snake(p + "layers.0.", c); conv(p + "layers.1.", c, c, 7); snake(p + "layers.2.", c); conv(p + "layers.3.", c, c, 1)
+
+    n = len(strides)
+    p = "encoder.layers."
+    conv(p + "0.", cm[0] * ch, 2, 7)
+    for i in range(n):
+        ci, co = cm[i] * ch, cm[i + 1] * ch
+        for j in range(3):
+            ru(f"{p}{i + 1}.layers.{j}.", ci)
+        snake(f"{p}{i + 1}.layers.3.", ci); conv(f"{p}{i + 1}.layers.4.", co, ci, 2 * strides[i])
+    snake(f"{p}{n + 1}.", cm[-1] * ch); conv(f"{p}{n + 2}.", 128, cm[-1] * ch, 3)
+    p = "decoder.layers."
+    conv(p + "0.", cm[-1] * ch, 64, 7)
+    for idx, i in enumerate(range(n, 0, -1)):
+        ci, co = cm[i] * ch, cm[i - 1] * ch
+        q = f"{p}{idx + 1}."
+        snake(q + "layers.0.", ci); conv(q + "layers.1.", co, ci, 2 * strides[i - 1], transpose=True)
+        for j in range(3):
+            ru(f"{q}layers.{2 + j}.", co)
+    snake(f"{p}{n + 1}.", cm[0] * ch); conv(f"{p}{n + 2}.", 2, cm[0] * ch, 7, bias=False)
+    return sd

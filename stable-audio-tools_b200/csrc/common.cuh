@@ -263,6 +263,13 @@ __device__ __forceinline__ float fast_sin(float x) {
   r = fmaf(k, 1.7484555e-07f, r);
   return __sinf(r);
 }
+// sin and cos of the same argument with the same reduction (Snake backward needs sin(2ax) = 2 s c and sin^2(ax))
+__device__ __forceinline__ void fast_sincos(float x, float* s, float* c) {
+  const float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(k, -6.2831854820251465f, x);
+  r = fmaf(k, 1.7484555e-07f, r);
+  __sincosf(r, s, c);
+}
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 }  // namespace b200sat

@@ -61,6 +61,9 @@ struct GemmParams {
   int n_half;
   int num_m_tiles, num_n_tiles;
   int ksplit, kb_per_split;  // split-K: tile index -> (k-slice, n, m); each slice covers kb_per_split k-blocks
+  // conv weight-gradient addressing (both operands are time-major activation planes behind 4-D maps {C, s, T/s, B}): the K loop walks
+  // (item, 64-step time block); each operand is read at its own (phase r, row offset) = one tap of the convolution
+  int wg_kb_per_item, wg_rA, wg_offA, wg_rB, wg_offB;
 };
 
 constexpr int BLOCK_M = 128;
@@ -176,7 +179,21 @@ __global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constan
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          if (a_mn || b_mn) {
+          if (p.wg_kb_per_item > 0) {
+            if (CTAS == 1 || cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], CTAS * Cfg::kStageBytes);
+            const int item = kb / p.wg_kb_per_item, t0 = (kb % p.wg_kb_per_item) * BLOCK_K;
+            const int nb0 = n_blk * BN + static_cast<int>(cta_rank) * (BN / CTAS);
+#pragma unroll
+            for (int i = 0; i < BLOCK_M / 64; ++i) {
+              if (CTAS == 2) tma_load_4d_pair(sa + i * 8192, &p.tmA, &full_bar[stage], m0 + 64 * i, p.wg_rA, t0 + p.wg_offA, item);
+              else tma_load_4d(sa + i * 8192, &p.tmA, &full_bar[stage], m0 + 64 * i, p.wg_rA, t0 + p.wg_offA, item);
+            }
+#pragma unroll
+            for (int i = 0; i < BN / CTAS / 64; ++i) {
+              if (CTAS == 2) tma_load_4d_pair(sb + i * 8192, &p.tmB, &full_bar[stage], nb0 + 64 * i, p.wg_rB, t0 + p.wg_offB, item);
+              else tma_load_4d(sb + i * 8192, &p.tmB, &full_bar[stage], nb0 + 64 * i, p.wg_rB, t0 + p.wg_offB, item);
+            }
+          } else if (a_mn || b_mn) {
             // MN-major operands: 64(mn) x 64(k) boxes, one per 64-wide block of the M / N extent (8 KB each)
             if (CTAS == 1 || cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], CTAS * Cfg::kStageBytes);
             if (a_mn) {
@@ -497,11 +514,14 @@ static int launch_gemm(GemmParams& p, cudaStream_t stream) {
     // gradient accumulation with few output tiles and a long K (tokens): split K across idle SMs, combine with fp32 reds
     const int mn = p.num_m_tiles * p.num_n_tiles;
     int ks = units / mn;
-    if (ks > 8) ks = 8;
+    // dense-layer wgrads: at most 8 slices (reduction traffic); conv wgrads have tiny outputs ([C,C] per tap) and a K extent of
+    // batch x time, so every SM takes a slice
+    if (ks > 8 && p.wg_kb_per_item == 0) ks = 8;
     while (ks > 1 && total_kb / ks < 16) --ks;
     if (ks > 1) { p.ksplit = ks; p.flags = (p.flags & ~GEMM_ACCUM) | GEMM_ATOMIC; }
   }
   p.kb_per_split = (total_kb + p.ksplit - 1) / p.ksplit;
+  p.ksplit = (total_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty slices
   const int tiles = p.num_m_tiles * p.num_n_tiles * p.ksplit;
   const int grid = (tiles < units ? tiles : units) * CTAS;
   B200SAT_CHECK_CUDA(launch_k(gemm_bf16_tcgen05<BN, CTAS>, dim3(grid), dim3(384), Cfg::kSmemBytes, stream, CTAS, p));
@@ -609,4 +629,37 @@ extern "C" int b200sat_gemm_bf16(const void* A, int lda, const void* B, int ldb,
     case 128: return launch_gemm<128, 1>(p, s);
     default: return launch_gemm<64, 1>(p, s);
   }
+}
+
+
+// Weight gradient of a 1-D convolution tap: dW[Ca, Cb] += sum over items b and time steps t < T_iter of
+//     A[b, (t + offA) * sA + rA, :]^T  (x)  B[b, (t + offB) * sB + rB, :]
+// with A, B time-major bf16 activation planes [B, T, C] read in place through 4-D tensor maps (rows outside [0, T/s) are
+// zero-filled = the convolution's zero padding).  One launch per tap; split-K over time with fp32 reds fills the machine.
+// Backward of the Conv1d / ConvTranspose1d weights of models/autoencoders.py:58-83, :233-283 (dW = dY (*) X).
+extern "C" int b200sat_conv_wgrad(const void* a_plane, int Ca, int Ta, int sA, int rA, int offA, const void* b_plane, int Cb, int Tb,
+                                  int sB, int rB, int offB, float* dW, int B, int T_iter, void* stream) {
+  if (!a_plane || !b_plane || !dW || B <= 0 || T_iter <= 0 || sA < 1 || sB < 1) { set_last_error("conv_wgrad: bad arguments"); return B200SAT_EINVAL; }
+  if (Ca % 64 || Cb % 64 || Ta % sA || Tb % sB) { set_last_error("conv_wgrad: channels must be multiples of 64 and T of the stride"); return B200SAT_EUNSUPPORTED; }
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  auto plane_map = [](CUtensorMap* tm, const void* base, int Bn, int T, int C, int s) {
+    uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(s), static_cast<uint64_t>(T / s), static_cast<uint64_t>(Bn)};
+    uint64_t strides[3] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(C) * s * 2, static_cast<uint64_t>(C) * T * 2};
+    uint32_t box[4] = {64, 1, 64, 1};
+    return encode_tmap_bf16(tm, base, 4, dims, strides, box, 1);
+  };
+  int rc;
+  if ((rc = plane_map(&p.tmA, a_plane, B, Ta, Ca, sA))) return rc;
+  if ((rc = plane_map(&p.tmB, b_plane, B, Tb, Cb, sB))) return rc;
+  p.D = dW; p.M = Ca; p.N = Cb; p.ldd = Cb;
+  p.wg_kb_per_item = (T_iter + BLOCK_K - 1) / BLOCK_K;
+  p.K = B * p.wg_kb_per_item * BLOCK_K;
+  p.wg_rA = rA; p.wg_offA = offA; p.wg_rB = rB; p.wg_offB = offB;
+  p.flags = GEMM_A_MN | GEMM_B_MN | GEMM_OUT_F32 | GEMM_ACCUM;
+  p.seg_in = 1; p.rope_seq = 1; p.rope_dmodel = 1; p.rope_dh = 64;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (Ca > 128 && Cb > 128) return launch_gemm<256, 2>(p, s);
+  if (Cb > 128) return launch_gemm<256, 1>(p, s);
+  return launch_gemm<128, 1>(p, s);
 }
