@@ -234,6 +234,68 @@ def measure_train(args, dev, rank, world, dist):
     return out
 
 
+def measure_ae_train(args, dev, rank, world, dist):
+    """BASELINE.json configs[3], generator step of the warm-up phase (training/autoencoders.py:436-497 with `warmed_up` False: the
+    discriminator is not evaluated): Oobleck encode -> VAE -> decode, MRSTFT sum/difference + left + right + KL, backward, AdamW.
+    16 clips x 65536 samples per GPU (the config's 32 per GPU exceeds nothing but halves the steps timed; both fit)."""
+    from b200sat.autoencoder_train import OobleckTrainModel
+    from b200sat.stft_loss import SumAndDifferenceSTFTLoss, autoencoder_mrstft_terms
+    B, T = 16, 65536
+    g = torch.Generator(device=dev).manual_seed(11)
+    model = OobleckTrainModel(_oobleck_state_dict(dev, g), device=dev)
+    opt = torch.optim.AdamW(model.parameters(), lr=1.5e-4, betas=(0.8, 0.99), fused=True)
+    fft, hop = [2048, 1024, 512, 256, 128, 64, 32], [512, 256, 128, 64, 32, 16, 8]
+    loss_sd = SumAndDifferenceSTFTLoss(fft_sizes=fft, hop_sizes=hop, win_lengths=fft, perceptual_weighting=True, sample_rate=44100)
+    gh = torch.Generator().manual_seed(42 + rank)
+    h_audio = (torch.randn(B, 2, T, generator=gh).clamp(-1, 1) * 0.5).pin_memory()
+    h_loss = torch.zeros(1).pin_memory()
+    params = list(model.parameters())
+
+    def step():
+        reals = h_audio.to(dev, non_blocking=True)
+        noise = torch.randn(B, 64, T // 2048, device=dev, generator=g)
+        decoded, kl, _ = model(reals, noise)
+        sd_, l_, r_ = autoencoder_mrstft_terms(loss_sd, decoded, reals)
+        loss = sd_ + 0.5 * l_ + 0.5 * r_ + 1e-4 * kl
+        opt.zero_grad(set_to_none=True)
+        (loss / world).backward()
+        if world > 1:   # one flat bucket: 156 M fp32 gradients
+            flat = torch.cat([p.grad.view(-1) for p in params])
+            dist.all_reduce(flat)
+            off = 0
+            for p in params:
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p)); off += p.numel()
+        opt.step()
+        h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+
+    for _ in range(3):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    k = 4
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(k):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = ms.item() / k
+    flop = B * 3 * 322.7e9
+    pk = peaks()
+    out = {"metric": "oobleck_generator_step_items_per_sec", "value": B * world / (ms_step * 1e-3), "unit": "clips/s", "ms_per_step": ms_step,
+           "batch_per_gpu": B, "samples_per_clip": T, "loss": float(h_loss.item()),
+           "includes": "H2D audio, encoder+VAE+decoder fwd, 4-term MRSTFT + KL, full backward, (all-reduce), AdamW(fused), D2H loss",
+           "excludes": "adversarial / feature-matching terms (EncodecDiscriminator not built yet)",
+           "tflops_per_gpu": flop / (ms_step * 1e-3) / 1e12, "frac_of_sustained_peak": flop / (ms_step * 1e-3) / 1e12 / pk["bf16_sustained"]}
+    del model, opt
+    torch.cuda.empty_cache()
+    return out
+
+
 def _graph_time_us(fn, reps=10, iters=3):
     """Kernel time with host launch overhead removed: capture `reps` calls in a CUDA graph, replay, CUDA events."""
     fn(); torch.cuda.synchronize()
@@ -390,11 +452,17 @@ def run_ours(args):
     d2h = h_out.numel() * 4
 
     train = None
+    ae_train = None
     if not args.no_train:
         del smp
         model._samplers.clear()
         torch.cuda.empty_cache()
         train = measure_train(args, dev, rank, world, dist)
+        try:
+            ae_train = measure_ae_train(args, dev, rank, world, dist)
+        except Exception as ex:   # secondary measurement: never lose the headline line
+            ae_train = {"error": repr(ex)[:300]}
+            torch.cuda.empty_cache()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -444,7 +512,7 @@ def run_ours(args):
         "config": workload_config(world), "sample_seconds_100_steps": ms_total / args.steps / 1e3,
         "e2e": {"value": e2e_val, "unit": "latent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "b200sat.generation.generate_diffusion_cond(host pinned noise/conditioning -> host latents)"},
-        "gpu_launches": launches, "clocks": clk, "roofline": roof, "whole_step": whole, "cpu_baseline": cpu, "train": train, "other_kernels": other,
+        "gpu_launches": launches, "clocks": clk, "roofline": roof, "whole_step": whole, "cpu_baseline": cpu, "train": train, "ae_train": ae_train, "other_kernels": other,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

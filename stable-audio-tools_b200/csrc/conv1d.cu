@@ -46,12 +46,13 @@ constexpr int CV_BK = 64;
 
 template <int BN>
 struct ConvCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (BN == 256) ? 3 : 5;
   static constexpr int kABytes = CV_BM * CV_BK * 2;
   static constexpr int kBBytes = BN * CV_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kStagingBytes = 16 * 4096;  // two 32-row x 64-byte transposition buffers (raw, activated) per epilogue warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 256;
 };
 
 __device__ __forceinline__ void split_store8(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* v) {
@@ -66,12 +67,52 @@ __device__ __forceinline__ void split_store8(__nv_bfloat16* hi, __nv_bfloat16* l
   if (lo) *reinterpret_cast<uint4*>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-template <int BN>
-__global__ void __launch_bounds__(384, 1) conv1d_tcgen05(const __grid_constant__ ConvParams p) {
+// Epilogue geometry.  TMEM hands every thread one output ROW (32 fp32 columns per tcgen05.ld); global memory wants whole lines.
+// Sixteen epilogue warps (four per TMEM lane quarter, one 32-column block each per 128 columns of tile) own a pair of 32-row x
+// 64-byte transposition buffers in shared memory (raw values, activated values); 16-byte chunks are XOR-swizzled with
+// (row >> 1) & 3 so that both the row-per-thread side and the line side (8 rows x 4 chunks per instruction) are bank-conflict
+// free.  Every global load / store of the bf16 planes then moves eight complete 64-byte row segments per instruction.
+constexpr int CV_EPI_WARPS = 16;
+constexpr int CV_THREADS = 128 + CV_EPI_WARPS * 32;
+
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// this thread's 32 values -> bf16 -> its row of the transposition buffer; LO: the rounding remainder goes straight to the lo plane
+template <bool LO>
+__device__ __forceinline__ void stage_row(uint32_t stg_row, int swz, const float* v, __nv_bfloat16* lo_row) {
+#pragma unroll
+  for (int jx = 0; jx < 4; ++jx) {
+    uint32_t hw[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) hw[e] = pack_bf16(v[8 * jx + 2 * e], v[8 * jx + 2 * e + 1]);
+    sts128(stg_row + ((jx ^ swz) << 4), make_uint4(hw[0], hw[1], hw[2], hw[3]));
+    if (LO) {
+      if (lo_row) {
+        uint32_t lw[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 h = unpack_bf16(hw[e]);
+          lw[e] = pack_bf16(v[8 * jx + 2 * e] - h.x, v[8 * jx + 2 * e + 1] - h.y);
+        }
+        *reinterpret_cast<uint4*>(lo_row + 8 * jx) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
+    }
+  }
+}
+
+template <int BN, bool LO>
+__global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* stage_base = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + Cfg::kStages;
   uint64_t* tmem_full = bars + 2 * Cfg::kStages;
@@ -92,7 +133,7 @@ __global__ void __launch_bounds__(384, 1) conv1d_tcgen05(const __grid_constant__
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 256); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CV_EPI_WARPS * 32); }
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols); tmem_relinquish(); }
@@ -172,28 +213,65 @@ __global__ void __launch_bounds__(384, 1) conv1d_tcgen05(const __grid_constant__
     }
   } else if (warp >= 4) {
     const int ew = warp - 4;
-    const int q = ew & 3;       // TMEM lane quarter
-    const int half = ew >> 2;   // column half (two epilogue warps per SM sub-partition)
+    const int q = ew & 3;                  // TMEM lane quarter = 32 rows of the tile
+    const int cg = ew >> 2;                // column group: BN/4 consecutive columns
+    constexpr int NB = BN / 128;           // 32-column blocks per warp per tile
+    const uint32_t stg_o = smem_u32(stage_base) + ew * 4096;   // raw values (the residual is staged here first, overwritten in place)
+    const uint32_t stg_a = stg_o + 2048;                       // activated values
+    const int lrow = lane >> 2, lchunk = lane & 3;             // line side: 8 rows x 4 chunks per instruction
+    const int swz = (lane >> 1) & 3;
+    const uint32_t my_o = stg_o + lane * 64, my_a = stg_a + lane * 64;
     int as = 0; uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int ph, n_blk, b, m_blk;
       decode(tile, ph, n_blk, b, m_blk);
+      int grow[4];   // line side: b * T_out + t of rows lrow + 8 i, or -1 when the row does not exist
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = m_blk * CV_BM + q * 32 + lrow + 8 * i;
+        int t = m;
+        bool ok = m < p.m_rows;
+        if (p.mode == 2) { t = m * p.stride + ph - p.pad; ok = ok && t >= 0 && t < p.T_out; }
+        grow[i] = ok ? b * p.T_out + t : -1;
+      }
+      size_t my_off = 0;
+      bool my_ok = false;
+      if (LO) {
+        int my_t = m_blk * CV_BM + q * 32 + lane;
+        my_ok = my_t < p.m_rows;
+        if (p.mode == 2) { my_t = my_t * p.stride + ph - p.pad; my_ok = my_ok && my_t >= 0 && my_t < p.T_out; }
+        my_off = (static_cast<size_t>(b) * p.T_out + (my_ok ? my_t : 0)) * p.Cout;
+      }
+      const int col0 = n_blk * BN + cg * (BN / 4);
+      // residual of the first block: in flight while the accumulator is still being produced
+      uint4 rres[4];
+      if (p.res_hi && col0 < p.Cout) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          rres[i] = grow[i] >= 0 ? __ldg(reinterpret_cast<const uint4*>(p.res_hi + static_cast<size_t>(grow[i]) * p.Cout + col0 + lchunk * 8)) : make_uint4(0, 0, 0, 0);
+      }
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      const int m = m_blk * CV_BM + q * 32 + lane;
-      int t = m;
-      bool ok = m < p.m_rows;
-      if (p.mode == 2) { t = m * p.stride + ph - p.pad; ok = ok && t >= 0 && t < p.T_out; }
-      const size_t row_off = (static_cast<size_t>(b) * p.T_out + (ok ? t : 0)) * p.Cout;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-      for (int cc = 0; cc < BN / 64; ++cc) {
-        const int c = half * (BN / 64) + cc;
-        const int col = n_blk * BN + c * 32;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + cg * (BN / 4);
+#pragma unroll
+      for (int cc = 0; cc < NB; ++cc) {
+        const int col = col0 + cc * 32;
         if (col >= p.Cout) break;
         uint32_t raw[32];
+        tmem_ld_32x32(taddr + cc * 32, raw);
+        __syncwarp();                                   // the previous block's line-side stores have read the buffers
+        if (p.res_hi) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { const int r = lrow + 8 * i; sts128(stg_o + r * 64 + ((lchunk ^ ((r >> 1) & 3)) << 4), rres[i]); }
+          if (cc + 1 < NB && col + 32 < p.Cout) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              rres[i] = grow[i] >= 0 ? __ldg(reinterpret_cast<const uint4*>(p.res_hi + static_cast<size_t>(grow[i]) * p.Cout + col + 32 + lchunk * 8)) : make_uint4(0, 0, 0, 0);
+          }
+          __syncwarp();
+        }
+        tmem_ld_wait_regs(raw);
         float v[32];
-        tmem_ld_32x32(taddr + c * 32, raw);
-        tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
         if (p.bias) {
@@ -201,45 +279,51 @@ __global__ void __launch_bounds__(384, 1) conv1d_tcgen05(const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 8; ++i) { const float4 t4 = __ldg(bp + i); v[4 * i] += t4.x; v[4 * i + 1] += t4.y; v[4 * i + 2] += t4.z; v[4 * i + 3] += t4.w; }
         }
-        if (ok) {
-          const size_t off = row_off + col;
-          if (p.res_hi) {
+        if (p.res_hi) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.res_hi + off) + i);
-              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+          for (int jx = 0; jx < 4; ++jx) {
+            const uint4 u = lds128(my_o + ((jx ^ swz) << 4));
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16(w[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
-            }
-            if (p.res_lo) {
+            for (int e = 0; e < 4; ++e) { const float2 f = unpack_bf16(w[e]); v[8 * jx + 2 * e] += f.x; v[8 * jx + 2 * e + 1] += f.y; }
+          }
+          if (LO) {
+            if (p.res_lo && my_ok) {   // fp32-class residual: the lo plane is read row-wise (inference-only path)
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.res_lo + off) + i);
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.res_lo + my_off + col) + i);
                 const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16(w[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
+                for (int e = 0; e < 4; ++e) { const float2 f = unpack_bf16(w[e]); v[8 * i + 2 * e] += f.x; v[8 * i + 2 * e + 1] += f.y; }
               }
             }
           }
-          if (p.out_hi) {
+        }
+        if (p.out_hi) stage_row<LO>(my_o, swz, v, (LO && p.out_lo && my_ok) ? p.out_lo + my_off + col : nullptr);
+        if (p.act_hi) {
+          const float4* ap = reinterpret_cast<const float4*>(p.snake_a + col);
+          const float4* ip = reinterpret_cast<const float4*>(p.snake_invb + col);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) split_store8(p.out_hi + off + 8 * i, p.out_lo ? p.out_lo + off + 8 * i : nullptr, v + 8 * i);
-          }
-          if (p.act_hi) {
-            const float4* ap = reinterpret_cast<const float4*>(p.snake_a + col);
-            const float4* ip = reinterpret_cast<const float4*>(p.snake_invb + col);
+          for (int i = 0; i < 8; ++i) {
+            const float4 a4 = __ldg(ap + i), b4 = __ldg(ip + i);
+            const float aa[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 a4 = __ldg(ap + i), b4 = __ldg(ip + i);
-              const float aa[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float s = fast_sin(v[4 * i + j] * aa[j]);
-                v[4 * i + j] += bb[j] * s * s;
-              }
+            for (int e = 0; e < 4; ++e) {
+              const float sn = fast_sin(v[4 * i + e] * aa[e]);
+              v[4 * i + e] += bb[e] * sn * sn;
             }
+          }
+          stage_row<LO>(my_a, swz, v, (LO && p.act_lo && my_ok) ? p.act_lo + my_off + col : nullptr);
+        }
+        __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) split_store8(p.act_hi + off + 8 * i, p.act_lo ? p.act_lo + off + 8 * i : nullptr, v + 8 * i);
+        for (int i = 0; i < 4; ++i) {
+          const int r = lrow + 8 * i;
+          if (grow[i] >= 0) {
+            const size_t o = static_cast<size_t>(grow[i]) * p.Cout + col + lchunk * 8;
+            const uint32_t so = r * 64 + ((lchunk ^ ((r >> 1) & 3)) << 4);
+            if (p.out_hi) *reinterpret_cast<uint4*>(p.out_hi + o) = lds128(stg_o + so);
+            if (p.act_hi) *reinterpret_cast<uint4*>(p.act_hi + o) = lds128(stg_a + so);
           }
         }
       }
@@ -253,19 +337,19 @@ __global__ void __launch_bounds__(384, 1) conv1d_tcgen05(const __grid_constant__
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::kTmemCols); }
 }
 
-template <int BN>
+template <int BN, bool LO>
 static int launch_conv(ConvParams& p, cudaStream_t stream) {
   using Cfg = ConvCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    B200SAT_CHECK_CUDA(cudaFuncSetAttribute(conv1d_tcgen05<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    B200SAT_CHECK_CUDA(cudaFuncSetAttribute(conv1d_tcgen05<BN, LO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   p.m_tiles = (p.m_rows + CV_BM - 1) / CV_BM;
   p.n_tiles = (p.Cout + BN - 1) / BN;
   const long tiles = static_cast<long>(p.m_tiles) * p.B * p.n_tiles * p.phases;
   const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-  conv1d_tcgen05<BN><<<grid, 384, Cfg::kSmemBytes, stream>>>(p);
+  conv1d_tcgen05<BN, LO><<<grid, CV_THREADS, Cfg::kSmemBytes, stream>>>(p);
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }
@@ -514,7 +598,9 @@ extern "C" int b200sat_conv1d_fwd(const void* in_hi, const void* in_lo, const vo
   p.out_hi = static_cast<__nv_bfloat16*>(out_hi); p.out_lo = static_cast<__nv_bfloat16*>(out_lo);
   p.act_hi = static_cast<__nv_bfloat16*>(act_hi); p.act_lo = static_cast<__nv_bfloat16*>(act_lo);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return bn == 256 ? launch_conv<256>(p, s) : launch_conv<128>(p, s);
+  const bool lo = p.res_lo || p.out_lo || p.act_lo;
+  if (bn == 256) return lo ? launch_conv<256, true>(p, s) : launch_conv<256, false>(p, s);
+  return lo ? launch_conv<128, true>(p, s) : launch_conv<128, false>(p, s);
 }
 
 extern "C" int b200sat_wn_pack(const float* v, const float* g, float* inv_norm_scratch, void* w_hi, void* w_lo, int Cout, int Cin,
