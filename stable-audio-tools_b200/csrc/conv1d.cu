@@ -18,6 +18,7 @@
 // (alpha, beta) and store the activated planes — so Snake never makes its own pass over HBM.
 #include "common.cuh"
 #include <cstring>
+#include <cstdlib>
 
 namespace b200sat {
 
@@ -39,6 +40,8 @@ struct ConvParams {
   int passes;  // 1 or 3
   int m_rows;  // GEMM rows per batch item
   int m_tiles, n_tiles, phases;
+  int window;        // 1: stride-1 conv whose taps share one (128 + (taps-1)*dil)-row A window per channel block
+  int win_rows;      // rows of one A item: 128 + (taps-1)*dil in window mode, 128 otherwise
 };
 
 constexpr int CV_BM = 128;
@@ -46,14 +49,19 @@ constexpr int CV_BK = 64;
 
 template <int BN>
 struct ConvCfg {
-  static constexpr int kStages = (BN == 256) ? 3 : 5;
-  static constexpr int kABytes = CV_BM * CV_BK * 2;
+  // Two rings.  A ring: one item = the input rows one 64-channel block of a tile needs.  For stride-1 convs that is the WINDOW
+  // [t0 - pad, t0 - pad + 128 + (taps-1)*dil) fetched ONCE and read by every tap through a row-shifted UMMA descriptor (the im2col
+  // reuse a per-tap fetch would throw away: 7x less shared-memory fill for the k7 convs); strided / transposed convs use one
+  // 128-row item per (tap, block).  B ring: one 64-deep K slice of the packed weights per MMA group.
+  static constexpr int kAItemBytes = 24 * 1024;            // up to 192 rows x 128 B
+  static constexpr int kAItems = (BN == 256) ? 2 : 3;
   static constexpr int kBBytes = BN * CV_BK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBStages = (BN == 256) ? 3 : 5;
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kStagingBytes = 16 * 4096;  // two 32-row x 64-byte transposition buffers (raw, activated) per epilogue warp
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kAItems * kAItemBytes + kBStages * kBBytes + kStagingBytes + 1024 + 256;
 };
+
 
 __device__ __forceinline__ void split_store8(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* v) {
   uint32_t h[4], l[4];
@@ -111,11 +119,15 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
   using Cfg = ConvCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stage_base = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kAItems * Cfg::kAItemBytes;
+  uint8_t* stage_base = smem_b + Cfg::kBStages * Cfg::kBBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + Cfg::kStagingBytes);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + Cfg::kStages;
-  uint64_t* tmem_full = bars + 2 * Cfg::kStages;
+  uint64_t* full_a = bars;
+  uint64_t* empty_a = full_a + Cfg::kAItems;
+  uint64_t* full_b = empty_a + Cfg::kAItems;
+  uint64_t* empty_b = full_b + Cfg::kBStages;
+  uint64_t* tmem_full = empty_b + Cfg::kBStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -124,15 +136,18 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
   const int tiles_per_phase = p.m_tiles * p.B * p.n_tiles;
   const int num_tiles = tiles_per_phase * p.phases;
   const int cin_blocks = p.Cin / CV_BK;
-  const int ksteps_per_pass = p.taps * cin_blocks;
-  const int num_k = p.passes * ksteps_per_pass;
+  const bool window = p.window != 0;                         // one A item per channel block, shared by all taps
+  const int taps_per_item = window ? p.taps : 1;
+  const int items_per_pass = window ? cin_blocks : p.taps * cin_blocks;
+  const int num_items = p.passes * items_per_pass;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
     tma_prefetch_desc(&p.tmB[0]);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < Cfg::kAItems; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
+    for (int i = 0; i < Cfg::kBStages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CV_EPI_WARPS * 32); }
     fence_barrier_init();
   }
@@ -152,21 +167,48 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
     m_blk = r % p.m_tiles;
   };
 
+  // item index -> (pass, tap (non-window modes only), channel block); K order: pass, [tap,] block, then the taps of a window
+  auto item_decode = [&](int it, int& pass, int& tap, int& cib) {
+    pass = it / items_per_pass;
+    const int rem = it % items_per_pass;
+    tap = window ? 0 : rem / cin_blocks;
+    cib = window ? rem : rem % cin_blocks;
+  };
+
   if (warp == 0) {
-    if (lane == 0) {
+    if (lane == 0) {   // B producer: one weight slice per MMA group
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int ph, n_blk, b, m_blk;
         decode(tile, ph, n_blk, b, m_blk);
+        for (int it = 0; it < num_items; ++it) {
+          int pass, tap0, cib;
+          item_decode(it, pass, tap0, cib);
+          const int b_plane = (pass == 1) ? 1 : 0;            // passes: hi*hi, hi*lo, lo*hi
+          for (int tt = 0; tt < taps_per_item; ++tt) {
+            const int tap = tap0 + tt;
+            mbar_wait(&empty_b[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_b[stage], Cfg::kBBytes);
+            tma_load_2d(smem_b + stage * Cfg::kBBytes, &p.tmB[b_plane], &full_b[stage], tap * p.Cin + cib * CV_BK, ph * p.Cout + n_blk * BN);
+            if (++stage == Cfg::kBStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0) {   // A producer: input rows of one channel block (window or per-tap tile)
+      int slot = 0; uint32_t phase = 0;
+      const uint32_t item_bytes = static_cast<uint32_t>(p.win_rows) * 128u;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int ph, n_blk, b, m_blk;
+        decode(tile, ph, n_blk, b, m_blk);
         const int m0 = m_blk * CV_BM;
-        for (int ks = 0; ks < num_k; ++ks) {
-          const int pass = ks / ksteps_per_pass;
-          const int rem = ks % ksteps_per_pass;
-          const int tap = rem / cin_blocks;
-          const int cib = rem % cin_blocks;
+        for (int it = 0; it < num_items; ++it) {
+          int pass, tap, cib;
+          item_decode(it, pass, tap, cib);
           int r = 0, row_off;
           if (p.mode == 0) {
-            row_off = tap * p.dil - p.pad;
+            row_off = window ? -p.pad : tap * p.dil - p.pad;  // window: tap k reads buffer rows [k*dil, k*dil + 128)
           } else if (p.mode == 1) {
             const int d = tap - p.pad;                      // input time = t_out*s + d
             const int j = (d >= 0) ? d / p.stride : -((-d + p.stride - 1) / p.stride);
@@ -175,37 +217,41 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
           } else {
             row_off = -tap;                                 // transposed conv phase: x[q - j]
           }
-          const int a_plane = (pass == 2) ? 1 : 0;          // passes: hi*hi, hi*lo, lo*hi
-          const int b_plane = (pass == 1) ? 1 : 0;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + Cfg::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_4d(sa, &p.tmA[a_plane], &full_bar[stage], cib * CV_BK, r, m0 + row_off, b);
-          tma_load_2d(sb, &p.tmB[b_plane], &full_bar[stage], tap * p.Cin + cib * CV_BK, ph * p.Cout + n_blk * BN);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          const int a_plane = (pass == 2) ? 1 : 0;
+          mbar_wait(&empty_a[slot], phase ^ 1);
+          mbar_arrive_expect_tx(&full_a[slot], item_bytes);
+          tma_load_4d(smem_a + slot * Cfg::kAItemBytes, &p.tmA[a_plane], &full_a[slot], cib * CV_BK, r, m0 + row_off, b);
+          if (++slot == Cfg::kAItems) { slot = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(CV_BM, BN, 0, 0);
-      int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+      int stage = 0; uint32_t phase = 0; int slot = 0; uint32_t sphase = 0; int as = 0; uint32_t aphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
-        for (int ks = 0; ks < num_k; ++ks) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
-          const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
+        for (int it = 0; it < num_items; ++it) {
+          mbar_wait(&full_a[slot], sphase);
+          const uint32_t sa0 = smem_u32(smem_a + slot * Cfg::kAItemBytes);
+          for (int tt = 0; tt < taps_per_item; ++tt) {
+            mbar_wait(&full_b[stage], phase);
+            tc_fence_after();
+            // tap tt reads the window shifted down by tt*dil rows: rows sit at a 128-byte pitch (SBO = 8 rows = 1024 B) and the
+            // 128-byte swizzle is a function of the shared-memory ADDRESS bits [7,10), so a shift by any number of rows is a plain
+            // start-address offset with the descriptor's base-offset field left 0 (measured: setting it to shift%8 gives wrong sums)
+            const uint32_t shift = static_cast<uint32_t>(tt * p.dil);
+            const uint64_t da = make_smem_desc_sw128(sa0 + shift * 128u, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes), 16, 1024);
 #pragma unroll
-          for (int k = 0; k < CV_BK / 16; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (ks | k) != 0);
-          umma_commit(&empty_bar[stage]);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            for (int k = 0; k < CV_BK / 16; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (it | tt | k) != 0);
+            umma_commit(&empty_b[stage]);
+            if (++stage == Cfg::kBStages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&empty_a[slot]);
+          if (++slot == Cfg::kAItems) { slot = 0; sphase ^= 1; }
         }
         umma_commit(&tmem_full[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
@@ -555,10 +601,10 @@ __global__ void vae_sample_kernel(const __nv_bfloat16* __restrict__ hi, const __
 
 using namespace b200sat;
 
-static int make_plane_map(CUtensorMap* tm, const void* base, int B, int T, int C, int s_in) {
+static int make_plane_map(CUtensorMap* tm, const void* base, int B, int T, int C, int s_in, int box_rows) {
   uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(s_in), static_cast<uint64_t>(T / s_in), static_cast<uint64_t>(B)};
   uint64_t strides[3] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(C) * s_in * 2, static_cast<uint64_t>(C) * T * 2};
-  uint32_t box[4] = {CV_BK, 1, CV_BM, 1};
+  uint32_t box[4] = {CV_BK, 1, static_cast<uint32_t>(box_rows), 1};
   return encode_tmap_bf16(tm, base, 4, dims, strides, box, 1);
 }
 
@@ -584,8 +630,15 @@ extern "C" int b200sat_conv1d_fwd(const void* in_hi, const void* in_lo, const vo
   const int s_in = (mode == 1) ? stride : 1;
   const int bn = (Cout >= 256) ? 256 : 128;
   int rc;
-  if ((rc = make_plane_map(&p.tmA[0], in_hi, B, T_in, Cin, s_in))) return rc;
-  if (in_lo && (rc = make_plane_map(&p.tmA[1], in_lo, B, T_in, Cin, s_in))) return rc;
+  {
+    // B200SAT_CONV_WINDOW=0 falls back to per-tap A tiles (A/B measurement of the shared window)
+    static const int win_env = [] { const char* e = getenv("B200SAT_CONV_WINDOW"); return e ? atoi(e) : 1; }();
+    const int wr = CV_BM + (p.taps - 1) * dil;
+    p.window = (mode == 0 && win_env != 0 && wr * 128 <= 24 * 1024) ? 1 : 0;
+    p.win_rows = p.window ? wr : CV_BM;
+  }
+  if ((rc = make_plane_map(&p.tmA[0], in_hi, B, T_in, Cin, s_in, p.win_rows))) return rc;
+  if (in_lo && (rc = make_plane_map(&p.tmA[1], in_lo, B, T_in, Cin, s_in, p.win_rows))) return rc;
   {
     uint64_t dims[2] = {static_cast<uint64_t>(wk), static_cast<uint64_t>(wrows)};
     uint64_t strides[1] = {static_cast<uint64_t>(wk) * 2};
