@@ -47,20 +47,24 @@ struct ConvParams {
 constexpr int CV_BM = 128;
 constexpr int CV_BK = 64;
 
-template <int BN>
+template <int BN, int MSUB>
 struct ConvCfg {
-  // Two rings.  A ring: one item = the input rows one 64-channel block of a tile needs.  For stride-1 convs that is the WINDOW
-  // [t0 - pad, t0 - pad + 128 + (taps-1)*dil) fetched ONCE and read by every tap through a row-shifted UMMA descriptor (the im2col
-  // reuse a per-tap fetch would throw away: 7x less shared-memory fill for the k7 convs); strided / transposed convs use one
-  // 128-row item per (tap, block).  B ring: one 64-deep K slice of the packed weights per MMA group.
+  // Two rings.  A ring: one item = the input rows one 64-channel block of one 128-row sub-tile needs.  For stride-1 convs that is
+  // the WINDOW [t0 - pad, t0 - pad + 128 + (taps-1)*dil) fetched ONCE and read by every tap through a row-shifted UMMA descriptor
+  // (the im2col reuse a per-tap fetch would throw away: 7x less shared-memory fill for the k7 convs); strided / transposed convs
+  // use one 128-row item per (tap, block).  B ring: one 64-deep K slice of the packed weights per MMA group.
+  // MSUB = 2 (stride-1 convs): a CTA tile is 256 time steps = two 128-row accumulators that share every B slice, which halves
+  // the weight bytes streamed per flop - with the window the weights are what fills shared memory.
   static constexpr int kAItemBytes = 24 * 1024;            // up to 192 rows x 128 B
-  static constexpr int kAItems = (BN == 256) ? 2 : 3;
+  static constexpr int kAItems = (MSUB == 2) ? 4 : ((BN == 256) ? 2 : 3);
   static constexpr int kBBytes = BN * CV_BK * 2;
-  static constexpr int kBStages = (BN == 256) ? 3 : 5;
-  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kBStages = (MSUB == 2) ? 4 : ((BN == 256) ? 3 : 5);
+  static constexpr int kTmemCols = 2 * MSUB * BN;
   static constexpr int kStagingBytes = 16 * 4096;  // two 32-row x 64-byte transposition buffers (raw, activated) per epilogue warp
   static constexpr int kSmemBytes = kAItems * kAItemBytes + kBStages * kBBytes + kStagingBytes + 1024 + 256;
+  static_assert(kTmemCols <= 512, "TMEM has 512 columns");
 };
+
 
 
 __device__ __forceinline__ void split_store8(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* v) {
@@ -114,9 +118,9 @@ __device__ __forceinline__ void stage_row(uint32_t stg_row, int swz, const float
   }
 }
 
-template <int BN, bool LO>
+template <int BN, bool LO, int MSUB>
 __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_constant__ ConvParams p) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, MSUB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -202,7 +206,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int ph, n_blk, b, m_blk;
         decode(tile, ph, n_blk, b, m_blk);
-        const int m0 = m_blk * CV_BM;
+        const int m0 = m_blk * (CV_BM * MSUB);
         for (int it = 0; it < num_items; ++it) {
           int pass, tap, cib;
           item_decode(it, pass, tap, cib);
@@ -218,10 +222,13 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
             row_off = -tap;                                 // transposed conv phase: x[q - j]
           }
           const int a_plane = (pass == 2) ? 1 : 0;
-          mbar_wait(&empty_a[slot], phase ^ 1);
-          mbar_arrive_expect_tx(&full_a[slot], item_bytes);
-          tma_load_4d(smem_a + slot * Cfg::kAItemBytes, &p.tmA[a_plane], &full_a[slot], cib * CV_BK, r, m0 + row_off, b);
-          if (++slot == Cfg::kAItems) { slot = 0; phase ^= 1; }
+#pragma unroll
+          for (int sub = 0; sub < MSUB; ++sub) {
+            mbar_wait(&empty_a[slot], phase ^ 1);
+            mbar_arrive_expect_tx(&full_a[slot], item_bytes);
+            tma_load_4d(smem_a + slot * Cfg::kAItemBytes, &p.tmA[a_plane], &full_a[slot], cib * CV_BK, r, m0 + sub * 128 + row_off, b);
+            if (++slot == Cfg::kAItems) { slot = 0; phase ^= 1; }
+          }
         }
       }
     }
@@ -232,26 +239,36 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BN;
+        const uint32_t tmem_d = tmem_base + as * (MSUB * BN);
         for (int it = 0; it < num_items; ++it) {
-          mbar_wait(&full_a[slot], sphase);
-          const uint32_t sa0 = smem_u32(smem_a + slot * Cfg::kAItemBytes);
+          uint32_t sa0[MSUB];
+          int slots[MSUB];
+#pragma unroll
+          for (int sub = 0; sub < MSUB; ++sub) {
+            mbar_wait(&full_a[slot], sphase);
+            sa0[sub] = smem_u32(smem_a + slot * Cfg::kAItemBytes);
+            slots[sub] = slot;
+            if (++slot == Cfg::kAItems) { slot = 0; sphase ^= 1; }
+          }
           for (int tt = 0; tt < taps_per_item; ++tt) {
             mbar_wait(&full_b[stage], phase);
             tc_fence_after();
             // tap tt reads the window shifted down by tt*dil rows: rows sit at a 128-byte pitch (SBO = 8 rows = 1024 B) and the
             // 128-byte swizzle is a function of the shared-memory ADDRESS bits [7,10), so a shift by any number of rows is a plain
             // start-address offset with the descriptor's base-offset field left 0 (measured: setting it to shift%8 gives wrong sums)
-            const uint32_t shift = static_cast<uint32_t>(tt * p.dil);
-            const uint64_t da = make_smem_desc_sw128(sa0 + shift * 128u, 16, 1024);
+            const uint32_t shift = static_cast<uint32_t>(tt * p.dil) * 128u;
             const uint64_t db = make_smem_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes), 16, 1024);
 #pragma unroll
-            for (int k = 0; k < CV_BK / 16; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (it | tt | k) != 0);
+            for (int sub = 0; sub < MSUB; ++sub) {
+              const uint64_t da = make_smem_desc_sw128(sa0[sub] + shift, 16, 1024);
+#pragma unroll
+              for (int k = 0; k < CV_BK / 16; ++k) umma_bf16(tmem_d + sub * BN, da + 2 * k, db + 2 * k, idesc, (it | tt | k) != 0);
+            }
             umma_commit(&empty_b[stage]);
             if (++stage == Cfg::kBStages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&empty_a[slot]);
-          if (++slot == Cfg::kAItems) { slot = 0; sphase ^= 1; }
+#pragma unroll
+          for (int sub = 0; sub < MSUB; ++sub) umma_commit(&empty_a[slots[sub]]);
         }
         umma_commit(&tmem_full[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
@@ -271,10 +288,15 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int ph, n_blk, b, m_blk;
       decode(tile, ph, n_blk, b, m_blk);
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int sub = 0; sub < MSUB; ++sub) {
+      const int m_base = m_blk * (CV_BM * MSUB) + sub * CV_BM;
       int grow[4];   // line side: b * T_out + t of rows lrow + 8 i, or -1 when the row does not exist
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int m = m_blk * CV_BM + q * 32 + lrow + 8 * i;
+        const int m = m_base + q * 32 + lrow + 8 * i;
         int t = m;
         bool ok = m < p.m_rows;
         if (p.mode == 2) { t = m * p.stride + ph - p.pad; ok = ok && t >= 0 && t < p.T_out; }
@@ -283,7 +305,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
       size_t my_off = 0;
       bool my_ok = false;
       if (LO) {
-        int my_t = m_blk * CV_BM + q * 32 + lane;
+        int my_t = m_base + q * 32 + lane;
         my_ok = my_t < p.m_rows;
         if (p.mode == 2) { my_t = my_t * p.stride + ph - p.pad; my_ok = my_ok && my_t >= 0 && my_t < p.T_out; }
         my_off = (static_cast<size_t>(b) * p.T_out + (my_ok ? my_t : 0)) * p.Cout;
@@ -296,9 +318,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
         for (int i = 0; i < 4; ++i)
           rres[i] = grow[i] >= 0 ? __ldg(reinterpret_cast<const uint4*>(p.res_hi + static_cast<size_t>(grow[i]) * p.Cout + col0 + lchunk * 8)) : make_uint4(0, 0, 0, 0);
       }
-      mbar_wait(&tmem_full[as], aphase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + cg * (BN / 4);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (as * MSUB + sub) * BN + cg * (BN / 4);
 #pragma unroll
       for (int cc = 0; cc < NB; ++cc) {
         const int col = col0 + cc * 32;
@@ -373,6 +393,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
           }
         }
       }
+      }   // sub-tile
       tc_fence_before();
       mbar_arrive(&tmem_empty[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
@@ -383,19 +404,19 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::kTmemCols); }
 }
 
-template <int BN, bool LO>
+template <int BN, bool LO, int MSUB>
 static int launch_conv(ConvParams& p, cudaStream_t stream) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, MSUB>;
   static bool attr_set = false;
   if (!attr_set) {
-    B200SAT_CHECK_CUDA(cudaFuncSetAttribute(conv1d_tcgen05<BN, LO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    B200SAT_CHECK_CUDA(cudaFuncSetAttribute(conv1d_tcgen05<BN, LO, MSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  p.m_tiles = (p.m_rows + CV_BM - 1) / CV_BM;
+  p.m_tiles = (p.m_rows + CV_BM * MSUB - 1) / (CV_BM * MSUB);
   p.n_tiles = (p.Cout + BN - 1) / BN;
   const long tiles = static_cast<long>(p.m_tiles) * p.B * p.n_tiles * p.phases;
   const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-  conv1d_tcgen05<BN, LO><<<grid, CV_THREADS, Cfg::kSmemBytes, stream>>>(p);
+  conv1d_tcgen05<BN, LO, MSUB><<<grid, CV_THREADS, Cfg::kSmemBytes, stream>>>(p);
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }
@@ -544,6 +565,163 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const __nv_bfloat16* __re
   }
 }
 
+// Fast paths of the two edge layers (stereo audio, 7 taps - every Oobleck config the reference ships):
+//
+// conv_in_fast: lane == CPT consecutive output channels with their CPT*CIN*K weights in registers; a warp walks 32 consecutive
+// time steps and reads each audio sample as a shared-memory broadcast, so a step costs CIN*K broadcast loads + CPT*CIN*K FMAs
+// and every store instruction writes one complete [Cout] row (256 B at Cout = 128).  ~25x faster than the generic kernel above,
+// which spent its time on two shared-memory loads per FMA.
+template <int CPT, int CIN, int K>
+__global__ void __launch_bounds__(256) conv_in_fast_kernel(const float* __restrict__ x, const float* __restrict__ w /*[Cout,CIN,K]*/,
+                                                           const float* __restrict__ bias, const float* __restrict__ sa,
+                                                           const float* __restrict__ sib, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
+                                                           __nv_bfloat16* act_hi, __nv_bfloat16* act_lo, int T, int Cout, int pad) {
+  constexpr int TT = 256, TS = 32, SPAN = TT + K - 1;
+  __shared__ float sx[CIN][SPAN];
+  const int b = blockIdx.y, t0 = blockIdx.x * TT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < CIN * SPAN; i += 256) {
+    const int ci = i / SPAN, tt = i % SPAN;
+    const int t = t0 + tt - pad;
+    sx[ci][tt] = (t >= 0 && t < T) ? x[(static_cast<long>(b) * CIN + ci) * T + t] : 0.f;
+  }
+  const int co0 = lane * CPT;
+  float wr[CPT][CIN * K], br[CPT], ar[CPT], ir[CPT];
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) {
+#pragma unroll
+    for (int j = 0; j < CIN * K; ++j) wr[c][j] = w[(co0 + c) * CIN * K + j];
+    br[c] = bias ? bias[co0 + c] : 0.f;
+    ar[c] = sa ? sa[co0 + c] : 0.f;
+    ir[c] = sib ? sib[co0 + c] : 0.f;
+  }
+  __syncthreads();
+  for (int s2 = 0; s2 < TS; ++s2) {
+    const int tl = warp * TS + s2;
+    const int t = t0 + tl;
+    if (t >= T) break;
+    float acc[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) acc[c] = br[c];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float xv = sx[ci][tl + k];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) acc[c] = fmaf(wr[c][ci * K + k], xv, acc[c]);
+      }
+    }
+    const size_t off = (static_cast<size_t>(b) * T + t) * Cout + co0;
+    auto store = [&](__nv_bfloat16* hi, __nv_bfloat16* lo) {
+      uint32_t hw[CPT / 2], lw[CPT / 2];
+#pragma unroll
+      for (int c = 0; c < CPT / 2; ++c) {
+        hw[c] = pack_bf16(acc[2 * c], acc[2 * c + 1]);
+        const float2 h = unpack_bf16(hw[c]);
+        lw[c] = pack_bf16(acc[2 * c] - h.x, acc[2 * c + 1] - h.y);
+      }
+      if (CPT == 4) {
+        *reinterpret_cast<uint2*>(hi + off) = make_uint2(hw[0], hw[CPT / 2 - 1]);
+        if (lo) *reinterpret_cast<uint2*>(lo + off) = make_uint2(lw[0], lw[CPT / 2 - 1]);
+      } else {
+        *reinterpret_cast<uint32_t*>(hi + off) = hw[0];
+        if (lo) *reinterpret_cast<uint32_t*>(lo + off) = lw[0];
+      }
+    };
+    if (out_hi) store(out_hi, out_lo);
+    if (act_hi) {
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) { const float sn = fast_sin(acc[c] * ar[c]); acc[c] += ir[c] * sn * sn; }
+      store(act_hi, act_lo);
+    }
+  }
+}
+
+// conv_out_fast: planes [B, T, Cin] -> y fp32 [B, COUT, T].  A block owns 64 time steps; lane = (time group of 4 steps) x (quarter of
+// the input channels, interleaved ci = 4 j + cq so that the fp32 shared-memory tile with a (Cin + 1)-word pitch is read
+// conflict-free); each thread keeps 4 x COUT accumulators, reads 10 tile values + K weight pairs per channel for 4*K*COUT FMAs,
+// and the four channel quarters are combined with two shuffles.  Output stores are 128-byte coalesced along time.
+template <int COUT, int K>
+__global__ void __launch_bounds__(64) conv_out_fast_kernel(const __nv_bfloat16* __restrict__ in_hi, const __nv_bfloat16* __restrict__ in_lo,
+                                                           const float* __restrict__ w /*[COUT,Cin,K]*/, const float* __restrict__ bias,
+                                                           float* __restrict__ y, int Cin, int T, int pad, int tanh_out) {
+  constexpr int TT = 64, ROWS = TT + K - 1;
+  extern __shared__ float sm[];
+  const int pitch = Cin + 1;
+  float* sx = sm;                     // [ROWS][pitch]
+  float* sw = sm + ROWS * pitch;      // [K][Cin][COUT]
+  const int b = blockIdx.y, t0 = blockIdx.x * TT;
+  for (int i = threadIdx.x; i < COUT * Cin * K; i += 64) {
+    const int co = i / (Cin * K), rem = i % (Cin * K), ci = rem / K, k = rem % K;
+    sw[(k * Cin + ci) * COUT + co] = w[i];
+  }
+  const int chunks = Cin / 8;
+  for (int i = threadIdx.x; i < ROWS * chunks; i += 64) {
+    const int r = i / chunks, c8 = (i % chunks) * 8;
+    const int t = t0 + r - pad;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (t >= 0 && t < T) {
+      const size_t off = (static_cast<size_t>(b) * T + t) * Cin + c8;
+      const uint4 u = *reinterpret_cast<const uint4*>(in_hi + off);
+      const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float2 f = unpack_bf16(uw[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+      if (in_lo) {
+        const uint4 u2 = *reinterpret_cast<const uint4*>(in_lo + off);
+        const uint32_t lw[4] = {u2.x, u2.y, u2.z, u2.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 f = unpack_bf16(lw[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sx[r * pitch + c8 + e] = v[e];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tq = lane >> 2, cq = lane & 3;
+  const int tl = (warp * 8 + tq) * 4;
+  float acc[4][COUT];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[a][co] = 0.f;
+  for (int j = 0; j < Cin / 4; ++j) {
+    const int ci = 4 * j + cq;
+    float xr[4 + K - 1];
+#pragma unroll
+    for (int r = 0; r < 4 + K - 1; ++r) xr[r] = sx[(tl + r) * pitch + ci];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      float wv[COUT];
+#pragma unroll
+      for (int co = 0; co < COUT; ++co) wv[co] = sw[(k * Cin + ci) * COUT + co];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[a][co] = fmaf(xr[a + k], wv[co], acc[a][co]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) {
+      acc[a][co] += __shfl_xor_sync(0xffffffffu, acc[a][co], 1);
+      acc[a][co] += __shfl_xor_sync(0xffffffffu, acc[a][co], 2);
+    }
+  const int t = t0 + tl + cq;      // lane cq of a time group writes step cq: 32 consecutive steps per warp
+  if (t < T) {
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) {
+      float v = (cq == 0) ? acc[0][co] : (cq == 1) ? acc[1][co] : (cq == 2) ? acc[2][co] : acc[3][co];
+      if (bias) v += bias[co];
+      y[(static_cast<size_t>(b) * COUT + co) * T + t] = tanh_out ? tanhf(v) : v;
+    }
+  }
+}
+
 // fp32 [B, C, T] -> channels-last hi/lo planes [B, T, C] (decoder input latents)
 __global__ void to_planes_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                  int B, int C, int T) {
@@ -628,14 +806,17 @@ extern "C" int b200sat_conv1d_fwd(const void* in_hi, const void* in_lo, const vo
   else { p.T_out = (T_in - 1) * stride - 2 * pad + taps; p.taps = 2; p.m_rows = T_in + 1; p.phases = stride; wrows = stride * Cout; wk = 2 * Cin; }
   if (p.T_out <= 0) { set_last_error("conv1d: empty output"); return B200SAT_EINVAL; }
   const int s_in = (mode == 1) ? stride : 1;
-  const int bn = (Cout >= 256) ? 256 : 128;
+  int bn = (Cout >= 256) ? 256 : 128;
+  bool tall_env = true;
   int rc;
   {
     // B200SAT_CONV_WINDOW=0 falls back to per-tap A tiles (A/B measurement of the shared window)
     static const int win_env = [] { const char* e = getenv("B200SAT_CONV_WINDOW"); return e ? atoi(e) : 1; }();
+    tall_env = win_env != 3;   // B200SAT_CONV_WINDOW=3: window but 128-row tiles (A/B measurement)
     const int wr = CV_BM + (p.taps - 1) * dil;
     p.window = (mode == 0 && win_env != 0 && wr * 128 <= 24 * 1024) ? 1 : 0;
     p.win_rows = p.window ? wr : CV_BM;
+    if (p.window && tall_env) bn = 128;   // 256 x 128 tiles (the weight box must match the kernel's BN)
   }
   if ((rc = make_plane_map(&p.tmA[0], in_hi, B, T_in, Cin, s_in, p.win_rows))) return rc;
   if (in_lo && (rc = make_plane_map(&p.tmA[1], in_lo, B, T_in, Cin, s_in, p.win_rows))) return rc;
@@ -652,8 +833,11 @@ extern "C" int b200sat_conv1d_fwd(const void* in_hi, const void* in_lo, const vo
   p.act_hi = static_cast<__nv_bfloat16*>(act_hi); p.act_lo = static_cast<__nv_bfloat16*>(act_lo);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool lo = p.res_lo || p.out_lo || p.act_lo;
-  if (bn == 256) return lo ? launch_conv<256, true>(p, s) : launch_conv<256, false>(p, s);
-  return lo ? launch_conv<128, true>(p, s) : launch_conv<128, false>(p, s);
+  // stride-1 convs with a shared window: 256 x 128 tiles (two accumulators per weight slice) for every width - the window makes A
+  // cheap, so tall tiles minimise the bytes of shared-memory fill per flop
+  if (p.window && tall_env) return lo ? launch_conv<128, true, 2>(p, s) : launch_conv<128, false, 2>(p, s);
+  if (bn == 256) return lo ? launch_conv<256, true, 1>(p, s) : launch_conv<256, false, 1>(p, s);
+  return lo ? launch_conv<128, true, 1>(p, s) : launch_conv<128, false, 1>(p, s);
 }
 
 extern "C" int b200sat_wn_pack(const float* v, const float* g, float* inv_norm_scratch, void* w_hi, void* w_lo, int Cout, int Cin,
@@ -684,6 +868,15 @@ extern "C" int b200sat_conv_in(const float* x, const float* w, const float* bias
                                void* out_hi, void* out_lo, void* act_hi, void* act_lo, int B, int Cin, int T, int Cout, int K, int pad,
                                void* stream) {
   if (!x || !w || B <= 0 || Cin <= 0 || Cin > 8 || Cout % 8 || K <= 0) { set_last_error("conv_in: bad arguments (Cin <= 8, Cout % 8 == 0)"); return B200SAT_EINVAL; }
+  if (Cin == 2 && K == 7 && (Cout == 128 || Cout == 64)) {
+    dim3 fgrid((T + 255) / 256, B);
+    auto* oh = static_cast<__nv_bfloat16*>(out_hi); auto* ol = static_cast<__nv_bfloat16*>(out_lo);
+    auto* ah = static_cast<__nv_bfloat16*>(act_hi); auto* al = static_cast<__nv_bfloat16*>(act_lo);
+    if (Cout == 128) conv_in_fast_kernel<4, 2, 7><<<fgrid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, w, bias, snake_a, snake_invb, oh, ol, ah, al, T, Cout, pad);
+    else conv_in_fast_kernel<2, 2, 7><<<fgrid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, w, bias, snake_a, snake_invb, oh, ol, ah, al, T, Cout, pad);
+    B200SAT_CHECK_CUDA(cudaGetLastError());
+    return B200SAT_OK;
+  }
   const int smem = (Cout * Cin * K + Cin * (64 + K - 1)) * 4;
   if (smem > 48 * 1024) { set_last_error("conv_in: weights do not fit in 48 KB of shared memory"); return B200SAT_EUNSUPPORTED; }
   dim3 grid((T + 63) / 64, B);
@@ -697,6 +890,14 @@ extern "C" int b200sat_conv_in(const float* x, const float* w, const float* bias
 extern "C" int b200sat_conv_out(const void* in_hi, const void* in_lo, const float* w, const float* bias, float* y, int B, int Cin,
                                 int T, int Cout, int K, int pad, int tanh_out, void* stream) {
   if (!in_hi || !w || !y || B <= 0 || Cout <= 0 || Cout > 8) { set_last_error("conv_out: bad arguments (Cout <= 8)"); return B200SAT_EINVAL; }
+  if (Cout == 2 && K == 7 && Cin % 8 == 0 && ((64 + 6) * (Cin + 1) + 2 * 7 * Cin) * 4 <= 48 * 1024) {
+    const int fsmem = ((64 + 6) * (Cin + 1) + 2 * 7 * Cin) * 4;
+    dim3 fgrid((T + 63) / 64, B);
+    conv_out_fast_kernel<2, 7><<<fgrid, 64, fsmem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(in_hi), static_cast<const __nv_bfloat16*>(in_lo), w, bias, y, Cin, T, pad, tanh_out);
+    B200SAT_CHECK_CUDA(cudaGetLastError());
+    return B200SAT_OK;
+  }
   const int smem = (Cout * K * Cin + (32 + K - 1) * (Cin + 1)) * 4;
   if (smem > 48 * 1024) { set_last_error("conv_out: tile does not fit in 48 KB of shared memory"); return B200SAT_EUNSUPPORTED; }
   dim3 grid((T + 31) / 32, B);
