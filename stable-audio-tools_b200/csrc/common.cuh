@@ -93,6 +93,17 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// shared -> global tensor store (bulk async group); the source must be made visible to the async proxy first (fence_proxy_async_smem)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the N most recent store groups of this thread have finished READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -290,7 +301,7 @@ __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + _
 namespace b200sat {
 // Encode a tiled bf16 tensor map; rank <= 4; dims/strides innermost first; strides in BYTES for dims 1..rank-1.
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                     const uint32_t* box, int swizzle128);
+                     const uint32_t* box, int swizzle128 /* 0 none, 1 = 128 B, 2 = 64 B */);
 int num_sms();
 void set_last_error(const char* msg);
 }  // namespace b200sat

@@ -25,6 +25,8 @@ namespace b200sat {
 struct ConvParams {
   CUtensorMap tmA[2];  // input planes hi, lo: dims {Cin, s_in, T_in/s_in, B}
   CUtensorMap tmB[2];  // packed weight planes hi, lo: dims {taps*Cin, rows}
+  CUtensorMap tmRes, tmOut, tmAct;  // hi planes of the residual / raw / activated outputs: dims {Cout, s_o, T_out/s_o, B}, box 32 x 32, 64-byte swizzle
+  int tma_epi;         // 1: the epilogue moves the hi planes with TMA (residual load, raw / activated stores)
   const float* bias;
   const float* snake_a;     // exp(alpha) per output channel (of the consumer's SnakeBeta), or null
   const float* snake_invb;  // 1/(exp(beta)+1e-9)
@@ -61,7 +63,7 @@ struct ConvCfg {
   static constexpr int kBStages = (MSUB == 2) ? 4 : ((BN == 256) ? 3 : 5);
   static constexpr int kTmemCols = 2 * MSUB * BN;
   static constexpr int kStagingBytes = 16 * 4096;  // two 32-row x 64-byte transposition buffers (raw, activated) per epilogue warp
-  static constexpr int kSmemBytes = kAItems * kAItemBytes + kBStages * kBBytes + kStagingBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kAItems * kAItemBytes + kBStages * kBBytes + kStagingBytes + 1024 + 512;
   static_assert(kTmemCols <= 512, "TMEM has 512 columns");
 };
 
@@ -133,7 +135,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
   uint64_t* empty_b = full_b + Cfg::kBStages;
   uint64_t* tmem_full = empty_b + Cfg::kBStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bar = tmem_empty + 2;                       // one per epilogue warp (TMA residual loads)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + CV_EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -153,6 +156,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
     for (int i = 0; i < Cfg::kAItems; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
     for (int i = 0; i < Cfg::kBStages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CV_EPI_WARPS * 32); }
+    for (int i = 0; i < CV_EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols); tmem_relinquish(); }
@@ -284,6 +288,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
     const int lrow = lane >> 2, lchunk = lane & 3;             // line side: 8 rows x 4 chunks per instruction
     const int swz = (lane >> 1) & 3;
     const uint32_t my_o = stg_o + lane * 64, my_a = stg_a + lane * 64;
+    const bool tma_epi = p.tma_epi != 0;
+    uint32_t rphase = 0;
     int as = 0; uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int ph, n_blk, b, m_blk;
@@ -311,9 +317,17 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
         my_off = (static_cast<size_t>(b) * p.T_out + (my_ok ? my_t : 0)) * p.Cout;
       }
       const int col0 = n_blk * BN + cg * (BN / 4);
+      // TMA coordinates of this warp's 32 rows in the {Cout, s_o, T_out/s_o, B} planes (mode 2 interleaves `stride` phases)
+      int trow = m_base + q * 32, tph = 0;
+      if (p.mode == 2) {
+        const int d = ph - p.pad;
+        const int off = (d >= 0) ? d / p.stride : -((-d + p.stride - 1) / p.stride);
+        tph = d - off * p.stride;
+        trow += off;
+      }
       // residual of the first block: in flight while the accumulator is still being produced
       uint4 rres[4];
-      if (p.res_hi && col0 < p.Cout) {
+      if (!tma_epi && p.res_hi && col0 < p.Cout) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           rres[i] = grow[i] >= 0 ? __ldg(reinterpret_cast<const uint4*>(p.res_hi + static_cast<size_t>(grow[i]) * p.Cout + col0 + lchunk * 8)) : make_uint4(0, 0, 0, 0);
@@ -325,16 +339,28 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
         if (col >= p.Cout) break;
         uint32_t raw[32];
         tmem_ld_32x32(taddr + cc * 32, raw);
-        __syncwarp();                                   // the previous block's line-side stores have read the buffers
-        if (p.res_hi) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { const int r = lrow + 8 * i; sts128(stg_o + r * 64 + ((lchunk ^ ((r >> 1) & 3)) << 4), rres[i]); }
-          if (cc + 1 < NB && col + 32 < p.Cout) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              rres[i] = grow[i] >= 0 ? __ldg(reinterpret_cast<const uint4*>(p.res_hi + static_cast<size_t>(grow[i]) * p.Cout + col + 32 + lchunk * 8)) : make_uint4(0, 0, 0, 0);
+        if (tma_epi) {
+          if (lane == 0) {
+            tma_store_wait_read<0>();                   // the previous block's stores have read the buffers
+            if (p.res_hi) {
+              mbar_arrive_expect_tx(&res_bar[ew], 2048);
+              tma_load_4d(stage_base + ew * 4096, &p.tmRes, &res_bar[ew], col, tph, trow, b);
+            }
           }
           __syncwarp();
+          if (p.res_hi) { mbar_wait(&res_bar[ew], rphase); rphase ^= 1; }
+        } else {
+          __syncwarp();                                 // the previous block's line-side stores have read the buffers
+          if (p.res_hi) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const int r = lrow + 8 * i; sts128(stg_o + r * 64 + ((lchunk ^ ((r >> 1) & 3)) << 4), rres[i]); }
+            if (cc + 1 < NB && col + 32 < p.Cout) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                rres[i] = grow[i] >= 0 ? __ldg(reinterpret_cast<const uint4*>(p.res_hi + static_cast<size_t>(grow[i]) * p.Cout + col + 32 + lchunk * 8)) : make_uint4(0, 0, 0, 0);
+            }
+            __syncwarp();
+          }
         }
         tmem_ld_wait_regs(raw);
         float v[32];
@@ -381,15 +407,25 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
           }
           stage_row<LO>(my_a, swz, v, (LO && p.act_lo && my_ok) ? p.act_lo + my_off + col : nullptr);
         }
-        __syncwarp();
+        if (tma_epi) {
+          fence_proxy_async_smem();                     // generic-proxy writes of the buffers -> visible to the TMA engine
+          __syncwarp();
+          if (lane == 0) {
+            if (p.out_hi) tma_store_4d(&p.tmOut, stage_base + ew * 4096, col, tph, trow, b);
+            if (p.act_hi) tma_store_4d(&p.tmAct, stage_base + ew * 4096 + 2048, col, tph, trow, b);
+            tma_store_commit();
+          }
+        } else {
+          __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = lrow + 8 * i;
-          if (grow[i] >= 0) {
-            const size_t o = static_cast<size_t>(grow[i]) * p.Cout + col + lchunk * 8;
-            const uint32_t so = r * 64 + ((lchunk ^ ((r >> 1) & 3)) << 4);
-            if (p.out_hi) *reinterpret_cast<uint4*>(p.out_hi + o) = lds128(stg_o + so);
-            if (p.act_hi) *reinterpret_cast<uint4*>(p.act_hi + o) = lds128(stg_a + so);
+          for (int i = 0; i < 4; ++i) {
+            const int r = lrow + 8 * i;
+            if (grow[i] >= 0) {
+              const size_t o = static_cast<size_t>(grow[i]) * p.Cout + col + lchunk * 8;
+              const uint32_t so = r * 64 + ((lchunk ^ ((r >> 1) & 3)) << 4);
+              if (p.out_hi) *reinterpret_cast<uint4*>(p.out_hi + o) = lds128(stg_o + so);
+              if (p.act_hi) *reinterpret_cast<uint4*>(p.act_hi + o) = lds128(stg_a + so);
+            }
           }
         }
       }
@@ -398,6 +434,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
       mbar_arrive(&tmem_empty[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if (tma_epi && lane == 0) tma_store_wait_read<0>();   // shared memory must outlive the last stores' reads
   }
   tc_fence_before();
   __syncthreads();
@@ -826,6 +863,25 @@ extern "C" int b200sat_conv1d_fwd(const void* in_hi, const void* in_lo, const vo
     uint32_t box[2] = {CV_BK, static_cast<uint32_t>(bn)};
     if ((rc = encode_tmap_bf16(&p.tmB[0], w_hi, 2, dims, strides, box, 1))) return rc;
     if (w_lo && (rc = encode_tmap_bf16(&p.tmB[1], w_lo, 2, dims, strides, box, 1))) return rc;
+  }
+  {
+    // epilogue planes through TMA: {Cout, s_o, T_out/s_o, B}, 32 x 32 boxes, 64-byte swizzle (= the staging buffers' layout)
+    static const int epi_env = [] { const char* e = getenv("B200SAT_CONV_TMA_EPI"); return e ? atoi(e) : 1; }();
+    const int s_o = (mode == 2) ? stride : 1;
+    // transposed convs keep the line-side path: their phase-interleaved rows start at negative coordinates, which the TMA store
+    // unit rejects (illegal instruction on sm_100a; loads accept them)
+    p.tma_epi = (epi_env && mode != 2) ? 1 : 0;
+    if (p.tma_epi) {
+      auto omap = [&](CUtensorMap* tm, const void* base) {
+        uint64_t dims[4] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(s_o), static_cast<uint64_t>(p.T_out / s_o), static_cast<uint64_t>(B)};
+        uint64_t strides[3] = {static_cast<uint64_t>(Cout) * 2, static_cast<uint64_t>(Cout) * s_o * 2, static_cast<uint64_t>(Cout) * p.T_out * 2};
+        uint32_t box[4] = {32, 1, 32, 1};
+        return encode_tmap_bf16(tm, base, 4, dims, strides, box, 2);
+      };
+      if (res_hi && (rc = omap(&p.tmRes, res_hi))) return rc;
+      if (out_hi && (rc = omap(&p.tmOut, out_hi))) return rc;
+      if (act_hi && (rc = omap(&p.tmAct, act_hi))) return rc;
+    }
   }
   p.bias = bias; p.snake_a = snake_a; p.snake_invb = snake_invb;
   p.res_hi = static_cast<const __nv_bfloat16*>(res_hi); p.res_lo = static_cast<const __nv_bfloat16*>(res_lo);
