@@ -334,6 +334,43 @@ def other_kernels(dev, pk):
     by = 2.0 * x.numel() * 2
     out.append({"kernel": "layernorm_kernel (2050 x 1536 bf16)", "bound": "hbm", "achieved": by / us / 1e3, "peak": pk["hbm"], "unit": "GB/s",
                 "frac": by / us / 1e3 / pk["hbm"], "avg_launch_ms": us / 1e3, "note": "12.6 MB working set is L2-resident: latency-, not HBM-bound"})
+    # same kernels at shapes that leave L2 / the short-sequence regime: LayerNorm at the training batch over six rotating buffers
+    # (302 MB in + out > 126 MB L2), self-attention at N = 4097 (BASELINE.json configs[4] seq sweep end point)
+    xs = [torch.randn(8 * (T_LAT + 1), D_MODEL, device=dev).bfloat16() for _ in range(6)]
+    ys = [torch.empty_like(a) for a in xs]
+
+    def ln6():
+        for a_, b_ in zip(xs, ys):
+            ops.layernorm(a_, gm, out=b_)
+    us = _graph_time_us(ln6, reps=4) / 6
+    by = 2.0 * xs[0].numel() * 2
+    out.append({"kernel": "layernorm_kernel (8200 x 1536 bf16, training batch, rotating buffers > L2)", "bound": "hbm", "achieved": by / us / 1e3,
+                "peak": pk["hbm"], "unit": "GB/s", "frac": by / us / 1e3 / pk["hbm"], "avg_launch_ms": us / 1e3})
+    del xs, ys
+    N4 = 4097
+    qkv4 = torch.randn(B, N4, 3, H, 64, device=dev).bfloat16()
+    o4 = torch.empty(B, N4, H, 64, device=dev, dtype=torch.bfloat16)
+    us = _graph_time_us(lambda: ops.attention(qkv4[:, :, 0], qkv4[:, :, 1], qkv4[:, :, 2], out=o4), reps=5)
+    fl = 4.0 * B * H * N4 * N4 * 64
+    out.append({"kernel": "attention_fwd_tcgen05 (self-attention B=2 H=24 N=4097 dh=64)", "bound": "tensor", "achieved": fl / us / 1e6,
+                "peak": pk["bf16"], "unit": "TFLOP/s", "frac": fl / us / 1e6 / pk["bf16"], "avg_launch_ms": us / 1e3})
+    del qkv4, o4
+    # SnakeBeta backward stream (Oobleck training): 16 x 65536 x 128 elements, reads d_act / x / d_skip, writes d_raw (8 B per element)
+    from b200sat._lib import lib as _lib, check as _check
+    rows, C = 16 * 65536, 128
+    pl = [torch.randn(rows, C, device=dev).bfloat16() for _ in range(4)]
+    sa_, sb_ = torch.rand(C, device=dev) + 0.5, torch.rand(C, device=dev) + 0.5
+    acc3 = [torch.zeros(C, device=dev) for _ in range(3)]
+    st = torch.cuda.current_stream
+
+    def snk():
+        _check(_lib().b200sat_snake_bwd(pl[0].data_ptr(), pl[1].data_ptr(), pl[2].data_ptr(), sa_.data_ptr(), sb_.data_ptr(), pl[3].data_ptr(),
+                                        acc3[0].data_ptr(), acc3[1].data_ptr(), acc3[2].data_ptr(), rows, C, st().cuda_stream), "snake_bwd")
+    us = _graph_time_us(snk, reps=5)
+    by = 8.0 * rows * C
+    out.append({"kernel": "snake_bwd_kernel (16 x 65536 x 128, with skip add and alpha/beta/bias reductions)", "bound": "hbm", "achieved": by / us / 1e3,
+                "peak": pk["hbm"], "unit": "GB/s", "frac": by / us / 1e3 / pk["hbm"], "avg_launch_ms": us / 1e3})
+    del pl
     # Oobleck: random-init weights of the stable_audio_2_0_vae architecture, 47 s stereo clip (1024 latents)
     g = torch.Generator(device=dev).manual_seed(0)
     sd = _oobleck_state_dict(dev, g)

@@ -34,52 +34,89 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 //   d_alpha = sum d_act * invb * sin(2 a x) * a * x                  (alpha is log-scale: da/dalpha = a)
 //   d_beta  = -sum d_act * sin^2(a x) * invb^2 * exp(beta)
 //   d_bias  = sum d_raw                                             (bias of the conv that produced x)
-// One pass over HBM: reads d_act, x (and d_skip), writes d_raw; 8 channels per thread, rows strided over the grid.
-__global__ void __launch_bounds__(256) snake_bwd_kernel(const __nv_bfloat16* __restrict__ d_act, const __nv_bfloat16* __restrict__ x_raw,
+// One pass over HBM: reads d_act, x (and d_skip), writes d_raw; VEC channels per thread (4 keeps the register count low enough
+// for 4 blocks per SM), two rows in flight per thread, rows strided over the grid.
+template <int VEC>
+__device__ __forceinline__ void load_vec(const __nv_bfloat16* p, float* f) {
+  if (VEC == 8) {
+    unpack8(*reinterpret_cast<const uint4*>(p), f);
+  } else {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+    f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void store_vec(__nv_bfloat16* p, const float* f) {
+  if (VEC == 8) {
+    *reinterpret_cast<uint4*>(p) = pack8(f);
+  } else {
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256, (VEC == 4) ? 4 : 2) snake_bwd_kernel(const __nv_bfloat16* __restrict__ d_act, const __nv_bfloat16* __restrict__ x_raw,
                                                         const __nv_bfloat16* __restrict__ d_skip, const float* __restrict__ sa,
                                                         const float* __restrict__ sib, __nv_bfloat16* __restrict__ d_raw,
                                                         float* __restrict__ dalpha, float* __restrict__ dbeta, float* __restrict__ dbias,
                                                         long rows, int C) {
-  __shared__ float red[24][257];
-  const int gpr = C >> 3;         // threads per row
+  __shared__ float red[3 * VEC][257];
+  const int gpr = C / VEC;        // threads per row
   const int rpi = 256 / gpr;      // rows per block iteration
   const int cg = threadIdx.x % gpr, rs = threadIdx.x / gpr;
-  float a[8], ib[8], ga[8], gb[8], gbias[8];
+  float a2[VEC], iba[VEC], ga[VEC], gc[VEC], gbias[VEC];
+  float gg[VEC];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { a[j] = sa[cg * 8 + j]; ib[j] = sib[cg * 8 + j]; ga[j] = gb[j] = gbias[j] = 0.f; }
-  for (long r = static_cast<long>(blockIdx.x) * rpi + rs; r < rows; r += static_cast<long>(gridDim.x) * rpi) {
-    const size_t off = static_cast<size_t>(r) * C + cg * 8;
-    float g[8], x[8], sk[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(d_act + off), g);
-    unpack8(*reinterpret_cast<const uint4*>(x_raw + off), x);
-    if (d_skip) unpack8(*reinterpret_cast<const uint4*>(d_skip + off), sk);
+  for (int j = 0; j < VEC; ++j) {
+    const float a = sa[cg * VEC + j];
+    a2[j] = 2.f * a;
+    iba[j] = sib[cg * VEC + j] * a;
+    ga[j] = gc[j] = gbias[j] = gg[j] = 0.f;
+  }
+  const long stride = static_cast<long>(gridDim.x) * rpi;
+  for (long r = static_cast<long>(blockIdx.x) * rpi + rs; r < rows; r += 2 * stride) {
+    const long r1 = r + stride;
+    const bool two = r1 < rows;
+    const size_t off0 = static_cast<size_t>(r) * C + cg * VEC, off1 = static_cast<size_t>(two ? r1 : r) * C + cg * VEC;
+    float g0[VEC], x0[VEC], k0[VEC], g1[VEC], x1[VEC], k1[VEC];
+    load_vec<VEC>(d_act + off0, g0); load_vec<VEC>(x_raw + off0, x0);
+    load_vec<VEC>(d_act + off1, g1); load_vec<VEC>(x_raw + off1, x1);
+    if (d_skip) { load_vec<VEC>(d_skip + off0, k0); load_vec<VEC>(d_skip + off1, k1); }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float s, c;
-      fast_sincos(a[j] * x[j], &s, &c);
-      const float s2 = 2.f * s * c;
-      const float t = g[j] * ib[j] * s2 * a[j];
-      const float dr = g[j] + t + (d_skip ? sk[j] : 0.f);
-      ga[j] += t * x[j];
-      gb[j] += g[j] * s * s;
-      gbias[j] += dr;
-      o[j] = dr;
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      float* g = h ? g1 : g0; float* x = h ? x1 : x0; float* sk = h ? k1 : k0;
+      float o[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        float s2, c2;
+        fast_sincos(a2[j] * x[j], &s2, &c2);            // sin(2ax), cos(2ax); sin^2(ax) = (1 - cos 2ax) / 2
+        const float t = g[j] * iba[j] * s2;
+        const float dr = g[j] + t + (d_skip ? sk[j] : 0.f);
+        ga[j] = fmaf(t, x[j], ga[j]);
+        gg[j] += g[j];
+        gc[j] = fmaf(g[j], c2, gc[j]);
+        gbias[j] += dr;
+        o[j] = dr;
+      }
+      store_vec<VEC>(d_raw + (h ? off1 : off0), o);
     }
-    *reinterpret_cast<uint4*>(d_raw + off) = pack8(o);
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < VEC; ++j) {
     red[j][threadIdx.x] = ga[j];
-    red[8 + j][threadIdx.x] = gb[j];
-    red[16 + j][threadIdx.x] = gbias[j];
+    red[VEC + j][threadIdx.x] = 0.5f * (gg[j] - gc[j]);   // sum d_act * sin^2(a x)
+    red[2 * VEC + j][threadIdx.x] = gbias[j];
   }
   __syncthreads();
   // thread (v, cg) sums over the rpi row slots
-  for (int i = threadIdx.x; i < 24 * gpr; i += 256) {
+  for (int i = threadIdx.x; i < 3 * VEC * gpr; i += 256) {
     const int v = i / gpr, g2 = i % gpr;
     float s = 0.f;
     for (int r2 = 0; r2 < rpi; ++r2) s += red[v][r2 * gpr + g2];
-    const int kind = v >> 3, ch = g2 * 8 + (v & 7);
+    const int kind = v / VEC, ch = g2 * VEC + (v % VEC);
     if (kind == 0) atomicAdd(dalpha + ch, s);
     else if (kind == 1) { const float ibv = sib[ch]; atomicAdd(dbeta + ch, -s * ibv * ibv * (1.0f / ibv - 1e-9f)); }
     else if (dbias) atomicAdd(dbias + ch, s);
@@ -248,13 +285,16 @@ extern "C" int b200sat_snake_bwd(const void* d_act, const void* x_raw, const voi
                                  void* d_raw, float* dalpha, float* dbeta, float* dbias, long rows, int C, void* stream) {
   if (!d_act || !x_raw || !snake_a || !snake_invb || !d_raw || !dalpha || !dbeta || rows <= 0) { set_last_error("snake_bwd: bad arguments"); return B200SAT_EINVAL; }
   if (C < 64 || C > 2048 || (C & (C - 1))) { set_last_error("snake_bwd: C must be a power of two in [64, 2048]"); return B200SAT_EUNSUPPORTED; }
-  const int rpi = 256 / (C >> 3);
-  long blocks = (rows + rpi - 1) / rpi;
-  const long cap = static_cast<long>(num_sms()) * 8;
+  const int vec = (C <= 1024) ? 4 : 8;
+  const int rpi = 256 / (C / vec);
+  long blocks = (rows + 2 * rpi - 1) / (2 * rpi);
+  const long cap = static_cast<long>(num_sms()) * (vec == 4 ? 4 : 2);
   if (blocks > cap) blocks = cap;
-  snake_bwd_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(d_act), static_cast<const __nv_bfloat16*>(x_raw), static_cast<const __nv_bfloat16*>(d_skip),
-      snake_a, snake_invb, static_cast<__nv_bfloat16*>(d_raw), dalpha, dbeta, dbias, rows, C);
+  if (blocks < 1) blocks = 1;
+  auto* da = static_cast<const __nv_bfloat16*>(d_act); auto* xr = static_cast<const __nv_bfloat16*>(x_raw);
+  auto* ds = static_cast<const __nv_bfloat16*>(d_skip); auto* dr = static_cast<__nv_bfloat16*>(d_raw);
+  if (vec == 4) snake_bwd_kernel<4><<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(da, xr, ds, snake_a, snake_invb, dr, dalpha, dbeta, dbias, rows, C);
+  else snake_bwd_kernel<8><<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(da, xr, ds, snake_a, snake_invb, dr, dalpha, dbeta, dbias, rows, C);
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }
