@@ -416,6 +416,11 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
+    # stdout carries exactly one line (the JSON): libraries that announce themselves on stdout (NCCL prints its version from C) are
+    # sent to stderr until the result is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from b200sat import init, ops, sampling
@@ -551,6 +556,8 @@ def run_ours(args):
                 "api": "b200sat.generation.generate_diffusion_cond(host pinned noise/conditioning -> host latents)"},
         "gpu_launches": launches, "clocks": clk, "roofline": roof, "whole_step": whole, "cpu_baseline": cpu, "train": train, "ae_train": ae_train, "other_kernels": other,
     }
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
