@@ -149,6 +149,18 @@ int b200sat_attention_bwd(const void* q, const void* k, const void* v, const voi
 int b200sat_layernorm_bwd(const void* x, long ldx, const void* dy, long lddy, const float* gamma, const void* dres, long ldr,
                           void* dx_out, long ldo, float* dgamma, int rows, int D, float eps, void* stream);
 
+/* adaLN variant (transformer.py:680-697, y = LN(x; gamma) * (1 + scale_b) + shift_b): gain gamma * (1 + mod_scale[b, :]) (fp32 [B, ld_mod],
+ * rows_per_batch rows of x per batch entry); dp (fp32 [B, D], +=) receives sum_n dy * xhat per batch entry: dgamma = sum_b (1 + scale_b) dp_b,
+ * dscale_b = gamma * dp_b, dshift_b = per-batch column sums of dy. */
+int b200sat_layernorm_mod_bwd(const void* x, long ldx, const void* dy, long lddy, const float* gamma, const float* mod_scale, long ld_mod,
+                              int rows_per_batch, const void* dres, long ldr, void* dx_out, long ldo, float* dp, int rows, int D, float eps,
+                              void* stream);
+
+/* adaLN gate backward (transformer.py:690-701, x = x + branch * g_b with g_b = sigmoid(1 - gate_b), fp32 [B, D]):
+ * dbranch = dh * g_b (bf16), dgate[b, :] += sum_n dh * branch (fp32; the host applies d sigmoid). */
+int b200sat_gate_bwd(const void* dh, long ldh, const void* branch, long ldb, const float* gate, void* dbranch, long ldo, float* dgate,
+                     int rows_per_batch, int batches, int D, void* stream);
+
 /* out[n] += sum_m dY[m,n]: bias gradients of nn.Linear. */
 int b200sat_colsum(const void* dy, long ld, float* out, int M, int N, void* stream);
 

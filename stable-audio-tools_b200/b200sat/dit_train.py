@@ -22,14 +22,14 @@ from .dit_engine import DiTConfig
 
 class _StackFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, h0, cemb, model):
+    def forward(ctx, h0, cemb, mod, model):
         ctx.model = model
-        return model._stack_forward(h0, cemb)
+        return model._stack_forward(h0, cemb, mod)
 
     @staticmethod
     def backward(ctx, dout):
-        dh0, dcemb = ctx.model._stack_backward(dout.contiguous())
-        return dh0, dcemb, None
+        dh0, dcemb, dmod = ctx.model._stack_backward(dout.contiguous())
+        return dh0, dcemb, dmod, None
 
 
 _LAYER_PARAMS = [  # (suffix, shape fn(d, ck)) in flat-buffer order
@@ -41,13 +41,17 @@ _LAYER_PARAMS = [  # (suffix, shape fn(d, ck)) in flat-buffer order
 
 
 class DiTTrainModel(nn.Module):
-    """`DiffusionTransformer` (models/dit.py) for training, `global_cond_type='prepend'`, continuous transformer."""
+    """`DiffusionTransformer` (models/dit.py) for training, continuous transformer, `global_cond_type` 'prepend' (Stable Audio Open)
+    or 'adaLN' (transformer.py:675-701: LayerNorm modulated by (1 + scale_b, shift_b), branch outputs gated by sigmoid(1 - gate_b)).
+    adaLN: the per-layer `to_scale_shift_gate` vectors and the `global_cond_embedder` MLP are O(B d) host plumbing in PyTorch autograd
+    (they enter and leave the stack as one [L, B, 6d] tensor); everything token-sized runs on the kernels."""
 
     def __init__(self, state_dict, device="cuda"):
         super().__init__()
         cfg = DiTConfig.from_state_dict(state_dict)
-        if cfg.global_cond_type != "prepend":
-            raise NotImplementedError("b200sat training path: only global_cond_type='prepend' is implemented")
+        if cfg.global_cond_type not in ("prepend", "adaLN"):
+            raise NotImplementedError(f"b200sat training path: global_cond_type {cfg.global_cond_type!r} is not implemented")
+        self.adaln = cfg.global_cond_type == "adaLN"
         self.cfg = cfg
         dev = torch.device(device)
         d, ck, L = cfg.embed_dim, cfg.cond_embed_dim, cfg.depth
@@ -138,11 +142,13 @@ class DiTTrainModel(nn.Module):
             dh_a=bf(M, d), dh_b=bf(M, d), dn=bf(M, d), du=bf(M, 8 * d), da=bf(M, d), dqkv=bf(M, 3 * d), dq2=bf(M, d),
             dkv2=bf(B * Lc, 2 * ck), dcemb=bf(B * Lc, ck),
         )
+        if self.adaln:   # un-gated branch outputs (for the gate gradients) and the gated gradient scratch
+            ws.update(br1=bf(L, M, d), br3=bf(L, M, d), dbr=bf(M, d))
         self._ws[key] = ws
         return ws
 
     # ------------------------------------------------------------------ stack forward / backward on the CUDA kernels
-    def _stack_forward(self, h0, cemb):
+    def _stack_forward(self, h0, cemb, mod=None):
         c = self.cfg
         d, H, ck, L = c.embed_dim, c.num_heads, c.cond_embed_dim, c.depth
         B, N, Lc = self._shape
@@ -153,8 +159,34 @@ class DiTTrainModel(nn.Module):
         rope = (*self.rope_tables(N), N, d, 64)
         ws["h"][0].copy_(h0)
         kvh = ck // 64
+        if self.adaln:
+            self._mod_dtype = mod.dtype
+            self._mod = mod.detach().float().contiguous()                       # [L, B, 6d]: scale_s, shift_s, gate_s, scale_f, shift_f, gate_f
+            self._gates = torch.sigmoid(1.0 - self._mod.view(L, B, 6, d)[:, :, [2, 5]]).contiguous()   # [L, B, 2, d]
         for i in range(L):
             h = ws["h"][i]
+            if self.adaln:
+                m6 = self._mod[i]
+                g_s, g_f = self._gates[i, :, 0].contiguous(), self._gates[i, :, 1].contiguous()
+                ops.layernorm(h, self._f32(i, "pre_norm.gamma"), scale=m6[:, 0:d], shift=m6[:, d:2 * d], rows_per_batch=N, out=ws["n1"][i])
+                ops.linear(ws["n1"][i], self._w(i, "self_attn.to_qkv.weight"), out=ws["qkv"][i], rope=rope)
+                qkv = ws["qkv"][i].view(B, N, 3, H, 64)
+                ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], out=ws["a1"][i].view(B, N, H, 64), lse=ws["lse1"][i])
+                ops.linear(ws["a1"][i], self._w(i, "self_attn.to_out.weight"), residual=h, out=ws["h1"][i], gate=g_s, row_remap=(N, 0, 0),
+                           save_pre=ws["br1"][i])
+                ops.layernorm(ws["h1"][i], self._f32(i, "cross_attend_norm.gamma"), out=ws["n2"][i])
+                ops.linear(ws["n2"][i], self._w(i, "cross_attn.to_q.weight"), out=ws["q2"][i])
+                ops.linear(self._cemb, self._w(i, "cross_attn.to_kv.weight"), out=ws["kv2"][i])
+                kv = ws["kv2"][i].view(B, Lc, 2, kvh, 64)
+                ops.attention(ws["q2"][i].view(B, N, H, 64), kv[:, :, 0], kv[:, :, 1], out=ws["a2"][i].view(B, N, H, 64), lse=ws["lse2"][i])
+                ops.linear(ws["a2"][i], self._w(i, "cross_attn.to_out.weight"), residual=ws["h1"][i], out=ws["h2"][i])
+                ops.layernorm(ws["h2"][i], self._f32(i, "ff_norm.gamma"), scale=m6[:, 3 * d:4 * d], shift=m6[:, 4 * d:5 * d], rows_per_batch=N,
+                              out=ws["n3"][i])
+                ops.linear(ws["n3"][i], self._w(i, "ff.ff.0.proj.weight"), bias=self._f32(i, "ff.ff.0.proj.bias"), swiglu=True,
+                           out=ws["act"][i], save_pre=ws["u"][i])
+                ops.linear(ws["act"][i], self._w(i, "ff.ff.2.weight"), bias=self._f32(i, "ff.ff.2.bias"), residual=ws["h2"][i], out=ws["h"][i + 1],
+                           gate=g_f, row_remap=(N, 0, 0), save_pre=ws["br3"][i])
+                continue
             ops.layernorm(h, self._f32(i, "pre_norm.gamma"), out=ws["n1"][i])
             ops.linear(ws["n1"][i], self._w(i, "self_attn.to_qkv.weight"), out=ws["qkv"][i], rope=rope)
             qkv = ws["qkv"][i].view(B, N, 3, H, 64)
@@ -184,15 +216,38 @@ class DiTTrainModel(nn.Module):
         dh.copy_(dout)
         ws["dcemb"].zero_()
         W, G = self._w, self._g
+        adaln = self.adaln
+        if adaln:
+            dmod = torch.zeros(L, B, 6, d, device=dh.device, dtype=torch.float32)
+            dgs = torch.zeros(L, 2, B, d, device=dh.device, dtype=torch.float32)     # d(sigmoid gates)
+            dpp = torch.zeros(L, 2, B, d, device=dh.device, dtype=torch.float32)     # per-batch sum dy*xhat of the two modulated norms
+            mod4 = self._mod.view(L, B, 6, d)
+
+        def mod_norm_bwd(i, which, x_saved, gamma_name, dres, out):
+            """LayerNorm-modulate backward (which: 0 self-attn, 1 feed-forward): fills dmod scale/shift, accumulates dgamma."""
+            sc = mod4[i, :, 3 * which]                                            # [B, d] view, row stride 6d
+            ops.layernorm_mod_bwd(x_saved, ws["dn"], self._f32(i, gamma_name), sc, N, dres=dres, out=out, dp=dpp[i, which])
+            P_ = dpp[i, which]
+            G(i, gamma_name).add_(((1.0 + sc) * P_).sum(0))
+            dmod[i, :, 3 * which] = self._f32(i, gamma_name)[None, :] * P_        # d scale
+            for b_ in range(B):                                                   # d shift = per-batch column sums of dy
+                ops.colsum(ws["dn"][b_ * N:(b_ + 1) * N], dmod[i, b_, 3 * which + 1])
+
         for i in reversed(range(L)):
-            # ---- feed-forward branch: h_out = h2 + W2 (a * silu(g)) + b2,  (a|g) = W1 n3 + b1
-            ops.colsum(dh, G(i, "ff.ff.2.bias"))
-            ops.gemm(dh, ws["act"][i], G(i, "ff.ff.2.weight"), d, 4 * d, M, a_mn=True, b_mn=True, accumulate=True)
-            ops.gemm(dh, W(i, "ff.ff.2.weight"), ws["du"], M, 4 * d, d, b_mn=True, swiglu_bwd_aux=ws["u"][i])
+            # ---- feed-forward branch: h_out = h2 + [gate *] (W2 (a * silu(g)) + b2),  (a|g) = W1 n3 + b1
+            dbr = dh
+            if adaln:
+                dbr = ops.gate_bwd(dh, ws["br3"][i], self._gates[i, :, 1].contiguous(), ws["dbr"], dgs[i, 1], N)
+            ops.colsum(dbr, G(i, "ff.ff.2.bias"))
+            ops.gemm(dbr, ws["act"][i], G(i, "ff.ff.2.weight"), d, 4 * d, M, a_mn=True, b_mn=True, accumulate=True)
+            ops.gemm(dbr, W(i, "ff.ff.2.weight"), ws["du"], M, 4 * d, d, b_mn=True, swiglu_bwd_aux=ws["u"][i])
             ops.colsum(ws["du"], G(i, "ff.ff.0.proj.bias"))
             ops.gemm(ws["du"], ws["n3"][i], G(i, "ff.ff.0.proj.weight"), 8 * d, d, M, a_mn=True, b_mn=True, accumulate=True)
             ops.gemm(ws["du"], W(i, "ff.ff.0.proj.weight"), ws["dn"], M, d, 8 * d, b_mn=True)
-            ops.layernorm_bwd(ws["h2"][i], ws["dn"], self._f32(i, "ff_norm.gamma"), dres=dh, out=dh_alt, dgamma=G(i, "ff_norm.gamma"))
+            if adaln:
+                mod_norm_bwd(i, 1, ws["h2"][i], "ff_norm.gamma", dh, dh_alt)
+            else:
+                ops.layernorm_bwd(ws["h2"][i], ws["dn"], self._f32(i, "ff_norm.gamma"), dres=dh, out=dh_alt, dgamma=G(i, "ff_norm.gamma"))
             dh, dh_alt = dh_alt, dh
             # ---- cross-attention branch
             ops.gemm(dh, ws["a2"][i], G(i, "cross_attn.to_out.weight"), d, d, M, a_mn=True, b_mn=True, accumulate=True)
@@ -208,19 +263,31 @@ class DiTTrainModel(nn.Module):
             ops.layernorm_bwd(ws["h1"][i], ws["dn"], self._f32(i, "cross_attend_norm.gamma"), dres=dh, out=dh_alt, dgamma=G(i, "cross_attend_norm.gamma"))
             dh, dh_alt = dh_alt, dh
             # ---- self-attention branch
-            ops.gemm(dh, ws["a1"][i], G(i, "self_attn.to_out.weight"), d, d, M, a_mn=True, b_mn=True, accumulate=True)
-            ops.gemm(dh, W(i, "self_attn.to_out.weight"), ws["da"], M, d, d, b_mn=True)
+            dbr = dh
+            if adaln:
+                dbr = ops.gate_bwd(dh, ws["br1"][i], self._gates[i, :, 0].contiguous(), ws["dbr"], dgs[i, 0], N)
+            ops.gemm(dbr, ws["a1"][i], G(i, "self_attn.to_out.weight"), d, d, M, a_mn=True, b_mn=True, accumulate=True)
+            ops.gemm(dbr, W(i, "self_attn.to_out.weight"), ws["da"], M, d, d, b_mn=True)
             qkv = ws["qkv"][i].view(B, N, 3, H, 64)
             dqkv = ws["dqkv"].view(B, N, 3, H, 64)
             ops.attention_bwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], ws["a1"][i].view(B, N, H, 64), ws["da"].view(B, N, H, 64),
                               ws["lse1"][i], dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], rope=(cos, sin))
             ops.gemm(ws["dqkv"], ws["n1"][i], G(i, "self_attn.to_qkv.weight"), 3 * d, d, M, a_mn=True, b_mn=True, accumulate=True)
             ops.gemm(ws["dqkv"], W(i, "self_attn.to_qkv.weight"), ws["dn"], M, d, 3 * d, b_mn=True)
-            ops.layernorm_bwd(ws["h"][i], ws["dn"], self._f32(i, "pre_norm.gamma"), dres=dh, out=dh_alt, dgamma=G(i, "pre_norm.gamma"))
+            if adaln:
+                mod_norm_bwd(i, 0, ws["h"][i], "pre_norm.gamma", dh, dh_alt)
+            else:
+                ops.layernorm_bwd(ws["h"][i], ws["dn"], self._f32(i, "pre_norm.gamma"), dres=dh, out=dh_alt, dgamma=G(i, "pre_norm.gamma"))
             dh, dh_alt = dh_alt, dh
             if self.grad_ready_hook is not None:
                 self.grad_ready_hook(i, self.layer_grad_slice(i))
-        return dh.clone(), ws["dcemb"].clone()
+        if adaln:   # gate = sigmoid(1 - g):  dg = -dsig * sig * (1 - sig)
+            sg = self._gates                                  # [L, B, 2, d]
+            dgate = -dgs.permute(0, 2, 1, 3) * sg * (1.0 - sg)
+            dmod[:, :, 2] = dgate[:, :, 0]
+            dmod[:, :, 5] = dgate[:, :, 1]
+            return dh.clone(), ws["dcemb"].clone(), dmod.view(L, B, 6 * d).to(self._mod_dtype)
+        return dh.clone(), ws["dcemb"].clone(), None
 
     # ------------------------------------------------------------------ full model forward (training branch of dit.py:231-431)
     def forward(self, x, t, cross_attn_cond=None, global_embed=None, cfg_dropout_prob=0.0):
@@ -244,12 +311,19 @@ class DiTTrainModel(nn.Module):
             ge = lin(F.silu(lin(global_embed.to(bf), "to_global_embed.0.weight")), "to_global_embed.2.weight")
             te = ge + te
         xin = F.conv1d(x, P["preprocess_conv.weight"].to(bf)) + x
-        h0 = torch.cat([te.unsqueeze(1), lin(xin.transpose(1, 2), "transformer.project_in.weight")], dim=1)   # [B, N, d]
-        N = T + 1
+        tok = lin(xin.transpose(1, 2), "transformer.project_in.weight")
         Lc = cemb.shape[1]
+        if self.adaln:   # dit.py:176-180, transformer.py:767-773, :836-837, :677: the global embedding modulates every block
+            h0, N, mod = tok, T, None
+            g6 = lin(F.silu(lin(te, "transformer.global_cond_embedder.0.weight", "transformer.global_cond_embedder.0.bias")),
+                     "transformer.global_cond_embedder.2.weight", "transformer.global_cond_embedder.2.bias")       # [B, 6d]
+            ssg = torch.stack([P[f"transformer.layers.{i}.to_scale_shift_gate"] for i in range(c.depth)])          # [L, 6d] fp32
+            mod = ssg.to(bf)[:, None, :] + g6[None, :, :]                                                            # [L, B, 6d]
+        else:
+            h0, N, mod = torch.cat([te.unsqueeze(1), tok], dim=1), T + 1, None                                       # [B, N, d]
         self._shape = (B, N, Lc)
-        hL = _StackFn.apply(h0.reshape(B * N, c.embed_dim).contiguous(), cemb.reshape(B * Lc, -1).contiguous(), self)
-        out = lin(hL.view(B, N, c.embed_dim), "transformer.project_out.weight").transpose(1, 2)[:, :, 1:]
+        hL = _StackFn.apply(h0.reshape(B * N, c.embed_dim).contiguous(), cemb.reshape(B * Lc, -1).contiguous(), mod, self)
+        out = lin(hL.view(B, N, c.embed_dim), "transformer.project_out.weight").transpose(1, 2)[:, :, N - T:]
         out = F.conv1d(out, P["postprocess_conv.weight"].to(bf)) + out
         return out
 

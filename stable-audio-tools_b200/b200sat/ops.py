@@ -235,6 +235,31 @@ def layernorm_bwd(x, dy, gamma, dres=None, out=None, dgamma=None, eps=1e-5):
     return out
 
 
+def layernorm_mod_bwd(x, dy, gamma, mod_scale, rows_per_batch, dres=None, out=None, dp=None, eps=1e-5):
+    """adaLN LayerNorm backward: gain gamma*(1+mod_scale[b]); dp fp32 [B, D] += per-batch sum of dy*xhat."""
+    rows, D = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    assert mod_scale.dtype == torch.float32 and dp.dtype == torch.float32 and dp.is_contiguous()
+    rc = lib().b200sat_layernorm_mod_bwd(x.data_ptr(), x.stride(0), dy.data_ptr(), dy.stride(0), gamma.data_ptr(), mod_scale.data_ptr(),
+                                         mod_scale.stride(0), rows_per_batch, _p(dres), dres.stride(0) if dres is not None else 0,
+                                         out.data_ptr(), out.stride(0), dp.data_ptr(), rows, D, float(eps), _stream())
+    LAUNCHES[0] += 1
+    check(rc, "layernorm_mod_bwd")
+    return out
+
+
+def gate_bwd(dh, branch, gate, dbranch, dgate, rows_per_batch):
+    """dbranch = dh * gate[b]; dgate[b] += sum_n dh * branch  (gate, dgate fp32 [B, D] contiguous)."""
+    M, D = dh.shape
+    assert gate.dtype == torch.float32 and gate.is_contiguous() and dgate.is_contiguous()
+    rc = lib().b200sat_gate_bwd(dh.data_ptr(), dh.stride(0), branch.data_ptr(), branch.stride(0), gate.data_ptr(), dbranch.data_ptr(),
+                                dbranch.stride(0), dgate.data_ptr(), rows_per_batch, M // rows_per_batch, D, _stream())
+    LAUNCHES[0] += 1
+    check(rc, "gate_bwd")
+    return dbranch
+
+
 def colsum(dy, out):
     M, N = dy.shape
     rc = lib().b200sat_colsum(dy.data_ptr(), dy.stride(0), out.data_ptr(), M, N, _stream())

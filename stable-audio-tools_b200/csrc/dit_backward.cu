@@ -8,11 +8,15 @@ namespace b200sat {
 //   g = dy * gamma;  dx = rstd * (g - mean(g) - xhat * mean(g * xhat));  dgamma += sum_rows dy * xhat
 // dx_out = dres + dx fuses the residual-stream gradient add of the pre-norm block (transformer.py:703-712).
 // Persistent grid: each warp walks rows, keeps its dgamma partials in registers; one atomicAdd per column per block.
-template <int MAXC>
+// MOD (adaLN, transformer.py:680-697: y = LN(x; gamma) * (1 + scale_b) + shift_b): the effective gain is gamma * (1 + scale[b, :]); the grid
+// is (blocks per batch entry, B) so a block only sees rows of one batch entry, and `dgamma` receives P[b, :] = sum_n dy * xhat PER BATCH
+// ENTRY, from which the host forms dgamma = sum_b (1 + scale_b) P_b and dscale_b = gamma * P_b (dshift_b = per-batch column sums of dy).
+template <int MAXC, bool MOD>
 __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                                                const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dres,
                                                                __nv_bfloat16* __restrict__ dx_out, float* __restrict__ dgamma, int rows,
-                                                               int D, long ldx, long lddy, long ldr, long ldo, float eps) {
+                                                               int D, long ldx, long lddy, long ldr, long ldo, float eps,
+                                                               const float* __restrict__ mod_scale, long ld_mod, int rows_per_batch) {
   extern __shared__ float s_dg[];  // [D]
   griddep_launch();
   griddep_wait();
@@ -26,7 +30,12 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
 #pragma unroll
     for (int j = 0; j < 8; ++j) dg[c][j] = 0.f;
 
-  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+  const int bidx = MOD ? blockIdx.y : 0;
+  const int row_begin = MOD ? bidx * rows_per_batch : 0;
+  const int row_end = MOD ? row_begin + rows_per_batch : rows;
+  const float* ms = MOD ? mod_scale + static_cast<long>(bidx) * ld_mod : nullptr;
+  if (MOD) dgamma += static_cast<long>(bidx) * D;
+  for (int row = row_begin + blockIdx.x * 8 + warp; row < row_end; row += gridDim.x * 8) {
     const __nv_bfloat16* xr = x + static_cast<long>(row) * ldx;
     const __nv_bfloat16* dr = dy + static_cast<long>(row) * lddy;
     // x and dy stay packed (bf16x2) in registers: 2 x MAXC x 4 words instead of 2 x MAXC x 8 floats (ncu r1: the fp32 version
@@ -66,7 +75,13 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
       if (ch < nchunk) {
         const uint32_t uw[4] = {xp[c].x, xp[c].y, xp[c].z, xp[c].w}, ww[4] = {dp[c].x, dp[c].y, dp[c].z, dp[c].w};
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + ch * 2), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + ch * 2 + 1);
-        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        if (MOD) {
+          const float4 s0 = __ldg(reinterpret_cast<const float4*>(ms) + ch * 2), s1 = __ldg(reinterpret_cast<const float4*>(ms) + ch * 2 + 1);
+          const float sm[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gm[j] *= 1.f + sm[j];
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 f = unpack_bf16(uw[j]), d = unpack_bf16(ww[j]);
@@ -88,7 +103,13 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
       if (ch < nchunk) {
         const uint32_t uw[4] = {xp[c].x, xp[c].y, xp[c].z, xp[c].w}, ww[4] = {dp[c].x, dp[c].y, dp[c].z, dp[c].w};
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + ch * 2), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + ch * 2 + 1);
-        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        if (MOD) {
+          const float4 s0 = __ldg(reinterpret_cast<const float4*>(ms) + ch * 2), s1 = __ldg(reinterpret_cast<const float4*>(ms) + ch * 2 + 1);
+          const float sm[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gm[j] *= 1.f + sm[j];
+        }
         uint4 ru = make_uint4(0, 0, 0, 0);
         if (rr) ru = __ldg(reinterpret_cast<const uint4*>(rr) + ch);
         const uint32_t rw[4] = {ru.x, ru.y, ru.z, ru.w};
@@ -137,9 +158,85 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
   if (col + 1 < N) atomicAdd(out + col + 1, a1);
 }
 
+// adaLN gate backward (transformer.py:690-701: x = x + branch * sigmoid(1 - gate_b)):  dbranch = dh * g_b,  dg_b += sum_n dh * branch.
+// grid (row blocks, B); thread = 8 channels; the per-batch column sums stay in registers until one atomic per channel per block.
+__global__ void __launch_bounds__(256) gate_bwd_kernel(const __nv_bfloat16* __restrict__ dh, long ldh, const __nv_bfloat16* __restrict__ branch,
+                                                       long ldb, const float* __restrict__ gate, __nv_bfloat16* __restrict__ dbranch, long ldo,
+                                                       float* __restrict__ dgate, int rows_per_batch, int D) {
+  griddep_launch();
+  griddep_wait();
+  const int b = blockIdx.y;
+  const int cg = threadIdx.x;
+  if (cg * 8 >= D) return;
+  const float4 q0 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<long>(b) * D) + cg * 2);
+  const float4 q1 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<long>(b) * D) + cg * 2 + 1);
+  const float gv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const long base = static_cast<long>(b) * rows_per_batch;
+  for (int r = blockIdx.x; r < rows_per_batch; r += gridDim.x) {
+    const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dh + (base + r) * ldh) + cg);
+    const uint4 ub = __ldg(reinterpret_cast<const uint4*>(branch + (base + r) * ldb) + cg);
+    const uint32_t dw[4] = {ud.x, ud.y, ud.z, ud.w}, bw[4] = {ub.x, ub.y, ub.z, ub.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 d = unpack_bf16(dw[j]), br = unpack_bf16(bw[j]);
+      acc[2 * j] = fmaf(d.x, br.x, acc[2 * j]);
+      acc[2 * j + 1] = fmaf(d.y, br.y, acc[2 * j + 1]);
+      ow[j] = pack_bf16(d.x * gv[2 * j], d.y * gv[2 * j + 1]);
+    }
+    reinterpret_cast<uint4*>(dbranch + (base + r) * ldo)[cg] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(dgate + static_cast<long>(b) * D + cg * 8 + j, acc[j]);
+}
+
 }  // namespace b200sat
 
 using namespace b200sat;
+
+extern "C" int b200sat_layernorm_mod_bwd(const void* x, long ldx, const void* dy, long lddy, const float* gamma, const float* mod_scale,
+                                         long ld_mod, int rows_per_batch, const void* dres, long ldr, void* dx_out, long ldo, float* dp,
+                                         int rows, int D, float eps, void* stream) {
+  if (!x || !dy || !gamma || !mod_scale || !dx_out || !dp || rows <= 0 || D <= 0 || rows_per_batch <= 0 || rows % rows_per_batch) {
+    set_last_error("layernorm_mod_bwd: bad arguments"); return B200SAT_EINVAL;
+  }
+  if (D % 8 || ldx % 8 || lddy % 8 || ldo % 8 || (dres && ldr % 8) || ld_mod % 4) { set_last_error("layernorm_mod_bwd: D and leading dims must be multiples of 8"); return B200SAT_EINVAL; }
+  if (D > 2048) { set_last_error("layernorm_mod_bwd: D > 2048 not implemented"); return B200SAT_EUNSUPPORTED; }
+  const int batches = rows / rows_per_batch;
+  int gx = (rows_per_batch + 7) / 8;
+  const int cap = (2 * num_sms() + batches - 1) / batches;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, batches);
+  if (D <= 1536)
+    B200SAT_CHECK_CUDA(launch_k(layernorm_bwd_kernel<6, true>, grid, dim3(256), D * sizeof(float), static_cast<cudaStream_t>(stream), 1,
+        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), gamma, static_cast<const __nv_bfloat16*>(dres),
+        static_cast<__nv_bfloat16*>(dx_out), dp, rows, D, ldx, lddy, ldr, ldo, eps, mod_scale, ld_mod, rows_per_batch));
+  else
+    B200SAT_CHECK_CUDA(launch_k(layernorm_bwd_kernel<8, true>, grid, dim3(256), D * sizeof(float), static_cast<cudaStream_t>(stream), 1,
+        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), gamma, static_cast<const __nv_bfloat16*>(dres),
+        static_cast<__nv_bfloat16*>(dx_out), dp, rows, D, ldx, lddy, ldr, ldo, eps, mod_scale, ld_mod, rows_per_batch));
+  B200SAT_CHECK_CUDA(cudaGetLastError());
+  return B200SAT_OK;
+}
+
+extern "C" int b200sat_gate_bwd(const void* dh, long ldh, const void* branch, long ldb, const float* gate, void* dbranch, long ldo, float* dgate,
+                                int rows_per_batch, int batches, int D, void* stream) {
+  if (!dh || !branch || !gate || !dbranch || !dgate || rows_per_batch <= 0 || batches <= 0 || D <= 0) { set_last_error("gate_bwd: bad arguments"); return B200SAT_EINVAL; }
+  if (D % 8 || D > 2048 || ldh % 8 || ldb % 8 || ldo % 8) { set_last_error("gate_bwd: D <= 2048, D and leading dims multiples of 8"); return B200SAT_EUNSUPPORTED; }
+  const int threads = ((D / 8 + 31) / 32) * 32;
+  int gx = rows_per_batch;
+  const int cap = (8 * num_sms() + batches - 1) / batches;
+  if (gx > cap) gx = cap;
+  B200SAT_CHECK_CUDA(launch_k(gate_bwd_kernel, dim3(gx, batches), dim3(threads), 0, static_cast<cudaStream_t>(stream), 1,
+      static_cast<const __nv_bfloat16*>(dh), ldh, static_cast<const __nv_bfloat16*>(branch), ldb, gate, static_cast<__nv_bfloat16*>(dbranch), ldo,
+      dgate, rows_per_batch, D));
+  B200SAT_CHECK_CUDA(cudaGetLastError());
+  return B200SAT_OK;
+}
 
 extern "C" int b200sat_layernorm_bwd(const void* x, long ldx, const void* dy, long lddy, const float* gamma, const void* dres, long ldr,
                                      void* dx_out, long ldo, float* dgamma, int rows, int D, float eps, void* stream) {
@@ -150,13 +247,13 @@ extern "C" int b200sat_layernorm_bwd(const void* x, long ldx, const void* dy, lo
   const int cap = 2 * num_sms();
   if (grid > cap) grid = cap;
   if (D <= 1536)
-    B200SAT_CHECK_CUDA(launch_k(layernorm_bwd_kernel<6>, dim3(grid), dim3(256), D * sizeof(float), static_cast<cudaStream_t>(stream), 1, 
+    B200SAT_CHECK_CUDA(launch_k(layernorm_bwd_kernel<6, false>, dim3(grid), dim3(256), D * sizeof(float), static_cast<cudaStream_t>(stream), 1, 
         static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), gamma, static_cast<const __nv_bfloat16*>(dres),
-        static_cast<__nv_bfloat16*>(dx_out), dgamma, rows, D, ldx, lddy, ldr, ldo, eps));
+        static_cast<__nv_bfloat16*>(dx_out), dgamma, rows, D, ldx, lddy, ldr, ldo, eps, static_cast<const float*>(nullptr), 0L, 0));
   else
-    B200SAT_CHECK_CUDA(launch_k(layernorm_bwd_kernel<8>, dim3(grid), dim3(256), D * sizeof(float), static_cast<cudaStream_t>(stream), 1, 
+    B200SAT_CHECK_CUDA(launch_k(layernorm_bwd_kernel<8, false>, dim3(grid), dim3(256), D * sizeof(float), static_cast<cudaStream_t>(stream), 1, 
         static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), gamma, static_cast<const __nv_bfloat16*>(dres),
-        static_cast<__nv_bfloat16*>(dx_out), dgamma, rows, D, ldx, lddy, ldr, ldo, eps));
+        static_cast<__nv_bfloat16*>(dx_out), dgamma, rows, D, ldx, lddy, ldr, ldo, eps, static_cast<const float*>(nullptr), 0L, 0));
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }

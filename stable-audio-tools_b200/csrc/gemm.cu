@@ -428,6 +428,11 @@ __global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constan
             const __nv_bfloat16* r = p.residual + static_cast<size_t>(out_row) * p.ldr + col;
             if (p.flags & GEMM_GATE) {
               const float* gp = p.gate + static_cast<size_t>(row / p.seg_in) * p.N + col;
+              if (p.aux) {   // training forward: keep the un-gated branch output (its product with dh is the gate gradient)
+                __nv_bfloat16* ua = p.aux + static_cast<size_t>(row) * p.ld_aux + col;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (i < ncols) ua[i] = __float2bfloat16_rn(v[i]);
+              }
 #pragma unroll
               for (int i = 0; i < 32; ++i) if (i < ncols) v[i] = bf16_round(v[i]) * __ldg(gp + i);
             }

@@ -15,13 +15,14 @@ def _cos(a, b):
     return torch.nn.functional.cosine_similarity(a.flatten().float(), b.flatten().float(), dim=0).item()
 
 
-def test_v_objective_step_matches_reference_golden():
+@pytest.mark.parametrize("gct", ["prepend", "adaLN"])
+def test_v_objective_step_matches_reference_golden(gct):
     from oracle import dit as odit
     from b200sat.dit_train import DiTTrainModel, v_objective_loss
-    z = np.load(os.path.join(G, "dit_prepend.npz"))
+    z = np.load(os.path.join(G, f"dit_{gct}.npz"))
     meta = json.loads(str(z["meta"]))
     f = {k: torch.from_numpy(z[k]) for k in z.files if k != "meta"}
-    sd = odit.make_state_dict(global_cond_type="prepend", seed=meta["weights_seed"], **meta["cfg"])
+    sd = odit.make_state_dict(global_cond_type=gct, seed=meta["weights_seed"], **meta["cfg"])
     model = DiTTrainModel(sd)
     model.zero_grad()
     loss = v_objective_loss(model, f["x"].cuda(), f["noise"].cuda(), f["t"].cuda(), f["cross"].cuda(), f["glob"].cuda())
@@ -38,19 +39,20 @@ def test_v_objective_step_matches_reference_golden():
         assert rel <= 6e-2 and _cos(g, ref) >= 0.995, (k, rel)
 
 
-def test_training_step_vs_oracle_autograd_medium():
+@pytest.mark.parametrize("gct", ["prepend", "adaLN"])
+def test_training_step_vs_oracle_autograd_medium(gct):
     from oracle import dit as odit
     from b200sat.dit_train import DiTTrainModel, v_objective_loss
     kw = dict(embed_dim=256, depth=3, num_heads=4, io_channels=64, cond_token_dim=128, global_cond_dim=256)
-    sd = odit.make_state_dict(seed=5, **kw)
+    sd = odit.make_state_dict(seed=5, global_cond_type=gct, **kw)
     sd = {k: v.bfloat16().float() for k, v in sd.items()}
     g = torch.Generator().manual_seed(6)
     B, T, L = 3, 300, 21
     x0 = torch.randn(B, 64, T, generator=g); nz = torch.randn(B, 64, T, generator=g); t = torch.rand(B, generator=g)
     c = torch.randn(B, L, 128, generator=g); ge = torch.randn(B, 256, generator=g)
-    names = [k for k in sd if k.endswith("weight") or k.endswith("gamma") or k.endswith("bias")]
+    names = [k for k in sd if k.endswith(("weight", "gamma", "bias", "to_scale_shift_gate"))]
     sdg = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in sd.items()}
-    model_fn = lambda xx, tt: odit.dit_forward(xx, tt, sdg, kw["depth"], c, ge)
+    model_fn = lambda xx, tt: odit.dit_forward(xx, tt, sdg, kw["depth"], c, ge, global_cond_type=gct)
     loss_ref, _, _ = odit.v_objective_loss(model_fn, x0, nz, t)
     loss_ref.backward()
     model = DiTTrainModel(sd)
