@@ -155,7 +155,8 @@ def measure_train(args, dev, rank, world, dist):
     sd = init.dit_state_dict(embed_dim=D_MODEL, depth=DEPTH, num_heads=HEADS, seed=0, device=dev, dtype=torch.float32)
     model = DiTTrainModel(sd, device=dev)
     del sd
-    opt = torch.optim.AdamW(model.parameters(), lr=5e-5, betas=(0.9, 0.999), weight_decay=1e-3, fused=True)
+    from b200sat.optim import FusedAdamWEMA
+    opt = FusedAdamWEMA(model, lr=5e-5, betas=(0.9, 0.999), weight_decay=1e-3, ema=True)   # stable_audio_2_0.json:95-102, EMA on
     red = GradAllReducer(model)
     g = torch.Generator().manual_seed(42 + rank)
     h_lat = torch.randn(B, 64, T_LAT, generator=g).pin_memory()
@@ -197,8 +198,8 @@ def measure_train(args, dev, rank, world, dist):
     flop = 3 * GFLOP_PER_TOKEN * 1e9 * B * (T_LAT + 1)
     pk = peaks()
     out = {"metric": "dit_training_latent_tokens_per_sec", "value": tokens / (ms_step * 1e-3), "unit": "latent-tokens/s", "ms_per_step": ms_step,
-           "steps": k, "batch_per_gpu": B, "seq_len": T_LAT, "loss": float(h_loss.item()), "optimizer": "AdamW(fused) fp32 masters",
-           "pre_encoded": True, "includes": "H2D of latents+conditioning, fwd, bwd, layer-bucketed all-reduce, optimizer step, D2H loss",
+           "steps": k, "batch_per_gpu": B, "seq_len": T_LAT, "loss": float(h_loss.item()), "optimizer": "b200sat fused AdamW + EMA + bf16 weight refresh (one pass over the fp32 masters)",
+           "pre_encoded": True, "includes": "H2D of latents+conditioning, fwd, bwd, layer-bucketed all-reduce, AdamW + EMA step, D2H loss",
            "tflops_per_gpu": flop / (ms_step * 1e-3) / 1e12, "frac_of_sustained_peak": flop / (ms_step * 1e-3) / 1e12 / pk["bf16_sustained"]}
     # same step with the frozen Oobleck encoder inside it (pre_encoded = False, training/diffusion.py:364-375): 8 x 47 s stereo
     # clips encoded one at a time (iterate_batch) in bf16, then the DiT step on the fresh latents

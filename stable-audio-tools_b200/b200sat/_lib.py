@@ -54,6 +54,8 @@ SIGNATURES = {
     "b200sat_layernorm_mod_bwd": (c_int, [c_void_p, c_long, c_void_p, c_long, c_fp, c_fp, c_long, c_int, c_void_p, c_long, c_void_p, c_long, c_fp,
                                           c_int, c_int, c_float, c_void_p]),
     "b200sat_gate_bwd": (c_int, [c_void_p, c_long, c_void_p, c_long, c_fp, c_void_p, c_long, c_fp, c_int, c_int, c_int, c_void_p]),
+    "b200sat_adamw_ema_step": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_void_p, c_long, c_long, c_float, c_float, c_float, c_float, c_float, c_int,
+                                       c_float, c_float, c_void_p]),
     "b200sat_snake_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_fp, c_fp, c_void_p, c_fp, c_fp, c_fp, c_long, c_int, c_void_p]),
     "b200sat_wn_pack_dgrad": (c_int, [c_fp, c_fp, c_fp, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200sat_wn_bwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_void_p]),

@@ -65,6 +65,7 @@ class DiTTrainModel(nn.Module):
         for k in misc:
             names.append(k); shapes.append(tuple(state_dict[k].shape))
         total = sum(math.prod(s) for s in shapes)
+        total = (total + 3) // 4 * 4                        # float4 granularity of the fused optimizer step
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
         self._p = {}
@@ -154,7 +155,9 @@ class DiTTrainModel(nn.Module):
         B, N, Lc = self._shape
         M = B * N
         ws = self._workspace(B, N, Lc)
-        self._bf.copy_(self.flat[: self.stack_numel])     # refresh bf16 working weights from the fp32 masters
+        if not getattr(self, "_bf_fresh", False):           # the fused optimizer step already wrote the bf16 working copy
+            self._bf.copy_(self.flat[: self.stack_numel])   # refresh bf16 working weights from the fp32 masters
+        self._bf_fresh = False
         self._cemb = cemb.contiguous()
         rope = (*self.rope_tables(N), N, d, 64)
         ws["h"][0].copy_(h0)

@@ -1,0 +1,62 @@
+"""Fused AdamW + EMA step over the flat fp32 master buffer of a b200sat training model (one libb200sat launch per step).
+
+Replaces, for `DiTTrainModel`, the three passes the reference makes per step: `torch.optim.AdamW.step` (training/utils.py:60-79),
+`ema_pytorch.EMA.update` (training/diffusion.py:239-247, 489-491) and the fp32 -> bf16 weight cast of autocast.
+EMA decay schedule = ema_pytorch 0.2.x `get_current_decay` (that package is not vendored in the reference: parity unpinned,
+restated from its published formula): epoch = step - update_after_step - 1; 0 if epoch <= 0 else
+clamp(1 - (1 + epoch/inv_gamma)^-power, min_value, beta).
+"""
+import torch
+
+from ._lib import lib, check
+from . import ops
+
+
+def ema_decay_at(step, beta=0.9999, inv_gamma=1.0, power=0.75, update_after_step=1, min_value=0.0):
+    epoch = step - update_after_step - 1
+    if epoch <= 0:
+        return 0.0
+    value = 1.0 - (1.0 + epoch / inv_gamma) ** (-power)
+    return float(min(max(value, min_value), beta))
+
+
+class FusedAdamWEMA:
+    """optimizer + EMA for a model exposing `.flat` / `.flat_grad` (fp32, same length) and optionally `._bf` (bf16 working copy of
+    the first `stack_numel` elements)."""
+
+    def __init__(self, model, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-3, ema=True, ema_beta=0.9999, ema_power=0.75,
+                 ema_inv_gamma=1.0, ema_update_after_step=1):
+        self.model = model
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.n = model.flat.numel()
+        if self.n % 4:
+            raise ValueError("flat parameter buffer length must be a multiple of 4")
+        self.m = torch.zeros_like(model.flat)
+        self.v = torch.zeros_like(model.flat)
+        self.ema = model.flat.detach().clone() if ema else None
+        self.ema_cfg = dict(beta=ema_beta, inv_gamma=ema_inv_gamma, power=ema_power, update_after_step=ema_update_after_step)
+        self.t = 0
+
+    def step(self, grad_scale=1.0):
+        mdl = self.model
+        self.t += 1
+        decay = ema_decay_at(self.t, **self.ema_cfg) if self.ema is not None else 0.0
+        w16 = getattr(mdl, "_bf", None)
+        n16 = (w16.numel() // 4) * 4 if w16 is not None else 0
+        rc = lib().b200sat_adamw_ema_step(mdl.flat.data_ptr(), mdl.flat_grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                          0 if self.ema is None else self.ema.data_ptr(), 0 if w16 is None else w16.data_ptr(), self.n, n16,
+                                          self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.t, decay, grad_scale,
+                                          torch.cuda.current_stream().cuda_stream)
+        ops.LAUNCHES[0] += 1
+        check(rc, "adamw_ema_step")
+        if w16 is not None and n16 == w16.numel():
+            mdl._bf_fresh = True      # the forward can skip its own fp32 -> bf16 refresh
+
+    def ema_state_dict(self):
+        """EMA weights under the reference parameter names."""
+        out, off = {}, 0
+        for n_, p in self.model._p.items():
+            k = p.numel()
+            out[n_] = self.ema[off:off + k].view(p.shape).clone()
+            off += k
+        return out
