@@ -2,7 +2,7 @@
 
 Tolerances: precision='fp32x3' (3-pass split-bf16 on tcgen05): decoded audio RMS(ours - ref) <= 1e-4 absolute (north-star bar;
 signal RMS ~0.15-1) and <= 5e-4 relative; small-width golden <= 1e-4 relative.  The residual ~1e-4 relative error at full
-width is the tensor core's truncating fp32 accumulation over K = 3 x 7 x 2048 products (tools/ae_precision_diag.py:
+width is the tensor core's truncating fp32 accumulation over K = 3 x 7 x 2048 products (tests/diag_ae_precision.py:
 fp32 cuDNN-class reference is 1e-6 from fp64, ours 1.5e-4); chunked accumulation is the round-2 fix.
 precision='bf16' is compared to the bf16 budget (5e-2 relative)."""
 import json

@@ -1,10 +1,10 @@
 """Oobleck encode/decode timings at BASELINE shapes (47 s clip = 1024 latents; 65536-sample clips)."""
 import os, sys, time, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "stable-audio-tools_b200"))
-from oracle import oobleck as oo
+sys.path.insert(0, os.path.join(ROOT, "stable-audio-tools_b200"))
+from b200sat.init import oobleck_state_dict
 from b200sat.autoencoder import OobleckEngine
-sd = oo.make_state_dict(seed=0)
+sd = oobleck_state_dict("cuda", torch.Generator(device="cuda").manual_seed(0))
 GF_PER_SAMPLE = 161.3e9 / 65536  # encoder (and decoder) forward flop per stereo sample
 for prec in ("bf16", "fp32x3"):
     eng = OobleckEngine(sd, precision=prec)
