@@ -10,7 +10,7 @@ namespace b200sat {
 // LayerNorm over the last dim (transformer.py:236-238: F.layer_norm(x, gamma, beta=0, eps)), optional adaLN
 // modulate h*(1+scale)+shift (transformer.py:680-682, :695-697).  One warp per row, values kept in registers.
 template <int MAXC>
-__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256, (MAXC <= 8) ? 4 : 1) layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, const float* __restrict__ scale,
                                                         const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
                                                         int rows, int D, long ldx, long ldy, int rows_per_batch, long ld_mod,
@@ -22,20 +22,18 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
   const int lane = threadIdx.x & 31;
   const __nv_bfloat16* xr = x + static_cast<long>(row) * ldx;
   const int nchunk = D / 8;  // 16-byte chunks
-  float v[MAXC][8];
+  // the row stays packed (bf16x2) in registers and is unpacked on the fly in each pass: 4 words per chunk instead of 8 floats keeps
+  // the kernel at <= 64 registers (4 blocks / SM); the fp32-resident version ran 2 blocks / SM at 31 % of the HBM roofline
+  uint4 xp[MAXC];
   float sum = 0.f;
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) {
     const int ch = lane + c * 32;
     if (ch < nchunk) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr) + ch);
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      xp[c] = __ldg(reinterpret_cast<const uint4*>(xr) + ch);
+      const uint32_t w[4] = {xp[c].x, xp[c].y, xp[c].z, xp[c].w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_bf16(w[j]);
-        v[c][2 * j] = f.x; v[c][2 * j + 1] = f.y;
-        sum += f.x + f.y;
-      }
+      for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16(w[j]); sum += f.x + f.y; }
     }
   }
 #pragma unroll
@@ -45,8 +43,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) {
     if (lane + c * 32 < nchunk) {
+      const uint32_t w[4] = {xp[c].x, xp[c].y, xp[c].z, xp[c].w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { const float d = v[c][j] - mean; sq += d * d; }
+      for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16(w[j]); const float d0 = f.x - mean, d1 = f.y - mean; sq += d0 * d0 + d1 * d1; }
     }
   }
 #pragma unroll
@@ -60,17 +59,32 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
     const int ch = lane + c * 32;
     if (ch < nchunk) {
       float o[8];
+      // parameters as two 16-byte loads per 8 columns (the scalar version issued 8 LDGs per parameter per chunk)
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + ch * 2), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + ch * 2 + 1);
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const uint32_t xw[4] = {xp[c].x, xp[c].y, xp[c].z, xp[c].w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int col = ch * 8 + j;
-        float t = (v[c][j] - mean) * rstd * __ldg(gamma + col);
-        if (beta) t += __ldg(beta + col);
-        if (sc) {
-          t = bf16_round(t);
-          t = bf16_round(t * bf16_round(1.0f + __ldg(sc + col)));
-          t = t + __ldg(sh + col);
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16(xw[j]);
+        o[2 * j] = (f.x - mean) * rstd * gm[2 * j];
+        o[2 * j + 1] = (f.y - mean) * rstd * gm[2 * j + 1];
+      }
+      if (beta) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + ch * 2), b1 = __ldg(reinterpret_cast<const float4*>(beta) + ch * 2 + 1);
+        const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += bt[j];
+      }
+      if (sc) {
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc) + ch * 2), s1 = __ldg(reinterpret_cast<const float4*>(sc) + ch * 2 + 1);
+        const float4 h0 = __ldg(reinterpret_cast<const float4*>(sh) + ch * 2), h1 = __ldg(reinterpret_cast<const float4*>(sh) + ch * 2 + 1);
+        const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float t = bf16_round(o[j]);
+          t = bf16_round(t * bf16_round(1.0f + sv[j]));
+          o[j] = t + hv[j];
         }
-        o[j] = t;
       }
       uint4 u;
       u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
@@ -325,7 +339,14 @@ extern "C" int b200sat_layernorm_fwd(const void* x, long ldx, const float* gamma
   const int grid = (rows + 7) / 8;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int rpb = rows_per_batch > 0 ? rows_per_batch : rows;
-  if (D <= 2048)
+  if ((reinterpret_cast<uintptr_t>(gamma) & 15) || (beta && (reinterpret_cast<uintptr_t>(beta) & 15)) ||
+      (scale && ((reinterpret_cast<uintptr_t>(scale) & 15) || (reinterpret_cast<uintptr_t>(shift) & 15) || (ld_mod & 3)))) {
+    set_last_error("layernorm: gamma / beta / scale / shift must be 16-byte aligned (row stride of scale/shift a multiple of 4)"); return B200SAT_EINVAL;
+  }
+  if (D <= 1536)
+    B200SAT_CHECK_CUDA(launch_k(layernorm_kernel<6>, dim3(grid), dim3(256), 0, s, 1, static_cast<const __nv_bfloat16*>(x), gamma, beta, scale, shift,
+                                             static_cast<__nv_bfloat16*>(y), rows, D, ldx, ldy, rpb, ld_mod, eps));
+  else if (D <= 2048)
     B200SAT_CHECK_CUDA(launch_k(layernorm_kernel<8>, dim3(grid), dim3(256), 0, s, 1, static_cast<const __nv_bfloat16*>(x), gamma, beta, scale, shift,
                                              static_cast<__nv_bfloat16*>(y), rows, D, ldx, ldy, rpb, ld_mod, eps));
   else
