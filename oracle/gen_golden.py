@@ -14,7 +14,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import ref_harness, dit as odit, oobleck as oo  # noqa: E402
+from oracle import ref_harness, dit as odit, oobleck as oo, discriminator as odisc  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 FFT = [2048, 1024, 512, 256, 128, 64, 32]
@@ -98,6 +98,23 @@ def main():
     np.savez_compressed(os.path.join(OUT, "mrstft.npz"), meta=json.dumps(meta),
                         **_np(dict(x=x, y=y, loss_sd=l_sd.detach(), grad_sd=xg.grad, loss_l=l_l, loss_plain=l_plain, mag256=mag,
                                    taps=mrl.stft_losses[0].prefilter.fir.weight.data.view(-1))))
+
+    # ---- Encodec multi-scale STFT discriminator (row G1): losses, the generator-side gradient, one scale's logits
+    import stable_audio_tools.models.discriminators as RD
+    disc = RD.EncodecDiscriminator(filters=64, in_channels=2, n_ffts=list(odisc.N_FFTS), hop_lengths=list(odisc.HOPS), win_lengths=list(odisc.N_FFTS))
+    dsd = odisc.make_state_dict(seed=51)
+    r = disc.load_state_dict(dsd, strict=False)
+    assert not r.unexpected_keys and all("window" in k for k in r.missing_keys)
+    g = torch.Generator().manual_seed(52)
+    reals = torch.randn(1, 2, 8192, generator=g) * 0.3
+    fakes = (reals + 0.1 * torch.randn(1, 2, 8192, generator=g)).requires_grad_(True)
+    dis, adv, fm = disc.loss(reals, fakes)
+    (0.1 * adv + 5.0 * fm).backward()            # generator weights of stable_audio_2_0_vae.json:88-91
+    with torch.no_grad():
+        logits, _ = disc(reals)
+    np.savez_compressed(os.path.join(OUT, "encodec_disc.npz"), meta=json.dumps({**meta, "weights_seed": 51}),
+                        **_np(dict(reals=reals, fakes=fakes.detach(), dis=dis.detach(), adv=adv.detach(), fm=fm.detach(), grad_fakes=fakes.grad,
+                                   logits4=logits[4])))
 
     # ---- in-repo v-DDIM sampler with a closed-form toy model (inference/sampling.py:253-307)
     toy = lambda x_, t_, **kw: torch.tanh(x_ * 0.7) * (0.3 + t_.view(-1, 1, 1)) - 0.1 * x_

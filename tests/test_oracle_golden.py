@@ -79,3 +79,26 @@ def test_vddim_matches_reference():
     toy = lambda x_, t_, **kw: torch.tanh(x_ * 0.7) * (0.3 + t_.view(-1, 1, 1)) - 0.1 * x_
     out = osamp.sample_v_ddim(toy, f["noise"], 25)
     assert (out - f["out"]).abs().max() <= 1e-6
+
+
+def test_encodec_discriminator_oracle_matches_reference_golden():
+    """Row G1: the discriminator oracle - STFT front end, five weight-normed 2-D conv scales, hinge + feature-matching
+    losses, and the generator-side gradient w.r.t. the decoded audio - against vectors produced by the reference classes."""
+    from oracle import discriminator as od
+    z = np.load(os.path.join(G, "encodec_disc.npz"))
+    meta = json.loads(str(z["meta"]))
+    sd = od.make_state_dict(seed=meta["weights_seed"])
+    reals = torch.from_numpy(z["reals"])
+    fakes = torch.from_numpy(z["fakes"]).requires_grad_(True)
+    dis, adv, fm = od.discriminator_loss(reals, fakes, sd)
+    (0.1 * adv + 5.0 * fm).backward()
+    for name, got in (("dis", dis), ("adv", adv), ("fm", fm)):
+        ref = float(z[name])
+        assert abs(float(got) - ref) <= 1e-5 * max(1.0, abs(ref)), (name, float(got), ref)
+    gref = torch.from_numpy(z["grad_fakes"])
+    assert ((fakes.grad - gref).norm() / gref.norm()).item() <= 1e-4
+    with torch.no_grad():
+        logits, fmaps = od.discriminator_forward(reals, sd)
+    l4 = torch.from_numpy(z["logits4"])
+    assert logits[4].shape == l4.shape and ((logits[4] - l4).norm() / l4.norm()).item() <= 1e-5
+    assert [tuple(f.shape[1:3]) for f in fmaps[0]] == [(64, 13)] * 5 and fmaps[0][0].shape[-1] == 1025
