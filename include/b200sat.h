@@ -234,6 +234,44 @@ int b200sat_vae_sample_bwd(const void* dz, const void* ms, const float* noise, c
 int b200sat_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, void* w_bf16, long n, long n_bf16, float lr, float beta1,
                            float beta2, float eps, float weight_decay, int step, float ema_decay, float grad_scale, void* stream);
 
+/* ---- Encodec multi-scale STFT discriminator (models/encodec.py:38-138, models/discriminators.py:13-58) ---------------------------
+ * One scale's activations are flattened planes [B, P, C], P = frames * (F + 8), F = n_fft/2 + 1: bins in columns [4, 4+F) of each frame's
+ * row group, zero pad columns either side, so a 2-D conv tap (dt, df) with dilation (d, 1) is the row shift dt*d*(F+8) + df. */
+
+/* The 64 -> 64 channel Conv2d layers (3x9 with dilation (d,1), 3x3) and their data gradients on the tcgen05 conv kernel: w packed by
+ * b200sat_wn_pack (K = ntaps; b200sat_wn_pack_dgrad mode 0 for the gradient), tap_off[ntaps] (host array) = row shift per tap, rows whose
+ * (row % fp) is outside [f0, f1) are written as zeros, optional LeakyReLU (encodec.py:80-87, :102-103). */
+int b200sat_conv2d_flat(const void* in, const void* w, const float* bias, void* out, int B, int P, int Cin, int Cout, int ntaps,
+                        const int* tap_off, int fp, int f0, int f1, float leaky, void* stream);
+
+/* Complex STFT front end (torchaudio Spectrogram normalized=True, center=False, power=None, hann, win = n_fft; encodec.py:72-74, :96-99):
+ * x fp32 [B,2,T] -> spec fp32 [B,P,4] = (re ch0, re ch1, im ch0, im ch1); pad columns are NOT written (pre-zero the buffer).
+ * backward != 0: spec holds d spec and x (fp32 [B,2,T]) ACCUMULATES d audio. */
+int b200sat_disc_stft(const float* x, float* spec, const float* window, const float* twiddle, int B, int T, int n_fft, int hop, int backward,
+                      void* stream);
+
+/* First conv (4 -> 64, 3x9) + LeakyReLU: spec -> out bf16 [B,P,64] (w fp32 [64,4,27] weight-normalised, encodec.py:77-79); and/or its data
+ * gradient dpre bf16 [B,P,64] -> dspec fp32 [B,P,4].  Either pair may be NULL. */
+int b200sat_disc_conv0(const float* spec, const float* w, const float* bias, void* out, const void* dpre, float* dspec, int B, int frames, int F,
+                       float leaky, void* stream);
+
+/* conv_post (64 -> 1, 3x3, encodec.py:88-90): act bf16 [B,P,64] -> logits fp32 [B,P] (pad columns 0). */
+int b200sat_disc_convpost(const void* act, const float* w, const float* bias, float* logits, int B, int frames, int F, void* stream);
+
+/* Hinge sums over the valid bins (discriminators.py:13-16): sums[0] += sum relu(1-lt), sums[1] += sum relu(1+lf), sums[2] += sum lf. */
+int b200sat_disc_hinge_sums(const float* lt, const float* lf, double* sums, int B, int frames, int F, void* stream);
+
+/* out[0] += sum |a - b| over two bf16 planes of n elements (feature matching, discriminators.py:24, :41-47). */
+int b200sat_disc_l1_sum(const void* a, const void* b, double* out, long n, void* stream);
+
+/* d logits: mode 0 generator (-scale), 1 discriminator/reals (-scale where 1-l>0), 2 discriminator/fakes (+scale where 1+l>0). */
+int b200sat_disc_logit_grad(const float* logits, float* g, int B, int frames, int F, int mode, float scale, void* stream);
+
+/* Backward through one feature map: d_pre = (d_in + conv_post^T(d_logit) + fm_coef*sign(post-other)) * (post>0 ? 1 : leaky); any of the
+ * three sources may be NULL; pad columns -> 0. */
+int b200sat_disc_act_bwd(const void* d_in, const float* d_logit, const float* w_post, const void* post, const void* other, float fm_coef,
+                         float leaky, void* d_pre, int B, int frames, int F, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

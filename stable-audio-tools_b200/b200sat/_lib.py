@@ -56,6 +56,15 @@ SIGNATURES = {
     "b200sat_gate_bwd": (c_int, [c_void_p, c_long, c_void_p, c_long, c_fp, c_void_p, c_long, c_fp, c_int, c_int, c_int, c_void_p]),
     "b200sat_adamw_ema_step": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_void_p, c_long, c_long, c_float, c_float, c_float, c_float, c_float, c_int,
                                        c_float, c_float, c_void_p]),
+    "b200sat_conv2d_flat": (c_int, [c_void_p, c_void_p, c_fp, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_float,
+                                    c_void_p]),
+    "b200sat_disc_stft": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200sat_disc_conv0": (c_int, [c_fp, c_fp, c_fp, c_void_p, c_void_p, c_fp, c_int, c_int, c_int, c_float, c_void_p]),
+    "b200sat_disc_convpost": (c_int, [c_void_p, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_void_p]),
+    "b200sat_disc_hinge_sums": (c_int, [c_fp, c_fp, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "b200sat_disc_l1_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_void_p]),
+    "b200sat_disc_logit_grad": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "b200sat_disc_act_bwd": (c_int, [c_void_p, c_fp, c_fp, c_void_p, c_void_p, c_float, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b200sat_snake_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_fp, c_fp, c_void_p, c_fp, c_fp, c_fp, c_long, c_int, c_void_p]),
     "b200sat_wn_pack_dgrad": (c_int, [c_fp, c_fp, c_fp, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200sat_wn_bwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_void_p]),

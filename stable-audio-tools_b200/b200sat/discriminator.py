@@ -1,0 +1,205 @@
+"""Encodec multi-scale STFT discriminator on libb200sat: forward (logits + feature maps), the hinge / feature-matching loss values,
+and the GENERATOR-side backward (gradient of adv + feature-matching w.r.t. the decoded audio).
+
+Reference: `EncodecDiscriminator` (models/discriminators.py:13-58) over `MultiScaleSTFTDiscriminator` / `DiscriminatorSTFT`
+(models/encodec.py:38-138) as configured by stable_audio_2_0_vae.json:80-91 (filters 64, five scales, stereo, stride (1,1), hinge).
+Layout and kernels: csrc/discriminator.cu (STFT front end, first / last conv, loss reductions, activation backward) and
+`b200sat_conv2d_flat` (the four 64 -> 64 channel Conv2d layers per scale on the tcgen05 conv kernel).
+
+Not built yet: the discriminator's own weight gradients (the D step of training/autoencoders.py:476-489).
+"""
+import ctypes
+import math
+
+import torch
+
+from ._lib import lib, check
+from . import ops
+
+LEAKY = 0.2
+DILATIONS = (1, 2, 4)
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _wn_dense(sd, p):
+    v = sd[p + "weight_v"].float()
+    g = sd[p + "weight_g"].float()
+    return (g * v / v.flatten(1).norm(dim=1).view(-1, 1, 1, 1)).contiguous()
+
+
+class _Scale:
+    def __init__(self, sd, pre, n_fft, hop, dev):
+        self.n, self.hop = n_fft, hop
+        self.F = n_fft // 2 + 1
+        self.Fp = self.F + 8
+        win = torch.hann_window(n_fft, periodic=True, dtype=torch.float64)
+        k = torch.arange(n_fft // 2, dtype=torch.float64)
+        self.window = win.float().to(dev).contiguous()
+        self.twiddle = torch.stack([torch.cos(2 * math.pi * k / n_fft), -torch.sin(2 * math.pi * k / n_fft)], dim=1).float().to(dev).contiguous()
+        # first conv (4 -> 64) and conv_post (64 -> 1): dense weight-normalised fp32 weights for the SIMT kernels
+        self.w0 = _wn_dense(sd, pre + "convs.0.conv.").to(dev).reshape(64, 4, 27).contiguous()
+        self.b0 = sd[pre + "convs.0.conv.bias"].float().to(dev).contiguous()
+        self.wp = _wn_dense(sd, pre + "conv_post.conv.").to(dev).reshape(64, 9).contiguous()      # [1,64,3,3] -> [c][tap]
+        self.bp = sd[pre + "conv_post.conv.bias"].float().to(dev).contiguous()
+        # the four 64 -> 64 convs: packed bf16 weights (forward and data-gradient layouts) + per-tap row shifts
+        self.convs = []
+        for j in range(1, 5):
+            q = f"{pre}convs.{j}.conv."
+            v = sd[q + "weight_v"].float().to(dev)
+            K = v.shape[2] * v.shape[3]
+            v3 = v.reshape(64, 64, K).contiguous()
+            g = sd[q + "weight_g"].float().to(dev).reshape(-1).contiguous()
+            inv = torch.empty(64, device=dev)
+            w_f = torch.empty(64, K * 64, device=dev, dtype=torch.bfloat16)
+            check(lib().b200sat_wn_pack(v3.data_ptr(), g.data_ptr(), inv.data_ptr(), w_f.data_ptr(), 0, 64, 64, K, 0, 1, _s()), "wn_pack")
+            w_d = torch.empty(64, K * 64, device=dev, dtype=torch.bfloat16)
+            check(lib().b200sat_wn_pack_dgrad(v3.data_ptr(), g.data_ptr(), inv.data_ptr(), w_d.data_ptr(), 64, 64, K, 0, 1, _s()), "wn_pack_dgrad")
+            if j <= 3:
+                d = DILATIONS[j - 1]
+                offs = [(k_ // 9 - 1) * d * self.Fp + (k_ % 9 - 4) for k_ in range(27)]
+            else:
+                offs = [(k_ // 3 - 1) * self.Fp + (k_ % 3 - 1) for k_ in range(9)]
+            self.convs.append(dict(w=w_f, wd=w_d, bias=sd[q + "bias"].float().to(dev).contiguous(), K=K, offs=(ctypes.c_int * K)(*offs)))
+        ops.LAUNCHES[0] += 12
+
+    def frames(self, T):
+        return (T - self.n) // self.hop + 1
+
+
+class EncodecDiscriminatorEngine:
+    def __init__(self, state_dict, n_ffts=(2048, 1024, 512, 256, 128), hop_lengths=(512, 256, 128, 64, 32), device="cuda",
+                 prefix="discriminators.discriminators."):
+        self.dev = torch.device(device)
+        sd = {k: v.detach() for k, v in state_dict.items()}
+        if sd[f"{prefix}0.convs.0.conv.weight_v"].shape[:2] != (64, 4):
+            raise NotImplementedError("b200sat discriminator: filters=64, stereo input (4 spectrogram channels) only")
+        self.scales = [_Scale(sd, f"{prefix}{i}.", n, h, self.dev) for i, (n, h) in enumerate(zip(n_ffts, hop_lengths))]
+
+    # ------------------------------------------------------------------ forward of one scale
+    def _flat_conv(self, sc, x, cv, out, bias, w):
+        B, P, _ = x.shape
+        check(lib().b200sat_conv2d_flat(x.data_ptr(), w.data_ptr(), _p(bias), out.data_ptr(), B, P, 64, 64, cv["K"], cv["offs"], sc.Fp, 4,
+                                        4 + sc.F, LEAKY if bias is not None else 0.0, _s()), "conv2d_flat")
+        ops.LAUNCHES[0] += 1
+        return out
+
+    def _scale_forward(self, sc, x):
+        """x fp32 [B, 2, T] -> (logits fp32 [B, P], [5 feature-map planes bf16 [B, P, 64]], frames)."""
+        B, C, T = x.shape
+        fr = sc.frames(T)
+        P = fr * sc.Fp
+        spec = torch.zeros(B, P, 4, device=self.dev)
+        check(lib().b200sat_disc_stft(x.data_ptr(), spec.data_ptr(), sc.window.data_ptr(), sc.twiddle.data_ptr(), B, T, sc.n, sc.hop, 0, _s()), "disc_stft")
+        f0 = torch.empty(B, P, 64, device=self.dev, dtype=torch.bfloat16)
+        check(lib().b200sat_disc_conv0(spec.data_ptr(), sc.w0.data_ptr(), sc.b0.data_ptr(), f0.data_ptr(), 0, 0, B, fr, sc.F, LEAKY, _s()), "disc_conv0")
+        fmaps = [f0]
+        for cv in sc.convs:
+            fmaps.append(self._flat_conv(sc, fmaps[-1], cv, torch.empty_like(f0), cv["bias"], cv["w"]))
+        logits = torch.empty(B, P, device=self.dev)
+        check(lib().b200sat_disc_convpost(fmaps[-1].data_ptr(), sc.wp.data_ptr(), sc.bp.data_ptr(), logits.data_ptr(), B, fr, sc.F, _s()), "disc_convpost")
+        ops.LAUNCHES[0] += 3
+        return logits, fmaps, fr
+
+    @torch.no_grad()
+    def forward(self, x):
+        """Like EncodecDiscriminator.forward: (logits, features) per scale, in the reference's [B, 1, frames, F] / [B, 64, frames, F] shapes
+        (materialised from the flattened planes - for inspection and tests; the losses below work on the planes directly)."""
+        x = x.to(self.dev, torch.float32).contiguous()
+        logits, feats = [], []
+        for sc in self.scales:
+            lg, fm, fr = self._scale_forward(sc, x)
+            B = x.shape[0]
+            logits.append(lg.view(B, fr, sc.Fp)[:, :, 4:4 + sc.F].unsqueeze(1).contiguous())
+            feats.append([f.view(B, fr, sc.Fp, 64)[:, :, 4:4 + sc.F].permute(0, 3, 1, 2).float() for f in fm])
+        return logits, feats
+
+    # ------------------------------------------------------------------ losses
+    def _loss_forward(self, reals, fakes):
+        reals = reals.to(self.dev, torch.float32).contiguous()
+        fakes = fakes.to(self.dev, torch.float32).contiguous()
+        B = reals.shape[0]
+        ns = len(self.scales)
+        hs = torch.zeros(ns, 3, device=self.dev, dtype=torch.float64)
+        l1 = torch.zeros(ns, 5, device=self.dev, dtype=torch.float64)
+        saved = []
+        n_logit, n_feat = [], []
+        for i, sc in enumerate(self.scales):
+            lt, ft, fr = self._scale_forward(sc, reals)
+            lf, ff, _ = self._scale_forward(sc, fakes)
+            check(lib().b200sat_disc_hinge_sums(lt.data_ptr(), lf.data_ptr(), hs[i].data_ptr(), B, fr, sc.F, _s()), "disc_hinge_sums")
+            for l in range(5):
+                check(lib().b200sat_disc_l1_sum(ft[l].data_ptr(), ff[l].data_ptr(), l1[i, l:].data_ptr(), ft[l].numel(), _s()), "disc_l1_sum")
+            ops.LAUNCHES[0] += 6
+            n_logit.append(B * fr * sc.F)
+            n_feat.append(B * 64 * fr * sc.F)
+            saved.append((ft, ff, lf, fr))
+        nl = torch.tensor(n_logit, device=self.dev, dtype=torch.float64)
+        nf = torch.tensor(n_feat, device=self.dev, dtype=torch.float64)
+        dis = ((hs[:, 0] + hs[:, 1]) / nl).sum() / ns
+        adv = (-hs[:, 2] / nl).sum() / ns
+        fm = (l1.sum(1) / nf / 5.0).sum() / ns
+        return dis.float(), adv.float(), fm.float(), saved, n_logit, n_feat, fakes.shape
+
+    @torch.no_grad()
+    def loss_values(self, reals, fakes):
+        """(dis_loss, adv_loss, feature_matching_distance) of EncodecDiscriminator.loss, values only."""
+        d, a, f, *_ = self._loss_forward(reals, fakes)
+        return d, a, f
+
+    def generator_terms(self, reals, fakes):
+        """(adv_loss, feature_matching_distance) differentiable w.r.t. `fakes` (the generator step's use of the discriminator,
+        training/autoencoders.py:436-441, 497)."""
+        return _GenFn.apply(fakes, reals, self)
+
+    def _generator_backward(self, saved, n_logit, n_feat, shape, d_adv, d_fm):
+        B, C, T = shape
+        ns = len(self.scales)
+        d_audio = torch.zeros(B, C, T, device=self.dev)
+        st = _s()
+        for i, sc in enumerate(self.scales):
+            ft, ff, lf, fr = saved[i]
+            P = fr * sc.Fp
+            g = torch.empty(B, P, device=self.dev)
+            check(lib().b200sat_disc_logit_grad(lf.data_ptr(), g.data_ptr(), B, fr, sc.F, 0, d_adv / (n_logit[i] * ns), st), "disc_logit_grad")
+            coef = d_fm / (n_feat[i] * 5.0 * ns)
+            d_pre = torch.empty(B, P, 64, device=self.dev, dtype=torch.bfloat16)
+            check(lib().b200sat_disc_act_bwd(0, g.data_ptr(), sc.wp.data_ptr(), ff[4].data_ptr(), ft[4].data_ptr(), coef, LEAKY, d_pre.data_ptr(), B, fr,
+                                             sc.F, st), "disc_act_bwd")
+            ops.LAUNCHES[0] += 2
+            for l in range(4, 0, -1):
+                cv = sc.convs[l - 1]
+                d_in = self._flat_conv(sc, d_pre, cv, torch.empty_like(d_pre), None, cv["wd"])
+                d_pre = torch.empty_like(d_in)
+                check(lib().b200sat_disc_act_bwd(d_in.data_ptr(), 0, 0, ff[l - 1].data_ptr(), ft[l - 1].data_ptr(), coef, LEAKY, d_pre.data_ptr(), B, fr,
+                                                 sc.F, st), "disc_act_bwd")
+                ops.LAUNCHES[0] += 1
+            dspec = torch.empty(B, P, 4, device=self.dev)
+            check(lib().b200sat_disc_conv0(0, sc.w0.data_ptr(), 0, 0, d_pre.data_ptr(), dspec.data_ptr(), B, fr, sc.F, LEAKY, st), "disc_conv0 dgrad")
+            check(lib().b200sat_disc_stft(d_audio.data_ptr(), dspec.data_ptr(), sc.window.data_ptr(), sc.twiddle.data_ptr(), B, T, sc.n, sc.hop, 1, st),
+                  "disc_stft backward")
+            ops.LAUNCHES[0] += 2
+        return d_audio
+
+
+class _GenFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fakes, reals, eng):
+        with torch.no_grad():
+            _, adv, fm, saved, n_logit, n_feat, shape = eng._loss_forward(reals, fakes.detach())
+        ctx.eng, ctx.saved, ctx.meta = eng, saved, (n_logit, n_feat, shape)
+        return adv, fm
+
+    @staticmethod
+    def backward(ctx, d_adv, d_fm):
+        n_logit, n_feat, shape = ctx.meta
+        # the two upstream scalars are read back once (they are loss weights in practice): one host sync per generator step
+        g = ctx.eng._generator_backward(ctx.saved, n_logit, n_feat, shape, float(d_adv), float(d_fm))
+        ctx.saved = None
+        return g, None, None

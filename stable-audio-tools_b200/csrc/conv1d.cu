@@ -42,6 +42,11 @@ struct ConvParams {
   int passes;  // 1 or 3
   int m_rows;  // GEMM rows per batch item
   int m_tiles, n_tiles, phases;
+  // flattened 2-D convolutions (discriminator, models/encodec.py:76-92): the activation plane is [B, frames * fp, C] with zero pad columns
+  // materialised, a 2-D tap is the row shift tap_off[tap]; rows whose (m % fp) falls outside [mask_f0, mask_f1) are stored as zeros
+  int tap_off[32];
+  int use_tap_table, mask_fp, mask_f0, mask_f1;
+  float leaky;       // > 0: LeakyReLU slope applied to the raw output (nn.LeakyReLU(0.2), encodec.py:68)
   int window;        // 1: stride-1 conv whose taps share one (128 + (taps-1)*dil)-row A window per channel block
   int win_rows;      // rows of one A item: 128 + (taps-1)*dil in window mode, 128 otherwise
 };
@@ -216,7 +221,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
           item_decode(it, pass, tap, cib);
           int r = 0, row_off;
           if (p.mode == 0) {
-            row_off = window ? -p.pad : tap * p.dil - p.pad;  // window: tap k reads buffer rows [k*dil, k*dil + 128)
+            row_off = window ? -p.pad : (p.use_tap_table ? p.tap_off[tap] : tap * p.dil - p.pad);  // window: tap k reads rows [k*dil, k*dil + 128)
           } else if (p.mode == 1) {
             const int d = tap - p.pad;                      // input time = t_out*s + d
             const int j = (d >= 0) ? d / p.stride : -((-d + p.stride - 1) / p.stride);
@@ -389,6 +394,17 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
                 for (int e = 0; e < 4; ++e) { const float2 f = unpack_bf16(w[e]); v[8 * i + 2 * e] += f.x; v[8 * i + 2 * e + 1] += f.y; }
               }
             }
+          }
+        }
+        if (p.leaky > 0.f) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * p.leaky;
+        }
+        if (p.mask_fp > 0) {
+          const int fcol = (m_base + q * 32 + lane) % p.mask_fp;
+          if (fcol < p.mask_f0 || fcol >= p.mask_f1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
           }
         }
         if (p.out_hi) stage_row<LO>(my_o, swz, v, (LO && p.out_lo && my_ok) ? p.out_lo + my_off + col : nullptr);
@@ -980,4 +996,41 @@ extern "C" int b200sat_vae_sample(const void* hi, const void* lo, const float* n
                                                                         noise, z, mean_scale_out, kl_sum, B, L, T);
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
+}
+
+// Flattened 2-D convolution on the tcgen05 conv kernel (see ConvParams::tap_off): in / out bf16 planes [B, P, C], w packed [Cout][ntaps*Cin]
+// (b200sat_wn_pack with K = ntaps), tap_off[ntaps] = row shift of each tap, rows with (row % fp) outside [f0, f1) are written as zeros
+// (fp = 0: no mask), optional LeakyReLU on the output.  Forward and data gradient of the Conv2d stacks of models/encodec.py:76-92.
+extern "C" int b200sat_conv2d_flat(const void* in, const void* w, const float* bias, void* out, int B, int P, int Cin, int Cout, int ntaps,
+                                   const int* tap_off, int fp, int f0, int f1, float leaky, void* stream) {
+  if (!in || !w || !out || !tap_off || B <= 0 || P <= 0 || ntaps <= 0 || ntaps > 32) { set_last_error("conv2d_flat: bad arguments (ntaps <= 32)"); return B200SAT_EINVAL; }
+  if (Cin % 64 || Cout % 32) { set_last_error("conv2d_flat: Cin must be a multiple of 64 and Cout of 32"); return B200SAT_EUNSUPPORTED; }
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.T_in = P; p.T_out = P; p.Cin = Cin; p.Cout = Cout; p.dil = 1; p.pad = 0; p.stride = 1; p.mode = 0; p.passes = 1;
+  p.taps = ntaps; p.m_rows = P; p.phases = 1;
+  p.use_tap_table = 1;
+  for (int i = 0; i < ntaps; ++i) p.tap_off[i] = tap_off[i];
+  p.mask_fp = fp; p.mask_f0 = f0; p.mask_f1 = f1; p.leaky = leaky;
+  p.window = 0; p.win_rows = CV_BM;
+  const int bn = (Cout >= 256) ? 256 : 128;
+  int rc;
+  if ((rc = make_plane_map(&p.tmA[0], in, B, P, Cin, 1, CV_BM))) return rc;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(ntaps) * Cin, static_cast<uint64_t>(Cout)};
+    uint64_t strides[1] = {static_cast<uint64_t>(ntaps) * Cin * 2};
+    uint32_t box[2] = {CV_BK, static_cast<uint32_t>(bn)};
+    if ((rc = encode_tmap_bf16(&p.tmB[0], w, 2, dims, strides, box, 1))) return rc;
+  }
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(Cout), 1, static_cast<uint64_t>(P), static_cast<uint64_t>(B)};
+    uint64_t strides[3] = {static_cast<uint64_t>(Cout) * 2, static_cast<uint64_t>(Cout) * 2, static_cast<uint64_t>(Cout) * P * 2};
+    uint32_t box[4] = {32, 1, 32, 1};
+    if ((rc = encode_tmap_bf16(&p.tmOut, out, 4, dims, strides, box, 2))) return rc;
+    p.tma_epi = 1;
+  }
+  p.bias = bias;
+  p.out_hi = static_cast<__nv_bfloat16*>(out);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return bn == 256 ? launch_conv<256, false, 1>(p, s) : launch_conv<128, false, 1>(p, s);
 }

@@ -1,0 +1,492 @@
+// b200sat — Encodec multi-scale STFT discriminator (models/encodec.py:38-138, models/discriminators.py:13-58): everything around the
+// 64 -> 64 channel 2-D convs (which run on the tcgen05 conv kernel through b200sat_conv2d_flat).
+//
+// Layout.  One scale's activations are a flattened time-major plane [B, P, C], P = frames * Fp, Fp = F + 8: the F = n_fft/2 + 1 bins
+// of a frame sit in columns [4, 4 + F) of its Fp-wide row group, the 4 + 4 pad columns hold zeros.  A 2-D tap (dt, df) of a conv with
+// dilation (d, 1) is the row shift dt * d * Fp + df; frequency padding = the zero columns, time padding = out-of-range rows.
+//   spectrogram   fp32 [B, P, 4]   channels (re ch0, re ch1, im ch0, im ch1) = torch.cat([z.real, z.imag], dim=1) for stereo
+//   feature maps  bf16 [B, P, 64]  (post LeakyReLU; pad columns zero)
+//   logits        fp32 [B, P]
+#include "common.cuh"
+
+namespace b200sat {
+
+__device__ __forceinline__ bool col_valid(int p, int Fp, int F) {
+  const int f = p % Fp;
+  return f >= 4 && f < 4 + F;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// STFT front end: torchaudio Spectrogram(n_fft, hop, win = n_fft, hann, normalized=True, center=False, power=None) (encodec.py:72-74).
+// One warp = one frame; both audio channels ride one complex FFT (z = ch0 + i ch1) and are separated by conjugate symmetry.
+__global__ void __launch_bounds__(256) disc_stft_fwd_kernel(const float* __restrict__ x, float* __restrict__ spec, const float* __restrict__ window,
+                                                            const float2* __restrict__ twiddle, int T, int n, int log2n, int hop, int frames,
+                                                            int frames_per_block, int Fp, float norm) {
+  extern __shared__ float2 fft_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  float2* buf0 = fft_smem + static_cast<size_t>(warp) * 2 * n;
+  float2* buf1 = buf0 + n;
+  const int b = blockIdx.y;
+  const float* x0 = x + static_cast<long>(b) * 2 * T;
+  const float* x1 = x0 + T;
+  const long P = static_cast<long>(frames) * Fp;
+  float4* sp = reinterpret_cast<float4*>(spec) + static_cast<long>(b) * P;
+  const int f_begin = blockIdx.x * frames_per_block;
+  const int f_end = min(frames, f_begin + frames_per_block);
+  const int half = n >> 1;
+  for (int f = f_begin + warp; f < f_end; f += nwarps) {
+    const int base = f * hop;
+    for (int i = lane; i < n; i += 32) {
+      const float w = __ldg(window + i);
+      buf0[i] = make_float2(__ldg(x0 + base + i) * w, __ldg(x1 + base + i) * w);
+    }
+    __syncwarp();
+    float2* in = buf0;
+    float2* out = buf1;
+    for (int s = 0; s < log2n; ++s) {
+      const int Ns = 1 << s, tw_stride = half >> s;
+      for (int j = lane; j < half; j += 32) {
+        const int k = j & (Ns - 1);
+        const float2 w = __ldg(twiddle + k * tw_stride);
+        const float2 a = in[j], bb = in[j + half];
+        const float2 bw = make_float2(bb.x * w.x - bb.y * w.y, bb.x * w.y + bb.y * w.x);
+        const int j0 = ((j - k) << 1) + k;
+        out[j0] = make_float2(a.x + bw.x, a.y + bw.y);
+        out[j0 + Ns] = make_float2(a.x - bw.x, a.y - bw.y);
+      }
+      __syncwarp();
+      float2* tmp = in; in = out; out = tmp;
+    }
+    for (int k = lane; k <= half; k += 32) {
+      const float2 zk = in[k];
+      const float2 zn = in[(n - k) & (n - 1)];
+      const float xr = 0.5f * (zk.x + zn.x), xi = 0.5f * (zk.y - zn.y);
+      const float yr = 0.5f * (zk.y + zn.y), yi = 0.5f * (zn.x - zk.x);
+      sp[static_cast<long>(f) * Fp + 4 + k] = make_float4(xr * norm, yr * norm, xi * norm, yi * norm);
+    }
+    __syncwarp();
+  }
+}
+
+// Backward: d spec -> d audio.  The per-bin gradients of both channels are Hermitian-extended and packed into one spectrum, one
+// inverse-direction FFT returns d/d(ch0 * w) in the real part and d/d(ch1 * w) in the imaginary part; windowed, scattered with atomics.
+__global__ void __launch_bounds__(256) disc_stft_bwd_kernel(const float* __restrict__ dspec, float* __restrict__ dx, const float* __restrict__ window,
+                                                            const float2* __restrict__ twiddle, int T, int n, int log2n, int hop, int frames,
+                                                            int frames_per_block, int Fp, float norm) {
+  extern __shared__ float2 fft_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  float2* buf0 = fft_smem + static_cast<size_t>(warp) * 2 * n;
+  float2* buf1 = buf0 + n;
+  const int b = blockIdx.y;
+  float* d0 = dx + static_cast<long>(b) * 2 * T;
+  float* d1 = d0 + T;
+  const long P = static_cast<long>(frames) * Fp;
+  const float4* sp = reinterpret_cast<const float4*>(dspec) + static_cast<long>(b) * P;
+  const int f_begin = blockIdx.x * frames_per_block;
+  const int f_end = min(frames, f_begin + frames_per_block);
+  const int half = n >> 1;
+  for (int f = f_begin + warp; f < f_end; f += nwarps) {
+    for (int k = lane; k <= half; k += 32) {
+      const float4 g = __ldg(sp + static_cast<long>(f) * Fp + 4 + k);
+      const float gxr = g.x * norm, gyr = g.y * norm, gxi = g.z * norm, gyi = g.w * norm;
+      if (k == 0 || k == half) {
+        buf0[k] = make_float2(gxr, gyr);
+      } else {
+        buf0[k] = make_float2(0.5f * (gxr - gyi), 0.5f * (gxi + gyr));
+        buf0[n - k] = make_float2(0.5f * (gxr + gyi), 0.5f * (-gxi + gyr));
+      }
+    }
+    __syncwarp();
+    float2* in = buf0;
+    float2* out = buf1;
+    for (int s = 0; s < log2n; ++s) {
+      const int Ns = 1 << s, tw_stride = half >> s;
+      for (int j = lane; j < half; j += 32) {
+        const int k = j & (Ns - 1);
+        float2 w = __ldg(twiddle + k * tw_stride);
+        w.y = -w.y;
+        const float2 a = in[j], bb = in[j + half];
+        const float2 bw = make_float2(bb.x * w.x - bb.y * w.y, bb.x * w.y + bb.y * w.x);
+        const int j0 = ((j - k) << 1) + k;
+        out[j0] = make_float2(a.x + bw.x, a.y + bw.y);
+        out[j0 + Ns] = make_float2(a.x - bw.x, a.y - bw.y);
+      }
+      __syncwarp();
+      float2* tmp = in; in = out; out = tmp;
+    }
+    const int base = f * hop;
+    for (int i = lane; i < n; i += 32) {
+      const float w = __ldg(window + i);
+      const float2 z = in[i];
+      atomicAdd(d0 + base + i, z.x * w);
+      atomicAdd(d1 + base + i, z.y * w);
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// First conv (4 -> 64 channels, 3 x 9, encodec.py:77-79) + LeakyReLU.  thread = one output position with 64 accumulators; the
+// 27 x 4 x 64 weights sit in shared memory as [tap][ci][co] and are read as broadcasts.
+constexpr int D0_TAPS = 27;
+__global__ void __launch_bounds__(128) disc_conv0_fwd_kernel(const float* __restrict__ spec, const float* __restrict__ w /*[64][4][27]*/,
+                                                             const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int B, int frames,
+                                                             int Fp, int F, float leaky) {
+  __shared__ float sw[D0_TAPS * 4 * 64];
+  __shared__ float sb[64];
+  for (int i = threadIdx.x; i < D0_TAPS * 4 * 64; i += blockDim.x) {
+    const int tap = i / 256, ci = (i / 64) % 4, co = i % 64;
+    sw[i] = w[(co * 4 + ci) * D0_TAPS + tap];
+  }
+  if (threadIdx.x < 64) sb[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
+  __syncthreads();
+  const long P = static_cast<long>(frames) * Fp;
+  const long total = static_cast<long>(B) * P;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int b = idx / P;
+    const long p = idx % P;
+    __nv_bfloat16* orow = out + idx * 64;
+    if (!col_valid(static_cast<int>(p % Fp), Fp, F)) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) reinterpret_cast<uint4*>(orow)[i] = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    float acc[64];
+#pragma unroll
+    for (int co = 0; co < 64; ++co) acc[co] = sb[co];
+    const float4* sp = reinterpret_cast<const float4*>(spec) + static_cast<long>(b) * P;
+#pragma unroll 1
+    for (int tap = 0; tap < D0_TAPS; ++tap) {
+      const long q = p + (tap / 9 - 1) * Fp + (tap % 9 - 4);
+      if (q < 0 || q >= P) continue;
+      const float4 v = __ldg(sp + q);
+      const float* wt = sw + tap * 256;
+#pragma unroll
+      for (int c4 = 0; c4 < 16; ++c4) {
+        const float4 w0 = *reinterpret_cast<const float4*>(wt + c4 * 4);
+        const float4 w1 = *reinterpret_cast<const float4*>(wt + 64 + c4 * 4);
+        const float4 w2 = *reinterpret_cast<const float4*>(wt + 128 + c4 * 4);
+        const float4 w3 = *reinterpret_cast<const float4*>(wt + 192 + c4 * 4);
+        acc[c4 * 4 + 0] += v.x * w0.x + v.y * w1.x + v.z * w2.x + v.w * w3.x;
+        acc[c4 * 4 + 1] += v.x * w0.y + v.y * w1.y + v.z * w2.y + v.w * w3.y;
+        acc[c4 * 4 + 2] += v.x * w0.z + v.y * w1.z + v.z * w2.z + v.w * w3.z;
+        acc[c4 * 4 + 3] += v.x * w0.w + v.y * w1.w + v.z * w2.w + v.w * w3.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float a0 = acc[i * 8 + 2 * e], a1 = acc[i * 8 + 2 * e + 1];
+        a0 = a0 > 0.f ? a0 : a0 * leaky; a1 = a1 > 0.f ? a1 : a1 * leaky;
+        pk[e] = pack_bf16(a0, a1);
+      }
+      reinterpret_cast<uint4*>(orow)[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
+// Data gradient of the first conv: d spec[p][ci] = sum_{tap, co} d_pre[p - off(tap)][co] * w[co][ci][tap].
+__global__ void __launch_bounds__(128) disc_conv0_dgrad_kernel(const __nv_bfloat16* __restrict__ dpre, const float* __restrict__ w /*[64][4][27]*/,
+                                                               float* __restrict__ dspec, int B, int frames, int Fp, int F) {
+  __shared__ float4 sw[D0_TAPS * 64];   // [tap][co] -> (ci 0..3)
+  for (int i = threadIdx.x; i < D0_TAPS * 64; i += blockDim.x) {
+    const int tap = i / 64, co = i % 64;
+    sw[i] = make_float4(w[(co * 4 + 0) * D0_TAPS + tap], w[(co * 4 + 1) * D0_TAPS + tap], w[(co * 4 + 2) * D0_TAPS + tap], w[(co * 4 + 3) * D0_TAPS + tap]);
+  }
+  __syncthreads();
+  const long P = static_cast<long>(frames) * Fp;
+  const long total = static_cast<long>(B) * P;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int b = idx / P;
+    const long p = idx % P;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col_valid(static_cast<int>(p % Fp), Fp, F)) {
+      const __nv_bfloat16* base = dpre + static_cast<long>(b) * P * 64;
+#pragma unroll 1
+      for (int tap = 0; tap < D0_TAPS; ++tap) {
+        const long q = p - ((tap / 9 - 1) * Fp + (tap % 9 - 4));
+        if (q < 0 || q >= P) continue;
+        const uint4* row = reinterpret_cast<const uint4*>(base + q * 64);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 u = __ldg(row + i);
+          const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 d = unpack_bf16(uw[e]);
+            const float4 w0 = sw[tap * 64 + i * 8 + 2 * e], w1 = sw[tap * 64 + i * 8 + 2 * e + 1];
+            acc.x += d.x * w0.x + d.y * w1.x; acc.y += d.x * w0.y + d.y * w1.y;
+            acc.z += d.x * w0.z + d.y * w1.z; acc.w += d.x * w0.w + d.y * w1.w;
+          }
+        }
+      }
+    }
+    reinterpret_cast<float4*>(dspec)[idx] = acc;
+  }
+}
+
+// Last conv (64 -> 1, 3 x 3, no activation; encodec.py:88-90): logits[p] = b + sum_{tap, c} act[p + off][c] * w[c][tap].
+__global__ void __launch_bounds__(128) disc_convpost_fwd_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ w /*[1][64][9]*/,
+                                                                const float* __restrict__ bias, float* __restrict__ logits, int B, int frames,
+                                                                int Fp, int F) {
+  __shared__ float sw[9 * 64];   // [tap][c]
+  for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) sw[i] = w[(i % 64) * 9 + i / 64];
+  __syncthreads();
+  const long P = static_cast<long>(frames) * Fp;
+  const long total = static_cast<long>(B) * P;
+  const float bv = bias ? bias[0] : 0.f;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int b = idx / P;
+    const long p = idx % P;
+    float acc = 0.f;
+    const bool ok = col_valid(static_cast<int>(p % Fp), Fp, F);
+    if (ok) {
+      acc = bv;
+      const __nv_bfloat16* base = act + static_cast<long>(b) * P * 64;
+#pragma unroll 1
+      for (int tap = 0; tap < 9; ++tap) {
+        const long q = p + (tap / 3 - 1) * Fp + (tap % 3 - 1);
+        if (q < 0 || q >= P) continue;
+        const uint4* row = reinterpret_cast<const uint4*>(base + q * 64);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 u = __ldg(row + i);
+          const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 d = unpack_bf16(uw[e]);
+            acc += d.x * sw[tap * 64 + i * 8 + 2 * e] + d.y * sw[tap * 64 + i * 8 + 2 * e + 1];
+          }
+        }
+      }
+    }
+    logits[idx] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Loss reductions (discriminators.py:13-58).  sums[0] += sum relu(1 - lt), sums[1] += sum relu(1 + lf), sums[2] += sum lf over valid bins.
+__global__ void __launch_bounds__(256) disc_hinge_sums_kernel(const float* __restrict__ lt, const float* __restrict__ lf, double* __restrict__ sums,
+                                                              long total, int Fp, int F) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    if (!col_valid(static_cast<int>(i % Fp), Fp, F)) continue;   // P is a multiple of Fp, so i % Fp is the column for every batch entry
+    if (lt) s0 += fmaxf(1.f - lt[i], 0.f);
+    if (lf) { s1 += fmaxf(1.f + lf[i], 0.f); s2 += lf[i]; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(sums + 0, static_cast<double>(s0)); atomicAdd(sums + 1, static_cast<double>(s1)); atomicAdd(sums + 2, static_cast<double>(s2));
+  }
+}
+
+// out[0] += sum |a - b| over two bf16 planes (feature matching, discriminators.py:24).  Pad columns are zero in both.
+__global__ void __launch_bounds__(256) disc_l1_sum_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                                          double* __restrict__ out, long n8) {
+  float s = 0.f;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const uint4 ua = __ldg(reinterpret_cast<const uint4*>(a) + i), ub = __ldg(reinterpret_cast<const uint4*>(b) + i);
+    const uint32_t aw[4] = {ua.x, ua.y, ua.z, ua.w}, bw[4] = {ub.x, ub.y, ub.z, ub.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 x = unpack_bf16(aw[e]), y = unpack_bf16(bw[e]);
+      s += fabsf(x.x - y.x) + fabsf(x.y - y.y);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, static_cast<double>(s));
+}
+
+// d logits for the three uses of a logit map: mode 0 generator (adv = -mean lf): g = -scale; mode 1 discriminator on reals
+// (relu(1 - l)): g = -scale [1 - l > 0]; mode 2 discriminator on fakes (relu(1 + l)): g = +scale [1 + l > 0].  Pad columns get 0.
+__global__ void __launch_bounds__(256) disc_logit_grad_kernel(const float* __restrict__ logits, float* __restrict__ g, long total, int Fp, int F,
+                                                              int mode, float scale) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    float v = 0.f;
+    if (col_valid(static_cast<int>(i % Fp), Fp, F)) {
+      const float l = logits[i];
+      v = (mode == 0) ? -scale : (mode == 1 ? ((1.f - l > 0.f) ? -scale : 0.f) : ((1.f + l > 0.f) ? scale : 0.f));
+    }
+    g[i] = v;
+  }
+}
+
+// Backward through one feature map: d_post = d_in (from the next conv's dgrad, optional) + conv_post^T(d logits) (last layer only,
+// optional) + fm_coef * sign(post - other) (feature matching: d/d post of mean |other - post|; optional);
+// d_pre = d_post * (post > 0 ? 1 : leaky), zero in the pad columns.  thread = 8 channels of one position.
+__global__ void __launch_bounds__(256) disc_act_bwd_kernel(const __nv_bfloat16* __restrict__ d_in, const float* __restrict__ d_logit,
+                                                           const float* __restrict__ w_post /*[64][9]*/, const __nv_bfloat16* __restrict__ post,
+                                                           const __nv_bfloat16* __restrict__ other, float fm_coef, float leaky,
+                                                           __nv_bfloat16* __restrict__ d_pre, int B, int frames, int Fp, int F) {
+  __shared__ float sw[9 * 64];   // [tap][c]
+  if (d_logit) {
+    for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) sw[i] = w_post[(i % 64) * 9 + i / 64];
+  }
+  __syncthreads();
+  const long P = static_cast<long>(frames) * Fp;
+  const long total = static_cast<long>(B) * P * 8;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long pos = idx >> 3;
+    const int ch = static_cast<int>(idx & 7);
+    const int b = pos / P;
+    const long p = pos % P;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (col_valid(static_cast<int>(p % Fp), Fp, F)) {
+      float d[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = 0.f;
+      if (d_in) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(d_in) + idx);
+        const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 f = unpack_bf16(uw[e]); d[2 * e] = f.x; d[2 * e + 1] = f.y; }
+      }
+      if (d_logit) {
+        const float* gl = d_logit + static_cast<long>(b) * P;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          const long q = p - ((tap / 3 - 1) * Fp + (tap % 3 - 1));
+          if (q < 0 || q >= P) continue;
+          const float g = __ldg(gl + q);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] += g * sw[tap * 64 + ch * 8 + j];
+        }
+      }
+      const uint4 up = __ldg(reinterpret_cast<const uint4*>(post) + idx);
+      const uint32_t pw[4] = {up.x, up.y, up.z, up.w};
+      float pv[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float2 f = unpack_bf16(pw[e]); pv[2 * e] = f.x; pv[2 * e + 1] = f.y; }
+      if (other) {
+        const uint4 uo = __ldg(reinterpret_cast<const uint4*>(other) + idx);
+        const uint32_t ow[4] = {uo.x, uo.y, uo.z, uo.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack_bf16(ow[e]);
+          const float e0 = pv[2 * e] - f.x, e1 = pv[2 * e + 1] - f.y;
+          d[2 * e] += fm_coef * ((e0 > 0.f) ? 1.f : ((e0 < 0.f) ? -1.f : 0.f));
+          d[2 * e + 1] += fm_coef * ((e1 > 0.f) ? 1.f : ((e1 < 0.f) ? -1.f : 0.f));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] *= (pv[j] > 0.f) ? 1.f : leaky;
+      o = make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), pack_bf16(d[4], d[5]), pack_bf16(d[6], d[7]));
+    }
+    reinterpret_cast<uint4*>(d_pre)[idx] = o;
+  }
+}
+
+static int fft_launch_cfg(int n_fft, int* log2n, int* warps, int* smem) {
+  int l = 0;
+  while ((1 << l) < n_fft) ++l;
+  if ((1 << l) != n_fft || n_fft < 32 || n_fft > 4096) return -1;
+  int w = 8;
+  while (w > 1 && w * 2 * n_fft * 8 > 160 * 1024) w >>= 1;
+  *log2n = l; *warps = w; *smem = w * 2 * n_fft * 8;
+  return 0;
+}
+
+}  // namespace b200sat
+
+using namespace b200sat;
+
+static inline int grid_for(long total, int threads, int per_sm) {
+  long g = (total + threads - 1) / threads;
+  const long cap = static_cast<long>(num_sms()) * per_sm;
+  if (g > cap) g = cap;
+  return static_cast<int>(g < 1 ? 1 : g);
+}
+
+extern "C" int b200sat_disc_stft(const float* x, float* spec, const float* window, const float* twiddle, int B, int T, int n_fft, int hop,
+                                 int backward, void* stream) {
+  if (!x || !spec || !window || !twiddle || B <= 0 || T < n_fft || hop <= 0) { set_last_error("disc_stft: bad arguments"); return B200SAT_EINVAL; }
+  int log2n, warps, smem;
+  if (fft_launch_cfg(n_fft, &log2n, &warps, &smem)) { set_last_error("disc_stft: n_fft must be a power of two in [32, 4096]"); return B200SAT_EUNSUPPORTED; }
+  const int frames = (T - n_fft) / hop + 1;
+  const int Fp = n_fft / 2 + 1 + 8;
+  // normalized=True: divide by sqrt(sum w^2); for the periodic hann window sum w^2 = 3 n / 8
+  const float norm = 1.0f / sqrtf(0.375f * static_cast<float>(n_fft));
+  static bool attr = false;
+  if (!attr) {
+    B200SAT_CHECK_CUDA(cudaFuncSetAttribute(disc_stft_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    B200SAT_CHECK_CUDA(cudaFuncSetAttribute(disc_stft_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr = true;
+  }
+  const int fpb = warps * 4;
+  dim3 grid((frames + fpb - 1) / fpb, B);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!backward)
+    disc_stft_fwd_kernel<<<grid, warps * 32, smem, s>>>(x, spec, window, reinterpret_cast<const float2*>(twiddle), T, n_fft, log2n, hop, frames, fpb, Fp, norm);
+  else   // x = d audio (accumulated, fp32 [B,2,T]), spec = d spec
+    disc_stft_bwd_kernel<<<grid, warps * 32, smem, s>>>(spec, const_cast<float*>(x), window, reinterpret_cast<const float2*>(twiddle), T, n_fft, log2n, hop,
+                                                       frames, fpb, Fp, norm);
+  B200SAT_CHECK_CUDA(cudaGetLastError());
+  return B200SAT_OK;
+}
+
+extern "C" int b200sat_disc_conv0(const float* spec, const float* w, const float* bias, void* out, const void* dpre, float* dspec, int B, int frames,
+                                  int F, float leaky, void* stream) {
+  if (!w || B <= 0 || frames <= 0 || F <= 0 || (!(spec && out) && !(dpre && dspec))) { set_last_error("disc_conv0: bad arguments"); return B200SAT_EINVAL; }
+  const int Fp = F + 8;
+  const long total = static_cast<long>(B) * frames * Fp;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (spec && out) disc_conv0_fwd_kernel<<<grid_for(total, 128, 8), 128, 0, s>>>(spec, w, bias, static_cast<__nv_bfloat16*>(out), B, frames, Fp, F, leaky);
+  if (dpre && dspec) disc_conv0_dgrad_kernel<<<grid_for(total, 128, 8), 128, 0, s>>>(static_cast<const __nv_bfloat16*>(dpre), w, dspec, B, frames, Fp, F);
+  B200SAT_CHECK_CUDA(cudaGetLastError());
+  return B200SAT_OK;
+}
+
+extern "C" int b200sat_disc_convpost(const void* act, const float* w, const float* bias, float* logits, int B, int frames, int F, void* stream) {
+  if (!act || !w || !logits || B <= 0 || frames <= 0 || F <= 0) { set_last_error("disc_convpost: bad arguments"); return B200SAT_EINVAL; }
+  const int Fp = F + 8;
+  const long total = static_cast<long>(B) * frames * Fp;
+  disc_convpost_fwd_kernel<<<grid_for(total, 128, 8), 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(act), w, bias, logits, B,
+                                                                                                  frames, Fp, F);
+  B200SAT_CHECK_CUDA(cudaGetLastError());
+  return B200SAT_OK;
+}
+
+extern "C" int b200sat_disc_hinge_sums(const float* lt, const float* lf, double* sums, int B, int frames, int F, void* stream) {
+  if ((!lt && !lf) || !sums || B <= 0 || frames <= 0 || F <= 0) { set_last_error("disc_hinge_sums: bad arguments"); return B200SAT_EINVAL; }
+  const long total = static_cast<long>(B) * frames * (F + 8);
+  disc_hinge_sums_kernel<<<grid_for(total, 256, 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(lt, lf, sums, total, F + 8, F);
+  B200SAT_CHECK_CUDA(cudaGetLastError());
+  return B200SAT_OK;
+}
+
+extern "C" int b200sat_disc_l1_sum(const void* a, const void* b, double* out, long n, void* stream) {
+  if (!a || !b || !out || n <= 0 || (n & 7)) { set_last_error("disc_l1_sum: bad arguments (n % 8 == 0)"); return B200SAT_EINVAL; }
+  disc_l1_sum_kernel<<<grid_for(n / 8, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(a),
+                                                                                             static_cast<const __nv_bfloat16*>(b), out, n / 8);
+  B200SAT_CHECK_CUDA(cudaGetLastError());
+  return B200SAT_OK;
+}
+
+extern "C" int b200sat_disc_logit_grad(const float* logits, float* g, int B, int frames, int F, int mode, float scale, void* stream) {
+  if (!logits || !g || B <= 0 || frames <= 0 || F <= 0 || mode < 0 || mode > 2) { set_last_error("disc_logit_grad: bad arguments"); return B200SAT_EINVAL; }
+  const long total = static_cast<long>(B) * frames * (F + 8);
+  disc_logit_grad_kernel<<<grid_for(total, 256, 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, g, total, F + 8, F, mode, scale);
+  B200SAT_CHECK_CUDA(cudaGetLastError());
+  return B200SAT_OK;
+}
+
+extern "C" int b200sat_disc_act_bwd(const void* d_in, const float* d_logit, const float* w_post, const void* post, const void* other, float fm_coef,
+                                    float leaky, void* d_pre, int B, int frames, int F, void* stream) {
+  if (!post || !d_pre || (!d_in && !d_logit && !other) || (d_logit && !w_post) || B <= 0 || frames <= 0 || F <= 0) {
+    set_last_error("disc_act_bwd: bad arguments"); return B200SAT_EINVAL;
+  }
+  const long total = static_cast<long>(B) * frames * (F + 8) * 8;
+  disc_act_bwd_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(d_in), d_logit, w_post, static_cast<const __nv_bfloat16*>(post), static_cast<const __nv_bfloat16*>(other), fm_coef,
+      leaky, static_cast<__nv_bfloat16*>(d_pre), B, frames, F + 8, F);
+  B200SAT_CHECK_CUDA(cudaGetLastError());
+  return B200SAT_OK;
+}
