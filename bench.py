@@ -290,9 +290,85 @@ def measure_ae_train(args, dev, rank, world, dist):
     out = {"metric": "oobleck_generator_step_items_per_sec", "value": B * world / (ms_step * 1e-3), "unit": "clips/s", "ms_per_step": ms_step,
            "batch_per_gpu": B, "samples_per_clip": T, "loss": float(h_loss.item()),
            "includes": "H2D audio, encoder+VAE+decoder fwd, 4-term MRSTFT + KL, full backward, (all-reduce), AdamW(fused), D2H loss",
-           "excludes": "adversarial / feature-matching terms (EncodecDiscriminator not built yet)",
+           "excludes": "adversarial / feature-matching terms (warm-up phase; see ae_adversarial for the post-warm-up steps)",
            "tflops_per_gpu": flop / (ms_step * 1e-3) / 1e12, "frac_of_sustained_peak": flop / (ms_step * 1e-3) / 1e12 / pk["bf16_sustained"]}
     del model, opt
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure_ae_adversarial(args, dev, rank, world, dist):
+    """BASELINE.json configs[3] after warm-up (training/autoencoders.py:436-515): alternating discriminator / generator steps of the Oobleck
+    autoencoder with the EncodecDiscriminator (hinge + feature matching, weights 0.1 / 5.0), MRSTFT sum/difference + L/R and KL.
+    Minimal graphs: D step = AE forward (no grad) + D forward/backward on reals and fakes; G step = AE forward/backward + D forward on
+    both + D data-gradient through the fake path.  8 clips x 65536 samples per GPU; two consecutive steps (one D, one G) are timed."""
+    from b200sat.autoencoder_train import OobleckTrainModel
+    from b200sat.discriminator import EncodecDiscriminatorTrain
+    from b200sat.init import encodec_disc_state_dict
+    from b200sat.stft_loss import SumAndDifferenceSTFTLoss, autoencoder_mrstft_terms
+    B, T = 8, 65536
+    g = torch.Generator(device=dev).manual_seed(21)
+    ae = OobleckTrainModel(_oobleck_state_dict(dev, g), device=dev)
+    disc = EncodecDiscriminatorTrain(encodec_disc_state_dict(dev, g), device=dev)
+    opt_g = torch.optim.AdamW(ae.parameters(), lr=1.5e-4, betas=(0.8, 0.99), fused=True)
+    opt_d = torch.optim.AdamW(disc.parameters(), lr=3e-4, betas=(0.8, 0.99), fused=True)
+    fft, hop = [2048, 1024, 512, 256, 128, 64, 32], [512, 256, 128, 64, 32, 16, 8]
+    loss_sd = SumAndDifferenceSTFTLoss(fft_sizes=fft, hop_sizes=hop, win_lengths=fft, perceptual_weighting=True, sample_rate=44100)
+    reals = (torch.randn(B, 2, T, device=dev, generator=g).clamp(-1, 1) * 0.5)
+
+    def allreduce(params):
+        if world > 1:
+            flat = torch.cat([p.grad.view(-1) for p in params])
+            dist.all_reduce(flat)
+            off = 0
+            for p in params:
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p)); off += p.numel()
+
+    def d_step():
+        noise = torch.randn(B, 64, T // 2048, device=dev, generator=g)
+        with torch.no_grad():
+            decoded = ae(reals, noise)[0]
+        dis = disc.discriminator_loss(reals, decoded)
+        opt_d.zero_grad(set_to_none=True)
+        (dis / world).backward()
+        allreduce(list(disc.parameters()))
+        opt_d.step()
+        return dis
+
+    def g_step():
+        noise = torch.randn(B, 64, T // 2048, device=dev, generator=g)
+        decoded, kl, _ = ae(reals, noise)
+        sd_, l_, r_ = autoencoder_mrstft_terms(loss_sd, decoded, reals)
+        adv, fm = disc.generator_terms(reals, decoded)
+        loss = sd_ + 0.5 * l_ + 0.5 * r_ + 1e-4 * kl + 0.1 * adv + 5.0 * fm
+        opt_g.zero_grad(set_to_none=True)
+        (loss / world).backward()
+        allreduce(list(ae.parameters()))
+        opt_g.step()
+        return loss
+
+    d_step(); g_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    d = d_step()
+    ev[1].record()
+    l = g_step()
+    ev[2].record()
+    torch.cuda.synchronize()
+    t_d, t_g = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+    ms = torch.tensor([(t_d + t_g) / 2], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = ms.item()
+    flop = B * 2.86e12      # SURVEY 8d: mean of the G step (2.44 TFLOP/item) and the D step (3.27 TFLOP/item), minimal graphs
+    out = {"metric": "oobleck_adversarial_step_items_per_sec", "value": B * world / (ms_step * 1e-3), "unit": "clips/s", "ms_per_step": ms_step,
+           "d_step_ms": t_d, "g_step_ms": t_g, "batch_per_gpu": B, "samples_per_clip": T, "dis_loss": float(d), "gen_loss": float(l),
+           "includes": "one discriminator step and one generator step (mean), AdamW(fused) on each parameter group, (all-reduce)",
+           "tflops_per_gpu": flop / (ms_step * 1e-3) / 1e12, "frac_of_sustained_peak": flop / (ms_step * 1e-3) / 1e12 / peaks()["bf16_sustained"]}
+    del ae, disc, opt_g, opt_d
     torch.cuda.empty_cache()
     return out
 
@@ -499,6 +575,7 @@ def run_ours(args):
 
     train = None
     ae_train = None
+    ae_adv = None
     if not args.no_train:
         del smp
         model._samplers.clear()
@@ -508,6 +585,11 @@ def run_ours(args):
             ae_train = measure_ae_train(args, dev, rank, world, dist)
         except Exception as ex:   # secondary measurement: never lose the headline line
             ae_train = {"error": repr(ex)[:300]}
+            torch.cuda.empty_cache()
+        try:
+            ae_adv = measure_ae_adversarial(args, dev, rank, world, dist)
+        except Exception as ex:
+            ae_adv = {"error": repr(ex)[:300]}
             torch.cuda.empty_cache()
     if rank != 0:
         if world > 1:
@@ -558,7 +640,7 @@ def run_ours(args):
         "config": workload_config(world), "sample_seconds_100_steps": ms_total / args.steps / 1e3,
         "e2e": {"value": e2e_val, "unit": "latent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "b200sat.generation.generate_diffusion_cond(host pinned noise/conditioning -> host latents)"},
-        "gpu_launches": launches, "clocks": clk, "roofline": roof, "whole_step": whole, "cpu_baseline": cpu, "train": train, "ae_train": ae_train, "other_kernels": other,
+        "gpu_launches": launches, "clocks": clk, "roofline": roof, "whole_step": whole, "cpu_baseline": cpu, "train": train, "ae_train": ae_train, "ae_adversarial": ae_adv, "other_kernels": other,
     }
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)

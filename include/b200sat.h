@@ -272,6 +272,11 @@ int b200sat_disc_logit_grad(const float* logits, float* g, int B, int frames, in
 int b200sat_disc_act_bwd(const void* d_in, const float* d_logit, const float* w_post, const void* post, const void* other, float fm_coef,
                          float leaky, void* d_pre, int B, int frames, int F, void* stream);
 
+/* Weight gradients of the first conv (dW fp32 [64,4,27] += sum_p d_pre[p] (x) spec[p + tap]) and of conv_post (dW fp32 [64,9] +=
+ * sum_p g[p] * act[p + tap], dbias += sum g) for the discriminator step (training/autoencoders.py:476-489). */
+int b200sat_disc_conv0_wgrad(const void* dpre, const float* spec, float* dW, int B, int frames, int F, void* stream);
+int b200sat_disc_convpost_wgrad(const float* g, const void* act, float* dW, float* dbias, int B, int frames, int F, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,12 +6,16 @@ Reference: `EncodecDiscriminator` (models/discriminators.py:13-58) over `MultiSc
 Layout and kernels: csrc/discriminator.cu (STFT front end, first / last conv, loss reductions, activation backward) and
 `b200sat_conv2d_flat` (the four 64 -> 64 channel Conv2d layers per scale on the tcgen05 conv kernel).
 
-Not built yet: the discriminator's own weight gradients (the D step of training/autoencoders.py:476-489).
+The discriminator step (training/autoencoders.py:476-489: hinge loss on reals and fakes, gradients w.r.t. the discriminator's
+weight-normed parameters) is `EncodecDiscriminatorTrain.discriminator_loss`: weight gradients of the 64 -> 64 convs are one
+`b200sat_conv_wgrad` launch per tap on the flattened planes, the two SIMT layers have their own kernels, weight-norm backward is
+`b200sat_wn_bwd`.
 """
 import ctypes
 import math
 
 import torch
+from torch import nn
 
 from ._lib import lib, check
 from . import ops
@@ -44,6 +48,8 @@ class _Scale:
         self.window = win.float().to(dev).contiguous()
         self.twiddle = torch.stack([torch.cos(2 * math.pi * k / n_fft), -torch.sin(2 * math.pi * k / n_fft)], dim=1).float().to(dev).contiguous()
         # first conv (4 -> 64) and conv_post (64 -> 1): dense weight-normalised fp32 weights for the SIMT kernels
+        self.pre = pre
+        self.raw = {k[len(pre):]: sd[k].float().to(dev) for k in sd if k.startswith(pre) and k.endswith(("weight_v", "weight_g", "bias"))}
         self.w0 = _wn_dense(sd, pre + "convs.0.conv.").to(dev).reshape(64, 4, 27).contiguous()
         self.b0 = sd[pre + "convs.0.conv.bias"].float().to(dev).contiguous()
         self.wp = _wn_dense(sd, pre + "conv_post.conv.").to(dev).reshape(64, 9).contiguous()      # [1,64,3,3] -> [c][tap]
@@ -66,7 +72,8 @@ class _Scale:
                 offs = [(k_ // 9 - 1) * d * self.Fp + (k_ % 9 - 4) for k_ in range(27)]
             else:
                 offs = [(k_ // 3 - 1) * self.Fp + (k_ % 3 - 1) for k_ in range(9)]
-            self.convs.append(dict(w=w_f, wd=w_d, bias=sd[q + "bias"].float().to(dev).contiguous(), K=K, offs=(ctypes.c_int * K)(*offs)))
+            self.convs.append(dict(w=w_f, wd=w_d, bias=sd[q + "bias"].float().to(dev).contiguous(), K=K, offs=(ctypes.c_int * K)(*offs),
+                                   offs_py=offs, v3=v3, g=g, inv=inv, name=f"convs.{j}.conv."))
         ops.LAUNCHES[0] += 12
 
     def frames(self, T):
@@ -105,6 +112,7 @@ class EncodecDiscriminatorEngine:
         logits = torch.empty(B, P, device=self.dev)
         check(lib().b200sat_disc_convpost(fmaps[-1].data_ptr(), sc.wp.data_ptr(), sc.bp.data_ptr(), logits.data_ptr(), B, fr, sc.F, _s()), "disc_convpost")
         ops.LAUNCHES[0] += 3
+        self._last_spec = spec
         return logits, fmaps, fr
 
     @torch.no_grad()
@@ -203,3 +211,124 @@ class _GenFn(torch.autograd.Function):
         g = ctx.eng._generator_backward(ctx.saved, n_logit, n_feat, shape, float(d_adv), float(d_fm))
         ctx.saved = None
         return g, None, None
+
+
+def _wn_small_bwd(v, g, dw):
+    """weight_norm backward for the two small SIMT layers (a few thousand values): dw dense, shaped like v."""
+    nrm = v.flatten(1).norm(dim=1).view(-1, 1, 1, 1)
+    dot = (dw * v).sum(dim=(1, 2, 3), keepdim=True)
+    return g / nrm * (dw - v * dot / (nrm * nrm)), dot / nrm
+
+
+def _discriminator_forward_backward(eng, reals, fakes):
+    """Hinge discriminator loss and the gradients of every discriminator parameter: returns (dis, {reference name: grad})."""
+    dev = eng.dev
+    reals = reals.to(dev, torch.float32).contiguous()
+    fakes = fakes.to(dev, torch.float32).contiguous()
+    B = reals.shape[0]
+    ns = len(eng.scales)
+    st = _s()
+    hs = torch.zeros(ns, 3, device=dev, dtype=torch.float64)
+    n_logit = []
+    grads = {}
+    for i, sc in enumerate(eng.scales):
+        paths = []
+        for x, mode in ((reals, 1), (fakes, 2)):
+            lg, fm, fr = eng._scale_forward(sc, x)
+            paths.append((lg, fm, eng._last_spec, mode))
+        fr = sc.frames(reals.shape[-1])
+        P = fr * sc.Fp
+        check(lib().b200sat_disc_hinge_sums(paths[0][0].data_ptr(), paths[1][0].data_ptr(), hs[i].data_ptr(), B, fr, sc.F, st), "disc_hinge_sums")
+        n_logit.append(B * fr * sc.F)
+        dW0 = torch.zeros(64, 4, 27, device=dev)
+        db0 = torch.zeros(64, device=dev)
+        dWp = torch.zeros(64, 9, device=dev)
+        dbp = torch.zeros(1, device=dev)
+        dwps = [torch.zeros(cv["K"], 64, 64, device=dev) for cv in sc.convs]
+        dbs = [torch.zeros(64, device=dev) for _ in sc.convs]
+        for lg, fm, spec, mode in paths:
+            g = torch.empty(B, P, device=dev)
+            check(lib().b200sat_disc_logit_grad(lg.data_ptr(), g.data_ptr(), B, fr, sc.F, mode, 1.0 / (n_logit[i] * ns), st), "disc_logit_grad")
+            check(lib().b200sat_disc_convpost_wgrad(g.data_ptr(), fm[4].data_ptr(), dWp.data_ptr(), dbp.data_ptr(), B, fr, sc.F, st), "disc_convpost_wgrad")
+            d_pre = torch.empty(B, P, 64, device=dev, dtype=torch.bfloat16)
+            check(lib().b200sat_disc_act_bwd(0, g.data_ptr(), sc.wp.data_ptr(), fm[4].data_ptr(), 0, 0.0, LEAKY, d_pre.data_ptr(), B, fr, sc.F, st), "disc_act_bwd")
+            ops.LAUNCHES[0] += 3
+            for l in range(4, 0, -1):
+                cv = sc.convs[l - 1]
+                for k_, off in enumerate(cv["offs_py"]):
+                    check(lib().b200sat_conv_wgrad(d_pre.data_ptr(), 64, P, 1, 0, 0, fm[l - 1].data_ptr(), 64, P, 1, 0, off, dwps[l - 1][k_].data_ptr(), B, P, st),
+                          "conv_wgrad")
+                ops.LAUNCHES[0] += cv["K"]
+                ops.colsum(d_pre.view(-1, 64), dbs[l - 1])
+                d_in = eng._flat_conv(sc, d_pre, cv, torch.empty_like(d_pre), None, cv["wd"])
+                d_pre = torch.empty_like(d_in)
+                check(lib().b200sat_disc_act_bwd(d_in.data_ptr(), 0, 0, fm[l - 1].data_ptr(), 0, 0.0, LEAKY, d_pre.data_ptr(), B, fr, sc.F, st), "disc_act_bwd")
+                ops.LAUNCHES[0] += 1
+            check(lib().b200sat_disc_conv0_wgrad(d_pre.data_ptr(), spec.data_ptr(), dW0.data_ptr(), B, fr, sc.F, st), "disc_conv0_wgrad")
+            ops.colsum(d_pre.view(-1, 64), db0)
+            ops.LAUNCHES[0] += 1
+        # weight-norm backward
+        pre = sc.pre
+        for l, cv in enumerate(sc.convs):
+            dv = torch.empty_like(cv["v3"])
+            dg = torch.empty_like(cv["g"])
+            check(lib().b200sat_wn_bwd(dwps[l].data_ptr(), cv["v3"].data_ptr(), cv["g"].data_ptr(), cv["inv"].data_ptr(), dv.data_ptr(), dg.data_ptr(), 64, 64,
+                                       cv["K"], st), "wn_bwd")
+            ops.LAUNCHES[0] += 1
+            grads[pre + cv["name"] + "weight_v"] = dv.view_as(sc.raw[cv["name"] + "weight_v"])
+            grads[pre + cv["name"] + "weight_g"] = dg.view_as(sc.raw[cv["name"] + "weight_g"])
+            grads[pre + cv["name"] + "bias"] = dbs[l]
+        v0, g0 = sc.raw["convs.0.conv.weight_v"], sc.raw["convs.0.conv.weight_g"]
+        dv0, dg0 = _wn_small_bwd(v0, g0, dW0.view_as(v0))
+        grads[pre + "convs.0.conv.weight_v"], grads[pre + "convs.0.conv.weight_g"], grads[pre + "convs.0.conv.bias"] = dv0, dg0, db0
+        vp, gp = sc.raw["conv_post.conv.weight_v"], sc.raw["conv_post.conv.weight_g"]
+        dvp, dgp = _wn_small_bwd(vp, gp, dWp.view(1, 64, 3, 3))
+        grads[pre + "conv_post.conv.weight_v"], grads[pre + "conv_post.conv.weight_g"], grads[pre + "conv_post.conv.bias"] = dvp, dgp, dbp
+    nl = torch.tensor(n_logit, device=dev, dtype=torch.float64)
+    dis = (((hs[:, 0] + hs[:, 1]) / nl).sum() / ns).float()
+    return dis, grads
+
+
+class _DiscDFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, reals, fakes, model, *params):
+        sd = {n: p.detach() for n, p in zip(model.names, params)}
+        eng = EncodecDiscriminatorEngine(sd, model.n_ffts, model.hop_lengths, device=params[0].device, prefix=model.prefix)
+        with torch.no_grad():
+            dis, grads = _discriminator_forward_backward(eng, reals.detach(), fakes.detach())
+        ctx.grads, ctx.names = grads, model.names
+        return dis
+
+    @staticmethod
+    def backward(ctx, d_dis):
+        grads = ctx.grads
+        ctx.grads = None
+        return (None, None, None) + tuple(grads[n] * d_dis for n in ctx.names)
+
+
+class EncodecDiscriminatorTrain(nn.Module):
+    """Trainable EncodecDiscriminator with the reference parameter names (`discriminators.discriminators.{i}.convs.{j}.conv.weight_g|v|bias`).
+    `discriminator_loss(reals, fakes)` = hinge `dis_loss` differentiable w.r.t. the parameters (the D step);
+    `generator_terms(reals, fakes)` = (adv_loss, feature_matching_distance) differentiable w.r.t. `fakes` (the G step)."""
+
+    def __init__(self, state_dict, n_ffts=(2048, 1024, 512, 256, 128), hop_lengths=(512, 256, 128, 64, 32), device="cuda",
+                 prefix="discriminators.discriminators."):
+        super().__init__()
+        self.n_ffts, self.hop_lengths, self.prefix = tuple(n_ffts), tuple(hop_lengths), prefix
+        self.names = [k for k in state_dict if k.startswith(prefix) and k.endswith(("weight_v", "weight_g", "bias"))]
+        for k in self.names:
+            self.register_parameter(k.replace(".", "__"), nn.Parameter(state_dict[k].detach().to(device, torch.float32).clone().contiguous()))
+
+    def reference_state_dict(self):
+        return {k: getattr(self, k.replace(".", "__")).detach() for k in self.names}
+
+    def engine(self):
+        p0 = getattr(self, self.names[0].replace(".", "__"))
+        return EncodecDiscriminatorEngine(self.reference_state_dict(), self.n_ffts, self.hop_lengths, device=p0.device, prefix=self.prefix)
+
+    def discriminator_loss(self, reals, fakes):
+        params = [getattr(self, k.replace(".", "__")) for k in self.names]
+        return _DiscDFn.apply(reals, fakes, self, *params)
+
+    def generator_terms(self, reals, fakes):
+        return self.engine().generator_terms(reals, fakes)

@@ -90,3 +90,24 @@ def oobleck_state_dict(dev, g, ch=128):
             ru(f"{q}layers.{2 + j}.", co)
     snake(f"{p}{n + 1}.", cm[0] * ch); conv(f"{p}{n + 2}.", 2, cm[0] * ch, 7, bias=False)
     return sd
+
+
+def encodec_disc_state_dict(dev, g, filters=64, in_channels=2, n_scales=5):
+    """Random weights with the reference names/shapes of EncodecDiscriminator(filters=64) (models/encodec.py:76-92)."""
+    import math
+    sd = {}
+
+    def conv(p, cout, cin, kh, kw):
+        v = torch.randn(cout, cin, kh, kw, device=dev, generator=g) / math.sqrt(cin * kh * kw)
+        sd[p + "weight_v"] = v
+        sd[p + "weight_g"] = v.flatten(1).norm(dim=1).view(-1, 1, 1, 1).clone()
+        sd[p + "bias"] = 0.05 * torch.randn(cout, device=dev, generator=g)
+
+    for i in range(n_scales):
+        pre = f"discriminators.discriminators.{i}."
+        conv(pre + "convs.0.conv.", filters, 2 * in_channels, 3, 9)
+        for j in range(1, 4):
+            conv(f"{pre}convs.{j}.conv.", filters, filters, 3, 9)
+        conv(pre + "convs.4.conv.", filters, filters, 3, 3)
+        conv(pre + "conv_post.conv.", 1, filters, 3, 3)
+    return sd

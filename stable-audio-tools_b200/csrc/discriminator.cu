@@ -384,6 +384,89 @@ __global__ void __launch_bounds__(256) disc_act_bwd_kernel(const __nv_bfloat16* 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Weight gradients of the two SIMT layers (the D step).  Persistent blocks keep their partial sums in registers over all their
+// positions and issue one atomic per weight at the end.
+// first conv: dW[co][ci][tap] += sum_p d_pre[p][co] * spec[p + off(tap)][ci];  thread = (co, tap group of 7), float4 over ci.
+__global__ void __launch_bounds__(256) disc_conv0_wgrad_kernel(const __nv_bfloat16* __restrict__ dpre, const float* __restrict__ spec,
+                                                               float* __restrict__ dW /*[64][4][27]*/, int B, int frames, int Fp, int F) {
+  const int co = threadIdx.x & 63, tg = threadIdx.x >> 6;
+  float4 acc[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long P = static_cast<long>(frames) * Fp;
+  const long total = static_cast<long>(B) * P;
+  // eight positions per iteration so that their loads are in flight together (one position per iteration is latency-bound)
+  for (long i0 = static_cast<long>(blockIdx.x) * 8; i0 < total; i0 += static_cast<long>(gridDim.x) * 8) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const long idx = i0 + u;
+      if (idx >= total) break;
+      const long p = idx % P;
+      if (!col_valid(static_cast<int>(p % Fp), Fp, F)) continue;
+      const float d = __bfloat162float(dpre[idx * 64 + co]);
+      const float4* sp = reinterpret_cast<const float4*>(spec) + (idx - p);
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        const int tap = tg + 4 * i;
+        if (tap < D0_TAPS) {
+          const long q = p + (tap / 9 - 1) * Fp + (tap % 9 - 4);
+          if (q >= 0 && q < P) {
+            const float4 v = __ldg(sp + q);
+            acc[i].x += d * v.x; acc[i].y += d * v.y; acc[i].z += d * v.z; acc[i].w += d * v.w;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const int tap = tg + 4 * i;
+    if (tap < D0_TAPS) {
+      atomicAdd(dW + (co * 4 + 0) * D0_TAPS + tap, acc[i].x); atomicAdd(dW + (co * 4 + 1) * D0_TAPS + tap, acc[i].y);
+      atomicAdd(dW + (co * 4 + 2) * D0_TAPS + tap, acc[i].z); atomicAdd(dW + (co * 4 + 3) * D0_TAPS + tap, acc[i].w);
+    }
+  }
+}
+
+// conv_post: dW[c][tap] += sum_p g[p] * act[p + off(tap)][c];  dbias += sum_p g[p].   thread = (c, tap group of 3)
+__global__ void __launch_bounds__(256) disc_convpost_wgrad_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ act,
+                                                                  float* __restrict__ dW /*[64][9]*/, float* __restrict__ dbias, int B, int frames,
+                                                                  int Fp, int F) {
+  const int c = threadIdx.x & 63, tg = threadIdx.x >> 6;
+  float acc[3] = {0.f, 0.f, 0.f};
+  float gsum = 0.f;
+  const long P = static_cast<long>(frames) * Fp;
+  const long total = static_cast<long>(B) * P;
+  for (long i0 = static_cast<long>(blockIdx.x) * 8; i0 < total; i0 += static_cast<long>(gridDim.x) * 8) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const long idx = i0 + u;
+      if (idx >= total) break;
+      const long p = idx % P;
+      const float gv = __ldg(g + idx);
+      if (gv == 0.f) continue;          // pad columns and inactive hinge positions
+      gsum += gv;
+      const __nv_bfloat16* base = act + (idx - p) * 64;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int tap = tg + 4 * i;
+        if (tap < 9) {
+          const long q = p + (tap / 3 - 1) * Fp + (tap % 3 - 1);
+          if (q >= 0 && q < P) acc[i] += gv * __bfloat162float(base[q * 64 + c]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int tap = tg + 4 * i;
+    if (tap < 9) atomicAdd(dW + c * 9 + tap, acc[i]);
+  }
+  if (threadIdx.x == 0 && dbias) atomicAdd(dbias, gsum);
+}
+
 static int fft_launch_cfg(int n_fft, int* log2n, int* warps, int* smem) {
   int l = 0;
   while ((1 << l) < n_fft) ++l;
@@ -487,6 +570,26 @@ extern "C" int b200sat_disc_act_bwd(const void* d_in, const float* d_logit, cons
   disc_act_bwd_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(d_in), d_logit, w_post, static_cast<const __nv_bfloat16*>(post), static_cast<const __nv_bfloat16*>(other), fm_coef,
       leaky, static_cast<__nv_bfloat16*>(d_pre), B, frames, F + 8, F);
+  B200SAT_CHECK_CUDA(cudaGetLastError());
+  return B200SAT_OK;
+}
+
+extern "C" int b200sat_disc_conv0_wgrad(const void* dpre, const float* spec, float* dW, int B, int frames, int F, void* stream) {
+  if (!dpre || !spec || !dW || B <= 0 || frames <= 0 || F <= 0) { set_last_error("disc_conv0_wgrad: bad arguments"); return B200SAT_EINVAL; }
+  const long total = static_cast<long>(B) * frames * (F + 8);
+  const long cap = static_cast<long>(num_sms()) * 8;
+  disc_conv0_wgrad_kernel<<<static_cast<int>((total + 7) / 8 < cap ? (total + 7) / 8 : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dpre), spec, dW, B, frames, F + 8, F);
+  B200SAT_CHECK_CUDA(cudaGetLastError());
+  return B200SAT_OK;
+}
+
+extern "C" int b200sat_disc_convpost_wgrad(const float* g, const void* act, float* dW, float* dbias, int B, int frames, int F, void* stream) {
+  if (!g || !act || !dW || B <= 0 || frames <= 0 || F <= 0) { set_last_error("disc_convpost_wgrad: bad arguments"); return B200SAT_EINVAL; }
+  const long total = static_cast<long>(B) * frames * (F + 8);
+  const long cap = static_cast<long>(num_sms()) * 8;
+  disc_convpost_wgrad_kernel<<<static_cast<int>((total + 7) / 8 < cap ? (total + 7) / 8 : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      g, static_cast<const __nv_bfloat16*>(act), dW, dbias, B, frames, F + 8, F);
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }

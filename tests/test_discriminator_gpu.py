@@ -85,3 +85,34 @@ def test_discriminator_losses_and_generator_gradient_match_reference_golden():
     cos = torch.nn.functional.cosine_similarity(got.flatten(), gref.flatten(), dim=0).item()
     print("generator gradient: cos", cos, "rel", _rel(got, gref))
     assert cos >= 0.98 and _rel(got, gref) <= 0.2
+
+
+def test_discriminator_step_gradients_match_oracle_autograd():
+    """The D step: hinge loss and the gradient of every weight-normed discriminator parameter vs fp32 autograd through the oracle
+    (bf16 activations / gradients with fp32 accumulation on the GPU side: cosine >= 0.99, error <= 8 % of the gradient norm, with an
+    absolute floor because the conv_post bias gradient is a cancellation: -sum[1 - lt > 0]/N + sum[1 + lf > 0]/N ~ 0)."""
+    from oracle import discriminator as od
+    from b200sat.discriminator import EncodecDiscriminatorTrain
+    sd = od.make_state_dict(seed=9)
+    g = torch.Generator().manual_seed(10)
+    reals = torch.randn(2, 2, 8192, generator=g) * 0.3
+    fakes = reals + 0.2 * torch.randn(2, 2, 8192, generator=g)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    dis_ref, _, _ = od.discriminator_loss(reals, fakes, leaves)
+    dis_ref.backward()
+    model = EncodecDiscriminatorTrain(sd)
+    dis = model.discriminator_loss(reals.cuda(), fakes.cuda())
+    dis.backward()
+    torch.cuda.synchronize()
+    assert abs(dis.item() - dis_ref.item()) <= 1e-2 * abs(dis_ref.item())
+    bad = []
+    for name in model.names:
+        got = getattr(model, name.replace(".", "__")).grad.cpu().flatten()
+        ref = leaves[name].grad.flatten()
+        err = (got - ref).norm().item()
+        if err <= 1e-6:
+            continue
+        cos = torch.nn.functional.cosine_similarity(got, ref, dim=0).item()
+        if not (cos >= 0.99 and err <= 8e-2 * ref.norm().item() + 1e-6):
+            bad.append((name, cos, err / (ref.norm().item() + 1e-30)))
+    assert not bad, bad[:8]
