@@ -198,6 +198,10 @@ int b200sat_stft_prefilter_backward(const float* dout, float* dx, const float* m
 int b200sat_conv_wgrad(const void* a_plane, int Ca, int Ta, int sA, int rA, int offA, const void* b_plane, int Cb, int Tb, int sB,
                        int rB, int offB, float* dW, int B, int T_iter, void* stream);
 
+/* All taps of a flattened 2-D conv weight gradient: dW[tap][Ca][Cb] += sum_{b,t} A[b,t,:]^T (x) B[b,t+tap_off[tap],:] (ntaps launches of the above). */
+int b200sat_conv_wgrad_taps(const void* a_plane, int Ca, const void* b_plane, int Cb, int T, const int* tap_off, int ntaps, float* dW, int B,
+                            void* stream);
+
 /* SnakeBeta backward fused with the skip-connection add and the parameter reductions (models/blocks.py:291-329 under autograd):
  * d_raw = d_skip + d_act * (1 + invb*a*sin(2 a x)); dalpha/dbeta [C] (log-scale parameters) and dbias [C] (= column sums of d_raw, the
  * bias gradient of the conv that produced x; optional) are accumulated with fp32 atomics.  Planes are bf16 [rows, C]. */

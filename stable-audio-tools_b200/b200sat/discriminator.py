@@ -255,9 +255,8 @@ def _discriminator_forward_backward(eng, reals, fakes):
             ops.LAUNCHES[0] += 3
             for l in range(4, 0, -1):
                 cv = sc.convs[l - 1]
-                for k_, off in enumerate(cv["offs_py"]):
-                    check(lib().b200sat_conv_wgrad(d_pre.data_ptr(), 64, P, 1, 0, 0, fm[l - 1].data_ptr(), 64, P, 1, 0, off, dwps[l - 1][k_].data_ptr(), B, P, st),
-                          "conv_wgrad")
+                check(lib().b200sat_conv_wgrad_taps(d_pre.data_ptr(), 64, fm[l - 1].data_ptr(), 64, P, cv["offs"], cv["K"], dwps[l - 1].data_ptr(), B, st),
+                      "conv_wgrad_taps")
                 ops.LAUNCHES[0] += cv["K"]
                 ops.colsum(d_pre.view(-1, 64), dbs[l - 1])
                 d_in = eng._flat_conv(sc, d_pre, cv, torch.empty_like(d_pre), None, cv["wd"])

@@ -46,6 +46,9 @@ struct ConvParams {
   // materialised, a 2-D tap is the row shift tap_off[tap]; rows whose (m % fp) falls outside [mask_f0, mask_f1) are stored as zeros
   int tap_off[32];
   int use_tap_table, mask_fp, mask_f0, mask_f1;
+  // window groups (2-D convs): `win_groups` windows per channel block, window g starts at row group_off[g] - pad and serves
+  // taps [g * taps_per_group, (g+1) * taps_per_group) at consecutive (dil-spaced) row shifts: the 9 frequency taps of one time offset
+  int win_groups, taps_per_group, group_off[4];
   float leaky;       // > 0: LeakyReLU slope applied to the raw output (nn.LeakyReLU(0.2), encodec.py:68)
   int window;        // 1: stride-1 conv whose taps share one (128 + (taps-1)*dil)-row A window per channel block
   int win_rows;      // rows of one A item: 128 + (taps-1)*dil in window mode, 128 otherwise
@@ -149,8 +152,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
   const int num_tiles = tiles_per_phase * p.phases;
   const int cin_blocks = p.Cin / CV_BK;
   const bool window = p.window != 0;                         // one A item per channel block, shared by all taps
-  const int taps_per_item = window ? p.taps : 1;
-  const int items_per_pass = window ? cin_blocks : p.taps * cin_blocks;
+  const int groups = (window && p.win_groups > 0) ? p.win_groups : 1;
+  const int taps_per_item = window ? (p.win_groups > 0 ? p.taps_per_group : p.taps) : 1;
+  const int items_per_pass = window ? groups * cin_blocks : p.taps * cin_blocks;
   const int num_items = p.passes * items_per_pass;
 
   if (warp == 0 && lane == 0) {
@@ -184,8 +188,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
   auto item_decode = [&](int it, int& pass, int& tap, int& cib) {
     pass = it / items_per_pass;
     const int rem = it % items_per_pass;
-    tap = window ? 0 : rem / cin_blocks;
-    cib = window ? rem : rem % cin_blocks;
+    tap = window ? (rem / cin_blocks) * taps_per_item : rem / cin_blocks;   // window: first tap of the item's group
+    cib = rem % cin_blocks;
   };
 
   if (warp == 0) {
@@ -221,7 +225,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
           item_decode(it, pass, tap, cib);
           int r = 0, row_off;
           if (p.mode == 0) {
-            row_off = window ? -p.pad : (p.use_tap_table ? p.tap_off[tap] : tap * p.dil - p.pad);  // window: tap k reads rows [k*dil, k*dil + 128)
+            // window: tap k of the group reads rows [k*dil, k*dil + 128) of the item
+            row_off = window ? (p.win_groups > 0 ? p.group_off[tap / taps_per_item] : 0) - p.pad
+                             : (p.use_tap_table ? p.tap_off[tap] : tap * p.dil - p.pad);
           } else if (p.mode == 1) {
             const int d = tap - p.pad;                      // input time = t_out*s + d
             const int j = (d >= 0) ? d / p.stride : -((-d + p.stride - 1) / p.stride);
@@ -1013,9 +1019,28 @@ extern "C" int b200sat_conv2d_flat(const void* in, const void* w, const float* b
   for (int i = 0; i < ntaps; ++i) p.tap_off[i] = tap_off[i];
   p.mask_fp = fp; p.mask_f0 = f0; p.mask_f1 = f1; p.leaky = leaky;
   p.window = 0; p.win_rows = CV_BM;
-  const int bn = (Cout >= 256) ? 256 : 128;
+  // taps that come in runs of consecutive rows (the frequency taps of one time offset) share one window per run:
+  // 3 windows of 128 + 8 rows instead of 27 per-tap tiles (B200SAT_DISC_WINDOW=0 keeps the per-tap path)
+  static const int win_env = [] { const char* e = getenv("B200SAT_DISC_WINDOW"); return e ? atoi(e) : 1; }();
+  bool tall = false;
+  if (win_env) {
+    int run = 1;
+    while (run < ntaps && tap_off[run] == tap_off[run - 1] + 1) ++run;
+    bool ok = run > 1 && ntaps % run == 0 && ntaps / run <= 4;
+    for (int g = 0; ok && g < ntaps / run; ++g)
+      for (int k = 1; k < run; ++k) ok = ok && tap_off[g * run + k] == tap_off[g * run] + k;
+    if (ok) {
+      p.window = 1; p.use_tap_table = 0;
+      p.win_groups = ntaps / run; p.taps_per_group = run;
+      for (int g = 0; g < p.win_groups; ++g) p.group_off[g] = tap_off[g * run];
+      p.dil = 1; p.pad = 0;
+      p.win_rows = CV_BM + run - 1;
+      tall = true;
+    }
+  }
+  const int bn = (Cout >= 256 && !tall) ? 256 : 128;
   int rc;
-  if ((rc = make_plane_map(&p.tmA[0], in, B, P, Cin, 1, CV_BM))) return rc;
+  if ((rc = make_plane_map(&p.tmA[0], in, B, P, Cin, 1, p.win_rows))) return rc;
   {
     uint64_t dims[2] = {static_cast<uint64_t>(ntaps) * Cin, static_cast<uint64_t>(Cout)};
     uint64_t strides[1] = {static_cast<uint64_t>(ntaps) * Cin * 2};
@@ -1032,5 +1057,6 @@ extern "C" int b200sat_conv2d_flat(const void* in, const void* w, const float* b
   p.bias = bias;
   p.out_hi = static_cast<__nv_bfloat16*>(out);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (tall) return launch_conv<128, false, 2>(p, s);
   return bn == 256 ? launch_conv<256, false, 1>(p, s) : launch_conv<128, false, 1>(p, s);
 }

@@ -668,3 +668,15 @@ extern "C" int b200sat_conv_wgrad(const void* a_plane, int Ca, int Ta, int sA, i
   if (Cb > 128) return launch_gemm<256, 1>(p, s);
   return launch_gemm<128, 1>(p, s);
 }
+
+// All taps of one conv weight gradient with a per-tap row shift table on the B operand (flattened 2-D convs): dW[tap][Ca][Cb] +=
+// sum_{b,t} A[b,t,:]^T (x) B[b,t + tap_off[tap],:].  One call = ntaps launches of the kernel above (saves the host round trips).
+extern "C" int b200sat_conv_wgrad_taps(const void* a_plane, int Ca, const void* b_plane, int Cb, int T, const int* tap_off, int ntaps, float* dW,
+                                       int B, void* stream) {
+  if (!tap_off || ntaps <= 0) { set_last_error("conv_wgrad_taps: bad arguments"); return B200SAT_EINVAL; }
+  for (int k = 0; k < ntaps; ++k) {
+    const int rc = b200sat_conv_wgrad(a_plane, Ca, T, 1, 0, 0, b_plane, Cb, T, 1, 0, tap_off[k], dW + static_cast<size_t>(k) * Ca * Cb, B, T, stream);
+    if (rc) return rc;
+  }
+  return B200SAT_OK;
+}

@@ -110,9 +110,9 @@ def test_discriminator_step_gradients_match_oracle_autograd():
         got = getattr(model, name.replace(".", "__")).grad.cpu().flatten()
         ref = leaves[name].grad.flatten()
         err = (got - ref).norm().item()
-        if err <= 1e-6:
+        if err <= 1e-5:    # e.g. conv_post.bias: exact cancellation in the reference (every hinge term active), O(1e-6) summation noise here
             continue
         cos = torch.nn.functional.cosine_similarity(got, ref, dim=0).item()
-        if not (cos >= 0.99 and err <= 8e-2 * ref.norm().item() + 1e-6):
+        if not (cos >= 0.99 and err <= 8e-2 * ref.norm().item() + 1e-5):
             bad.append((name, cos, err / (ref.norm().item() + 1e-30)))
     assert not bad, bad[:8]
