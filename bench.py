@@ -347,25 +347,31 @@ def measure_ae_adversarial(args, dev, rank, world, dist):
         opt_g.step()
         return loss
 
-    d_step(); g_step()
+    for _ in range(2):      # two warm-up rounds: the caching allocator sees both steps' buffer sizes in both orders
+        d_step(); g_step()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     ev[0].record()
     d = d_step()
     ev[1].record()
     l = g_step()
     ev[2].record()
+    d = d_step()
+    ev[3].record()
+    l = g_step()
+    ev[4].record()
     torch.cuda.synchronize()
-    t_d, t_g = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+    t_d = 0.5 * (ev[0].elapsed_time(ev[1]) + ev[2].elapsed_time(ev[3]))
+    t_g = 0.5 * (ev[1].elapsed_time(ev[2]) + ev[3].elapsed_time(ev[4]))
     ms = torch.tensor([(t_d + t_g) / 2], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = ms.item()
     flop = B * 2.86e12      # mean of the G step (2.44 TFLOP/item) and the D step (3.27 TFLOP/item), minimal graphs
     out = {"metric": "oobleck_adversarial_step_items_per_sec", "value": B * world / (ms_step * 1e-3), "unit": "clips/s", "ms_per_step": ms_step,
-           "d_step_ms": t_d, "g_step_ms": t_g, "batch_per_gpu": B, "samples_per_clip": T, "dis_loss": float(d), "gen_loss": float(l),
+           "d_step_ms": t_d, "g_step_ms": t_g, "batch_per_gpu": B, "samples_per_clip": T, "dis_loss": float(d.detach()), "gen_loss": float(l.detach()),
            "includes": "one discriminator step and one generator step (mean), AdamW(fused) on each parameter group, (all-reduce)",
            "tflops_per_gpu": flop / (ms_step * 1e-3) / 1e12, "frac_of_sustained_peak": flop / (ms_step * 1e-3) / 1e12 / peaks()["bf16_sustained"]}
     del ae, disc, opt_g, opt_d
