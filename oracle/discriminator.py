@@ -48,18 +48,18 @@ def disc_stft(x, sd, pre, n_fft, hop, win):
     return F.conv2d(z, _wn(sd, p), sd[p + "bias"], padding=(1, 1)), fmap
 
 
-def discriminator_forward(x, sd, pre="discriminators.discriminators."):
+def discriminator_forward(x, sd, pre="discriminators.discriminators.", n_ffts=N_FFTS, hops=HOPS):
     logits, fmaps = [], []
-    for i, (n, h) in enumerate(zip(N_FFTS, HOPS)):
+    for i, (n, h) in enumerate(zip(n_ffts, hops)):
         lg, fm = disc_stft(x, sd, f"{pre}{i}.", n, h, n)
         logits.append(lg); fmaps.append(fm)
     return logits, fmaps
 
 
-def discriminator_loss(reals, fakes, sd, pre="discriminators.discriminators."):
+def discriminator_loss(reals, fakes, sd, pre="discriminators.discriminators.", n_ffts=N_FFTS, hops=HOPS):
     """EncodecDiscriminator.loss (hinge, normalize_losses=False) - discriminators.py:31-58: (dis_loss, adv_loss, feature_matching)."""
-    lt, ft = discriminator_forward(reals, sd, pre)
-    lf, ff = discriminator_forward(fakes, sd, pre)
+    lt, ft = discriminator_forward(reals, sd, pre, n_ffts, hops)
+    lf, ff = discriminator_forward(fakes, sd, pre, n_ffts, hops)
     dis = adv = fm = 0.0
     for i in range(len(lt)):
         fm = fm + sum((a - b).abs().mean() for a, b in zip(ft[i], ff[i])) / len(ft[i])

@@ -129,7 +129,8 @@ class EncodecDiscriminatorEngine:
         return logits, feats
 
     # ------------------------------------------------------------------ losses
-    def _loss_forward(self, reals, fakes):
+    def _loss_forward(self, reals, fakes, keep_all=False):
+        """keep_all: also keep the real-path logits and both spectrograms (needed by the discriminator-side backward)."""
         reals = reals.to(self.dev, torch.float32).contiguous()
         fakes = fakes.to(self.dev, torch.float32).contiguous()
         B = reals.shape[0]
@@ -140,14 +141,16 @@ class EncodecDiscriminatorEngine:
         n_logit, n_feat = [], []
         for i, sc in enumerate(self.scales):
             lt, ft, fr = self._scale_forward(sc, reals)
+            spec_r = self._last_spec
             lf, ff, _ = self._scale_forward(sc, fakes)
+            spec_f = self._last_spec
             check(lib().b200sat_disc_hinge_sums(lt.data_ptr(), lf.data_ptr(), hs[i].data_ptr(), B, fr, sc.F, _s()), "disc_hinge_sums")
             for l in range(5):
                 check(lib().b200sat_disc_l1_sum(ft[l].data_ptr(), ff[l].data_ptr(), l1[i, l:].data_ptr(), ft[l].numel(), _s()), "disc_l1_sum")
             ops.LAUNCHES[0] += 6
             n_logit.append(B * fr * sc.F)
             n_feat.append(B * 64 * fr * sc.F)
-            saved.append((ft, ff, lf, fr))
+            saved.append((ft, ff, lf, fr, lt, spec_r, spec_f) if keep_all else (ft, ff, lf, fr))
         nl = torch.tensor(n_logit, device=self.dev, dtype=torch.float64)
         nf = torch.tensor(n_feat, device=self.dev, dtype=torch.float64)
         dis = ((hs[:, 0] + hs[:, 1]) / nl).sum() / ns
@@ -172,7 +175,7 @@ class EncodecDiscriminatorEngine:
         d_audio = torch.zeros(B, C, T, device=self.dev)
         st = _s()
         for i, sc in enumerate(self.scales):
-            ft, ff, lf, fr = saved[i]
+            ft, ff, lf, fr = saved[i][:4]
             P = fr * sc.Fp
             g = torch.empty(B, P, device=self.dev)
             check(lib().b200sat_disc_logit_grad(lf.data_ptr(), g.data_ptr(), B, fr, sc.F, 0, d_adv / (n_logit[i] * ns), st), "disc_logit_grad")
@@ -220,33 +223,23 @@ def _wn_small_bwd(v, g, dw):
     return g / nrm * (dw - v * dot / (nrm * nrm)), dot / nrm
 
 
-def _discriminator_forward_backward(eng, reals, fakes):
-    """Hinge discriminator loss and the gradients of every discriminator parameter: returns (dis, {reference name: grad})."""
+def _discriminator_backward(eng, saved, n_logit, B):
+    """Gradients of the hinge discriminator loss w.r.t. every discriminator parameter from the activations `_loss_forward(keep_all=True)`
+    kept: {reference name: grad}."""
     dev = eng.dev
-    reals = reals.to(dev, torch.float32).contiguous()
-    fakes = fakes.to(dev, torch.float32).contiguous()
-    B = reals.shape[0]
     ns = len(eng.scales)
     st = _s()
-    hs = torch.zeros(ns, 3, device=dev, dtype=torch.float64)
-    n_logit = []
     grads = {}
     for i, sc in enumerate(eng.scales):
-        paths = []
-        for x, mode in ((reals, 1), (fakes, 2)):
-            lg, fm, fr = eng._scale_forward(sc, x)
-            paths.append((lg, fm, eng._last_spec, mode))
-        fr = sc.frames(reals.shape[-1])
+        ft, ff, lf, fr, lt, spec_r, spec_f = saved[i]
         P = fr * sc.Fp
-        check(lib().b200sat_disc_hinge_sums(paths[0][0].data_ptr(), paths[1][0].data_ptr(), hs[i].data_ptr(), B, fr, sc.F, st), "disc_hinge_sums")
-        n_logit.append(B * fr * sc.F)
         dW0 = torch.zeros(64, 4, 27, device=dev)
         db0 = torch.zeros(64, device=dev)
         dWp = torch.zeros(64, 9, device=dev)
         dbp = torch.zeros(1, device=dev)
         dwps = [torch.zeros(cv["K"], 64, 64, device=dev) for cv in sc.convs]
         dbs = [torch.zeros(64, device=dev) for _ in sc.convs]
-        for lg, fm, spec, mode in paths:
+        for lg, fm, spec, mode in ((lt, ft, spec_r, 1), (lf, ff, spec_f, 2)):
             g = torch.empty(B, P, device=dev)
             check(lib().b200sat_disc_logit_grad(lg.data_ptr(), g.data_ptr(), B, fr, sc.F, mode, 1.0 / (n_logit[i] * ns), st), "disc_logit_grad")
             check(lib().b200sat_disc_convpost_wgrad(g.data_ptr(), fm[4].data_ptr(), dWp.data_ptr(), dbp.data_ptr(), B, fr, sc.F, st), "disc_convpost_wgrad")
@@ -283,9 +276,13 @@ def _discriminator_forward_backward(eng, reals, fakes):
         vp, gp = sc.raw["conv_post.conv.weight_v"], sc.raw["conv_post.conv.weight_g"]
         dvp, dgp = _wn_small_bwd(vp, gp, dWp.view(1, 64, 3, 3))
         grads[pre + "conv_post.conv.weight_v"], grads[pre + "conv_post.conv.weight_g"], grads[pre + "conv_post.conv.bias"] = dvp, dgp, dbp
-    nl = torch.tensor(n_logit, device=dev, dtype=torch.float64)
-    dis = (((hs[:, 0] + hs[:, 1]) / nl).sum() / ns).float()
-    return dis, grads
+    return grads
+
+
+def _discriminator_forward_backward(eng, reals, fakes):
+    """Hinge discriminator loss and the gradients of every discriminator parameter: returns (dis, {reference name: grad})."""
+    dis, _, _, saved, n_logit, _, shape = eng._loss_forward(reals, fakes, keep_all=True)
+    return dis, _discriminator_backward(eng, saved, n_logit, shape[0])
 
 
 class _DiscDFn(torch.autograd.Function):
@@ -303,6 +300,48 @@ class _DiscDFn(torch.autograd.Function):
         grads = ctx.grads
         ctx.grads = None
         return (None, None, None) + tuple(grads[n] * d_dis for n in ctx.names)
+
+
+class _DiscLossFn(torch.autograd.Function):
+    """EncodecDiscriminator.loss as ONE node: (dis, adv, fm) = f(reals, fakes, *params); dis is differentiable w.r.t. the parameters,
+    adv / fm w.r.t. `fakes` - the contract the reference training step relies on (training/autoencoders.py:436-515)."""
+
+    @staticmethod
+    def forward(ctx, reals, fakes, names, n_ffts, hops, prefix, *params):
+        sd = {n: p.detach() for n, p in zip(names, params)}
+        eng = EncodecDiscriminatorEngine(sd, n_ffts, hops, device=params[0].device, prefix=prefix)
+        with torch.no_grad():
+            dis, adv, fm, saved, n_logit, n_feat, shape = eng._loss_forward(reals.detach(), fakes.detach(), keep_all=True)
+        ctx.eng, ctx.saved, ctx.meta, ctx.names = eng, saved, (n_logit, n_feat, shape), names
+        ctx.need_fakes = fakes.requires_grad
+        ctx.need_params = any(p.requires_grad for p in params)
+        return dis, adv, fm
+
+    @staticmethod
+    def backward(ctx, d_dis, d_adv, d_fm):
+        n_logit, n_feat, shape = ctx.meta
+        g_fakes = None
+        if ctx.need_fakes:
+            g_fakes = ctx.eng._generator_backward(ctx.saved, n_logit, n_feat, shape, float(d_adv), float(d_fm))
+        g_params = (None,) * len(ctx.names)
+        if ctx.need_params:
+            grads = _discriminator_backward(ctx.eng, ctx.saved, n_logit, shape[0])
+            g_params = tuple(grads[n] * d_dis for n in ctx.names)
+        ctx.saved = None
+        return (None, g_fakes, None, None, None, None) + g_params
+
+
+def reference_discriminator_loss(module, reals, fakes):
+    """Drop-in body for `EncodecDiscriminator.loss(reals, fakes)` (models/discriminators.py:31-58) on an UNMODIFIED reference module:
+    parameters are read from `module.discriminators` (old-style weight_norm: `...conv.weight_g|weight_v|bias`)."""
+    msd = module.discriminators
+    prefix = "discriminators."
+    names, params = [], []
+    for n, p in msd.named_parameters():
+        names.append(prefix + n); params.append(p)
+    n_ffts = tuple(d.n_fft for d in msd.discriminators)
+    hops = tuple(d.hop_length for d in msd.discriminators)
+    return _DiscLossFn.apply(reals, fakes, names, n_ffts, hops, "discriminators.discriminators.", *params)
 
 
 class EncodecDiscriminatorTrain(nn.Module):

@@ -8,6 +8,8 @@ calls — takes the ORIGINAL reference code (for unsupported options on CUDA und
   stable_audio_tools.models.autoencoders.OobleckEncoder.forward          -> OobleckEngine (encoder half, returns mean|scale)
   stable_audio_tools.models.autoencoders.OobleckDecoder.forward          -> OobleckEngine.decode
   stable_audio_tools.inference.sampling.sample_k (dpmpp-3m-sde, v-ddim)  -> CUDA-graph sampler (b200sat.sampling)
+  stable_audio_tools.models.discriminators.EncodecDiscriminator.loss     -> b200sat.discriminator (WITH autograd: dis w.r.t. the
+                                                                            discriminator parameters, adv / fm w.r.t. the fakes)
 
 Engines are built lazily from `module.state_dict()` and rebuilt when any parameter's version counter changes (optimizer
 step, load_state_dict).  `train.py` / `run_gradio.py` stay byte-identical: call `install()` from a `sitecustomize` /
@@ -167,6 +169,44 @@ def install(strict=False, engine_factories=None):
     orig_gen_sample_k = getattr(gen_mod, "sample_k", None)
     if orig_gen_sample_k is not None:
         gen_mod.sample_k = sample_k          # generation.py does `from .sampling import sample_k`
+
+    # ---------------------------------------------------------------- EncodecDiscriminator.loss (discriminators.py:31-58)
+    try:
+        disc_mod = importlib.import_module("stable_audio_tools.models.discriminators")
+    except Exception:   # optional dependency chain of the reference not importable: leave the discriminator alone
+        disc_mod = None
+    if disc_mod is not None:
+        orig_disc_loss = disc_mod.EncodecDiscriminator.loss
+
+        def _disc_supported(m):
+            bad = []
+            if getattr(m, "normalize_losses", False): bad.append("normalize_losses")
+            if getattr(m, "loss_type", "hinge") != "hinge": bad.append("loss_type != hinge")
+            for d in m.discriminators.discriminators:
+                c0 = d.convs[0].conv
+                if tuple(c0.weight_v.shape[:2]) != (64, 4): bad.append("filters != 64 or non-stereo input")
+                if any(tuple(c.conv.stride) != (1, 1) for c in d.convs): bad.append("stride != (1,1)")
+                if getattr(d, "spec_scale_pow", 0.0) != 0.0: bad.append("spec_scale_pow")
+                if d.win_length != d.n_fft or not d.normalized: bad.append("win_length != n_fft / normalized=False")
+            return sorted(set(bad))
+
+        def disc_loss(self, reals, fakes):
+            fast = _on_device(reals)
+            if fast:
+                bad = _disc_supported(self)
+                if bad and strict:
+                    raise NotImplementedError("b200sat discriminator does not implement: " + ", ".join(bad))
+                fast = not bad
+            if not fast:
+                return orig_disc_loss(self, reals, fakes)
+            fn = ef.get("disc_loss")
+            if fn is None:
+                from .discriminator import reference_discriminator_loss as fn
+            dis, adv, fm = fn(self, reals, fakes)
+            return dis, adv, fm
+
+        disc_mod.EncodecDiscriminator.loss = disc_loss
+        _installed["disc_loss"] = (disc_mod.EncodecDiscriminator, "loss", orig_disc_loss)
 
     _installed.update(dit_forward=(dit_mod.DiffusionTransformer, "forward", orig_dit_forward),
                       enc_forward=(ae_mod.OobleckEncoder, "forward", orig_enc_forward),

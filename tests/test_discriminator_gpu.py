@@ -116,3 +116,61 @@ def test_discriminator_step_gradients_match_oracle_autograd():
         if not (cos >= 0.99 and err <= 8e-2 * ref.norm().item() + 1e-5):
             bad.append((name, cos, err / (ref.norm().item() + 1e-30)))
     assert not bad, bad[:8]
+
+
+def test_reference_module_drop_in_loss_is_consistent_with_the_two_step_functions():
+    """`reference_discriminator_loss` (what install() binds to EncodecDiscriminator.loss) on a stand-in module with the reference's
+    parameter tree: one autograd node gives dis / adv / fm; its parameter gradients equal the D-step function's and its gradient
+    w.r.t. the fakes equals the G-step function's."""
+    from torch import nn
+    from oracle import discriminator as od
+    from b200sat.discriminator import EncodecDiscriminatorTrain, reference_discriminator_loss
+    sd = od.make_state_dict(seed=13)
+
+    class Holder(nn.Module):
+        def __init__(self, pre):
+            super().__init__()
+            for k in ("weight_g", "weight_v", "bias"):
+                self.register_parameter(k, nn.Parameter(sd[pre + k].clone().cuda()))
+
+    class Wrap(nn.Module):
+        def __init__(self, pre):
+            super().__init__()
+            self.conv = Holder(pre + "conv.")
+
+    class Sub(nn.Module):
+        def __init__(self, i, n_fft, hop):
+            super().__init__()
+            pre = f"discriminators.discriminators.{i}."
+            self.n_fft, self.hop_length = n_fft, hop
+            self.convs = nn.ModuleList([Wrap(f"{pre}convs.{j}.") for j in range(5)])
+            self.conv_post = Wrap(pre + "conv_post.")
+
+    class MS(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.discriminators = nn.ModuleList([Sub(i, n, h) for i, (n, h) in enumerate(zip(od.N_FFTS, od.HOPS))])
+
+    class Disc(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.discriminators = MS()
+
+    m = Disc()
+    g = torch.Generator().manual_seed(14)
+    reals = (torch.randn(1, 2, 8192, generator=g) * 0.3).cuda()
+    fakes = (reals + 0.2 * torch.randn(1, 2, 8192, generator=g).cuda()).requires_grad_(True)
+    dis, adv, fm = reference_discriminator_loss(m, reals, fakes)
+    (dis + 0.1 * adv + 5.0 * fm).backward()
+    ref = EncodecDiscriminatorTrain(sd)
+    f2 = fakes.detach().clone().requires_grad_(True)
+    d2 = ref.discriminator_loss(reals, f2.detach())
+    d2.backward()
+    a2, m2 = ref.generator_terms(reals, f2)
+    (0.1 * a2 + 5.0 * m2).backward()
+    torch.cuda.synchronize()
+    assert abs(dis.item() - d2.item()) <= 1e-6 and abs(adv.item() - a2.item()) <= 1e-6 and abs(fm.item() - m2.item()) <= 1e-6
+    assert _rel(fakes.grad, f2.grad) <= 1e-3
+    for n, p in m.discriminators.named_parameters():
+        want = getattr(ref, ("discriminators." + n).replace(".", "__")).grad
+        assert (p.grad - want).norm().item() <= 2e-3 * want.norm().item() + 1e-5, n

@@ -104,3 +104,42 @@ def test_sample_k_falls_back_for_unsupported_samplers(installed):
     toy = lambda x_, t_, **kw: torch.zeros_like(x_)
     out = S.sample_k(toy, torch.randn(1, 4, 8), steps=3, sampler_type="v-ddim", sigma_max=1.0, device="cpu")   # model_fn is not a DiT wrapper
     assert out.shape == (1, 4, 8)
+
+
+def test_discriminator_loss_routing_and_fallbacks(installed):
+    """EncodecDiscriminator.loss on the unmodified reference class: routed (with the reference's parameter names) for the supported
+    option set, original code for normalize_losses / non-device tensors; the routed callable here is the oracle, fed from the module's
+    own `named_parameters`, so the name mapping `discriminators.<module path>` is checked against the reference's result."""
+    import stable_audio_tools.models.discriminators as RD
+    from oracle import discriminator as od
+    calls = []
+
+    def fake(module, reals, fakes):
+        sd = {"discriminators." + n: p for n, p in module.discriminators.named_parameters()}
+        calls.append(len(sd))
+        return od.discriminator_loss(reals, fakes, sd, n_ffts=(128, 256), hops=(32, 64))
+
+    import b200sat.install as inst
+    inst.uninstall()
+    inst._TEST_TREAT_CPU_AS_DEVICE = True
+    try:
+        inst.install(engine_factories={"dit": _FakeDiT, "oobleck": _FakeAE, "disc_loss": fake})
+        kw = dict(filters=64, in_channels=2, n_ffts=[128, 256], hop_lengths=[32, 64], win_lengths=[128, 256])
+        m = RD.EncodecDiscriminator(**kw)
+        g = torch.Generator().manual_seed(0)
+        reals = torch.randn(1, 2, 2048, generator=g) * 0.3
+        fakes = reals + 0.1 * torch.randn(1, 2, 2048, generator=g)
+        got = m.loss(reals, fakes)
+        assert calls == [36]
+        ref = inst._installed["disc_loss"][2](m, reals, fakes)
+        for a, b in zip(got, ref):
+            assert abs(float(a) - float(b)) <= 1e-5 * max(1.0, abs(float(b)))
+        m2 = RD.EncodecDiscriminator(normalize_losses=True, **kw)
+        m2.loss(reals, fakes)
+        assert calls == [36]                       # unsupported option -> original reference code
+        inst._TEST_TREAT_CPU_AS_DEVICE = False
+        m.loss(reals, fakes)
+        assert calls == [36]                       # CPU tensors -> original reference code
+    finally:
+        inst._TEST_TREAT_CPU_AS_DEVICE = False
+        inst.uninstall()
