@@ -109,12 +109,19 @@ def main():
     reals = torch.randn(1, 2, 8192, generator=g) * 0.3
     fakes = (reals + 0.1 * torch.randn(1, 2, 8192, generator=g)).requires_grad_(True)
     dis, adv, fm = disc.loss(reals, fakes)
-    (0.1 * adv + 5.0 * fm).backward()            # generator weights of stable_audio_2_0_vae.json:88-91
+    (0.1 * adv + 5.0 * fm).backward(retain_graph=True)   # generator weights of stable_audio_2_0_vae.json:88-91
+    gfakes = fakes.grad.clone()
+    disc.zero_grad()
+    dis.backward()                                        # the discriminator step's gradients (three representative parameters)
+    pd = dict(disc.discriminators.named_parameters())
+    dsel = {k: pd[k].grad.clone() for k in ("discriminators.4.convs.0.conv.weight_v", "discriminators.0.convs.2.conv.weight_g",
+                                            "discriminators.2.convs.4.conv.bias", "discriminators.1.conv_post.conv.weight_v")}
+    fakes.grad = gfakes
     with torch.no_grad():
         logits, _ = disc(reals)
     np.savez_compressed(os.path.join(OUT, "encodec_disc.npz"), meta=json.dumps({**meta, "weights_seed": 51}),
                         **_np(dict(reals=reals, fakes=fakes.detach(), dis=dis.detach(), adv=adv.detach(), fm=fm.detach(), grad_fakes=fakes.grad,
-                                   logits4=logits[4])))
+                                   logits4=logits[4], **{"dgrad." + k: v for k, v in dsel.items()})))
 
     # ---- in-repo v-DDIM sampler with a closed-form toy model (inference/sampling.py:253-307)
     toy = lambda x_, t_, **kw: torch.tanh(x_ * 0.7) * (0.3 + t_.view(-1, 1, 1)) - 0.1 * x_

@@ -97,6 +97,13 @@ def test_encodec_discriminator_oracle_matches_reference_golden():
         assert abs(float(got) - ref) <= 1e-5 * max(1.0, abs(ref)), (name, float(got), ref)
     gref = torch.from_numpy(z["grad_fakes"])
     assert ((fakes.grad - gref).norm() / gref.norm()).item() <= 1e-4
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    od.discriminator_loss(reals, fakes.detach(), leaves)[0].backward()     # the discriminator step
+    for k in z.files:
+        if k.startswith("dgrad."):
+            ref = torch.from_numpy(z[k])
+            got = leaves["discriminators." + k[6:]].grad
+            assert ((got - ref).norm() / (ref.norm() + 1e-30)).item() <= 2e-3 or (got - ref).norm().item() <= 1e-7, k   # fp32 summation order (the reference recomputes under checkpoint)
     with torch.no_grad():
         logits, fmaps = od.discriminator_forward(reals, sd)
     l4 = torch.from_numpy(z["logits4"])
