@@ -15,7 +15,7 @@ Engines are built lazily from `module.state_dict()` and rebuilt when any paramet
 step, load_state_dict).  `train.py` / `run_gradio.py` stay byte-identical: call `install()` from a `sitecustomize` /
 `.pth` hook, or set `SAT_B200=1` and import `b200sat.autoinstall`.
 
-Training through the reference wrappers is NOT rerouted by install() in round 1: the training path lives in
+Training through the reference wrappers is NOT rerouted by install() in round 1 (except the discriminator loss): the training path lives in
 `b200sat.dit_train.DiTTrainModel` (same parameter names, flat fp32 master/grad buffers); see INTEGRATION.md.
 """
 import functools
