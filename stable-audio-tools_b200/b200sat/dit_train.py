@@ -21,14 +21,28 @@ from .dit_engine import DiTConfig
 
 
 class _StackFn(torch.autograd.Function):
+    """The saved activations of the stack live in the model's shape-keyed workspace (one live forward per model), not on `ctx`:
+    every forward stamps a generation number and the backward refuses to run against a workspace that a later forward overwrote
+    (gradient accumulation over micro-batches must call backward before the next forward; anything else raises instead of
+    silently producing wrong gradients)."""
+
     @staticmethod
     def forward(ctx, h0, cemb, mod, model):
         ctx.model = model
-        return model._stack_forward(h0, cemb, mod)
+        out = model._stack_forward(h0, cemb, mod)
+        ctx.gen = model._gen
+        ctx.shape = model._shape
+        return out
 
     @staticmethod
     def backward(ctx, dout):
-        dh0, dcemb, dmod = ctx.model._stack_backward(dout.contiguous())
+        model = ctx.model
+        if ctx.gen != model._gen:
+            raise RuntimeError("b200sat DiTTrainModel: backward() of a forward pass whose saved activations were overwritten by a later "
+                               "forward of the same model (run backward before the next forward, or use torch.no_grad() for the "
+                               "intervening evaluation pass)")
+        model._shape = ctx.shape
+        dh0, dcemb, dmod = model._stack_backward(dout.contiguous())
         return dh0, dcemb, dmod, None
 
 
@@ -85,7 +99,11 @@ class DiTTrainModel(nn.Module):
         self._bf = torch.empty(self.stack_numel, device=dev, dtype=torch.bfloat16)   # bf16 working copy of the stack weights
         self._ws = {}
         self._rope = {}
+        self._gen = 0                 # forward generation (see _StackFn)
+        self._bf_fresh = False        # True only right after FusedAdamWEMA.step wrote the bf16 working copy
         self.grad_ready_hook = None   # callable(layer_index, flat_grad_slice) fired when a layer's gradients are final
+        # any write to the fp32 masters that does not go through the fused optimizer invalidates the bf16 working copy
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_working_copy())
 
     # ------------------------------------------------------------------ parameter plumbing
     def state_dict_reference(self):
@@ -95,6 +113,10 @@ class DiTTrainModel(nn.Module):
 
     def zero_grad(self, set_to_none=False):
         self.flat_grad.zero_()
+
+    def invalidate_working_copy(self):
+        """Call after writing `flat` / the parameters outside FusedAdamWEMA.step (checkpoint load, EMA swap, manual edits)."""
+        self._bf_fresh = False
 
     def layer_grad_slice(self, i):
         return self.flat_grad[i * self._layer_numel:(i + 1) * self._layer_numel]
@@ -155,9 +177,10 @@ class DiTTrainModel(nn.Module):
         B, N, Lc = self._shape
         M = B * N
         ws = self._workspace(B, N, Lc)
-        if not getattr(self, "_bf_fresh", False):           # the fused optimizer step already wrote the bf16 working copy
+        if not self._bf_fresh:                              # the fused optimizer step already wrote the bf16 working copy
             self._bf.copy_(self.flat[: self.stack_numel])   # refresh bf16 working weights from the fp32 masters
         self._bf_fresh = False
+        self._gen += 1
         self._cemb = cemb.contiguous()
         rope = (*self.rope_tables(N), N, d, 64)
         ws["h"][0].copy_(h0)
@@ -339,3 +362,67 @@ def v_objective_loss(model, x0, noise, t, cross_attn_cond, global_embed, cfg_dro
     target = noise * alpha - x0 * sigma
     out = model(noised, t, cross_attn_cond=cross_attn_cond, global_embed=global_embed, cfg_dropout_prob=cfg_dropout_prob)
     return F.mse_loss(out.float(), target)
+
+
+class _RefTrainFn(torch.autograd.Function):
+    """Outer autograd node of the drop-in training route: inputs are the activations AND the reference module's own parameters, so
+    the gradients computed into the shadow model's flat buffer are handed back to autograd as the parameters' gradients."""
+
+    @staticmethod
+    def forward(ctx, trainer, x, t, cross, glob, cfg_dropout_prob, *params):
+        shadow = trainer.shadow
+        with torch.enable_grad():
+            xi = x.detach().requires_grad_(x.requires_grad)
+            ci = cross.detach().requires_grad_(cross.requires_grad)
+            gi = None if glob is None else glob.detach().requires_grad_(glob.requires_grad)
+            out = shadow(xi, t.detach(), cross_attn_cond=ci, global_embed=gi, cfg_dropout_prob=cfg_dropout_prob)
+        ctx.trainer, ctx.inner = trainer, (out, xi, ci, gi)
+        return out.detach()
+
+    @staticmethod
+    def backward(ctx, dout):
+        trainer = ctx.trainer
+        shadow = trainer.shadow
+        out, xi, ci, gi = ctx.inner
+        shadow.flat_grad.zero_()
+        for t_ in (xi, ci, gi):
+            if t_ is not None:
+                t_.grad = None
+        torch.autograd.backward(out, dout)
+        grads = []
+        for (name, p), need in zip(trainer.pairs, ctx.needs_input_grad[6:]):
+            grads.append(shadow._p[name].grad.to(p.dtype, copy=True) if need else None)   # copies: flat_grad is reused next step
+        return (None, xi.grad, None, ci.grad, None if gi is None else gi.grad, None, *grads)
+
+
+class ReferenceDiTTrainer:
+    """Training route of `b200sat.install()`: an UNMODIFIED reference `DiffusionTransformer` (models/dit.py) keeps owning its
+    nn.Parameters (names, shapes, optimizer state, EMA copies and checkpoints unchanged); each autograd-tracked forward mirrors them
+    into a shadow `DiTTrainModel` (fp32 masters + bf16 working copy, refreshed only when a parameter version changed), runs the
+    stack forward/backward on the kernels, and returns the gradients through autograd to the module's parameters."""
+
+    def __init__(self, module):
+        sd = module.state_dict()
+        dev = next(module.parameters()).device
+        self.shadow = DiTTrainModel(sd, device=dev)
+        named = dict(module.named_parameters())
+        missing = [n for n in self.shadow._names if n not in named]
+        if missing:
+            raise KeyError(f"parameters without a counterpart in the reference module: {missing[:4]}")
+        self.pairs = [(n, named[n]) for n in self.shadow._names]
+        self._versions = None
+        self._sync()
+
+    def _sync(self):
+        ver = tuple((p._version, p.data_ptr()) for _, p in self.pairs)
+        if ver == self._versions:
+            return
+        with torch.no_grad():
+            for n, p in self.pairs:
+                self.shadow._p[n].copy_(p)
+        self.shadow.invalidate_working_copy()
+        self._versions = ver
+
+    def forward(self, x, t, cross_attn_cond=None, global_embed=None, cfg_dropout_prob=0.0):
+        self._sync()
+        return _RefTrainFn.apply(self, x, t, cross_attn_cond, global_embed, float(cfg_dropout_prob), *[p for _, p in self.pairs])

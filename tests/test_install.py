@@ -1,12 +1,12 @@
-"""CPU: `b200sat.install()` re-routes the UNMODIFIED reference modules (imported from /root/reference in the authoring
-container) and keeps their semantics.  The engines are substituted by oracle-backed fakes so the routing, the option
+"""CPU: `b200sat.install()` re-routes the UNMODIFIED reference modules (imported from baseline/_ref, the pip-installed copy of
+the reference) and keeps their semantics.  The engines are substituted by oracle-backed fakes so the routing, the option
 screening, the fallbacks and the cache invalidation are tested without a GPU.  Skipped where the reference is absent."""
 import pytest
 import torch
 
-from oracle import ref_harness
+from baseline import ref_loader as ref_harness
 
-pytestmark = pytest.mark.skipif(not ref_harness.available(), reason="reference not mounted (GPU box)")
+pytestmark = pytest.mark.skipif(not ref_harness.available(), reason="baseline/_ref not installed")
 
 
 class _FakeDiT:
@@ -23,6 +23,20 @@ class _FakeDiT:
     def forward(self, x, t, cross_attn_cond=None, global_embed=None, cfg_scale=1.0, scale_phi=0.0, negative_cross_attn_cond=None):
         return self.odit.dit_forward(x, t, self.sd, self.depth, cross_attn_cond, global_embed, cfg_scale=cfg_scale, scale_phi=scale_phi,
                                      global_cond_type=self.gct, negative_cross_attn_cond=negative_cross_attn_cond)
+
+
+class _FakeTrainer:
+    """Stands in for b200sat.dit_train.ReferenceDiTTrainer on CPU: records the call and runs the reference's own forward."""
+    calls = 0
+
+    def __init__(self, module):
+        self.module = module
+
+    def forward(self, x, t, cross_attn_cond=None, global_embed=None, cfg_dropout_prob=0.0):
+        import b200sat.install as inst
+        _FakeTrainer.calls += 1
+        return inst._installed["dit_forward"][2](self.module, x, t, cross_attn_cond=cross_attn_cond, global_embed=global_embed,
+                                                  cfg_dropout_prob=cfg_dropout_prob)
 
 
 class _FakeAE:
@@ -48,7 +62,7 @@ def installed():
     import b200sat.install as inst
     R = ref_harness.load()
     inst._TEST_TREAT_CPU_AS_DEVICE = True
-    inst.install(strict=True, engine_factories={"dit": _FakeDiT, "oobleck": _FakeAE})
+    inst.install(strict=True, engine_factories={"dit": _FakeDiT, "oobleck": _FakeAE, "dit_train": _FakeTrainer})
     yield R, inst
     inst.uninstall()
     inst._TEST_TREAT_CPU_AS_DEVICE = False
@@ -74,9 +88,16 @@ def test_dit_forward_routing_cache_and_fallbacks(installed):
         got3 = m(x, t, cross_attn_cond=c, global_embed=g, cfg_scale=5.0, scale_phi=0.5)
         ref3 = orig(m, x, t, cross_attn_cond=c, global_embed=g, cfg_scale=5.0, scale_phi=0.5)
     assert _FakeDiT.builds == 2 and torch.allclose(got3, ref3, atol=1e-5), "engine must be rebuilt after a weight update"
-    # autograd-tracked calls take the original reference code path
+    # autograd-tracked calls go to the training route (one trainer per module), never to the inference engine
+    _FakeTrainer.calls = 0
     out = m(x, t, cross_attn_cond=c, global_embed=g)
-    assert out.requires_grad and _FakeDiT.builds == 2
+    out2 = m(x, t, cross_attn_cond=c, global_embed=g, cfg_dropout_prob=0.0)
+    assert out.requires_grad and _FakeDiT.builds == 2 and _FakeTrainer.calls == 2 and torch.allclose(out, out2)
+    # a frozen model (requires_grad False everywhere) is inference even with grad mode on
+    m.requires_grad_(False)
+    out3 = m(x, t, cross_attn_cond=c, global_embed=g)
+    assert not out3.requires_grad and _FakeTrainer.calls == 2
+    m.requires_grad_(True)
     # unsupported options raise under strict=True instead of being approximated
     with torch.no_grad(), pytest.raises(NotImplementedError):
         m(x, t, cross_attn_cond=c, global_embed=g, return_info=True)
@@ -143,3 +164,127 @@ def test_discriminator_loss_routing_and_fallbacks(installed):
     finally:
         inst._TEST_TREAT_CPU_AS_DEVICE = False
         inst.uninstall()
+
+
+def _oracle_sampler(eng, noise, steps, sampler_type, sigma_min, sigma_max, rho, cross_attn_cond=None, global_embed=None, cfg_scale=1.0,
+                    scale_phi=0.0, negative_cross_attn_cond=None):
+    """engine_factories['sampler'] hook: the v-DDIM loop of b200sat.sampling's tables driven by the fake engine (CPU)."""
+    from b200sat import sampling
+    assert sampler_type == "v-ddim"
+    coef, cin, tt = sampling.v_ddim_tables(steps, min(sigma_max, 1.0))
+    x = noise.float()
+    for i in range(steps):
+        t = torch.full((x.shape[0],), float(tt[i]))
+        v = eng.forward(x * cin[i], t, cross_attn_cond=cross_attn_cond, global_embed=global_embed, cfg_scale=cfg_scale, scale_phi=scale_phi,
+                        negative_cross_attn_cond=negative_cross_attn_cond)
+        den = v * coef[i, 0] + x * coef[i, 1]
+        x = coef[i, 2] * x + coef[i, 3] * den
+    return x
+
+
+def test_generate_diffusion_cond_takes_the_fast_sampler_route():
+    """The reference's OWN generate_diffusion_cond -> get_conditioning_inputs -> sample_k call chain (inference/generation.py:91-220):
+    its kwargs always carry input_concat_cond / prepend_cond / prepend_cond_mask = None, which must not block the fast route; a
+    negative prompt is forwarded; a cfg_interval other than (0, 1) falls back."""
+    import b200sat.install as inst
+    from baseline import ref_models
+    R = ref_harness.load(force_sdpa=True)
+    inst.uninstall()
+    cfg = ref_models.sao_config(depth=2, embed_dim=128, num_heads=2, cond_token_dim=64, global_cond_dim=128)
+    model = ref_models.build_diffusion_cond(R, cfg, seed=5)
+    ct = ref_models.conditioning_tensors(model, 2, prompt_tokens=5, seed=1)
+    neg = ref_models.conditioning_tensors(model, 2, prompt_tokens=5, seed=2)
+    kw = dict(steps=5, cfg_scale=4.0, batch_size=2, sample_size=48, seed=11, device="cpu", sampler_type="v-ddim", return_latents=True)
+    ref = R.generation.generate_diffusion_cond(model, conditioning_tensors=ct, **kw)
+    ref_neg = R.generation.generate_diffusion_cond(model, conditioning_tensors=ct, negative_conditioning_tensors=neg, **kw)
+    assert not torch.allclose(ref, ref_neg, atol=1e-3)
+    inst._TEST_TREAT_CPU_AS_DEVICE = True
+    try:
+        inst.install(strict=True, engine_factories={"dit": _FakeDiT, "oobleck": _FakeAE, "dit_train": _FakeTrainer, "sampler": _oracle_sampler})
+        n0 = dict(inst.STATS)
+        got = R.generation.generate_diffusion_cond(model, conditioning_tensors=ct, **kw)
+        assert inst.STATS["sample_k_fast"] == n0["sample_k_fast"] + 1 and inst.STATS["sample_k_ref"] == n0["sample_k_ref"]
+        assert torch.allclose(got, ref, atol=2e-4), float((got - ref).abs().max())
+        got_neg = R.generation.generate_diffusion_cond(model, conditioning_tensors=ct, negative_conditioning_tensors=neg, **kw)
+        assert inst.STATS["sample_k_fast"] == n0["sample_k_fast"] + 2
+        assert torch.allclose(got_neg, ref_neg, atol=2e-4), "negative prompt must reach the engine"
+        # cfg_interval != (0, 1): strict raises; non-strict runs the reference loop and the reference model code
+        with pytest.raises(NotImplementedError):
+            R.generation.generate_diffusion_cond(model, conditioning_tensors=ct, cfg_interval=(0.2, 0.8), **kw)
+        inst.uninstall()
+        inst.install(strict=False, engine_factories={"dit": _FakeDiT, "oobleck": _FakeAE, "dit_train": _FakeTrainer, "sampler": _oracle_sampler})
+        n1 = dict(inst.STATS)
+        got_ci = R.generation.generate_diffusion_cond(model, conditioning_tensors=ct, cfg_interval=(0.2, 0.8), **kw)
+        assert inst.STATS["sample_k_ref"] == n1["sample_k_ref"] + 1 and inst.STATS["dit_fast"] == n1["dit_fast"]
+        inst.uninstall()
+        ref_ci = R.generation.generate_diffusion_cond(model, conditioning_tensors=ct, cfg_interval=(0.2, 0.8), **kw)
+        assert torch.allclose(got_ci, ref_ci, atol=2e-4)
+    finally:
+        inst._TEST_TREAT_CPU_AS_DEVICE = False
+        inst.uninstall()
+
+
+def test_unsupported_architectures_fall_back_instead_of_approximating():
+    import b200sat.install as inst
+    R = ref_harness.load(force_sdpa=True)
+    kw = dict(embed_dim=128, depth=1, num_heads=2, io_channels=64, cond_token_dim=64, global_cond_dim=128, project_cond_tokens=False,
+              transformer_type="continuous_transformer")
+    variants = {
+        "layer_scale": R.dit.DiffusionTransformer(layer_scale=True, **kw),
+        "io_channels": R.dit.DiffusionTransformer(**{**kw, "io_channels": 32}),
+        "remove_norms": R.dit.DiffusionTransformer(remove_norms=True, **kw),
+    }
+    for name, m in variants.items():
+        bad = inst._dit_supported(m, {})
+        assert bad, f"{name}: must be reported as unsupported"
+    ok = R.dit.DiffusionTransformer(**kw)
+    assert inst._dit_supported(ok, {}) == []
+    assert inst._dit_supported(ok, {"cfg_interval": (0.1, 1.0)}) == ["cfg_interval"]
+
+
+def test_engine_cache_is_weak_and_tracks_dtype_and_storage():
+    import gc
+    import b200sat.install as inst
+    built = []
+    cache = inst._EngineCache(lambda m: built.append(1) or object())
+    lin = torch.nn.Linear(4, 4)
+    e0 = cache.get(lin)
+    assert cache.get(lin) is e0 and len(built) == 1
+    lin.half()
+    assert cache.get(lin) is not e0 and len(built) == 2, "a dtype change must rebuild the engine"
+    lin.float()
+    assert len(cache.store) == 1
+    del lin
+    gc.collect()
+    assert len(cache.store) == 0, "engines of collected modules must be dropped"
+
+
+def test_fp32_model_outside_autocast_is_not_silently_run_in_bf16():
+    import b200sat.install as inst
+    m = torch.nn.Linear(4, 4)
+    assert not inst._half_compute(m, fp32_models=False)
+    assert inst._half_compute(m, fp32_models=True)
+    assert inst._half_compute(m.bfloat16(), fp32_models=False)
+
+
+def test_autoinstall_pth_hook(tmp_path):
+    """b200sat.pth + SAT_B200=1: the first create_model_from_config call installs the routing; train.py is untouched."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import site, sys\n"
+        f"site.addsitedir({os.path.join(root, 'stable-audio-tools_b200')!r})\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "assert ('b200sat.autoinstall' in sys.modules) == (__import__('os').environ.get('SAT_B200') == '1')\n"
+        "from baseline import ref_loader, ref_models\n"
+        "R = ref_loader.load(force_sdpa=True)\n"
+        "import b200sat.install as inst\n"
+        "assert not inst._installed\n"
+        "cfg = ref_models.sao_config(depth=1, embed_dim=128, num_heads=2, cond_token_dim=64, global_cond_dim=128)\n"
+        "import stable_audio_tools.models.factory as F\n"
+        "m = F.create_model_from_config(cfg)\n"
+        "print('INSTALLED' if inst._installed else 'PLAIN')\n")
+    for flag, want in (("1", "INSTALLED"), ("0", "PLAIN")):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SAT_B200=flag), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-1500:]
+        assert r.stdout.strip().splitlines()[-1] == want
