@@ -1,0 +1,203 @@
+"""GPU: the zero-edit drop-in, exercised for real.  The UNMODIFIED reference (baseline/_ref, built by its own
+`create_model_from_config`) runs on the B200 twice — as shipped (cuBLAS / SDPA-or-flash / cuDNN, bf16 or fp32) and after
+`b200sat.install(strict=True)` — on the same GPU, same weights, same seeds, same dtype.  Tolerances:
+
+  * bf16 DiT paths: both implementations are compared with the reference's fp32 CUDA result; ours must be at least as close as
+    1.5x the reference's own bf16 error plus 2e-3 (the north star's "1e-3 rel" is below what bf16 itself delivers: the
+    reference's bf16 path deviates 4e-3 .. 3e-2 from its fp32 path on these cases; both numbers are printed).
+  * Oobleck (fp32 reference, TF32 off, vs our split-bf16 "fp32x3" mode): decoded audio abs RMS <= 1e-4, latents rel <= 1e-3.
+"""
+import copy
+import functools
+import math
+
+import pytest
+import torch
+
+from baseline import ref_loader, ref_models
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_loader.available(), reason="baseline/_ref not installed")]
+
+
+def rel(a, b):
+    return float((a.float() - b.float()).norm() / b.float().norm())
+
+
+@pytest.fixture(scope="module")
+def R():
+    return ref_loader.load()
+
+
+@pytest.fixture
+def inst():
+    import b200sat.install as inst
+    inst.uninstall()
+    yield inst
+    inst.uninstall()
+
+
+def _model(R, depth, dtype, seed=0, pretransform=False, gct="prepend", **kw):
+    cfg = ref_models.sao_config(depth=depth, pretransform=pretransform, global_cond_type=gct, **kw)
+    return ref_models.build_diffusion_cond(R, cfg, seed=seed, device="cuda", dtype=dtype)
+
+
+@pytest.mark.parametrize("depth,gct", [(24, "prepend"), (4, "adaLN")])
+def test_dit_forward_dropin_same_gpu_same_dtype(R, inst, depth, gct):
+    """DiffusionTransformer.forward at the Stable-Audio-Open width and (for 'prepend') full 24-layer depth, CFG batch, N = 1024."""
+    torch.manual_seed(0)
+    m32 = _model(R, depth, torch.float32, gct=gct)
+    m16 = copy.deepcopy(m32).to(torch.bfloat16)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(1, 64, 1024, device="cuda", generator=g)
+    t = torch.tensor([0.6], device="cuda")
+    c = torch.randn(1, 130, 768, device="cuda", generator=g)
+    ge = torch.randn(1, 1536, device="cuda", generator=g)
+    kw = dict(cross_attn_cond=c, global_embed=ge, cfg_scale=7.0)
+    with torch.no_grad():
+        ref32 = m32.model.model(x, t, **kw)
+        ref16 = m16.model.model(x, t, **kw).float()
+        inst.install(strict=True)
+        n0 = inst.STATS["dit_fast"]
+        ours = m16.model.model(x, t, **kw).float()
+        assert inst.STATS["dit_fast"] == n0 + 1, "the call must have been routed through the engine"
+        # an fp32 model outside autocast must NOT be silently computed in bf16 (strict -> raises)
+        with pytest.raises(NotImplementedError):
+            m32.model.model(x, t, **kw)
+    e_ref, e_ours, d = rel(ref16, ref32), rel(ours, ref32), rel(ours, ref16)
+    print(f"\n[dropin DiT depth={depth} {gct}] reference bf16 vs fp32 {e_ref:.3e} | ours vs fp32 {e_ours:.3e} | ours vs reference bf16 {d:.3e}")
+    assert e_ours <= 1.5 * e_ref + 2e-3
+
+
+def test_generate_diffusion_cond_dropin_v_ddim(R, inst):
+    """The reference's own generate_diffusion_cond (inference/generation.py:91-220), deterministic v-DDIM sampler, 50 steps, full depth."""
+    m32 = _model(R, 24, torch.float32)
+    m16 = copy.deepcopy(m32).to(torch.bfloat16)
+    ct32 = ref_models.conditioning_tensors(m32, 1, device="cuda", seed=3)
+    ct16 = {k: (v[0].to(torch.bfloat16), v[1]) for k, v in ct32.items()}
+    kw = dict(steps=50, cfg_scale=7.0, batch_size=1, sample_size=1024, seed=5, device="cuda", sampler_type="v-ddim", return_latents=True)
+    ref32 = R.generation.generate_diffusion_cond(m32, conditioning_tensors=ct32, **kw)
+    ref16 = R.generation.generate_diffusion_cond(m16, conditioning_tensors=ct16, **kw).float()
+    inst.install(strict=True)
+    n0 = inst.STATS["sample_k_fast"]
+    ours = R.generation.generate_diffusion_cond(m16, conditioning_tensors=ct16, **kw).float()
+    assert inst.STATS["sample_k_fast"] == n0 + 1, "generate_diffusion_cond must reach the CUDA-graph sampler"
+    e_ref, e_ours = rel(ref16, ref32), rel(ours, ref32)
+    print(f"\n[dropin generate v-ddim 50 steps] reference bf16 vs fp32 {e_ref:.3e} | ours vs fp32 {e_ours:.3e} | ours vs reference bf16 {rel(ours, ref16):.3e}")
+    assert torch.isfinite(ours).all()
+    assert e_ours <= 1.5 * e_ref + 2e-3
+
+
+def test_dpmpp_3m_sde_100_steps_bench_shape_injected_noise(R, inst):
+    """The headline workload end to end: 24 layers, N = 1024 (+1), CFG 7, 100 dpmpp-3m-sde steps.  Reference side: the real
+    modules driven by the reference's own sample_k -> (restated) k-diffusion loop with a RECORDED noise sequence; our side: the
+    CUDA-graph sampler fed the same sequence.  The SDE loop amplifies rounding differences, so both are judged against the
+    reference's fp32 run."""
+    import k_diffusion as K
+    from b200sat import sampling
+    from b200sat.dit_engine import DiTEngine
+    steps = 100
+    m32 = _model(R, 24, torch.float32)
+    m16 = copy.deepcopy(m32).to(torch.bfloat16)
+    ct32 = ref_models.conditioning_tensors(m32, 1, device="cuda", seed=3)
+    ci32 = m32.get_conditioning_inputs(ct32)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    noise = torch.randn(1, 64, 1024, device="cuda", generator=g)
+    step_noise = torch.randn(steps, 1, 64, 1024, device="cuda", generator=g)
+
+    def run_reference(model, dtype):
+        it = iter(range(steps))
+        orig = K.sampling.sample_dpmpp_3m_sde
+        K.sampling.sample_dpmpp_3m_sde = functools.partial(orig, noise_sampler=lambda s, sn: step_noise[next(it)].to(dtype))
+        try:
+            ci = {k: (v.to(dtype) if v is not None and v.is_floating_point() else v) for k, v in ci32.items()}
+            return R.sampling.sample_k(model.model, noise.to(dtype), None, steps, sampler_type="dpmpp-3m-sde", sigma_min=0.03, sigma_max=1000.0,
+                                       rho=1.0, device="cuda", cfg_scale=7.0, batch_cfg=True, rescale_cfg=True, **ci).float()
+        finally:
+            K.sampling.sample_dpmpp_3m_sde = orig
+
+    ref32 = run_reference(m32, torch.float32)
+    ref16 = run_reference(m16, torch.bfloat16)
+    eng = DiTEngine(m16.model.model.state_dict(), device="cuda")
+    ours = sampling.sample_k_dpmpp_3m_sde(eng, noise, steps, 0.03, 1000.0, 1.0, ci32["cross_attn_cond"], ci32["global_cond"], 7.0, 0.0,
+                                          step_noise=step_noise)
+    e_ref, e_ours = rel(ref16, ref32), rel(ours, ref32)
+    print(f"\n[100-step dpmpp-3m-sde, bench shape] reference bf16 vs fp32 {e_ref:.3e} | ours vs fp32 {e_ours:.3e} | ours vs reference bf16 {rel(ours, ref16):.3e}")
+    assert torch.isfinite(ours).all()
+    assert e_ours <= 1.5 * e_ref + 2e-3
+
+
+def test_pretransform_encode_decode_dropin(R, inst):
+    """AutoencoderPretransform.encode / decode (models/pretransforms.py:51-74) of the Oobleck VAE, BASELINE.json configs[0] shape
+    (2 x 2 x 65536), reference = fp32 cuDNN with TF32 off."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model = _model(R, 1, torch.float32, pretransform=True, embed_dim=128, num_heads=2, cond_token_dim=64, global_cond_dim=128)
+    pt = model.pretransform
+    g = torch.Generator(device="cuda").manual_seed(2)
+    audio = torch.randn(2, 2, 65536, device="cuda", generator=g).clamp(-1, 1) * 0.5
+    with torch.no_grad():
+        torch.manual_seed(1)
+        z_ref = pt.encode(audio)
+        y_ref = pt.decode(z_ref)
+        inst.install(strict=True)
+        n0 = inst.STATS["ae_fast"]
+        torch.manual_seed(1)
+        z = pt.encode(audio)
+        y = pt.decode(z_ref)
+        assert inst.STATS["ae_fast"] == n0 + 2
+    rms = lambda a: float(a.float().pow(2).mean().sqrt())
+    print(f"\n[dropin pretransform] latents rel {rel(z, z_ref):.3e} | decoded abs RMS err {rms(y - y_ref):.3e} (signal RMS {rms(y_ref):.3f}), rel {rel(y, y_ref):.3e}")
+    assert rel(z, z_ref) <= 1e-3
+    assert rms(y - y_ref) <= 1e-4 * max(1.0, rms(y_ref) / 0.15)
+
+
+def _training_batch(B, T, device):
+    g = torch.Generator().manual_seed(4)
+    lat = torch.randn(B, 64, T, generator=g).to(device)
+    meta = [{"prompt": 0, "seconds_start": 0.0, "seconds_total": 40.0 + i, "padding_mask": torch.ones(T, dtype=torch.bool)} for i in range(B)]
+    return lat, meta
+
+
+@pytest.mark.parametrize("gct", ["prepend", "adaLN"])
+def test_reference_training_step_dropin(R, inst, gct):
+    """One `DiffusionCondTrainingWrapper.training_step` (training/diffusion.py:332-487) of the UNMODIFIED Lightning wrapper, bf16
+    autocast (Lightning `bf16-mixed`), pre-encoded latents: loss and parameter gradients with and without install()."""
+    T_ = ref_loader.load_training()
+    import types
+    cfg = ref_models.sao_config(depth=2, global_cond_type=gct)
+    base = ref_models.build_diffusion_cond(R, cfg, seed=7, device="cuda", dtype=torch.float32).train().requires_grad_(True)
+    lat, meta = _training_batch(4, 256, "cuda")
+
+    def one_step(model, p_drop):
+        torch.manual_seed(11)
+        wrap = T_.diffusion.DiffusionCondTrainingWrapper(model, lr=1e-4, use_ema=False, pre_encoded=True, cfg_dropout_prob=p_drop).cuda()
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+        wrap.trainer = types.SimpleNamespace(optimizers=[opt])
+        model.zero_grad(set_to_none=True)
+        torch.manual_seed(12)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = wrap.training_step((lat, meta), 0)
+        loss.backward()
+        return float(loss), {n: p.grad.detach().float().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    for p_drop in (0.0, 0.5):
+        m_ref, m_ours = copy.deepcopy(base), copy.deepcopy(base)
+        inst.uninstall()
+        l_ref, g_ref = one_step(m_ref, p_drop)
+        inst.install(strict=True)
+        n0 = inst.STATS["dit_train"]
+        l_ours, g_ours = one_step(m_ours, p_drop)
+        assert inst.STATS["dit_train"] == n0 + 1, "training_step must take the kernel training route"
+        inst.uninstall()
+        assert set(g_ours) == set(g_ref)
+        assert abs(l_ours - l_ref) <= 2e-2 * abs(l_ref), (l_ours, l_ref)
+        worst = 0.0
+        for n in g_ref:
+            a, b = g_ours[n].flatten(), g_ref[n].flatten()
+            if float(b.norm()) == 0.0:
+                continue
+            cos = float(torch.dot(a, b) / (a.norm() * b.norm()))
+            worst = max(worst, 1 - cos)
+            assert cos >= 0.99, (n, cos)
+            assert abs(float(a.norm()) / float(b.norm()) - 1) <= 8e-2, (n, float(a.norm()), float(b.norm()))
+        print(f"\n[dropin training_step {gct} p_drop={p_drop}] loss ref {l_ref:.5f} ours {l_ours:.5f}; worst 1-cos over {len(g_ref)} gradients {worst:.2e}")
