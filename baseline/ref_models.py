@@ -59,8 +59,9 @@ def rerandomize_zero_init(module, std=0.02, seed=1):
 
 def build_diffusion_cond(ref, config, seed=0, device="cpu", dtype=torch.float32):
     """ref = baseline.ref_loader.load().  Returns the reference's ConditionedDiffusionModelWrapper (eval mode)."""
-    torch.manual_seed(seed)
-    model = ref.factory.create_model_from_config(config)
+    with torch.device(device):          # parameters are created on the target device (a 1 B-parameter CPU init takes ~30 s)
+        torch.manual_seed(seed)
+        model = ref.factory.create_model_from_config(config)
     rerandomize_zero_init(model.model, seed=seed + 1)
     if model.pretransform is not None:
         # random-init weight-norm gains make the encoder's output grow ~2x per block: scale the gains so activations stay O(1)

@@ -1,13 +1,23 @@
 #!/usr/bin/env python
-"""bench.py — BASELINE.json metric on B200: DiT 100-step dpmpp-3m-sde sampling (configs[1]) latent-steps/sec.
+"""bench.py — BASELINE.json metric on B200.
 
   python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
-  python bench.py --impl reference ...                     (the reference's CPU path = the oracle port, on the host cores)
+  python bench.py --impl reference ...                     (the reference's own modules from baseline/_ref on the host cores)
 
-A "step" is one pass of the hot path over one batch: a full 100-step sampling run of the Stable-Audio-Open-1.0 DiT
-(d=1536, 24 layers, 24 heads, 1024 latents + 1 prepended token, cross-attention to 130x768 conditioning, CFG scale 7 =>
-effective batch 2), random-init weights, synthetic conditioning.  Multi-GPU: the sampling loop of one sample is
-sequential, so ranks are independent replicas (different seeds), no data-path collective ("replicas only", weak scaling).
+Headline (`value`, every N): the Stable-Audio-Open-1.0 latent-diffusion TRAINING STEP of BASELINE.json configs[2] —
+per GPU a batch of 8 x 47 s 44.1 kHz stereo clips (synthetic audio, 2 097 152 samples each), frozen Oobleck encoder ->
+1024 latents per clip, random T5-shaped conditioning (128 x 768 + two number tokens), v-objective, bf16 compute with fp32
+master weights, fused AdamW + EMA, and — for N > 1 — the data-parallel gradient all-reduce (NCCL over NVLink, layer-bucketed,
+overlapped with the backward).  value = latent tokens/s over all ranks (8192 per GPU per step).  `e2e` is the same step fed from
+pinned HOST buffers (audio + conditioning H2D inside the timed region, loss D2H).  This is the half of the two-part metric that
+shards with a collective, so the driver's 1 -> 8 scaling curve measures the all-reduce.
+
+Second half of the metric (`sample`, every N, compact): BASELINE.json configs[1], 100-step dpmpp-3m-sde sampling of the same DiT
+(1024 latents, CFG 7 => effective batch 2), latent-steps/s and seconds per sample; ranks are independent replicas.
+
+`gpu_reference`: the UNMODIFIED reference (baseline/_ref: its own create_model_from_config, DiffusionCondTrainingWrapper.training_step,
+generate_diffusion_cond) on the same GPU(s) in the same run — the comparator BASELINE.md section 4 names (PyTorch + SDPA/flash, cuDNN,
+torch.optim.AdamW, bf16 autocast).
 """
 import argparse
 import json
@@ -15,7 +25,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -26,10 +35,12 @@ import torch  # noqa: E402
 
 SAMPLE_STEPS = 100
 T_LAT, L_CTX, D_MODEL, DEPTH, HEADS = 1024, 130, 1536, 24, 24
+T_AUDIO = T_LAT * 2048
 CFG_SCALE, SIGMA_MIN, SIGMA_MAX, RHO = 7.0, 0.03, 1000.0, 1.0
-BATCH = 1
-# algorithmic work: 2.216 GFLOP per token forward at N=1025
-GFLOP_PER_TOKEN = 2.216
+TRAIN_BATCH = 8
+GFLOP_PER_TOKEN = 2.216          # DiT forward per token at N = 1025
+ENC_TFLOP_PER_CLIP = 5.163       # Oobleck encoder forward, 47 s stereo clip
+CPU_SAMPLE_LAT = 256             # the CPU arm's bounded sample: one clip of 256 latents (524 288 samples) per step
 
 
 def peaks():
@@ -97,23 +108,99 @@ def host_threads():
     return n
 
 
-def oracle_cfg_step_seconds(n_steps, threads):
-    """The reference's CPU path for this workload = the oracle port (torch fp32), one CFG denoising step per call."""
-    from oracle import dit as odit
+def workload_config(n):
+    return {"workload": "Stable-Audio-Open-1.0 latent-diffusion training step, v-objective (BASELINE.json configs[2])",
+            "batch_per_gpu": TRAIN_BATCH, "global_batch": TRAIN_BATCH * n, "clip": "47.55 s stereo @ 44.1 kHz (2097152 samples)",
+            "seq_len": T_LAT, "frozen_encoder_in_step": True, "conditioning": "random T5-shaped 128x768 + 2 number tokens, cfg_dropout 0.1",
+            "optimizer": "AdamW lr 5e-5 wd 1e-3 + EMA (fused, fp32 masters)", "parallelism": f"dp{n}" + (" (NCCL all-reduce, layer buckets overlapped with backward)" if n > 1 else ""),
+            "l2": "no explicit flush: every step streams > 20 GB (weights, saved activations, optimizer state) >> 126 MB L2"}
+
+
+# ================================================================================================================
+# the reference's own modules (baseline/_ref): CPU arm, cpu_baseline, GPU comparator
+# ================================================================================================================
+class _PromptOverride(torch.nn.Module):
+    """MultiConditioner whose text branch is replaced by a fixed random embedding (the text encoder is outside the path and needs
+    a checkpoint download); the number conditioners are the reference's own modules and run every step."""
+
+    def __init__(self, inner, prompt):
+        super().__init__()
+        self.inner = inner
+        self.register_buffer("prompt", prompt)
+
+    def forward(self, meta, device):
+        ct = self.inner(meta, device)
+        b = len(meta)
+        ct["prompt"] = (self.prompt[:b].to(ct["seconds_total"][0].dtype), torch.ones(b, self.prompt.shape[1], device=self.prompt.device, dtype=torch.bool))
+        return ct
+
+
+def _reference_trainer(device, batch, t_lat, with_encoder, seed=0):
+    """Returns (step_fn(audio_or_latents) -> loss tensor, wrapper).  The step is the reference's DiffusionCondTrainingWrapper.training_step
+    + backward + its configured AdamW + the EMA update, under bf16 autocast on CUDA (Lightning 'bf16-mixed'), fp32 on CPU."""
+    import types
+    from baseline import ref_loader, ref_models
+    R = ref_loader.load()
+    T_ = ref_loader.load_training()
+    cfg = ref_models.sao_config(pretransform=with_encoder)
+    with torch.device(device):
+        torch.manual_seed(seed)
+        model = R.factory.create_model_from_config(cfg)
+    ref_models.rerandomize_zero_init(model.model, seed=seed + 1)
+    model = model.to(device)
+    if model.pretransform is not None:
+        with torch.no_grad():
+            for n_, p in model.pretransform.named_parameters():
+                if n_.endswith("weight_g"):
+                    p.mul_(0.5)
+    g = torch.Generator().manual_seed(seed + 2)
+    model.conditioner = _PromptOverride(model.conditioner, torch.randn(batch, 128, 768, generator=g).to(device))
+    tc = cfg["training"]
+    wrap = T_.diffusion.DiffusionCondTrainingWrapper(model, use_ema=True, pre_encoded=not with_encoder, cfg_dropout_prob=tc["cfg_dropout_prob"],
+                                                     optimizer_configs=tc["optimizer_configs"]).to(device)
+    opt = wrap.configure_optimizers()[0]
+    wrap.trainer = types.SimpleNamespace(optimizers=[opt])
+    n_in = t_lat * 2048 if with_encoder else t_lat
+    meta = [{"prompt": 0, "seconds_start": 0.0, "seconds_total": 47.0, "padding_mask": torch.ones(n_in, dtype=torch.bool)} for _ in range(batch)]
+    is_cuda = torch.device(device).type == "cuda"
+
+    hooks = {"post_backward": None, "meta": meta}
+
+    def step(x):
+        if is_cuda:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                loss = wrap.training_step((x, hooks["meta"]), 0)
+        else:
+            loss = wrap.training_step((x, hooks["meta"]), 0)
+        loss.backward()
+        if hooks["post_backward"] is not None:
+            hooks["post_backward"]()
+        opt.step()
+        wrap.on_before_zero_grad()          # Lightning's order: EMA update before zero_grad (training/diffusion.py:489-491)
+        opt.zero_grad(set_to_none=True)
+        return loss.detach()
+
+    step.hooks = hooks
+    return step, wrap, R
+
+
+def cpu_reference_train(n_steps, threads, budget_s=150.0, warmup=1):
+    """The reference's CPU path on a bounded sample: one clip of CPU_SAMPLE_LAT latents per step (1/4 of a 47 s clip), full step
+    (frozen encoder forward, DiT forward + checkpointed backward, AdamW, EMA), torch fp32.  Stops early when `budget_s` is spent."""
     torch.set_num_threads(threads)
-    sd = odit.make_state_dict(embed_dim=D_MODEL, depth=DEPTH, num_heads=HEADS, seed=0)
-    g = torch.Generator().manual_seed(1)
-    x = torch.randn(BATCH, 64, T_LAT, generator=g)
-    c = torch.randn(BATCH, L_CTX, 768, generator=g)
-    ge = torch.randn(BATCH, D_MODEL, generator=g)
-    t = torch.full((BATCH,), 0.7)
-    times = []
-    with torch.no_grad():
-        for _ in range(n_steps):
-            t0 = time.perf_counter()
-            odit.dit_forward(x, t, sd, DEPTH, c, ge, cfg_scale=CFG_SCALE)
-            times.append(time.perf_counter() - t0)
-    return times
+    step, wrap, R = _reference_trainer("cpu", 1, CPU_SAMPLE_LAT, with_encoder=True)
+    g = torch.Generator().manual_seed(5)
+    audio = torch.randn(1, 2, CPU_SAMPLE_LAT * 2048, generator=g).clamp(-1, 1) * 0.5
+    for _ in range(warmup):
+        step(audio)
+    times, t_start = [], time.perf_counter()
+    for _ in range(n_steps):
+        t0 = time.perf_counter()
+        step(audio)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    return times, R.attention_backend
 
 
 def run_reference(args):
@@ -121,377 +208,296 @@ def run_reference(args):
     if rank != 0:
         return
     threads = host_threads()
-    oracle_cfg_step_seconds(max(1, min(args.warmup, 1)), threads)  # warm-up (bounded: one CFG step)
-    times = oracle_cfg_step_seconds(args.steps, threads)
+    times, attn = cpu_reference_train(args.steps, threads, budget_s=170.0, warmup=1)   # warm-up bounded to one step
     sec = sum(times) / len(times)
-    val = BATCH / sec
+    val = CPU_SAMPLE_LAT / sec
+    sample = (f"each step = the full training step on ONE clip of {CPU_SAMPLE_LAT} latents ({CPU_SAMPLE_LAT * 2048} samples; the workload has 8 x 1024 per GPU): "
+              f"reference DiffusionCondTrainingWrapper.training_step (frozen Oobleck encode + DiT fwd/bwd with its checkpointing) + AdamW + EMA, torch fp32, "
+              f"{attn} attention; {len(times)} of the requested {args.steps} steps fit the time budget")
     line = {
-        "impl": "reference", "metric": "dit_sampling_latent_steps_per_sec", "value": val, "unit": "latent-steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": val, "unit": "latent-steps/s", "cores": threads, "kind": "port",
-                         "sample": "each step = 1 CFG denoising step (effective batch 2, N=1025) of the 100-step workload, torch fp32 oracle port"},
-        "e2e": {"value": val, "unit": "latent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": "dit_training_latent_tokens_per_sec", "value": val, "unit": "latent-tokens/s",
+        "n_gpus": args.gpus, "steps": len(times), "steps_requested": args.steps, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": "latent-tokens/s", "cores": threads, "torch_threads": torch.get_num_threads(), "kind": "reference", "sample": sample},
+        "e2e": {"value": val, "unit": "latent-tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n):
-    return {"workload": "Stable-Audio-Open-1.0 DiT 100-step dpmpp-3m-sde sampling (BASELINE.json configs[1])",
-            "model": "DiT d=1536 L=24 H=24 ff=6144 ctx=130x768 prepend", "seq_len": T_LAT, "batch_per_gpu": BATCH,
-            "cfg_scale": CFG_SCALE, "sampler": "dpmpp-3m-sde", "sample_steps": SAMPLE_STEPS,
-            "sigma_min": SIGMA_MIN, "sigma_max": SIGMA_MAX, "parallelism": f"replicas x{n} (independent seeds, no collective)",
-            "l2": "no explicit flush: every denoising step streams 2.1 GB of bf16 weights (>> 126 MB L2)"}
-
-
-def measure_train(args, dev, rank, world, dist):
-    """BASELINE.json configs[2] (DiT part): v-objective training step, batch 8 x 1024 latents per GPU (pre-encoded latents,
-    random T5-shaped conditioning), bf16 compute / fp32 master weights, AdamW, layer-bucketed NCCL all-reduce when N > 1."""
-    from b200sat import init
-    from b200sat.dit_train import DiTTrainModel, v_objective_loss
-    from b200sat.ddp import GradAllReducer
-    B = 8
-    sd = init.dit_state_dict(embed_dim=D_MODEL, depth=DEPTH, num_heads=HEADS, seed=0, device=dev, dtype=torch.float32)
-    model = DiTTrainModel(sd, device=dev)
-    del sd
-    from b200sat.optim import FusedAdamWEMA
-    opt = FusedAdamWEMA(model, lr=5e-5, betas=(0.9, 0.999), weight_decay=1e-3, ema=True)   # stable_audio_2_0.json:95-102, EMA on
-    red = GradAllReducer(model)
-    g = torch.Generator().manual_seed(42 + rank)
-    h_lat = torch.randn(B, 64, T_LAT, generator=g).pin_memory()
-    h_cross = torch.randn(B, L_CTX, 768, generator=g).pin_memory()
-    h_glob = torch.randn(B, D_MODEL, generator=g).pin_memory()
-    h_loss = torch.zeros(1).pin_memory()
-    gd = torch.Generator(device=dev).manual_seed(7 + rank)
-
-    def step():
-        lat = h_lat.to(dev, non_blocking=True); cross = h_cross.to(dev, non_blocking=True); glob = h_glob.to(dev, non_blocking=True)
-        noise = torch.randn(lat.shape, device=dev, generator=gd)
-        t = torch.rand(B, device=dev, generator=gd)
-        model.zero_grad()
-        loss = v_objective_loss(model, lat, noise, t, cross, glob, cfg_dropout_prob=0.1)
-        (loss * red.loss_scale).backward()
-        red.finish()
-        opt.step()
-        h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
-
-    for _ in range(3):
-        step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    k = max(3, min(args.steps * 2, 10))
+# ================================================================================================================
+# our arm
+# ================================================================================================================
+def _timed(fn, k, barrier, dev, dist, world):
+    """K calls of fn bracketed by barrier + synchronize, CUDA events, max over ranks -> total ms."""
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(k):
-        step()
-    e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_step = ms.item() / k
-    tokens = B * T_LAT * world
-    flop = 3 * GFLOP_PER_TOKEN * 1e9 * B * (T_LAT + 1)
-    pk = peaks()
-    out = {"metric": "dit_training_latent_tokens_per_sec", "value": tokens / (ms_step * 1e-3), "unit": "latent-tokens/s", "ms_per_step": ms_step,
-           "steps": k, "batch_per_gpu": B, "seq_len": T_LAT, "loss": float(h_loss.item()), "optimizer": "b200sat fused AdamW + EMA + bf16 weight refresh (one pass over the fp32 masters)",
-           "pre_encoded": True, "includes": "H2D of latents+conditioning, fwd, bwd, layer-bucketed all-reduce, AdamW + EMA step, D2H loss",
-           "tflops_per_gpu": flop / (ms_step * 1e-3) / 1e12, "frac_of_sustained_peak": flop / (ms_step * 1e-3) / 1e12 / pk["bf16_sustained"]}
-    # same step with the frozen Oobleck encoder inside it (pre_encoded = False, training/diffusion.py:364-375): 8 x 47 s stereo
-    # clips encoded one at a time (iterate_batch) in bf16, then the DiT step on the fresh latents
-    try:
-        from b200sat.autoencoder import OobleckEngine
-        ae = OobleckEngine(_oobleck_state_dict(dev, torch.Generator(device=dev).manual_seed(3)), precision="bf16", device=dev)
-        audio = (torch.randn(B, 2, T_LAT * 2048, device=dev, generator=gd).clamp(-1, 1) * 0.5)
-
-        def step_enc():
-            lat = ae.encode_audio(audio, noise=None, iterate_batch=True)
-            cross = h_cross.to(dev, non_blocking=True); glob = h_glob.to(dev, non_blocking=True)
-            noise = torch.randn(lat.shape, device=dev, generator=gd)
-            t = torch.rand(B, device=dev, generator=gd)
-            model.zero_grad()
-            loss = v_objective_loss(model, lat, noise, t, cross, glob, cfg_dropout_prob=0.1)
-            (loss * red.loss_scale).backward()
-            red.finish()
-            opt.step()
-
-        step_enc(); torch.cuda.synchronize()
-        e0.record()
-        for _ in range(3):
-            step_enc()
-        e1.record(); torch.cuda.synchronize()
-        ms_enc = e0.elapsed_time(e1) / 3
-        out["with_frozen_encoder"] = {"ms_per_step": ms_enc, "value": tokens / world / (ms_enc * 1e-3) * world, "unit": "latent-tokens/s",
-                                      "note": "per-rank time (not max-reduced); encoder = 8 x 5.16 TFLOP forward, bf16 single-pass convs"}
-        del ae, audio
-    except Exception as ex:  # keep the headline numbers if the secondary measurement fails
-        out["with_frozen_encoder"] = {"error": repr(ex)[:200]}
-    del model, opt
-    torch.cuda.empty_cache()
-    return out
-
-
-def measure_ae_train(args, dev, rank, world, dist):
-    """BASELINE.json configs[3], generator step of the warm-up phase (training/autoencoders.py:436-497 with `warmed_up` False: the
-    discriminator is not evaluated): Oobleck encode -> VAE -> decode, MRSTFT sum/difference + left + right + KL, backward, AdamW.
-    16 clips x 65536 samples per GPU (the config's 32 per GPU exceeds nothing but halves the steps timed; both fit)."""
-    from b200sat.autoencoder_train import OobleckTrainModel
-    from b200sat.stft_loss import SumAndDifferenceSTFTLoss, autoencoder_mrstft_terms
-    B, T = 16, 65536
-    g = torch.Generator(device=dev).manual_seed(11)
-    model = OobleckTrainModel(_oobleck_state_dict(dev, g), device=dev)
-    opt = torch.optim.AdamW(model.parameters(), lr=1.5e-4, betas=(0.8, 0.99), fused=True)
-    fft, hop = [2048, 1024, 512, 256, 128, 64, 32], [512, 256, 128, 64, 32, 16, 8]
-    loss_sd = SumAndDifferenceSTFTLoss(fft_sizes=fft, hop_sizes=hop, win_lengths=fft, perceptual_weighting=True, sample_rate=44100)
-    gh = torch.Generator().manual_seed(42 + rank)
-    h_audio = (torch.randn(B, 2, T, generator=gh).clamp(-1, 1) * 0.5).pin_memory()
-    h_loss = torch.zeros(1).pin_memory()
-    params = list(model.parameters())
-
-    def step():
-        reals = h_audio.to(dev, non_blocking=True)
-        noise = torch.randn(B, 64, T // 2048, device=dev, generator=g)
-        decoded, kl, _ = model(reals, noise)
-        sd_, l_, r_ = autoencoder_mrstft_terms(loss_sd, decoded, reals)
-        loss = sd_ + 0.5 * l_ + 0.5 * r_ + 1e-4 * kl
-        opt.zero_grad(set_to_none=True)
-        (loss / world).backward()
-        if world > 1:   # one flat bucket: 156 M fp32 gradients
-            flat = torch.cat([p.grad.view(-1) for p in params])
-            dist.all_reduce(flat)
-            off = 0
-            for p in params:
-                p.grad.copy_(flat[off:off + p.numel()].view_as(p)); off += p.numel()
-        opt.step()
-        h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
-
-    for _ in range(3):
-        step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    k = 4
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(k):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_step = ms.item() / k
-    flop = B * 3 * 322.7e9
-    pk = peaks()
-    out = {"metric": "oobleck_generator_step_items_per_sec", "value": B * world / (ms_step * 1e-3), "unit": "clips/s", "ms_per_step": ms_step,
-           "batch_per_gpu": B, "samples_per_clip": T, "loss": float(h_loss.item()),
-           "includes": "H2D audio, encoder+VAE+decoder fwd, 4-term MRSTFT + KL, full backward, (all-reduce), AdamW(fused), D2H loss",
-           "excludes": "adversarial / feature-matching terms (warm-up phase; see ae_adversarial for the post-warm-up steps)",
-           "tflops_per_gpu": flop / (ms_step * 1e-3) / 1e12, "frac_of_sustained_peak": flop / (ms_step * 1e-3) / 1e12 / pk["bf16_sustained"]}
-    del model, opt
-    torch.cuda.empty_cache()
-    return out
-
-
-def measure_ae_adversarial(args, dev, rank, world, dist):
-    """BASELINE.json configs[3] after warm-up (training/autoencoders.py:436-515): alternating discriminator / generator steps of the Oobleck
-    autoencoder with the EncodecDiscriminator (hinge + feature matching, weights 0.1 / 5.0), MRSTFT sum/difference + L/R and KL.
-    Minimal graphs: D step = AE forward (no grad) + D forward/backward on reals and fakes; G step = AE forward/backward + D forward on
-    both + D data-gradient through the fake path.  8 clips x 65536 samples per GPU; two consecutive steps (one D, one G) are timed."""
-    from b200sat.autoencoder_train import OobleckTrainModel
-    from b200sat.discriminator import EncodecDiscriminatorTrain
-    from b200sat.init import encodec_disc_state_dict
-    from b200sat.stft_loss import SumAndDifferenceSTFTLoss, autoencoder_mrstft_terms
-    B, T = 8, 65536
-    g = torch.Generator(device=dev).manual_seed(21)
-    ae = OobleckTrainModel(_oobleck_state_dict(dev, g), device=dev)
-    disc = EncodecDiscriminatorTrain(encodec_disc_state_dict(dev, g), device=dev)
-    opt_g = torch.optim.AdamW(ae.parameters(), lr=1.5e-4, betas=(0.8, 0.99), fused=True)
-    opt_d = torch.optim.AdamW(disc.parameters(), lr=3e-4, betas=(0.8, 0.99), fused=True)
-    fft, hop = [2048, 1024, 512, 256, 128, 64, 32], [512, 256, 128, 64, 32, 16, 8]
-    loss_sd = SumAndDifferenceSTFTLoss(fft_sizes=fft, hop_sizes=hop, win_lengths=fft, perceptual_weighting=True, sample_rate=44100)
-    reals = (torch.randn(B, 2, T, device=dev, generator=g).clamp(-1, 1) * 0.5)
-
-    def allreduce(params):
-        if world > 1:
-            flat = torch.cat([p.grad.view(-1) for p in params])
-            dist.all_reduce(flat)
-            off = 0
-            for p in params:
-                p.grad.copy_(flat[off:off + p.numel()].view_as(p)); off += p.numel()
-
-    def d_step():
-        noise = torch.randn(B, 64, T // 2048, device=dev, generator=g)
-        with torch.no_grad():
-            decoded = ae(reals, noise)[0]
-        dis = disc.discriminator_loss(reals, decoded)
-        opt_d.zero_grad(set_to_none=True)
-        (dis / world).backward()
-        allreduce(list(disc.parameters()))
-        opt_d.step()
-        return dis
-
-    def g_step():
-        noise = torch.randn(B, 64, T // 2048, device=dev, generator=g)
-        decoded, kl, _ = ae(reals, noise)
-        sd_, l_, r_ = autoencoder_mrstft_terms(loss_sd, decoded, reals)
-        adv, fm = disc.generator_terms(reals, decoded)
-        loss = sd_ + 0.5 * l_ + 0.5 * r_ + 1e-4 * kl + 0.1 * adv + 5.0 * fm
-        opt_g.zero_grad(set_to_none=True)
-        (loss / world).backward()
-        allreduce(list(ae.parameters()))
-        opt_g.step()
-        return loss
-
-    for _ in range(2):      # two warm-up rounds: the caching allocator sees both steps' buffer sizes in both orders
-        d_step(); g_step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-    ev[0].record()
-    d = d_step()
-    ev[1].record()
-    l = g_step()
-    ev[2].record()
-    d = d_step()
-    ev[3].record()
-    l = g_step()
-    ev[4].record()
-    torch.cuda.synchronize()
-    t_d = 0.5 * (ev[0].elapsed_time(ev[1]) + ev[2].elapsed_time(ev[3]))
-    t_g = 0.5 * (ev[1].elapsed_time(ev[2]) + ev[3].elapsed_time(ev[4]))
-    ms = torch.tensor([(t_d + t_g) / 2], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_step = ms.item()
-    flop = B * 2.86e12      # SURVEY 8d: mean of the G step (2.44 TFLOP/item) and the D step (3.27 TFLOP/item), minimal graphs
-    out = {"metric": "oobleck_adversarial_step_items_per_sec", "value": B * world / (ms_step * 1e-3), "unit": "clips/s", "ms_per_step": ms_step,
-           "d_step_ms": t_d, "g_step_ms": t_g, "batch_per_gpu": B, "samples_per_clip": T, "dis_loss": float(d.detach()), "gen_loss": float(l.detach()),
-           "includes": "one discriminator step and one generator step (mean), AdamW(fused) on each parameter group, (all-reduce)",
-           "tflops_per_gpu": flop / (ms_step * 1e-3) / 1e12, "frac_of_sustained_peak": flop / (ms_step * 1e-3) / 1e12 / peaks()["bf16_sustained"]}
-    del ae, disc, opt_g, opt_d
-    torch.cuda.empty_cache()
-    return out
-
-
-def _graph_time_us(fn, reps=10, iters=3):
-    """Kernel time with host launch overhead removed: capture `reps` calls in a CUDA graph, replay, CUDA events."""
-    fn(); torch.cuda.synchronize()
-    side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
         fn()
-    torch.cuda.current_stream().wait_stream(side)
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        for _ in range(reps):
-            fn()
-    g.replay(); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        g.replay()
-    e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1e3 / (reps * iters)
-
-
-def other_kernels(dev, pk):
-    """Roofline rows for the other named kernels of the hot path (attention, Oobleck convs, MRSTFT, LayerNorm), timed live."""
-    from b200sat import ops
-    from b200sat.autoencoder import OobleckEngine
-    from b200sat.stft_loss import SumAndDifferenceSTFTLoss, autoencoder_mrstft_terms
-    out = []
-    B, N, H = 2, T_LAT + 1, HEADS
-    qkv = torch.randn(B, N, 3, H, 64, device=dev).bfloat16()
-    o = torch.empty(B, N, H, 64, device=dev, dtype=torch.bfloat16)
-    us = _graph_time_us(lambda: ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], out=o), reps=20)
-    fl = 4.0 * B * H * N * N * 64
-    out.append({"kernel": "attention_fwd_tcgen05 (self-attention B=2 H=24 N=1025 dh=64)", "bound": "tensor", "achieved": fl / us / 1e6,
-                "peak": pk["bf16"], "unit": "TFLOP/s", "frac": fl / us / 1e6 / pk["bf16"], "avg_launch_ms": us / 1e3})
-    x = torch.randn(2050, D_MODEL, device=dev).bfloat16(); gm = torch.ones(D_MODEL, device=dev); y = torch.empty_like(x)
-    us = _graph_time_us(lambda: ops.layernorm(x, gm, out=y), reps=20)
-    by = 2.0 * x.numel() * 2
-    out.append({"kernel": "layernorm_kernel (2050 x 1536 bf16)", "bound": "hbm", "achieved": by / us / 1e3, "peak": pk["hbm"], "unit": "GB/s",
-                "frac": by / us / 1e3 / pk["hbm"], "avg_launch_ms": us / 1e3, "note": "12.6 MB working set is L2-resident: latency-, not HBM-bound"})
-    # same kernels at shapes that leave L2 / the short-sequence regime: LayerNorm at the training batch over six rotating buffers
-    # (302 MB in + out > 126 MB L2), self-attention at N = 4097 (BASELINE.json configs[4] seq sweep end point)
-    xs = [torch.randn(8 * (T_LAT + 1), D_MODEL, device=dev).bfloat16() for _ in range(6)]
-    ys = [torch.empty_like(a) for a in xs]
-
-    def ln6():
-        for a_, b_ in zip(xs, ys):
-            ops.layernorm(a_, gm, out=b_)
-    us = _graph_time_us(ln6, reps=4) / 6
-    by = 2.0 * xs[0].numel() * 2
-    out.append({"kernel": "layernorm_kernel (8200 x 1536 bf16, training batch, rotating buffers > L2)", "bound": "hbm", "achieved": by / us / 1e3,
-                "peak": pk["hbm"], "unit": "GB/s", "frac": by / us / 1e3 / pk["hbm"], "avg_launch_ms": us / 1e3})
-    del xs, ys
-    N4 = 4097
-    qkv4 = torch.randn(B, N4, 3, H, 64, device=dev).bfloat16()
-    o4 = torch.empty(B, N4, H, 64, device=dev, dtype=torch.bfloat16)
-    us = _graph_time_us(lambda: ops.attention(qkv4[:, :, 0], qkv4[:, :, 1], qkv4[:, :, 2], out=o4), reps=5)
-    fl = 4.0 * B * H * N4 * N4 * 64
-    out.append({"kernel": "attention_fwd_tcgen05 (self-attention B=2 H=24 N=4097 dh=64)", "bound": "tensor", "achieved": fl / us / 1e6,
-                "peak": pk["bf16"], "unit": "TFLOP/s", "frac": fl / us / 1e6 / pk["bf16"], "avg_launch_ms": us / 1e3})
-    del qkv4, o4
-    # SnakeBeta backward stream (Oobleck training): 16 x 65536 x 128 elements, reads d_act / x / d_skip, writes d_raw (8 B per element)
-    from b200sat._lib import lib as _lib, check as _check
-    rows, C = 16 * 65536, 128
-    pl = [torch.randn(rows, C, device=dev).bfloat16() for _ in range(4)]
-    sa_, sb_ = torch.rand(C, device=dev) + 0.5, torch.rand(C, device=dev) + 0.5
-    acc3 = [torch.zeros(C, device=dev) for _ in range(3)]
-    st = torch.cuda.current_stream
-
-    def snk():
-        _check(_lib().b200sat_snake_bwd(pl[0].data_ptr(), pl[1].data_ptr(), pl[2].data_ptr(), sa_.data_ptr(), sb_.data_ptr(), pl[3].data_ptr(),
-                                        acc3[0].data_ptr(), acc3[1].data_ptr(), acc3[2].data_ptr(), rows, C, st().cuda_stream), "snake_bwd")
-    us = _graph_time_us(snk, reps=5)
-    by = 8.0 * rows * C
-    out.append({"kernel": "snake_bwd_kernel (16 x 65536 x 128, with skip add and alpha/beta/bias reductions)", "bound": "hbm", "achieved": by / us / 1e3,
-                "peak": pk["hbm"], "unit": "GB/s", "frac": by / us / 1e3 / pk["hbm"], "avg_launch_ms": us / 1e3})
-    del pl
-    # Oobleck: random-init weights of the stable_audio_2_0_vae architecture, 47 s stereo clip (1024 latents)
-    g = torch.Generator(device=dev).manual_seed(0)
-    sd = _oobleck_state_dict(dev, g)
-    for prec in ("bf16", "fp32x3"):
-        eng = OobleckEngine(sd, precision=prec, device=dev)
-        a = torch.randn(1, 2, T_LAT * 2048, device=dev) * 0.3
-        z = eng.encode(a); torch.cuda.synchronize()
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        e0.record(); z = eng.encode(a); e1.record(); w = eng.decode(z); e2.record(); torch.cuda.synchronize()
-        fl = 5.163e12
-        for name, ms in (("OobleckEncoder fwd", e0.elapsed_time(e1)), ("OobleckDecoder fwd", e1.elapsed_time(e2))):
-            out.append({"kernel": f"conv1d_tcgen05 stack: {name}, 47 s stereo clip, precision={prec}", "bound": "tensor", "achieved": fl / ms / 1e9,
-                        "peak": pk["bf16_sustained"], "unit": "TFLOP/s (algorithmic; fp32x3 executes 3x the MMAs)", "frac": fl / ms / 1e9 / pk["bf16_sustained"], "ms": ms})
-        del eng, a, z, w
-        torch.cuda.empty_cache()
-    FFT = [2048, 1024, 512, 256, 128, 64, 32]
-    loss = SumAndDifferenceSTFTLoss(FFT, [n // 4 for n in FFT], FFT, perceptual_weighting=True, sample_rate=44100)
-    reals = torch.randn(8, 2, 65536, device=dev) * 0.3; dec = reals + 0.05 * torch.randn_like(reals)
-    autoencoder_mrstft_terms(loss, dec, reals); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5):
-        autoencoder_mrstft_terms(loss, dec, reals)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 5
-    gf = 0.55 * 8  # BASELINE.md: ~0.55 GFLOP fp32 per item per generator step
-    out.append({"kernel": "MRSTFT (FIR + 7-resolution Stockham STFT + loss sums), 8 x 2 x 65536, all four generator-loss terms", "bound": "hbm",
-                "achieved": 8 * 2 * 2 * 65536 * 4 / ms / 1e6, "peak": pk["hbm"], "unit": "GB/s", "frac": 8 * 2 * 2 * 65536 * 4 / ms / 1e6 / pk["hbm"], "ms": ms,
-                "gflops_fp32": gf / ms, "reference_materialised_traffic_gbs": 8 * 120e6 / ms / 1e6,
-                "note": "fused: 8.4 MB of waveforms in, 84 scalars out; bound by fp32 SIMT/shared memory, not HBM (frac is vs the HBM peak only "
-                        "because the contract wants one; the reference moves ~120 MB per item through HBM for the same result, "
-                        "reference_materialised_traffic_gbs is that traffic divided by our time)"})
-    return out
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return ms.item()
 
 
 def _oobleck_state_dict(dev, g):
     from b200sat.init import oobleck_state_dict
     return oobleck_state_dict(dev, g)
+
+
+class OurTrainer:
+    """The configs[2] step on the b200sat engines (public training API: OobleckEngine.encode_audio, DiTTrainModel, v_objective_loss,
+    GradAllReducer, FusedAdamWEMA)."""
+
+    def __init__(self, dev, rank, world):
+        from b200sat import init
+        from b200sat.autoencoder import OobleckEngine
+        from b200sat.ddp import GradAllReducer
+        from b200sat.dit_train import DiTTrainModel
+        from b200sat.optim import FusedAdamWEMA
+        self.dev, self.rank, self.world = dev, rank, world
+        sd = init.dit_state_dict(embed_dim=D_MODEL, depth=DEPTH, num_heads=HEADS, seed=0, device=dev, dtype=torch.float32)
+        self.model = DiTTrainModel(sd, device=dev)
+        del sd
+        self.opt = FusedAdamWEMA(self.model, lr=5e-5, betas=(0.9, 0.999), weight_decay=1e-3, ema=True)   # stable_audio_2_0.json:95-102
+        self.red = GradAllReducer(self.model)
+        self.ae = OobleckEngine(_oobleck_state_dict(dev, torch.Generator(device=dev).manual_seed(3)), precision="bf16", device=dev)
+        B = TRAIN_BATCH
+        g = torch.Generator().manual_seed(42 + rank)                      # train.py:30-33: seed + rank
+        self.h_audio = [(torch.randn(B, 2, T_AUDIO, generator=g).clamp(-1, 1) * 0.5).pin_memory() for _ in range(2)]
+        self.h_cross = torch.randn(B, L_CTX, 768, generator=g).pin_memory()
+        self.h_glob = torch.randn(B, D_MODEL, generator=g).pin_memory()
+        self.h_loss = torch.zeros(1).pin_memory()
+        self.audio = self.h_audio[0].to(dev)
+        self.cross, self.glob = self.h_cross.to(dev), self.h_glob.to(dev)
+        self.lat = torch.randn(B, 64, T_LAT, device=dev)
+        self.gd = torch.Generator(device=dev).manual_seed(7 + rank)
+        self.sobol = torch.quasirandom.SobolEngine(1, scramble=True, seed=11 + rank)     # training/diffusion.py:256,383
+        self.copy_stream = torch.cuda.Stream()
+        self.d_audio = [torch.empty_like(self.audio) for _ in range(2)]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.flip = 0
+
+    def _dit_step(self, lat, cross, glob):
+        from b200sat.dit_train import v_objective_loss
+        B = lat.shape[0]
+        noise = torch.randn(lat.shape, device=self.dev, generator=self.gd)
+        t = self.sobol.draw(B)[:, 0].to(self.dev, non_blocking=True)
+        self.model.zero_grad()
+        loss = v_objective_loss(self.model, lat, noise, t, cross, glob, cfg_dropout_prob=0.1)
+        (loss * self.red.loss_scale).backward()
+        self.red.finish()
+        self.opt.step()
+        return loss
+
+    def step_resident(self):
+        """Inputs already in HBM: frozen encoder (one clip at a time, autoencoders.py:470-474) -> VAE sample -> DiT step."""
+        vae_noise = torch.randn(TRAIN_BATCH, 64, T_LAT, device=self.dev, generator=self.gd)
+        lat = self.ae.encode_audio(self.audio, noise=vae_noise, iterate_batch=True)
+        return self._dit_step(lat, self.cross, self.glob)
+
+    def step_pre_encoded(self):
+        return self._dit_step(self.lat, self.cross, self.glob)
+
+    def prefetch(self):
+        """H2D of the NEXT batch on the copy stream (what a pinned-memory DataLoader does), double-buffered."""
+        i = self.flip
+        with torch.cuda.stream(self.copy_stream):
+            self.d_audio[i].copy_(self.h_audio[i], non_blocking=True)
+            self.ready[i].record(self.copy_stream)
+
+    def step_e2e(self):
+        i = self.flip
+        torch.cuda.current_stream().wait_event(self.ready[i])
+        audio = self.d_audio[i]
+        self.flip ^= 1
+        self.prefetch()                                   # next batch's copy overlaps this step's compute
+        cross = self.h_cross.to(self.dev, non_blocking=True); glob = self.h_glob.to(self.dev, non_blocking=True)
+        vae_noise = torch.randn(TRAIN_BATCH, 64, T_LAT, device=self.dev, generator=self.gd)
+        lat = self.ae.encode_audio(audio, noise=vae_noise, iterate_batch=True)
+        loss = self._dit_step(lat, cross, glob)
+        self.h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+
+    def free(self):
+        self.red._limit(False)
+        del self.model, self.opt, self.ae, self.audio, self.d_audio
+        torch.cuda.empty_cache()
+
+
+def measure_sampling(args, dev, rank, world, dist, barrier):
+    from b200sat import init, sampling
+    from b200sat.generation import DiffusionCondModel, generate_diffusion_cond
+    sd = init.dit_state_dict(embed_dim=D_MODEL, depth=DEPTH, num_heads=HEADS, seed=0, device=dev)
+    model = DiffusionCondModel.from_state_dict(sd, device=dev)
+    eng = model.engine
+    del sd
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    noise = torch.randn(1, 64, T_LAT, device=dev, generator=g)
+    cross = torch.randn(1, L_CTX, 768, device=dev, generator=g)
+    glob = torch.randn(1, D_MODEL, device=dev, generator=g)
+    smp = model.sampler(1, T_LAT, L_CTX, True, CFG_SCALE, 0.0)
+    one = lambda: sampling.sample_k_dpmpp_3m_sde(eng, noise, SAMPLE_STEPS, SIGMA_MIN, SIGMA_MAX, RHO, cross, glob, CFG_SCALE, 0.0, sampler=smp)
+    for _ in range(3):
+        out = one()
+    assert torch.isfinite(out).all(), "non-finite latents"
+    k = max(3, min(args.steps, 8))
+    ms = _timed(one, k, barrier, dev, dist, world)
+    h_noise = noise.cpu().pin_memory(); h_cross = cross.cpu().pin_memory(); h_glob = glob.cpu().pin_memory()
+    h_out = torch.empty(1, 64, T_LAT).pin_memory()
+
+    def e2e():
+        lat = generate_diffusion_cond(model, steps=SAMPLE_STEPS, cfg_scale=CFG_SCALE, batch_size=1,
+                                      conditioning_tensors={"cross_attn_cond": h_cross, "global_cond": h_glob}, sample_size=T_AUDIO,
+                                      sampler_type="dpmpp-3m-sde", sigma_min=SIGMA_MIN, sigma_max=SIGMA_MAX, rho=RHO, noise=h_noise,
+                                      return_latents=True, device=dev)
+        h_out.copy_(lat, non_blocking=True)
+
+    e2e()
+    ms2 = _timed(e2e, k, barrier, dev, dist, world)
+    tflop = SAMPLE_STEPS * 2 * (T_LAT + 1) * GFLOP_PER_TOKEN / 1e3
+    res = {"workload": "configs[1]: 100-step dpmpp-3m-sde, 1024 latents, CFG 7 (batch 2), bf16; replicas x%d" % world,
+           "latent_steps_per_s": SAMPLE_STEPS * world * k / (ms * 1e-3), "seconds_per_sample": ms / k / 1e3,
+           "e2e_latent_steps_per_s": SAMPLE_STEPS * world * k / (ms2 * 1e-3), "samples_timed": k,
+           "frac_of_sustained_peak": tflop / (ms / k * 1e-3) / peaks()["bf16_sustained"]}
+    del smp
+    model._samplers.clear()
+    return res, eng
+
+
+def gpu_reference(args, dev, rank, world, dist, barrier, do_train=True, do_sample=True):
+    """The unmodified reference on the same GPU(s), same run: bf16, its own attention dispatch, cuDNN convs, torch AdamW."""
+    out = {"impl": "stable-audio-tools 0.0.19 (baseline/_ref, unmodified), torch %s" % torch.__version__, "compile": os.environ.get("ENABLE_TORCH_COMPILE", "0")}
+    if do_train:
+        try:
+            step, wrap, R = _reference_trainer(dev, TRAIN_BATCH, T_LAT, with_encoder=True)
+            out["attention"] = R.attention_backend
+            g = torch.Generator().manual_seed(42 + rank)
+            audio = (torch.randn(TRAIN_BATCH, 2, T_AUDIO, generator=g).clamp(-1, 1) * 0.5).to(dev)
+            ddp = "none"
+            if world > 1:
+                from torch.nn.parallel import DistributedDataParallel as DDP
+                plain = wrap.diffusion.model
+                try:
+                    wrap.diffusion.model = DDP(plain, device_ids=[dev.index], find_unused_parameters=True)   # train.py:147 default strategy
+                    step(audio)
+                    ddp = "torch DDP (ddp_find_unused_parameters_true, train.py's default multi-GPU strategy)"
+                except Exception as ex:
+                    # DDP's reducer and the reference's re-entrant per-layer checkpoint can disagree; fall back to one flat all-reduce
+                    wrap.diffusion.model = plain
+                    wrap.trainer.optimizers[0].zero_grad(set_to_none=True)
+                    params = [p for p in plain.parameters() if p.requires_grad]
+
+                    def allreduce():
+                        gs = [p.grad for p in params if p.grad is not None]
+                        flat = torch.cat([g_.reshape(-1) for g_ in gs])
+                        dist.all_reduce(flat)
+                        flat.div_(world)
+                        off = 0
+                        for g_ in gs:
+                            g_.copy_(flat[off:off + g_.numel()].view_as(g_)); off += g_.numel()
+                    step.hooks["post_backward"] = allreduce
+                    ddp = "flat all-reduce after backward (torch DDP failed: %s)" % repr(ex)[:100]
+            for _ in range(2):
+                step(audio)
+            k = 3
+            ms = _timed(lambda: step(audio), k, barrier, dev, dist, world) / k
+            out["train"] = {"tokens_per_s": TRAIN_BATCH * T_LAT * world / (ms * 1e-3), "ms_per_step": ms, "steps": k, "ddp": ddp,
+                            "what": "DiffusionCondTrainingWrapper.training_step (pretransform.encode iterate_batch + DiT with its checkpointing) "
+                                    "+ backward + torch AdamW + EMA, bf16 autocast, same batch/shape"}
+            lat = torch.randn(TRAIN_BATCH, 64, T_LAT, device=dev)
+            wrap.pre_encoded = True
+            step.hooks["meta"] = [{"prompt": 0, "seconds_start": 0.0, "seconds_total": 47.0, "padding_mask": torch.ones(T_LAT, dtype=torch.bool)}
+                                  for _ in range(TRAIN_BATCH)]
+            step(lat)
+            ms = _timed(lambda: step(lat), k, barrier, dev, dist, world) / k
+            out["train_pre_encoded"] = {"tokens_per_s": TRAIN_BATCH * T_LAT * world / (ms * 1e-3), "ms_per_step": ms}
+            del step, wrap, audio, lat
+        except Exception as ex:
+            out["train"] = {"error": repr(ex)[:300]}
+        torch.cuda.empty_cache()
+    if do_sample:
+        try:
+            from baseline import ref_loader, ref_models
+            R = ref_loader.load()
+            out["attention"] = R.attention_backend
+            with torch.device(dev):
+                torch.manual_seed(0)
+                model = R.factory.create_model_from_config(ref_models.sao_config(pretransform=False))
+            ref_models.rerandomize_zero_init(model.model, seed=1)
+            model = model.to(device=dev, dtype=torch.bfloat16).eval().requires_grad_(False)
+            ct = ref_models.conditioning_tensors(model, 1, device=dev, seed=3)
+            ct = {k_: (v[0].to(torch.bfloat16), v[1]) for k_, v in ct.items()}
+
+            def one():
+                return R.generation.generate_diffusion_cond(model, steps=SAMPLE_STEPS, cfg_scale=CFG_SCALE, conditioning_tensors=ct, batch_size=1,
+                                                            sample_size=T_LAT, seed=1 + rank, device=dev, sampler_type="dpmpp-3m-sde",
+                                                            sigma_min=SIGMA_MIN, sigma_max=SIGMA_MAX, rho=RHO, return_latents=True)
+            devnull = open(os.devnull, "w")
+            saved = sys.stderr
+            sys.stderr = devnull                      # tqdm bars of the reference loop
+            try:
+                one()
+                k = 2
+                ms = _timed(one, k, barrier, dev, dist, world) / k
+            finally:
+                sys.stderr = saved
+            out["sample"] = {"latent_steps_per_s": SAMPLE_STEPS * world / (ms * 1e-3), "seconds_per_sample": ms / 1e3, "samples_timed": k,
+                             "what": "reference generate_diffusion_cond -> sample_k(dpmpp-3m-sde) with the restated k-diffusion loop (k-diffusion is not "
+                                     "installable here; i.i.d. noise instead of the Brownian tree), eager, bf16 weights"}
+            del model
+        except Exception as ex:
+            out["sample"] = {"error": repr(ex)[:300]}
+        torch.cuda.empty_cache()
+    return out
+
+
+def roofline_rows(dev, eng_w, pk):
+    """Live microbenchmarks (CUDA events, inputs > L2) of the two kernels that dominate the headline step."""
+    from b200sat import ops
+    from b200sat.autoencoder import OobleckEngine, _Planes
+    rows = []
+    # (1) conv1d_tcgen05<128,0,2>, the k7 dilated conv of a ResidualUnit at C = 128, T = 2 097 152: the largest launch class of the encoder
+    ae = OobleckEngine(_oobleck_state_dict(dev, torch.Generator(device=dev).manual_seed(3)), precision="bf16", device=dev)
+    ru = ae.enc["blocks"][0]["rus"][0]
+    x = _Planes(1, T_AUDIO, 128, dev, False); x.hi.normal_()
+    h = _Planes(1, T_AUDIO, 128, dev, False)
+    fn = lambda: ae._conv(x, ru["c7"], act=h, snake=ru["s1"], dil=1, pad=3)
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    fl = 2.0 * T_AUDIO * 128 * 128 * 7
+    rows.append({"kernel": "conv1d_tcgen05<128,0,2> (ResidualUnit k7 conv + SnakeBeta epilogue, C=128, T=2097152, bf16)", "bound": "tensor", "achieved": fl / ms / 1e9,
+                 "peak": pk["bf16"], "unit": "TFLOP/s", "frac": fl / ms / 1e9 / pk["bf16"], "avg_launch_ms": ms, "traffic": None,
+                 "peak_source": pk["src"] + " burst", "share_of_step": "conv1d_tcgen05 = the frozen-encoder part of the step (see profiles/r2_*)",
+                 "hbm_GBps_algorithmic": 2.0 * T_AUDIO * 128 * 2 / ms / 1e6})
+    del ae, x, h
+    torch.cuda.empty_cache()
+    # (2) gemm_bf16_tcgen05<256,2>: FF1 + SwiGLU at the training batch (M = 8200, N = 12288, K = 1536), 24 distinct weight matrices
+    M = TRAIN_BATCH * (T_LAT + 1)
+    xin = torch.randn(M, D_MODEL, device=dev).bfloat16()
+    outb = torch.empty(M, 4 * D_MODEL, device=dev, dtype=torch.bfloat16)
+    ws = eng_w
+    for w_, b_ in ws[:3]:
+        ops.linear(xin, w_, bias=b_, swiglu=True, out=outb)
+    torch.cuda.synchronize()
+    e0.record()
+    for w_, b_ in ws:
+        ops.linear(xin, w_, bias=b_, swiglu=True, out=outb)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / len(ws)
+    fl = 2.0 * M * (8 * D_MODEL) * D_MODEL
+    rows.append({"kernel": "gemm_bf16_tcgen05<256,2> (FF1 + SwiGLU epilogue, M=8200 N=12288 K=1536)", "bound": "tensor", "achieved": fl / ms / 1e9,
+                 "peak": pk["bf16"], "unit": "TFLOP/s", "frac": fl / ms / 1e9 / pk["bf16"], "avg_launch_ms": ms, "traffic": None, "peak_source": pk["src"] + " burst"})
+    return rows
 
 
 def run_ours(args):
@@ -507,162 +513,136 @@ def run_ours(args):
     sys.stdout.flush()
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from b200sat import init, ops, sampling
-    from b200sat.generation import DiffusionCondModel, generate_diffusion_cond
     dev = torch.device("cuda", local)
-    sd = init.dit_state_dict(embed_dim=D_MODEL, depth=DEPTH, num_heads=HEADS, seed=0, device=dev)
-    model = DiffusionCondModel.from_state_dict(sd, device=dev)
-    eng = model.engine
-    del sd
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    noise = torch.randn(BATCH, 64, T_LAT, device=dev, generator=g)
-    cross = torch.randn(BATCH, L_CTX, 768, device=dev, generator=g)
-    glob = torch.randn(BATCH, D_MODEL, device=dev, generator=g)
-    smp = model.sampler(BATCH, T_LAT, L_CTX, True, CFG_SCALE, 0.0)
-
-    def one_sample():
-        return sampling.sample_k_dpmpp_3m_sde(eng, noise, SAMPLE_STEPS, SIGMA_MIN, SIGMA_MAX, RHO, cross, glob, CFG_SCALE, 0.0, sampler=smp)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from b200sat import ops
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        out = one_sample()
-    assert torch.isfinite(out).all(), "non-finite latents"
-    # ---------------- device-resident timing (`value`)
+    W = max(args.warmup, 3)
+    tr = OurTrainer(dev, rank, world)
+    for _ in range(W):
+        loss = tr.step_resident()
+    assert torch.isfinite(loss).all(), "non-finite training loss"
+    # ---------------- headline: device-resident inputs (`value`)
     clocks = ClockSampler(local)
     barrier()
     if rank == 0:
         clocks.start()
     n0 = ops.LAUNCHES[0]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        one_sample()
-    e1.record()
-    barrier()
+    ms_total = _timed(tr.step_resident, args.steps, barrier, dev, dist, world)
     launches = ops.LAUNCHES[0] - n0
     clk = clocks.stop() if rank == 0 else None
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = ms.item()
-    value = SAMPLE_STEPS * BATCH * world * args.steps / (ms_total * 1e-3)
+    ms_step = ms_total / args.steps
+    tokens = TRAIN_BATCH * T_LAT * world
+    value = tokens / (ms_step * 1e-3)
+    # ---------------- end to end: host buffers in, loss out (`e2e`)
+    tr.prefetch()
+    tr.step_e2e()
+    ms_e2e = _timed(tr.step_e2e, args.steps, barrier, dev, dist, world) / args.steps
+    torch.cuda.current_stream().wait_event(tr.ready[tr.flip])
+    h2d = tr.h_audio[0].numel() * 4 + tr.h_cross.numel() * 4 + tr.h_glob.numel() * 4 + TRAIN_BATCH * 4
+    loss_val = float(tr.h_loss.item())
+    # ---------------- the same step on pre-encoded latents (pre_encoded: true, training/diffusion.py:344)
+    for _ in range(2):
+        tr.step_pre_encoded()
+    kpe = max(5, min(args.steps, 20))
+    ms_pre = _timed(tr.step_pre_encoded, kpe, barrier, dev, dist, world) / kpe
+    pk = peaks()
+    flop_dit = 3 * GFLOP_PER_TOKEN * 1e9 * TRAIN_BATCH * (T_LAT + 1)
+    flop_step = flop_dit + TRAIN_BATCH * ENC_TFLOP_PER_CLIP * 1e12
+    nccl_cfg = {"nccl_ctas": tr.red.nccl_ctas, "sm_reserve": tr.red.sm_reserve} if world > 1 else None
+    ff1 = [(tr.model._w(i, "ff.ff.0.proj.weight").clone(), tr.model._f32(i, "ff.ff.0.proj.bias").clone()) for i in range(DEPTH)] if rank == 0 and not args.quick else None
+    tr.free()
+    del tr
+    torch.cuda.empty_cache()
 
-    # ---------------- end-to-end through the public API with HOST buffers (`e2e`)
-    h_noise = noise.cpu().pin_memory(); h_cross = cross.cpu().pin_memory(); h_glob = glob.cpu().pin_memory()
-    h_out = torch.empty(BATCH, 64, T_LAT).pin_memory()
-
-    def one_e2e():
-        lat = generate_diffusion_cond(model, steps=SAMPLE_STEPS, cfg_scale=CFG_SCALE, batch_size=BATCH,
-                                      conditioning_tensors={"cross_attn_cond": h_cross, "global_cond": h_glob},
-                                      sample_size=T_LAT * 2048, sampler_type="dpmpp-3m-sde", sigma_min=SIGMA_MIN,
-                                      sigma_max=SIGMA_MAX, rho=RHO, noise=h_noise, return_latents=True, device=dev)
-        h_out.copy_(lat, non_blocking=True)
-
-    one_e2e()
-    barrier()
-    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(args.steps):
-        one_e2e()
-    t1.record()
-    barrier()
-    ms2 = torch.tensor([t0.elapsed_time(t1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_val = SAMPLE_STEPS * BATCH * world * args.steps / (ms2.item() * 1e-3)
-    h2d = h_noise.numel() * 4 + h_cross.numel() * 4 + h_glob.numel() * 4
-    d2h = h_out.numel() * 4
-
-    train = None
-    ae_train = None
-    ae_adv = None
-    if not args.no_train:
-        del smp
-        model._samplers.clear()
+    sample, eng = (None, None)
+    if not args.no_sample:
+        sample, eng = measure_sampling(args, dev, rank, world, dist, barrier)
+        del eng
         torch.cuda.empty_cache()
-        train = measure_train(args, dev, rank, world, dist)
+    ref = None
+    if not args.no_gpu_reference:
+        ref = gpu_reference(args, dev, rank, world, dist, barrier, do_sample=not args.no_sample)
+        if ref.get("train", {}).get("tokens_per_s"):
+            ref["ours_over_reference_train"] = value / ref["train"]["tokens_per_s"]
+        if ref.get("train_pre_encoded", {}).get("tokens_per_s"):
+            ref["ours_over_reference_train_pre_encoded"] = tokens / (ms_pre * 1e-3) / ref["train_pre_encoded"]["tokens_per_s"]
+        if sample and ref.get("sample", {}).get("latent_steps_per_s"):
+            ref["ours_over_reference_sample"] = sample["latent_steps_per_s"] / ref["sample"]["latent_steps_per_s"]
+
+    extras = {}
+    if rank == 0 and world == 1 and not args.quick:
+        from tools import bench_extras as bx
+        for name, fn in (("ae_train", bx.measure_ae_train), ("ae_adversarial", bx.measure_ae_adversarial)):
+            try:
+                extras[name] = fn(args, dev, rank, world, dist)
+            except Exception as ex:   # secondary measurement: never lose the headline line
+                extras[name] = {"error": repr(ex)[:300]}
+                torch.cuda.empty_cache()
         try:
-            ae_train = measure_ae_train(args, dev, rank, world, dist)
-        except Exception as ex:   # secondary measurement: never lose the headline line
-            ae_train = {"error": repr(ex)[:300]}
-            torch.cuda.empty_cache()
-        try:
-            ae_adv = measure_ae_adversarial(args, dev, rank, world, dist)
+            extras["other_kernels"] = bx.other_kernels(dev, pk)
         except Exception as ex:
-            ae_adv = {"error": repr(ex)[:300]}
-            torch.cuda.empty_cache()
+            extras["other_kernels"] = {"error": repr(ex)[:300]}
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
-    # ---------------- roofline of the dominant kernel: the FF1 SwiGLU GEMM (M=2050, N=2x6144, K=1536), timed live
-    pk = peaks()
-    M = 2 * BATCH * (T_LAT + 1)
-    xin = torch.randn(M, D_MODEL, device=dev).bfloat16()
-    outb = torch.empty(M, 4 * D_MODEL, device=dev, dtype=torch.bfloat16)
-    ws = [(eng.w[f"transformer.layers.{i}.ff.ff.0.proj.weight"], eng.w[f"transformer.layers.{i}.ff.ff.0.proj.bias"]) for i in range(DEPTH)]
-    for w_, b_ in ws[:3]:
-        ops.linear(xin, w_, bias=b_, swiglu=True, out=outb)
-    torch.cuda.synchronize()
-    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 4
-    r0.record()
-    for _ in range(reps):
-        for w_, b_ in ws:  # 24 different 37.7 MB weight matrices: inputs larger than L2
-            ops.linear(xin, w_, bias=b_, swiglu=True, out=outb)
-    r1.record()
-    torch.cuda.synchronize()
-    k_ms = r0.elapsed_time(r1) / (reps * DEPTH)
-    k_flop = 2.0 * M * (8 * D_MODEL) * D_MODEL
-    achieved = k_flop / (k_ms * 1e-3) / 1e12
-    roof = {"kernel": "gemm_bf16_tcgen05<256> (FF1 + SwiGLU epilogue, M=2050 N=12288 K=1536)", "bound": "tensor",
-            "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"], "peak_source": pk["src"] + " burst (kernel timed alone)",
-            "avg_launch_ms": k_ms, "traffic": 47.5e6,
-            "traffic_source": "profiles/r1_ncu_full_summary.txt: dram read 44.2 MB + write 3.3 MB per launch (ncu --set full); algorithmic 69 MB"}
-    other = other_kernels(dev, pk) if not args.no_train else None
-    step_tflop = SAMPLE_STEPS * 2 * BATCH * (T_LAT + 1) * GFLOP_PER_TOKEN / 1e3
-    whole = {"tflop_per_sample": step_tflop, "achieved_tflops": step_tflop * args.steps * world / (ms_total * 1e-3) / world,
-             "frac_of_sustained_peak": step_tflop * args.steps / (ms_total * 1e-3) / pk["bf16_sustained"]}
-
-    # ---------------- CPU baseline (oracle port) on a bounded sample
-    threads = host_threads()
+    roof_rows = []
+    if ff1 is not None:
+        try:
+            roof_rows = roofline_rows(dev, ff1, pk)
+        except Exception as ex:
+            roof_rows = [{"error": repr(ex)[:300]}]
+    roof = roof_rows[0] if roof_rows and "kernel" in roof_rows[0] else {"bound": "tensor", "achieved": None, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": None, "traffic": None}
     cpu = None
-    if not args.no_cpu_baseline:
-        ts = oracle_cfg_step_seconds(2, threads)
-        cpu_sec = min(ts)
-        cpu = {"value": BATCH / cpu_sec, "unit": "latent-steps/s", "cores": threads, "kind": "port",
-               "sample": "2 CFG denoising steps (of the 100-step workload; effective batch 2, N=1025), torch fp32 oracle port; best of 2"}
-
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            threads = host_threads()
+            ts, attn = cpu_reference_train(2, threads, budget_s=60.0, warmup=1)
+            cpu = {"value": CPU_SAMPLE_LAT / min(ts), "unit": "latent-tokens/s", "cores": threads, "kind": "reference",
+                   "sample": f"{len(ts)} full training steps on one clip of {CPU_SAMPLE_LAT} latents (best), reference modules from baseline/_ref, torch fp32, {attn}"}
+        except Exception as ex:
+            cpu = {"error": repr(ex)[:200]}
     line = {
-        "metric": "dit_sampling_latent_steps_per_sec", "value": value, "unit": "latent-steps/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic (random-init weights, random conditioning)",
-        "config": workload_config(world), "sample_seconds_100_steps": ms_total / args.steps / 1e3,
-        "e2e": {"value": e2e_val, "unit": "latent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "b200sat.generation.generate_diffusion_cond(host pinned noise/conditioning -> host latents)"},
-        "gpu_launches": launches, "clocks": clk, "roofline": roof, "whole_step": whole, "cpu_baseline": cpu, "train": train, "ae_train": ae_train, "ae_adversarial": ae_adv, "other_kernels": other,
+        "metric": "dit_training_latent_tokens_per_sec", "value": value, "unit": "latent-tokens/s", "n_gpus": world,
+        "steps": args.steps, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic (random-init weights, random audio and conditioning)", "config": workload_config(world),
+        "e2e": {"value": tokens / (ms_e2e * 1e-3), "unit": "latent-tokens/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "api": "b200sat OobleckEngine.encode_audio + DiTTrainModel/v_objective_loss + GradAllReducer + FusedAdamWEMA; pinned host audio/conditioning in (double-buffered), loss out"},
+        "gpu_launches": launches, "clocks": clk, "loss": loss_val,
+        "sample": sample,
+        "gpu_reference": ref,
+        "train_pre_encoded": {"tokens_per_s": tokens / (ms_pre * 1e-3), "ms_per_step": ms_pre, "frac_of_sustained_peak": flop_dit / (ms_pre * 1e-3) / 1e12 / pk["bf16_sustained"]},
+        "whole_step": {"tflop_per_gpu": flop_step / 1e12, "achieved_tflops_per_gpu": flop_step / (ms_step * 1e-3) / 1e12,
+                       "frac_of_sustained_peak": flop_step / (ms_step * 1e-3) / 1e12 / pk["bf16_sustained"], "ddp": nccl_cfg},
+        "roofline": roof, "roofline_more": roof_rows[1:], "cpu_baseline": cpu,
     }
+    line.update(extras)
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
+    ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--no-sample", action="store_true", help="skip the sampling half of the metric")
+    ap.add_argument("--quick", action="store_true", help="skip the secondary measurements (AE training steps, kernel rows)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -21,6 +21,10 @@ extern "C" {
 const char* b200sat_last_error(void);
 int b200sat_version(void);
 int b200sat_num_sms(void);
+/* Grid budget of the persistent kernels while a collective shares the GPU (the reference's DDP all-reduce overlaps its backward,
+ * train.py:124-164): limit > 0 caps the SM count the persistent GEMM / conv kernels size their grids from (rounded down to an even
+ * number), limit <= 0 restores the whole device.  Returns the previous limit. */
+int b200sat_set_sm_limit(int limit);
 unsigned long long b200sat_launch_count(void);
 
 /* GEMM flags (bitmask) */

@@ -19,6 +19,7 @@ SIGNATURES = {
     "b200sat_last_error": (c_char_p, []),
     "b200sat_version": (c_int, []),
     "b200sat_num_sms": (c_int, []),
+    "b200sat_set_sm_limit": (c_int, [c_int]),
     "b200sat_launch_count": (c_ull, []),
     "b200sat_gemm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_fp, c_void_p, c_int, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

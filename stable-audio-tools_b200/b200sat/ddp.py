@@ -6,24 +6,68 @@ backward finishes layers 23 -> 0, and each finished layer is a contiguous ~176 M
 asynchronous all-reduce per finished layer on a side stream, so the exchange of layer i overlaps the backward kernels of
 layers i-1 ... 0; buckets are layer-sized (>= 64 MB: NVSwitch cost is launch-latency, not link-count, bound).  The mean is
 obtained by scaling the loss by 1/world_size before backward (no extra pass over 4.2 GB of gradients).
+
+SM sharing (round-2 finding): the persistent GEMM kernels launch one CTA per SM.  An NCCL kernel that occupies 16-32 SMs while a
+GEMM launches forces the GEMM's last CTAs into a second wave behind the collective (the +7 ms / step measured at N = 2 in round 1).
+So (a) the gradient all-reduce runs on its own communicator limited to `nccl_ctas` CTAs (NVSwitch needs few CTAs for the
+bandwidth this exchange requires: 4.2 GB per ~50 ms of backward), and (b) while reductions are in flight the library sizes its
+persistent grids for `num_sms - sm_reserve` SMs (`b200sat_set_sm_limit`), restored in `finish()`.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
 
+def _grad_group(nccl_ctas):
+    """A dedicated NCCL communicator for the gradient exchange with a bounded CTA count; None = default group."""
+    if not (dist.is_initialized() and dist.get_backend() == "nccl") or nccl_ctas <= 0:
+        return None
+    try:
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.config.max_ctas = int(nccl_ctas)
+        opts.config.min_ctas = min(int(nccl_ctas), 4)
+        return dist.new_group(ranks=list(range(dist.get_world_size())), backend="nccl", pg_options=opts)
+    except Exception:   # older torch / NCCL without per-communicator config: fall back to the default communicator
+        return None
+
+
 class GradAllReducer:
-    def __init__(self, model, group=None):
+    def __init__(self, model, group=None, nccl_ctas=None, sm_reserve=None):
         self.model = model
-        self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.works = []
         self.cuda = model.flat_grad.is_cuda
         self.stream = torch.cuda.Stream() if self.cuda else None
+        if nccl_ctas is None:
+            nccl_ctas = int(os.environ.get("B200SAT_DDP_NCCL_CTAS", "8"))
+        if sm_reserve is None:
+            sm_reserve = int(os.environ.get("B200SAT_DDP_SM_RESERVE", "16"))
+        self.sm_reserve = sm_reserve if (self.cuda and self.world > 1) else 0
+        self.group = group
+        self.nccl_ctas = 0
+        if group is None and self.cuda and self.world > 1:
+            g = _grad_group(nccl_ctas)
+            if g is not None:
+                self.group, self.nccl_ctas = g, nccl_ctas
+        self._limited = False
         model.grad_ready_hook = self._on_layer if self.world > 1 else None
 
     @property
     def loss_scale(self):
         return 1.0 / self.world
+
+    def _limit(self, on):
+        if not self.sm_reserve or on == self._limited:
+            return
+        from ._lib import lib
+        L = lib()
+        if on:
+            L.b200sat_set_sm_limit(0)
+            L.b200sat_set_sm_limit(max(2, L.b200sat_num_sms() - self.sm_reserve))
+        else:
+            L.b200sat_set_sm_limit(0)
+        self._limited = on
 
     def _launch(self, t):
         if self.cuda:
@@ -35,6 +79,7 @@ class GradAllReducer:
 
     def _on_layer(self, layer_index, grad_slice):
         self._launch(grad_slice)
+        self._limit(True)      # every persistent kernel launched from here on leaves room for the collective
 
     def finish(self):
         """Call after loss.backward(): reduces the non-stack parameters and joins the side stream."""
@@ -46,3 +91,4 @@ class GradAllReducer:
         self.works.clear()
         if self.cuda:
             torch.cuda.current_stream().wait_stream(self.stream)
+        self._limit(False)

@@ -19,6 +19,7 @@ int pdl_enabled() {
   return v;
 }
 
+static int g_sm_limit = 0;   // 0 = all SMs; set while a collective kernel needs SMs of its own (b200sat_set_sm_limit)
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -26,7 +27,7 @@ int num_sms() {
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   }
-  return n;
+  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -77,6 +78,14 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 extern "C" const char* b200sat_last_error() { return b200sat::g_err; }
 extern "C" int b200sat_version() { return 100; }
 extern "C" int b200sat_num_sms() { return b200sat::num_sms(); }
+// Persistent kernels size their grids from num_sms(): while NCCL's all-reduce kernel shares the GPU with the backward pass
+// (b200sat/ddp.py), leaving it `reserve` SMs keeps every persistent CTA resident in ONE wave instead of queueing a second wave behind
+// the collective.  limit <= 0 restores the full device; the value is rounded down to an even count (CTA pairs).  Returns the old limit.
+extern "C" int b200sat_set_sm_limit(int limit) {
+  const int old = b200sat::g_sm_limit;
+  b200sat::g_sm_limit = limit > 0 ? (limit & ~1) : 0;
+  return old;
+}
 // Number of kernel launches issued by this library since load (claimed in bench.py's gpu_launches).
 namespace b200sat { unsigned long long g_launches = 0; }
 extern "C" unsigned long long b200sat_launch_count() { return b200sat::g_launches; }

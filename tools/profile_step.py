@@ -1,12 +1,51 @@
-"""Small driver for ncu: a few eager (non-graph) denoising steps of the bench workload (configs[1])."""
-import os, sys, torch
+"""One step of a workload between cudaProfilerStart/Stop, after untimed warm-up, for
+    ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/x.csv python tools/profile_step.py train
+Workloads: train (configs[2] step, frozen encoder + DiT fwd/bwd + optimizer), train_pre (pre-encoded), sample (3 denoising steps, eager),
+ae (one 47 s encode + decode, bf16)."""
+import os
+import sys
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "stable-audio-tools_b200"))
-from b200sat import init, sampling as bs
-from b200sat.dit_engine import DiTEngine
-steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-eng = DiTEngine(init.dit_state_dict())
-noise = torch.randn(1, 64, 1024, device="cuda"); c = torch.randn(1, 130, 768, device="cuda"); g = torch.randn(1, 1536, device="cuda")
-out = bs.sample_k_dpmpp_3m_sde(eng, noise, steps=steps, cross_attn_cond=c, global_embed=g, cfg_scale=7.0, use_graph=False)
-torch.cuda.synchronize()
-print("ok", torch.isfinite(out).all().item())
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+
+
+def main():
+    what = sys.argv[1] if len(sys.argv) > 1 else "train"
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    if what in ("train", "train_pre"):
+        tr = bench.OurTrainer(dev, 0, 1)
+        fn = tr.step_resident if what == "train" else tr.step_pre_encoded
+        warm = 2
+    elif what == "sample":
+        from b200sat import init, sampling
+        from b200sat.dit_engine import DiTEngine
+        eng = DiTEngine(init.dit_state_dict(seed=0, device=dev), device=dev)
+        g = torch.Generator(device=dev).manual_seed(1)
+        noise = torch.randn(1, 64, 1024, device=dev, generator=g); cross = torch.randn(1, 130, 768, device=dev, generator=g)
+        glob = torch.randn(1, 1536, device=dev, generator=g)
+        fn = lambda: sampling.sample_k_dpmpp_3m_sde(eng, noise, 3, 0.03, 1000.0, 1.0, cross, glob, 7.0, 0.0, use_graph=False)
+        warm = 1
+    elif what == "ae":
+        from b200sat.autoencoder import OobleckEngine
+        ae = OobleckEngine(bench._oobleck_state_dict(dev, torch.Generator(device=dev).manual_seed(3)), precision="bf16", device=dev)
+        a = torch.randn(1, 2, bench.T_AUDIO, device=dev) * 0.3
+        fn = lambda: ae.decode(ae.encode(a))
+        warm = 1
+    else:
+        raise SystemExit("unknown workload " + what)
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    fn()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+
+
+if __name__ == "__main__":
+    main()
