@@ -167,6 +167,21 @@ def install_stubs():
             def all_gather(self, t):
                 return t.unsqueeze(0)
 
+            # manual-optimisation surface used by AutoencoderTrainingWrapper.training_step (training/autoencoders.py:449-515)
+            def optimizers(self):
+                opts = getattr(self, "_b200sat_optimizers", None)
+                if opts is None:
+                    cfg = self.configure_optimizers()
+                    opts = cfg[0] if isinstance(cfg, tuple) else cfg
+                    self._b200sat_optimizers = opts
+                return opts[0] if len(opts) == 1 else opts
+
+            def lr_schedulers(self):
+                return None
+
+            def manual_backward(self, loss):
+                loss.backward()
+
         class Callback:
             pass
 
@@ -179,14 +194,14 @@ def install_stubs():
         class EMA(torch.nn.Module):
             """Stand-in with ema_pytorch's constructor signature; update() follows its published decay schedule
             (1 - (1 + step/inv_gamma)^-power clipped to [min_value, beta]) — unpinned, not on the measured path."""
-            def __init__(self, model, beta=0.9999, power=2 / 3, update_every=10, update_after_step=100, inv_gamma=1.0, min_value=0.0,
-                         include_online_model=True, **kw):
+            def __init__(self, model, ema_model=None, beta=0.9999, power=2 / 3, update_every=10, update_after_step=100, inv_gamma=1.0,
+                         min_value=0.0, include_online_model=True, **kw):
                 super().__init__()
                 import copy
                 self.beta, self.power, self.inv_gamma, self.min_value = beta, power, inv_gamma, min_value
                 self.update_every, self.update_after_step = update_every, update_after_step
                 self.online = [model]
-                self.ema_model = copy.deepcopy(model).requires_grad_(False)
+                self.ema_model = (copy.deepcopy(model) if ema_model is None else ema_model).requires_grad_(False)
                 self.step = 0
 
             @torch.no_grad()
@@ -219,7 +234,10 @@ def load(force_sdpa=None):
         sys.path.insert(0, REF_DIR)
     import torch
     import stable_audio_tools.models.transformer as transformer
-    attn = "flash_attn_func" if getattr(transformer, "flash_attn_func", None) is not None else "sdpa"
+    if not hasattr(transformer, "_b200sat_flash_attn_func"):
+        transformer._b200sat_flash_attn_func = getattr(transformer, "flash_attn_func", None)   # what the reference imported itself
+    transformer.flash_attn_func = transformer._b200sat_flash_attn_func                         # every load() decides afresh
+    attn = "flash_attn_func" if transformer.flash_attn_func is not None else "sdpa"
     if attn == "flash_attn_func":
         disable = force_sdpa
         if disable is None:

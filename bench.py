@@ -140,7 +140,7 @@ def _reference_trainer(device, batch, t_lat, with_encoder, seed=0):
     + backward + its configured AdamW + the EMA update, under bf16 autocast on CUDA (Lightning 'bf16-mixed'), fp32 on CPU."""
     import types
     from baseline import ref_loader, ref_models
-    R = ref_loader.load()
+    R = ref_loader.load(force_sdpa=True if torch.device(device).type == "cpu" else None)   # flash_attn has no CPU kernels
     T_ = ref_loader.load_training()
     cfg = ref_models.sao_config(pretransform=with_encoder)
     with torch.device(device):

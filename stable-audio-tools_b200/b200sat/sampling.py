@@ -185,7 +185,7 @@ class GraphSampler:
 
 def sample_k_dpmpp_3m_sde(engine, noise, steps=100, sigma_min=0.03, sigma_max=1000.0, rho=1.0, cross_attn_cond=None,
                           global_embed=None, cfg_scale=1.0, scale_phi=0.0, eta=1.0, s_noise=1.0, step_noise=None,
-                          sampler=None, use_graph=True):
+                          sampler=None, use_graph=True, negative_cross_attn_cond=None):
     """`sample_k(model_fn, noise, steps=..., sampler_type='dpmpp-3m-sde', ...)` for a DiTEngine (inference/sampling.py:331-387)."""
     B, C, T = noise.shape
     L = 0 if cross_attn_cond is None else cross_attn_cond.shape[1]
@@ -193,15 +193,16 @@ def sample_k_dpmpp_3m_sde(engine, noise, steps=100, sigma_min=0.03, sigma_max=10
     coef, cin, tt = dpmpp_3m_sde_tables(sig, eta, s_noise)
     if sampler is None:
         sampler = GraphSampler(engine, B, C, T, L, global_embed is not None, cfg_scale, scale_phi, use_graph)
-    return sampler.run(noise, coef, cin, tt, cross_attn_cond, global_embed, step_noise, init_scale=float(sig[0])).clone()
+    return sampler.run(noise, coef, cin, tt, cross_attn_cond, global_embed, step_noise, init_scale=float(sig[0]),
+                       negative_cross_attn_cond=negative_cross_attn_cond).clone()
 
 
 def sample_v_ddim(engine, noise, steps=100, sigma_max=1.0, cross_attn_cond=None, global_embed=None, cfg_scale=1.0,
-                  scale_phi=0.0, sampler=None, use_graph=True):
+                  scale_phi=0.0, sampler=None, use_graph=True, negative_cross_attn_cond=None):
     """`sample_k(..., sampler_type='v-ddim')` -> in-repo `sample(model, x, steps, eta=0)` (inference/sampling.py:253-307,:405-407)."""
     B, C, T = noise.shape
     L = 0 if cross_attn_cond is None else cross_attn_cond.shape[1]
     coef, cin, tt = v_ddim_tables(steps, min(sigma_max, 1.0))
     if sampler is None:
         sampler = GraphSampler(engine, B, C, T, L, global_embed is not None, cfg_scale, scale_phi, use_graph)
-    return sampler.run(noise, coef, cin, tt, cross_attn_cond, global_embed, None).clone()
+    return sampler.run(noise, coef, cin, tt, cross_attn_cond, global_embed, None, negative_cross_attn_cond=negative_cross_attn_cond).clone()

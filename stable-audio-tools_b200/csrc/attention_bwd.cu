@@ -17,6 +17,7 @@
 //   attention_bwd_dq  : CTA = (128 queries, head, batch); loops over key tiles; dQ accumulates in TMEM.
 #include "common.cuh"
 #include <cstring>
+#include <cstdlib>
 
 namespace b200sat {
 
@@ -27,6 +28,13 @@ __device__ __forceinline__ float bw_exp2(float x) {
 }
 
 constexpr int BW_T = 128 * 64 * 2;  // one 128 x 64 bf16 tile = 16 KB
+
+template <int CW>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[CW]);
+template <>
+__device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld_32x32(taddr, v); }
+template <>
+__device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld_32x16(taddr, v); }
 
 struct AttnBwdParams {
   CUtensorMap tmQ, tmK, tmV, tmdO;
@@ -143,7 +151,13 @@ constexpr int BW_STAGES = 4;    // inner-tile ring: the scores of tile j+3 are i
 constexpr int BW_NB = 3;       // score-tile buffers in TMEM and operand-tile buffers in shared memory (MMA thread runs BW_NB tiles ahead)
 constexpr int DKV_SMEM = 2 * BW_T /*K,V*/ + BW_STAGES * 2 * BW_HT /*(Q,dO) ring*/ + BW_NB * BW_T /*P^T*/ + BW_NB * BW_T /*dS^T*/ + 2 * BW_NB * 64 * 4 + 256;
 
-__global__ void __launch_bounds__(320, 1) attention_bwd_dkv_tcgen05(const __grid_constant__ AttnBwdParams p) {
+// SW = number of softmax warps: 8 (two threads per score row, 32 columns each) or 16 (four threads per row, 16 columns each).
+// Round 2: the kernels hold ONE CTA per SM (192 KB of tiles, all 512 TMEM columns), so 8 warps = 2 per scheduler could not hide the
+// tcgen05.ld / MUFU / shared-memory latencies of their own tile (measured ~1500 clk per 128x64 tile against a 512-clk MUFU bound).
+template <int SW>
+__global__ void __launch_bounds__(64 + SW * 32, 1) attention_bwd_dkv_tcgen05(const __grid_constant__ AttnBwdParams p) {
+  constexpr int CW = 256 / SW;   // score columns per thread
+  constexpr int NT = SW * 32;    // softmax threads
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sK = smem;
   uint8_t* sV = smem + BW_T;
@@ -173,7 +187,7 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dkv_tcgen05(const __grid
     if (smem_u32(smem) & 1023u) __trap();
     mbar_init(kv_full, 1);
     for (int i = 0; i < BW_STAGES; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
-    for (int i = 0; i < BW_NB; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 256); mbar_init(&acc_free[i], 1); }
+    for (int i = 0; i < BW_NB; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], NT); mbar_init(&acc_free[i], 1); }
     fence_barrier_init();
   }
   griddep_launch();
@@ -239,11 +253,11 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dkv_tcgen05(const __grid
       }
     }
   } else {
-    // 8 warps: two threads per key row, each owning 32 of the 64 query columns of a tile
+    // SW warps: SW/4 threads per key row, each owning CW of the 64 query columns of a tile
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int sub = (warp - 2) >> 2;            // which CW-column slice
     const int r = quarter * 32 + lane;          // key row of this thread
-    const int tid = (warp - 2) * 32 + lane;     // 0..255 among the softmax threads
+    const int tid = (warp - 2) * 32 + lane;     // 0..NT-1 among the softmax threads
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const bool key_ok = (k0 + r) < p.Nk;
     const int sw = r & 7;
@@ -262,29 +276,29 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dkv_tcgen05(const __grid
       if (tid < 64) s_lse[buf * 64 + tid] = stat_next;
       else if (tid < 128) s_delta[buf * 64 + (tid & 63)] = stat_next;
       stat_next = fetch_stat(it + 1);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
       mbar_wait(&s_full[buf], (it / BW_NB) & 1);
       tc_fence_after();
-      uint32_t rs[32], rp[32];
-      tmem_ld_32x32(tmem_base + lane_off + buf * 64 + half * 32, rs);
-      tmem_ld_32x32(tmem_base + 192 + lane_off + buf * 64 + half * 32, rp);
+      uint32_t rs[CW], rp[CW];
+      tmem_ld_cols<CW>(tmem_base + lane_off + buf * 64 + sub * CW, rs);
+      tmem_ld_cols<CW>(tmem_base + 192 + lane_off + buf * 64 + sub * CW, rp);
       tmem_ld_wait();
-      uint32_t pk[16], dk_[16];
+      uint32_t pk[CW / 2], dk_[CW / 2];
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const float l0 = s_lse[buf * 64 + half * 32 + i], l1 = s_lse[buf * 64 + half * 32 + i + 1];
-        const float p0 = key_ok ? bw_exp2(fmaf(__uint_as_float(rs[i]), p.scale_log2, -l0)) : 0.f;
-        const float p1 = key_ok ? bw_exp2(fmaf(__uint_as_float(rs[i + 1]), p.scale_log2, -l1)) : 0.f;
+      for (int i = 0; i < CW; i += 2) {
+        const float2 l2 = *reinterpret_cast<const float2*>(&s_lse[buf * 64 + sub * CW + i]);
+        const float2 d2 = *reinterpret_cast<const float2*>(&s_delta[buf * 64 + sub * CW + i]);
+        const float p0 = key_ok ? bw_exp2(fmaf(__uint_as_float(rs[i]), p.scale_log2, -l2.x)) : 0.f;
+        const float p1 = key_ok ? bw_exp2(fmaf(__uint_as_float(rs[i + 1]), p.scale_log2, -l2.y)) : 0.f;
         pk[i >> 1] = pack_bf16(p0, p1);
-        dk_[i >> 1] = pack_bf16(p0 * (__uint_as_float(rp[i]) - s_delta[buf * 64 + half * 32 + i]),
-                                p1 * (__uint_as_float(rp[i + 1]) - s_delta[buf * 64 + half * 32 + i + 1]));
+        dk_[i >> 1] = pack_bf16(p0 * (__uint_as_float(rp[i]) - d2.x), p1 * (__uint_as_float(rp[i + 1]) - d2.y));
       }
       if (it >= BW_NB) mbar_wait(&acc_free[buf], ((it / BW_NB) - 1) & 1);   // accumulate MMAs of tile it-BW_NB finished reading this buffer
       uint8_t* pt_row = sPT + buf * BW_T + r * 128;
       uint8_t* ds_row = sdST + buf * BW_T + r * 128;
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int ch = half * 4 + t;
+      for (int t = 0; t < CW / 8; ++t) {
+        const int ch = sub * (CW / 8) + t;
         *reinterpret_cast<uint4*>(pt_row + ((ch ^ sw) << 4)) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
         *reinterpret_cast<uint4*>(ds_row + ((ch ^ sw) << 4)) = make_uint4(dk_[4 * t], dk_[4 * t + 1], dk_[4 * t + 2], dk_[4 * t + 3]);
       }
@@ -294,27 +308,30 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dkv_tcgen05(const __grid
     }
     mbar_wait(&acc_free[(iters - 1) % BW_NB], ((iters - 1) / BW_NB) & 1);
     tc_fence_after();
-    float g[32];
-    const int krow = k0 + r;
-    {
-      uint32_t raw[32];
-      tmem_ld_32x32(tm_dV + lane_off + half * 32, raw);
-      tmem_ld_wait();
+    if (sub < 2) {   // read-out: two threads per key row, 32 dims each (the rotary pairs (i, i+16) stay inside one thread)
+      const int half = sub;
+      float g[32];
+      const int krow = k0 + r;
+      {
+        uint32_t raw[32];
+        tmem_ld_32x32(tm_dV + lane_off + half * 32, raw);
+        tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) g[i] = __uint_as_float(raw[i]);
-    }
-    if (key_ok) store_grad_half(p.dV + b * p.dv_bs + krow * p.dv_ss + hk * p.dv_hs + half * 32, g, 1.0f, nullptr, nullptr);
-    {
-      uint32_t raw[32];
-      tmem_ld_32x32(tm_dK + lane_off + half * 32, raw);
-      tmem_ld_wait();
+        for (int i = 0; i < 32; ++i) g[i] = __uint_as_float(raw[i]);
+      }
+      if (key_ok) store_grad_half(p.dV + b * p.dv_bs + krow * p.dv_ss + hk * p.dv_hs + half * 32, g, 1.0f, nullptr, nullptr);
+      {
+        uint32_t raw[32];
+        tmem_ld_32x32(tm_dK + lane_off + half * 32, raw);
+        tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) g[i] = __uint_as_float(raw[i]);
-    }
-    if (key_ok) {
-      const bool rot = p.rope_cos != nullptr && half == 0;
-      store_grad_half(p.dK + b * p.dk_bs + krow * p.dk_ss + hk * p.dk_hs + half * 32, g, p.scale,
-                      rot ? p.rope_cos + krow * 16 : nullptr, rot ? p.rope_sin + krow * 16 : nullptr);
+        for (int i = 0; i < 32; ++i) g[i] = __uint_as_float(raw[i]);
+      }
+      if (key_ok) {
+        const bool rot = p.rope_cos != nullptr && half == 0;
+        store_grad_half(p.dK + b * p.dk_bs + krow * p.dk_ss + hk * p.dk_hs + half * 32, g, p.scale,
+                        rot ? p.rope_cos + krow * 16 : nullptr, rot ? p.rope_sin + krow * 16 : nullptr);
+      }
     }
     tc_fence_before();
   }
@@ -326,7 +343,10 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dkv_tcgen05(const __grid
 // ------------------------------------------------------------------------------------------------------------
 constexpr int DQ_SMEM = 2 * BW_T /*Q,dO*/ + BW_STAGES * 2 * BW_HT /*(K,V) ring*/ + BW_NB * BW_T /*dS*/ + 256;
 
-__global__ void __launch_bounds__(320, 1) attention_bwd_dq_tcgen05(const __grid_constant__ AttnBwdParams p) {
+template <int SW>
+__global__ void __launch_bounds__(64 + SW * 32, 1) attention_bwd_dq_tcgen05(const __grid_constant__ AttnBwdParams p) {
+  constexpr int CW = 256 / SW;
+  constexpr int NT = SW * 32;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sdO = smem + BW_T;
@@ -352,7 +372,7 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dq_tcgen05(const __grid_
     if (smem_u32(smem) & 1023u) __trap();
     mbar_init(q_full, 1);
     for (int i = 0; i < BW_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < BW_NB; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 256); mbar_init(&acc_free[i], 1); }
+    for (int i = 0; i < BW_NB; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], NT); mbar_init(&acc_free[i], 1); }
     fence_barrier_init();
   }
   griddep_launch();
@@ -415,7 +435,7 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dq_tcgen05(const __grid_
     }
   } else {
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int sub = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const int qrow = q0 + r;
@@ -426,16 +446,16 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dq_tcgen05(const __grid_
     const int sw = r & 7;
     for (int j = 0; j < nkv; ++j) {
       const int buf = j % BW_NB;
-      const int nvalid = p.Nk - j * 64 - half * 32;
+      const int nvalid = p.Nk - j * 64 - sub * CW;
       mbar_wait(&s_full[buf], (j / BW_NB) & 1);
       tc_fence_after();
-      uint32_t rs[32], rp[32];
-      tmem_ld_32x32(tmem_base + lane_off + buf * 64 + half * 32, rs);
-      tmem_ld_32x32(tmem_base + 192 + lane_off + buf * 64 + half * 32, rp);
+      uint32_t rs[CW], rp[CW];
+      tmem_ld_cols<CW>(tmem_base + lane_off + buf * 64 + sub * CW, rs);
+      tmem_ld_cols<CW>(tmem_base + 192 + lane_off + buf * 64 + sub * CW, rp);
       tmem_ld_wait();
-      uint32_t dk_[16];
+      uint32_t dk_[CW / 2];
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
+      for (int i = 0; i < CW; i += 2) {
         const float p0 = (i < nvalid) ? bw_exp2(fmaf(__uint_as_float(rs[i]), p.scale_log2, -lse2)) : 0.f;
         const float p1 = (i + 1 < nvalid) ? bw_exp2(fmaf(__uint_as_float(rs[i + 1]), p.scale_log2, -lse2)) : 0.f;
         dk_[i >> 1] = pack_bf16(p0 * (__uint_as_float(rp[i]) - dl), p1 * (__uint_as_float(rp[i + 1]) - dl));
@@ -443,8 +463,8 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dq_tcgen05(const __grid_
       if (j >= BW_NB) mbar_wait(&acc_free[buf], ((j / BW_NB) - 1) & 1);
       uint8_t* ds_row = sdS + buf * BW_T + r * 128;
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int ch = half * 4 + t;
+      for (int t = 0; t < CW / 8; ++t) {
+        const int ch = sub * (CW / 8) + t;
         *reinterpret_cast<uint4*>(ds_row + ((ch ^ sw) << 4)) = make_uint4(dk_[4 * t], dk_[4 * t + 1], dk_[4 * t + 2], dk_[4 * t + 3]);
       }
       fence_proxy_async_smem();
@@ -453,18 +473,21 @@ __global__ void __launch_bounds__(320, 1) attention_bwd_dq_tcgen05(const __grid_
     }
     mbar_wait(&acc_free[(nkv - 1) % BW_NB], ((nkv - 1) / BW_NB) & 1);
     tc_fence_after();
-    float g[32];
-    {
-      uint32_t raw[32];
-      tmem_ld_32x32(tm_dQ + lane_off + half * 32, raw);
-      tmem_ld_wait();
+    if (sub < 2) {
+      const int half = sub;
+      float g[32];
+      {
+        uint32_t raw[32];
+        tmem_ld_32x32(tm_dQ + lane_off + half * 32, raw);
+        tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) g[i] = __uint_as_float(raw[i]);
-    }
-    if (q_ok) {
-      const bool rot = p.rope_cos != nullptr && half == 0;
-      store_grad_half(p.dQ + b * p.dq_bs + qrow * p.dq_ss + h * p.dq_hs + half * 32, g, p.scale,
-                      rot ? p.rope_cos + qrow * 16 : nullptr, rot ? p.rope_sin + qrow * 16 : nullptr);
+        for (int i = 0; i < 32; ++i) g[i] = __uint_as_float(raw[i]);
+      }
+      if (q_ok) {
+        const bool rot = p.rope_cos != nullptr && half == 0;
+        store_grad_half(p.dQ + b * p.dq_bs + qrow * p.dq_ss + h * p.dq_hs + half * 32, g, p.scale,
+                        rot ? p.rope_cos + qrow * 16 : nullptr, rot ? p.rope_sin + qrow * 16 : nullptr);
+      }
     }
     tc_fence_before();
   }
@@ -517,17 +540,27 @@ extern "C" int b200sat_attention_bwd(const void* q, const void* k, const void* v
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
   static bool attr_set = false;
   if (!attr_set) {
-    B200SAT_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_dkv_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
-    B200SAT_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_dq_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+    B200SAT_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_dkv_tcgen05<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    B200SAT_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_dq_tcgen05<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+    B200SAT_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_dkv_tcgen05<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    B200SAT_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_dq_tcgen05<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
     attr_set = true;
   }
+  // B200SAT_ATTN_BWD_WARPS = 8 | 16 softmax warps per CTA (read per call so one process can compare both)
+  const char* sw_env = getenv("B200SAT_ATTN_BWD_WARPS");
+  const int sw_warps = (sw_env && atoi(sw_env) == 8) ? 8 : 16;
   pq = p;
   if ((rc = bw_head_map(&pq.tmQ, q, B, Hq, Nq, sq[0], sq[1], sq[2], 128))) return rc;
   if ((rc = bw_head_map(&pq.tmK, k, B, Hkv, Nk, sk[0], sk[1], sk[2], 64))) return rc;
   if ((rc = bw_head_map(&pq.tmV, v, B, Hkv, Nk, sv[0], sv[1], sv[2], 64))) return rc;
   if ((rc = bw_head_map(&pq.tmdO, d_o, B, Hq, Nq, sdo[0], sdo[1], sdo[2], 128))) return rc;
-  B200SAT_CHECK_CUDA(launch_k(attention_bwd_dkv_tcgen05, dim3((Nk + 127) / 128, Hkv, B), dim3(320), DKV_SMEM, s, 1, p));
-  B200SAT_CHECK_CUDA(launch_k(attention_bwd_dq_tcgen05, dim3((Nq + 127) / 128, Hq, B), dim3(320), DQ_SMEM, s, 1, pq));
+  if (sw_warps == 8) {
+    B200SAT_CHECK_CUDA(launch_k(attention_bwd_dkv_tcgen05<8>, dim3((Nk + 127) / 128, Hkv, B), dim3(320), DKV_SMEM, s, 1, p));
+    B200SAT_CHECK_CUDA(launch_k(attention_bwd_dq_tcgen05<8>, dim3((Nq + 127) / 128, Hq, B), dim3(320), DQ_SMEM, s, 1, pq));
+  } else {
+    B200SAT_CHECK_CUDA(launch_k(attention_bwd_dkv_tcgen05<16>, dim3((Nk + 127) / 128, Hkv, B), dim3(576), DKV_SMEM, s, 1, p));
+    B200SAT_CHECK_CUDA(launch_k(attention_bwd_dq_tcgen05<16>, dim3((Nq + 127) / 128, Hq, B), dim3(576), DQ_SMEM, s, 1, pq));
+  }
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }
