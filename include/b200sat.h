@@ -238,9 +238,12 @@ int b200sat_vae_sample_bwd(const void* dz, const void* ms, const float* noise, c
 /* Fused AdamW (decoupled weight decay, bias correction at `step` >= 1) + EMA + bf16 working-copy refresh over a flat fp32 buffer:
  * g' = g*grad_scale; m, v updated; p = p(1 - lr wd) - lr/(1-b1^t) * m / (sqrt(v/(1-b2^t)) + eps); ema = ema*ema_decay + p*(1-ema_decay)
  * (ema NULL = off); the first n_bf16 elements of p are also written as bf16 to w_bf16 (NULL = off).  One HBM pass for
- * torch.optim.AdamW + ema_pytorch.EMA.update (training/diffusion.py:239-247, 489-491; training/utils.py:60-79) + the weight cast. */
+ * torch.optim.AdamW + ema_pytorch.EMA.update (training/diffusion.py:239-247, 489-491; training/utils.py:60-79) + the weight cast.
+ * ema_before_step != 0: the EMA averages the weights as they were BEFORE this update — AutoencoderTrainingWrapper.training_step calls
+ * autoencoder_ema.update() ahead of opt_gen.step() (training/autoencoders.py:499-506); 0 = after it (DiffusionCondTrainingWrapper). */
 int b200sat_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, void* w_bf16, long n, long n_bf16, float lr, float beta1,
-                           float beta2, float eps, float weight_decay, int step, float ema_decay, float grad_scale, void* stream);
+                           float beta2, float eps, float weight_decay, int step, float ema_decay, float grad_scale, int ema_before_step,
+                           void* stream);
 
 /* ---- Encodec multi-scale STFT discriminator (models/encodec.py:38-138, models/discriminators.py:13-58) ---------------------------
  * One scale's activations are flattened planes [B, P, C], P = frames * (F + 8), F = n_fft/2 + 1: bins in columns [4, 4+F) of each frame's

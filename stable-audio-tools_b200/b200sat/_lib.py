@@ -56,7 +56,7 @@ SIGNATURES = {
                                           c_int, c_int, c_float, c_void_p]),
     "b200sat_gate_bwd": (c_int, [c_void_p, c_long, c_void_p, c_long, c_fp, c_void_p, c_long, c_fp, c_int, c_int, c_int, c_void_p]),
     "b200sat_adamw_ema_step": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_void_p, c_long, c_long, c_float, c_float, c_float, c_float, c_float, c_int,
-                                       c_float, c_float, c_void_p]),
+                                       c_float, c_float, c_int, c_void_p]),
     "b200sat_conv2d_flat": (c_int, [c_void_p, c_void_p, c_fp, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_float,
                                     c_void_p]),
     "b200sat_disc_stft": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_void_p]),

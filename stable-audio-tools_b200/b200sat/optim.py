@@ -20,13 +20,46 @@ def ema_decay_at(step, beta=0.9999, inv_gamma=1.0, power=0.75, update_after_step
     return float(min(max(value, min_value), beta))
 
 
+class FlatParameters:
+    """Re-homes a list of nn.Parameters into ONE flat fp32 buffer (and their .grad into a second one) so that the fused optimizer
+    step is a single pass: `p.data` / `p.grad` become views, names / shapes / autograd behaviour are unchanged (AccumulateGrad adds
+    in place into the existing .grad views).  Exposes the `.flat` / `.flat_grad` pair FusedAdamWEMA expects."""
+
+    def __init__(self, params):
+        self.params = [p for p in params]
+        if not self.params:
+            raise ValueError("no parameters")
+        dev = self.params[0].device
+        total = sum(p.numel() for p in self.params)
+        total = (total + 3) // 4 * 4
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        self._p = {}
+        off = 0
+        for i, p in enumerate(self.params):
+            k = p.numel()
+            view = self.flat[off:off + k].view(p.shape)
+            view.copy_(p.detach())
+            p.data = view
+            p.grad = self.flat_grad[off:off + k].view(p.shape)
+            self._p[str(i)] = p
+            off += k
+
+    def zero_grad(self, set_to_none=False):
+        self.flat_grad.zero_()
+
+    def parameters(self):
+        return iter(self.params)
+
+
 class FusedAdamWEMA:
     """optimizer + EMA for a model exposing `.flat` / `.flat_grad` (fp32, same length) and optionally `._bf` (bf16 working copy of
     the first `stack_numel` elements)."""
 
     def __init__(self, model, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-3, ema=True, ema_beta=0.9999, ema_power=0.75,
-                 ema_inv_gamma=1.0, ema_update_after_step=1):
+                 ema_inv_gamma=1.0, ema_update_after_step=1, ema_before_step=False):
         self.model = model
+        self.ema_before_step = bool(ema_before_step)
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.n = model.flat.numel()
         if self.n % 4:
@@ -37,6 +70,13 @@ class FusedAdamWEMA:
         self.ema_cfg = dict(beta=ema_beta, inv_gamma=ema_inv_gamma, power=ema_power, update_after_step=ema_update_after_step)
         self.t = 0
 
+    def zero_grad(self, set_to_none=False):
+        self.model.flat_grad.zero_()
+
+    @property
+    def param_groups(self):
+        return [{"lr": self.lr}]
+
     def step(self, grad_scale=1.0):
         mdl = self.model
         self.t += 1
@@ -46,7 +86,7 @@ class FusedAdamWEMA:
         rc = lib().b200sat_adamw_ema_step(mdl.flat.data_ptr(), mdl.flat_grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                           0 if self.ema is None else self.ema.data_ptr(), 0 if w16 is None else w16.data_ptr(), self.n, n16,
                                           self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.t, decay, grad_scale,
-                                          torch.cuda.current_stream().cuda_stream)
+                                          int(self.ema_before_step), torch.cuda.current_stream().cuda_stream)
         ops.LAUNCHES[0] += 1
         check(rc, "adamw_ema_step")
         if w16 is not None and n16 == w16.numel():

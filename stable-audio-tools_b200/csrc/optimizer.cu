@@ -7,6 +7,8 @@ namespace b200sat {
 
 struct AdamArgs {
   float lr, beta1, beta2, eps, weight_decay, bc1, bc2, ema_decay, grad_scale;
+  int ema_before_step;   // 1: the EMA takes the weights BEFORE this update (AutoencoderTrainingWrapper calls ema.update() ahead of
+                         //    opt_gen.step(), training/autoencoders.py:499-506); 0: after it (DiffusionCondTrainingWrapper.on_before_zero_grad)
 };
 
 __global__ void __launch_bounds__(256) adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -20,6 +22,7 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(float* __restrict__ p, c
     const float4 gg = reinterpret_cast<const float4*>(g)[i];
     float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
     float pe[4] = {pp.x, pp.y, pp.z, pp.w};
+    const float po[4] = {pp.x, pp.y, pp.z, pp.w};
     const float ge[4] = {gg.x, gg.y, gg.z, gg.w};
     float me[4] = {mm.x, mm.y, mm.z, mm.w}, ve[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
@@ -35,10 +38,11 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(float* __restrict__ p, c
     reinterpret_cast<float4*>(v)[i] = make_float4(ve[0], ve[1], ve[2], ve[3]);
     if (ema) {
       float4 ee = reinterpret_cast<float4*>(ema)[i];
-      ee.x = ee.x * a.ema_decay + pe[0] * (1.f - a.ema_decay);
-      ee.y = ee.y * a.ema_decay + pe[1] * (1.f - a.ema_decay);
-      ee.z = ee.z * a.ema_decay + pe[2] * (1.f - a.ema_decay);
-      ee.w = ee.w * a.ema_decay + pe[3] * (1.f - a.ema_decay);
+      const float* src = a.ema_before_step ? po : pe;
+      ee.x = ee.x * a.ema_decay + src[0] * (1.f - a.ema_decay);
+      ee.y = ee.y * a.ema_decay + src[1] * (1.f - a.ema_decay);
+      ee.z = ee.z * a.ema_decay + src[2] * (1.f - a.ema_decay);
+      ee.w = ee.w * a.ema_decay + src[3] * (1.f - a.ema_decay);
       reinterpret_cast<float4*>(ema)[i] = ee;
     }
     if (w16 && (i << 2) < n16) {
@@ -53,14 +57,14 @@ using namespace b200sat;
 
 extern "C" int b200sat_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, void* w_bf16, long n, long n_bf16, float lr,
                                       float beta1, float beta2, float eps, float weight_decay, int step, float ema_decay, float grad_scale,
-                                      void* stream) {
+                                      int ema_before_step, void* stream) {
   if (!p || !g || !m || !v || n <= 0 || step < 1) { set_last_error("adamw_ema_step: bad arguments"); return B200SAT_EINVAL; }
   if ((n & 3) || (n_bf16 & 3) || n_bf16 > n) { set_last_error("adamw_ema_step: element counts must be multiples of 4 (pad the flat buffer)"); return B200SAT_EINVAL; }
   AdamArgs a;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
   a.bc1 = 1.f - powf(beta1, static_cast<float>(step));
   a.bc2 = 1.f - powf(beta2, static_cast<float>(step));
-  a.ema_decay = ema_decay; a.grad_scale = grad_scale;
+  a.ema_decay = ema_decay; a.grad_scale = grad_scale; a.ema_before_step = ema_before_step ? 1 : 0;
   const long n4 = n >> 2;
   long blocks = (n4 + 255) / 256;
   const long cap = static_cast<long>(num_sms()) * 16;

@@ -1,0 +1,93 @@
+"""GPU: the ASSEMBLED autoencoder training step against four consecutive calls of the reference's own
+`AutoencoderTrainingWrapper.training_step` (golden written by oracle/gen_golden_training.py from the unmodified wrapper, CPU fp32):
+generator / discriminator alternation, loss weights and names, warm-up switch, AuralossLoss argument order, AdamW per group.
+
+Tolerances (stated): the engines run bf16 activations, the golden is fp32 — loss terms within 3 % (+1e-3 abs), discriminator hinge loss
+within 1e-3 abs, gradients of the watched parameters cosine >= 0.97 and norm within 15 %, and after the AdamW update the parameter
+DELTA (new - old) cosine >= 0.9 (Adam's first steps are sign-like, so tiny gradients flip freely)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ae_training_step.npz")
+
+
+def _cos(a, b):
+    a, b = a.flatten().double(), b.flatten().double()
+    return float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-30))
+
+
+def test_four_steps_match_the_reference_wrapper():
+    from oracle import oobleck as oo
+    from b200sat.ae_training import AutoencoderTrainingStep
+    from b200sat.autoencoder_train import OobleckTrainModel
+    from b200sat.discriminator import EncodecDiscriminatorTrain
+    G = np.load(GOLD, allow_pickle=False)
+    meta = json.loads(str(G["meta"]))
+    dev = "cuda"
+    sd = oo.make_state_dict(channels=64, c_mults=(1, 2, 4), strides=(2, 4, 4), enc_latent=128, dec_latent=64, seed=meta["ae_weights_seed"])
+    ae = OobleckTrainModel(sd, strides=(2, 4, 4), device=dev)
+    dsd = {k[len("disc_init."):]: torch.from_numpy(G[k]) for k in G.files if k.startswith("disc_init.")}
+    disc = EncodecDiscriminatorTrain(dsd, n_ffts=tuple(meta["disc_fft"]), hop_lengths=tuple(meta["disc_hop"]), device=dev)
+    step = AutoencoderTrainingStep(ae, disc, loss_config=meta["loss_config"], optimizer_configs=meta["optimizer_configs"], sample_rate=44100,
+                                   warmup_steps=0, use_ema=False)
+    reals = torch.from_numpy(G["reals"]).to(dev)
+    ae_named = {n: getattr(ae, n.replace(".", "__")) for n in ae.names}
+    disc_named = {n: getattr(disc, n.replace(".", "__")) for n in disc.names}
+    for s in range(4):
+        is_d = s % 2 == 1
+        named = disc_named if is_d else ae_named
+        watch = sorted(k[len(f"s{s}.grad."):] for k in G.files if k.startswith(f"s{s}.grad."))
+        before = {n: named[n].detach().clone() for n in watch}
+        noise = torch.from_numpy(G[f"s{s}.vae_noise"]).to(dev)
+        loss, log = step.training_step(reals, vae_noise=noise)
+        ref_loss = float(G[f"s{s}.loss"])
+        print(f"\n[T2 step {s} {'D' if is_d else 'G'}] loss ours {float(loss):.5f} reference {ref_loss:.5f}")
+        if is_d:
+            assert set(log) == {"train/disc_lr", "train/discriminator_loss"}
+            assert abs(float(loss) - ref_loss) <= 1e-3 + 5e-3 * abs(ref_loss)
+        else:
+            assert abs(float(loss) - ref_loss) <= 3e-2 * abs(ref_loss)
+            for k in ("loss_adv", "feature_matching_loss", "mrstft_loss", "stft_loss_left", "stft_loss_right", "kl_loss"):
+                ours, ref = float(log["train/" + k]), float(G[f"s{s}.log.{k}"])
+                print(f"    {k:24s} ours {ours:+.5f} reference {ref:+.5f}")
+                assert abs(ours - ref) <= 3e-2 * abs(ref) + 1e-3, (k, ours, ref)
+            assert abs(float(log["train/gen_lr"]) - float(G[f"s{s}.log.gen_lr"])) < 1e-12
+        for n in watch:
+            g_ref = torch.from_numpy(G[f"s{s}.grad.{n}"]).to(dev)
+            p_ref = torch.from_numpy(G[f"s{s}.param.{n}"]).to(dev)
+            g = named[n].grad
+            cg = _cos(g, g_ref)
+            nr = float(g.norm() / (g_ref.norm() + 1e-30))
+            cd = _cos(named[n].detach() - before[n], p_ref - before[n]) if s == 0 or s == 1 else None
+            print(f"    grad {n:60s} cos {cg:.4f} norm ratio {nr:.3f}" + (f"  delta cos {cd:.3f}" if cd is not None else ""))
+            assert cg >= 0.97, (n, cg)
+            assert abs(nr - 1) <= 0.15, (n, nr)
+            if cd is not None:
+                assert cd >= 0.9, (n, cd)
+    assert step.global_step == 4
+
+
+def test_flat_parameters_keep_autograd_semantics():
+    from b200sat.optim import FlatParameters, FusedAdamWEMA
+    lin = torch.nn.Linear(8, 5).cuda()
+    ref = torch.nn.Linear(8, 5).cuda()
+    ref.load_state_dict(lin.state_dict())
+    fp = FlatParameters(list(lin.parameters()))
+    opt = FusedAdamWEMA(fp, lr=1e-2, betas=(0.8, 0.99), weight_decay=1e-3, ema=True, ema_before_step=True)
+    ropt = torch.optim.AdamW(ref.parameters(), lr=1e-2, betas=(0.8, 0.99), weight_decay=1e-3)
+    x = torch.randn(16, 8, device="cuda")
+    w0 = lin.weight.detach().clone()
+    for _ in range(3):
+        opt.zero_grad(); ropt.zero_grad()
+        lin(x).square().mean().backward(); ref(x).square().mean().backward()
+        assert lin.weight.grad.data_ptr() == fp.flat_grad.data_ptr(), ".grad must stay a view of the flat buffer"
+        opt.step(); ropt.step()
+    assert torch.allclose(lin.weight, ref.weight, atol=1e-6) and torch.allclose(lin.bias, ref.bias, atol=1e-6)
+    # EMA before step with update_after_step=1: first two updates copy the (pre-step) weights
+    assert opt.ema is not None and torch.isfinite(opt.ema).all()
+    assert not torch.allclose(lin.weight, w0)
