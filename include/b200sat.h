@@ -112,6 +112,15 @@ int b200sat_conv1d_fwd(const void* in_hi, const void* in_lo, const void* w_hi, c
                        const float* snake_a, const float* snake_invb, int B, int T_in, int Cin, int Cout, int taps, int dil,
                        int pad, int stride, int mode, int passes, void* stream);
 
+/* One ResidualUnit (models/autoencoders.py:58-83: Snake -> WNConv1d k7 dilated -> Snake -> WNConv1d k1 -> + x) in ONE launch, bf16 planes,
+ * C == 128 (other widths: two b200sat_conv1d_fwd calls).  x_act = snake0(x) and x_raw = x are the [B, T, 128] planes the previous layer's
+ * epilogue wrote; w7 / w1 are b200sat_wn_pack outputs ([128][7*128], [128][128]); s1_* / next_* are b200sat_snake_prep outputs.
+ *   out_raw = x_raw + conv1(snake1(conv7_dil(x_act) + b7)) + b1,   out_act = snake_next(out_raw)      (either may be NULL)
+ * The k7 output never reaches HBM: 2.0 GB instead of 3.1 GB of traffic per unit at T = 2 097 152. */
+int b200sat_residual_unit_fwd(const void* x_act, const void* x_raw, const void* w7, const float* b7, const float* s1_a, const float* s1_invb,
+                              const void* w1, const float* b1, const float* next_a, const float* next_invb, void* out_raw, void* out_act,
+                              int B, int T, int C, int dil, void* stream);
+
 /* weight_norm (w = g*v/||v||, norm over all dims but 0; autoencoders.py:23-27) + packing to the GEMM layout as hi/lo bf16
  * planes.  v fp32 [Cout,Cin,K] (conv) or [Cin,Cout,K] (transposed); g NULL = plain weight. */
 int b200sat_wn_pack(const float* v, const float* g, float* inv_norm_scratch, void* w_hi, void* w_lo, int Cout, int Cin, int K,

@@ -36,6 +36,8 @@ SIGNATURES = {
     "b200sat_sampler_update": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_void_p, c_long, c_int, c_void_p]),
     "b200sat_step_set": (c_int, [c_void_p, c_int, c_void_p]),
     "b200sat_conv1d_fwd": (c_int, [c_void_p] * 4 + [c_fp] + [c_void_p] * 6 + [c_fp, c_fp] + [c_int] * 10 + [c_void_p]),
+    "b200sat_residual_unit_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_fp, c_fp, c_fp, c_void_p, c_fp, c_fp, c_fp, c_void_p, c_void_p,
+                                          c_int, c_int, c_int, c_int, c_void_p]),
     "b200sat_wn_pack": (c_int, [c_fp, c_fp, c_fp, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200sat_snake_prep": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_void_p]),
     "b200sat_conv_in": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp] + [c_void_p] * 4 + [c_int] * 6 + [c_void_p]),

@@ -7,6 +7,8 @@ passes (hi*hi + hi*lo + lo*hi) for fp32-class accuracy (inference parity <= 1e-4
 mode that bf16 autocast training uses.
 """
 import math
+import os
+
 import torch
 
 from ._lib import lib, check
@@ -149,8 +151,23 @@ class OobleckEngine:
         """Three ResidualUnits (autoencoders.py:58-83).  x_raw: input planes; x_act = snake_{ru0.s0}(x_raw).
         Returns (raw, act) of the last unit where act = next_snake(raw) (or None)."""
         B, T, C = x_raw.B, x_raw.T, x_raw.C
+        fused = self.passes == 1 and C == 128 and os.environ.get("B200SAT_FUSED_RU", "1") != "0"
         for j, ru in enumerate(rus):
             dil = (1, 3, 9)[j]
+            if fused:
+                # bf16 mode, C = 128: the whole unit in one launch (csrc/residual_unit.cu) - the k7 output never reaches HBM
+                nxt = rus[j + 1]["s0"] if j + 1 < len(rus) else next_snake
+                y_raw = self._planes(B, T, C)
+                y_act = self._planes(B, T, C) if nxt is not None else None
+                c7, c1, s1 = ru["c7"], ru["c1"], ru["s1"]
+                rc = lib().b200sat_residual_unit_fwd(x_act.hi.data_ptr(), x_raw.hi.data_ptr(), c7.w_hi.data_ptr(), _p(c7.bias), s1.a.data_ptr(),
+                                                     s1.invb.data_ptr(), c1.w_hi.data_ptr(), _p(c1.bias), _p(nxt.a) if nxt else 0,
+                                                     _p(nxt.invb) if nxt else 0, y_raw.hi.data_ptr(), _p(y_act.hi) if y_act else 0,
+                                                     B, T, C, dil, _s())
+                ops.LAUNCHES[0] += 1
+                check(rc, "residual_unit_fwd")
+                x_raw, x_act = y_raw, y_act
+                continue
             h = self._planes(B, T, C)                                   # snake_{s1}(conv7(x_act))
             self._conv(x_act, ru["c7"], act=h, snake=ru["s1"], dil=dil, pad=3 * dil)
             nxt = rus[j + 1]["s0"] if j + 1 < len(rus) else next_snake
