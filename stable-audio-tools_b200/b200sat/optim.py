@@ -30,8 +30,10 @@ class FlatParameters:
         if not self.params:
             raise ValueError("no parameters")
         dev = self.params[0].device
-        total = sum(p.numel() for p in self.params)
-        total = (total + 3) // 4 * 4
+        # every parameter starts on a 64-byte boundary: the kernels read biases / SnakeBeta vectors with 16-byte loads and the weight
+        # packers may vectorise; the padding elements stay zero (zero gradient => AdamW leaves them at zero)
+        al = lambda n: (n + 15) // 16 * 16
+        total = sum(al(p.numel()) for p in self.params)
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_grad = torch.zeros(total, device=dev, dtype=torch.float32)
         self._p = {}
@@ -43,7 +45,7 @@ class FlatParameters:
             p.data = view
             p.grad = self.flat_grad[off:off + k].view(p.shape)
             self._p[str(i)] = p
-            off += k
+            off += al(k)
 
     def zero_grad(self, set_to_none=False):
         self.flat_grad.zero_()
@@ -94,9 +96,9 @@ class FusedAdamWEMA:
 
     def ema_state_dict(self):
         """EMA weights under the reference parameter names."""
-        out, off = {}, 0
+        out = {}
+        base = self.model.flat.data_ptr()
         for n_, p in self.model._p.items():
-            k = p.numel()
+            off, k = (p.data_ptr() - base) // 4, p.numel()       # parameters are views of `flat` (possibly padded apart)
             out[n_] = self.ema[off:off + k].view(p.shape).clone()
-            off += k
         return out

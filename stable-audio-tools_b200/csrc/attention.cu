@@ -108,37 +108,38 @@ __global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);  // B = V is MN-major (keys along rows)
-      const uint32_t aQ = smem_u32(sQ);
-      auto issue_s = [&](int j) {
-        const int s = j % AT_KV_STAGES;
-        mbar_wait(&kv_full[s], (j / AT_KV_STAGES) & 1);
-        tc_fence_after();
-        const uint32_t aK = smem_u32(sKV + s * 2 * AT_KT);
-        const uint32_t tS = tmem_base + (j & 1) * 64;
+    // MMA issue: the whole warp walks the loop (uniform control flow), one elected lane issues (see umma_bf16_lo in common.cuh)
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);  // B = V is MN-major (keys along rows)
+    const uint32_t loQ = desc_lo_kmajor(smem_u32(sQ));
+    const uint32_t loK0 = desc_lo_kmajor(smem_u32(sKV));
+    const uint32_t loV0 = desc_lo_mnmajor(smem_u32(sKV) + AT_KT, 1024);
+    const uint32_t loP0 = desc_lo_kmajor(smem_u32(sP));
+    auto issue_s = [&](int j) {
+      const int s = j % AT_KV_STAGES;
+      mbar_wait(&kv_full[s], (j / AT_KV_STAGES) & 1);
+      tc_fence_after();
+      const uint32_t loK = loK0 + s * ((2 * AT_KT) >> 4);
+      const uint32_t tS = tmem_base + (j & 1) * 64;
 #pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
-          umma_bf16(tS, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024), idesc_s, k != 0);
-        umma_commit(&s_full[j & 1]);
-      };
-      mbar_wait(q_full, 0);
-      issue_s(0);
-      if (num_kv > 1) issue_s(1);
-      for (int j = 0; j < num_kv; ++j) {
-        const int s = j % AT_KV_STAGES;
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t aP = smem_u32(sP + (j & 1) * AT_QT);
-        const uint32_t aV = smem_u32(sKV + s * 2 * AT_KT + AT_KT);
+      for (int k = 0; k < AT_D / 16; ++k) umma_bf16_lo(tS, loQ + 2 * k, loK + 2 * k, idesc_s, k != 0, leader);
+      umma_commit_if(&s_full[j & 1], leader);
+    };
+    mbar_wait(q_full, 0);
+    issue_s(0);
+    if (num_kv > 1) issue_s(1);
+    for (int j = 0; j < num_kv; ++j) {
+      const int s = j % AT_KV_STAGES;
+      mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t loP = loP0 + (j & 1) * (AT_QT >> 4);
+      const uint32_t loV = loV0 + s * ((2 * AT_KT) >> 4);
 #pragma unroll
-        for (int k = 0; k < AT_BN / 16; ++k)
-          umma_bf16(tmem_O, make_smem_desc_sw128(aP + k * 32, 16, 1024), make_smem_desc_sw128(aV + k * 2048, 1024, 1024), idesc_o, (j | k) != 0);
-        umma_commit(&pv_done[j & 1]);
-        umma_commit(&kv_empty[s]);
-        if (j + 2 < num_kv) issue_s(j + 2);   // its S buffer was consumed before p_full(j) completed
-      }
+      for (int k = 0; k < AT_BN / 16; ++k) umma_bf16_lo(tmem_O, loP + 2 * k, loV + 128 * k, idesc_o, (j | k) != 0, leader);
+      umma_commit_if(&pv_done[j & 1], leader);
+      umma_commit_if(&kv_empty[s], leader);
+      if (j + 2 < num_kv) issue_s(j + 2);   // its S buffer was consumed before p_full(j) completed
     }
   } else {
     // ===================== softmax / output warps: two threads per query row, 32 keys each per tile =====================

@@ -215,42 +215,45 @@ __global__ void __launch_bounds__(64 + SW * 32, 1) attention_bwd_dkv_tcgen05(con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t id_s = make_idesc_bf16(128, 64, 0, 0);
-      constexpr uint32_t id_acc = make_idesc_bf16(128, 64, 0, 1);
-      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
-      auto issue_scores = [&](int it) {
-        const int s = it % BW_STAGES;
-        mbar_wait(&qdo_full[s], (it / BW_STAGES) & 1);
-        tc_fence_after();
-        const uint32_t aQ = smem_u32(sRing + s * 2 * BW_HT), adO = aQ + BW_HT;
-        const uint32_t tS = tmem_base + (it % BW_NB) * 64, tP = tmem_base + 192 + (it % BW_NB) * 64;
+    // MMA issue by the whole warp in uniform control flow, one elected lane issues (umma_bf16_lo, common.cuh): ~2 instructions per MMA
+    // instead of ~18 - the 32-cycle 128x64x16 MMAs were starved by descriptor arithmetic in the issuing thread
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    constexpr uint32_t id_s = make_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t id_acc = make_idesc_bf16(128, 64, 0, 1);
+    const uint32_t loK = desc_lo_kmajor(smem_u32(sK)), loV = desc_lo_kmajor(smem_u32(sV));
+    const uint32_t loQ0 = desc_lo_kmajor(smem_u32(sRing)), lodO0 = desc_lo_kmajor(smem_u32(sRing) + BW_HT);
+    const uint32_t loQm0 = desc_lo_mnmajor(smem_u32(sRing), 1024), lodOm0 = desc_lo_mnmajor(smem_u32(sRing) + BW_HT, 1024);
+    const uint32_t loPT0 = desc_lo_kmajor(smem_u32(sPT)), lodST0 = desc_lo_kmajor(smem_u32(sdST));
+    constexpr uint32_t kStageStep = (2 * BW_HT) >> 4, kBufStep = BW_T >> 4;
+    auto issue_scores = [&](int it) {
+      const int s = it % BW_STAGES;
+      mbar_wait(&qdo_full[s], (it / BW_STAGES) & 1);
+      tc_fence_after();
+      const uint32_t loQ = loQ0 + s * kStageStep, lodO = lodO0 + s * kStageStep;
+      const uint32_t tS = tmem_base + (it % BW_NB) * 64, tP = tmem_base + 192 + (it % BW_NB) * 64;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // S^T[keys, q] = K Q^T
-          umma_bf16(tS, make_smem_desc_sw128(aK + k * 32, 16, 1024), make_smem_desc_sw128(aQ + k * 32, 16, 1024), id_s, k != 0);
+      for (int k = 0; k < 4; ++k) umma_bf16_lo(tS, loK + 2 * k, loQ + 2 * k, id_s, k != 0, leader);     // S^T[keys, q] = K Q^T
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // dP^T[keys, q] = V dO^T
-          umma_bf16(tP, make_smem_desc_sw128(aV + k * 32, 16, 1024), make_smem_desc_sw128(adO + k * 32, 16, 1024), id_s, k != 0);
-        umma_commit(&s_full[it % BW_NB]);
-      };
-      mbar_wait(kv_full, 0);
-      for (int i = 0; i < BW_NB && i < iters; ++i) issue_scores(i);
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % BW_STAGES;
-        mbar_wait(&p_full[it % BW_NB], (it / BW_NB) & 1);
-        tc_fence_after();
-        const uint32_t aQ = smem_u32(sRing + s * 2 * BW_HT), adO = aQ + BW_HT;
-        const uint32_t aPT = smem_u32(sPT + (it % BW_NB) * BW_T), adST = smem_u32(sdST + (it % BW_NB) * BW_T);
+      for (int k = 0; k < 4; ++k) umma_bf16_lo(tP, loV + 2 * k, lodO + 2 * k, id_s, k != 0, leader);    // dP^T[keys, q] = V dO^T
+      umma_commit_if(&s_full[it % BW_NB], leader);
+    };
+    mbar_wait(kv_full, 0);
+    for (int i = 0; i < BW_NB && i < iters; ++i) issue_scores(i);
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % BW_STAGES;
+      mbar_wait(&p_full[it % BW_NB], (it / BW_NB) & 1);
+      tc_fence_after();
+      const uint32_t loQm = loQm0 + s * kStageStep, lodOm = lodOm0 + s * kStageStep;
+      const uint32_t loPT = loPT0 + (it % BW_NB) * kBufStep, lodST = lodST0 + (it % BW_NB) * kBufStep;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // dV[keys, d] += P^T dO   (dO tile re-read MN-major: rows = queries = MMA K)
-          umma_bf16(tm_dV, make_smem_desc_sw128(aPT + k * 32, 16, 1024), make_smem_desc_sw128(adO + k * 2048, 1024, 1024), id_acc, (it | k) != 0);
+      for (int k = 0; k < 4; ++k)   // dV[keys, d] += P^T dO   (dO tile re-read MN-major: rows = queries = MMA K)
+        umma_bf16_lo(tm_dV, loPT + 2 * k, lodOm + 128 * k, id_acc, (it | k) != 0, leader);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // dK[keys, d] += dS^T Q
-          umma_bf16(tm_dK, make_smem_desc_sw128(adST + k * 32, 16, 1024), make_smem_desc_sw128(aQ + k * 2048, 1024, 1024), id_acc, (it | k) != 0);
-        umma_commit(&qdo_empty[s]);
-        umma_commit(&acc_free[it % BW_NB]);
-        if (it + BW_NB < iters) issue_scores(it + BW_NB);   // its TMEM buffers were drained before p_full(it) completed
-      }
+      for (int k = 0; k < 4; ++k)   // dK[keys, d] += dS^T Q
+        umma_bf16_lo(tm_dK, lodST + 2 * k, loQm + 128 * k, id_acc, (it | k) != 0, leader);
+      umma_commit_if(&qdo_empty[s], leader);
+      umma_commit_if(&acc_free[it % BW_NB], leader);
+      if (it + BW_NB < iters) issue_scores(it + BW_NB);   // its TMEM buffers were drained before p_full(it) completed
     }
   } else {
     // SW warps: SW/4 threads per key row, each owning CW of the 64 query columns of a tile
@@ -399,39 +402,40 @@ __global__ void __launch_bounds__(64 + SW * 32, 1) attention_bwd_dq_tcgen05(cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t id_s = make_idesc_bf16(128, 64, 0, 0);
-      constexpr uint32_t id_acc = make_idesc_bf16(128, 64, 0, 1);
-      const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO);
-      auto issue_scores = [&](int j) {
-        const int s = j % BW_STAGES;
-        mbar_wait(&kv_full[s], (j / BW_STAGES) & 1);
-        tc_fence_after();
-        const uint32_t aK = smem_u32(sRing + s * 2 * BW_HT), aV = aK + BW_HT;
-        const uint32_t tS = tmem_base + (j % BW_NB) * 64, tP = tmem_base + 192 + (j % BW_NB) * 64;
+    const uint32_t leader = elect_one() ? 1u : 0u;      // see the dK/dV kernel
+    constexpr uint32_t id_s = make_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t id_acc = make_idesc_bf16(128, 64, 0, 1);
+    const uint32_t loQ = desc_lo_kmajor(smem_u32(sQ)), lodO = desc_lo_kmajor(smem_u32(sdO));
+    const uint32_t loK0 = desc_lo_kmajor(smem_u32(sRing)), loV0 = desc_lo_kmajor(smem_u32(sRing) + BW_HT);
+    const uint32_t loKm0 = desc_lo_mnmajor(smem_u32(sRing), 1024);
+    const uint32_t lodS0 = desc_lo_kmajor(smem_u32(sdS));
+    constexpr uint32_t kStageStep = (2 * BW_HT) >> 4, kBufStep = BW_T >> 4;
+    auto issue_scores = [&](int j) {
+      const int s = j % BW_STAGES;
+      mbar_wait(&kv_full[s], (j / BW_STAGES) & 1);
+      tc_fence_after();
+      const uint32_t loK = loK0 + s * kStageStep, loV = loV0 + s * kStageStep;
+      const uint32_t tS = tmem_base + (j % BW_NB) * 64, tP = tmem_base + 192 + (j % BW_NB) * 64;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // S[q, keys] = Q K^T
-          umma_bf16(tS, make_smem_desc_sw128(aQ + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 32, 16, 1024), id_s, k != 0);
+      for (int k = 0; k < 4; ++k) umma_bf16_lo(tS, loQ + 2 * k, loK + 2 * k, id_s, k != 0, leader);     // S[q, keys] = Q K^T
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // dP[q, keys] = dO V^T
-          umma_bf16(tP, make_smem_desc_sw128(adO + k * 32, 16, 1024), make_smem_desc_sw128(aV + k * 32, 16, 1024), id_s, k != 0);
-        umma_commit(&s_full[j % BW_NB]);
-      };
-      mbar_wait(q_full, 0);
-      for (int i = 0; i < BW_NB && i < nkv; ++i) issue_scores(i);
-      for (int j = 0; j < nkv; ++j) {
-        const int s = j % BW_STAGES;
-        mbar_wait(&p_full[j % BW_NB], (j / BW_NB) & 1);
-        tc_fence_after();
-        const uint32_t aK = smem_u32(sRing + s * 2 * BW_HT);
-        const uint32_t adS = smem_u32(sdS + (j % BW_NB) * BW_T);
+      for (int k = 0; k < 4; ++k) umma_bf16_lo(tP, lodO + 2 * k, loV + 2 * k, id_s, k != 0, leader);    // dP[q, keys] = dO V^T
+      umma_commit_if(&s_full[j % BW_NB], leader);
+    };
+    mbar_wait(q_full, 0);
+    for (int i = 0; i < BW_NB && i < nkv; ++i) issue_scores(i);
+    for (int j = 0; j < nkv; ++j) {
+      const int s = j % BW_STAGES;
+      mbar_wait(&p_full[j % BW_NB], (j / BW_NB) & 1);
+      tc_fence_after();
+      const uint32_t loKm = loKm0 + s * kStageStep;
+      const uint32_t lodS = lodS0 + (j % BW_NB) * kBufStep;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // dQ[q, d] += dS K   (K tile re-read MN-major: rows = keys = MMA K)
-          umma_bf16(tm_dQ, make_smem_desc_sw128(adS + k * 32, 16, 1024), make_smem_desc_sw128(aK + k * 2048, 1024, 1024), id_acc, (j | k) != 0);
-        umma_commit(&kv_empty[s]);
-        umma_commit(&acc_free[j % BW_NB]);
-        if (j + BW_NB < nkv) issue_scores(j + BW_NB);
-      }
+      for (int k = 0; k < 4; ++k)   // dQ[q, d] += dS K   (K tile re-read MN-major: rows = keys = MMA K)
+        umma_bf16_lo(tm_dQ, lodS + 2 * k, loKm + 128 * k, id_acc, (j | k) != 0, leader);
+      umma_commit_if(&kv_empty[s], leader);
+      umma_commit_if(&acc_free[j % BW_NB], leader);
+      if (j + BW_NB < nkv) issue_scores(j + BW_NB);
     }
   } else {
     const int quarter = warp & 3;

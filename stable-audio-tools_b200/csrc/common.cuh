@@ -129,6 +129,62 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Lean issue path for small MMAs (attention: 128 x 64 x 16 = 32 tensor-pipe cycles each).  ncu (profiles/r2_ncu_attention_summary.txt)
+// showed the single issuing thread spending ~18 SASS instructions per MMA rebuilding 64-bit shared-memory descriptors inside a divergent
+// `if (lane == 0)` region (waterfall loop + R2UR per operand): the tensor pipe idled at 18-20 %.  Here the WHOLE warp runs the issue loop
+// (warp-uniform control flow, so descriptor words stay in uniform registers), the descriptor's constant high word is folded in
+// (128-byte swizzle, SBO = 1024, version 1), the low word is (addr >> 4) | (LBO >> 4) << 16 and advances by plain 32-bit adds, and the
+// instruction itself is predicated on one elected lane.
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo_kmajor(uint32_t saddr) { return (saddr >> 4) | (1u << 16); }            // LBO = 16 (unused)
+__device__ __forceinline__ uint32_t desc_lo_mnmajor(uint32_t saddr, uint32_t lbo_bytes) { return (saddr >> 4) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t lo_a, uint32_t lo_b, uint32_t idesc, uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %6};\n"
+      "mov.b64 db, {%2, %6};\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.ne.b32 q, %5, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
+      "}\n"
+      ::"r"(tmem_d), "r"(lo_a), "r"(lo_b), "r"(idesc), "r"(accumulate), "r"(leader), "r"(kDescHiSw128)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_if(uint64_t* bar, uint32_t leader) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.b32 q, %1, 0;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(leader)
+      : "memory");
+}
+// cta_group::2 flavours of the lean issue path (the pair GEMM): same descriptor low-word arithmetic, leader CTA's elected lane issues
+__device__ __forceinline__ void umma_bf16_pair_lo(uint32_t tmem_d, uint32_t lo_a, uint32_t lo_b, uint32_t idesc, uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %6};\n"
+      "mov.b64 db, {%2, %6};\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.ne.b32 q, %5, 0;\n"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n"
+      "}\n"
+      ::"r"(tmem_d), "r"(lo_a), "r"(lo_b), "r"(idesc), "r"(accumulate), "r"(leader), "r"(kDescHiSw128)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_if(uint64_t* bar, uint32_t leader) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.b32 q, %2, 0;\n"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+      "}\n" ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3)), "r"(leader)
+      : "memory");
+}
 // Arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -248,7 +248,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // MMA issue: whole warp in uniform control flow, one elected lane issues (umma_bf16_lo: ~2 instructions per MMA instead of ~9)
+      const uint32_t leader = elect_one() ? 1u : 0u;
       constexpr uint32_t idesc = make_idesc_bf16(CV_BM, BN, 0, 0);
       int stage = 0; uint32_t phase = 0; int slot = 0; uint32_t sphase = 0; int as = 0; uint32_t aphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -256,12 +257,12 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * (MSUB * BN);
         for (int it = 0; it < num_items; ++it) {
-          uint32_t sa0[MSUB];
+          uint32_t la0[MSUB];
           int slots[MSUB];
 #pragma unroll
           for (int sub = 0; sub < MSUB; ++sub) {
             mbar_wait(&full_a[slot], sphase);
-            sa0[sub] = smem_u32(smem_a + slot * Cfg::kAItemBytes);
+            la0[sub] = desc_lo_kmajor(smem_u32(smem_a + slot * Cfg::kAItemBytes));
             slots[sub] = slot;
             if (++slot == Cfg::kAItems) { slot = 0; sphase ^= 1; }
           }
@@ -271,21 +272,21 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
             // tap tt reads the window shifted down by tt*dil rows: rows sit at a 128-byte pitch (SBO = 8 rows = 1024 B) and the
             // 128-byte swizzle is a function of the shared-memory ADDRESS bits [7,10), so a shift by any number of rows is a plain
             // start-address offset with the descriptor's base-offset field left 0 (measured: setting it to shift%8 gives wrong sums)
-            const uint32_t shift = static_cast<uint32_t>(tt * p.dil) * 128u;
-            const uint64_t db = make_smem_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes), 16, 1024);
+            const uint32_t shift = static_cast<uint32_t>(tt * p.dil) * (128u >> 4);
+            const uint32_t lb = desc_lo_kmajor(smem_u32(smem_b + stage * Cfg::kBBytes));
 #pragma unroll
             for (int sub = 0; sub < MSUB; ++sub) {
-              const uint64_t da = make_smem_desc_sw128(sa0[sub] + shift, 16, 1024);
 #pragma unroll
-              for (int k = 0; k < CV_BK / 16; ++k) umma_bf16(tmem_d + sub * BN, da + 2 * k, db + 2 * k, idesc, (it | tt | k) != 0);
+              for (int k = 0; k < CV_BK / 16; ++k)
+                umma_bf16_lo(tmem_d + sub * BN, la0[sub] + shift + 2 * k, lb + 2 * k, idesc, (it | tt | k) != 0, leader);
             }
-            umma_commit(&empty_b[stage]);
+            umma_commit_if(&empty_b[stage], leader);
             if (++stage == Cfg::kBStages) { stage = 0; phase ^= 1; }
           }
 #pragma unroll
-          for (int sub = 0; sub < MSUB; ++sub) umma_commit(&empty_a[slots[sub]]);
+          for (int sub = 0; sub < MSUB; ++sub) umma_commit_if(&empty_a[slots[sub]], leader);
         }
-        umma_commit(&tmem_full[as]);
+        umma_commit_if(&tmem_full[as], leader);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }

@@ -239,12 +239,16 @@ __global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && cta_rank == 0) {
+    if (cta_rank == 0) {
       // ===================== MMA issuer (leader CTA only in pair mode) =====================
+      // The whole warp walks the loop in uniform control flow and one elected lane issues (umma_bf16_lo in common.cuh): the
+      // descriptor low words live in uniform registers and advance by 32-bit adds.  Before, ~25 SASS instructions of 64-bit
+      // descriptor arithmetic + a waterfall loop separated consecutive MMAs - more than the 96-cycle 256x192x16 pair MMA itself.
+      const uint32_t leader = elect_one() ? 1u : 0u;
       const uint32_t idesc = make_idesc_bf16(BLOCK_M * CTAS, BN, a_mn ? 1u : 0u, b_mn ? 1u : 0u);
       // per UMMA_K step: K-major advances 32 B inside the swizzle row; MN-major advances 16 k-rows = 2048 B
       const uint32_t a_step = a_mn ? (2048u >> 4) : 2u, b_step = b_mn ? (2048u >> 4) : 2u;
-      const uint32_t a_lbo = a_mn ? 8192u : 16u, b_lbo = b_mn ? 8192u : 16u;
+      const uint32_t a_hi = (a_mn ? (8192u >> 4) : 1u) << 16, b_hi = (b_mn ? (8192u >> 4) : 1u) << 16;
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -259,18 +263,17 @@ __global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constan
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
-          const uint64_t da = make_smem_desc_sw128(sa, a_lbo, 1024);
-          const uint64_t db = make_smem_desc_sw128(sb, b_lbo, 1024);
+          const uint32_t la = (sa >> 4) | a_hi;
+          const uint32_t lb = ((sa + Cfg::kABytes) >> 4) | b_hi;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            if (CTAS == 2) umma_bf16_pair(tmem_d, da + a_step * k, db + b_step * k, idesc, (kb != kb_begin) || (k != 0));
-            else umma_bf16(tmem_d, da + a_step * k, db + b_step * k, idesc, (kb != kb_begin) || (k != 0));
+            if (CTAS == 2) umma_bf16_pair_lo(tmem_d, la + a_step * k, lb + b_step * k, idesc, (kb != kb_begin) || (k != 0), leader);
+            else umma_bf16_lo(tmem_d, la + a_step * k, lb + b_step * k, idesc, (kb != kb_begin) || (k != 0), leader);
           }
-          if (CTAS == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+          if (CTAS == 2) umma_commit_pair_if(&empty_bar[stage], leader); else umma_commit_if(&empty_bar[stage], leader);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        if (CTAS == 2) umma_commit_pair(&tmem_full[as]); else umma_commit(&tmem_full[as]);
+        if (CTAS == 2) umma_commit_pair_if(&tmem_full[as], leader); else umma_commit_if(&tmem_full[as], leader);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }

@@ -168,40 +168,42 @@ __global__ void __launch_bounds__(RU_THREADS, 1) residual_unit_tcgen05(const __g
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // MMA issue: whole warp in uniform control flow, one elected lane issues (umma_bf16_lo, common.cuh)
+      const uint32_t leader = elect_one() ? 1u : 0u;
       constexpr uint32_t idesc = make_idesc_bf16(128, RU_C, 0, 0);
       int stage = 0; uint32_t phase = 0; int slot = 0; uint32_t sphase = 0;
       uint32_t tphase = 0;   // per-tile parity of the single-stage accumulator barriers
+      const uint32_t lh0 = desc_lo_kmajor(smem_u32(smem_h));
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         // ---- conv7: accumulator 1 is free (h_full of the previous tile has been waited on below)
         for (int cib = 0; cib < 2; ++cib) {
-          uint32_t sa0[2];
+          uint32_t la0[2];
           int slots[2];
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
             mbar_wait(&full_a[slot], sphase);
-            sa0[sub] = smem_u32(smem_a + slot * RU_AITEM_BYTES);
+            la0[sub] = desc_lo_kmajor(smem_u32(smem_a + slot * RU_AITEM_BYTES));
             slots[sub] = slot;
             if (++slot == RU_AITEMS) { slot = 0; sphase ^= 1; }
           }
           for (int tt = 0; tt < RU_TAPS; ++tt) {
             mbar_wait(&full_b[stage], phase);
             tc_fence_after();
-            const uint32_t shift = static_cast<uint32_t>(tt * p.dil) * 128u;   // tap tt = the window shifted down tt*dil rows
-            const uint64_t db = make_smem_desc_sw128(smem_u32(smem_b + stage * RU_BBYTES), 16, 1024);
+            const uint32_t shift = static_cast<uint32_t>(tt * p.dil) * (128u >> 4);   // tap tt = the window shifted down tt*dil rows
+            const uint32_t lb = desc_lo_kmajor(smem_u32(smem_b + stage * RU_BBYTES));
 #pragma unroll
             for (int sub = 0; sub < 2; ++sub) {
-              const uint64_t da = make_smem_desc_sw128(sa0[sub] + shift, 16, 1024);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(tmem_acc1 + sub * RU_C, da + 2 * k, db + 2 * k, idesc, (cib | tt | k) != 0);
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_lo(tmem_acc1 + sub * RU_C, la0[sub] + shift + 2 * k, lb + 2 * k, idesc, (cib | tt | k) != 0, leader);
             }
-            umma_commit(&empty_b[stage]);
+            umma_commit_if(&empty_b[stage], leader);
             if (++stage == RU_BSTAGES) { stage = 0; phase ^= 1; }
           }
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub) umma_commit(&empty_a[slots[sub]]);
+          for (int sub = 0; sub < 2; ++sub) umma_commit_if(&empty_a[slots[sub]], leader);
         }
-        umma_commit(acc1_full);
+        umma_commit_if(acc1_full, leader);
         // ---- conv1 on the activated intermediate (H tiles written by the epilogue warps)
         mbar_wait(h_full, tphase);
         mbar_wait(acc2_empty, tphase ^ 1);
@@ -209,17 +211,17 @@ __global__ void __launch_bounds__(RU_THREADS, 1) residual_unit_tcgen05(const __g
         for (int kb = 0; kb < 2; ++kb) {
           mbar_wait(&full_b[stage], phase);
           tc_fence_after();
-          const uint64_t db = make_smem_desc_sw128(smem_u32(smem_b + stage * RU_BBYTES), 16, 1024);
+          const uint32_t lb = desc_lo_kmajor(smem_u32(smem_b + stage * RU_BBYTES));
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
-            const uint64_t dh = make_smem_desc_sw128(smem_u32(smem_h + (sub * 2 + kb) * 16384), 16, 1024);
+            const uint32_t lh = lh0 + (sub * 2 + kb) * (16384 >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tmem_acc2 + sub * RU_C, dh + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < 4; ++k) umma_bf16_lo(tmem_acc2 + sub * RU_C, lh + 2 * k, lb + 2 * k, idesc, (kb | k) != 0, leader);
           }
-          umma_commit(&empty_b[stage]);
+          umma_commit_if(&empty_b[stage], leader);
           if (++stage == RU_BSTAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(acc2_full);
+        umma_commit_if(acc2_full, leader);
         tphase ^= 1;
       }
     }
