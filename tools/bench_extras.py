@@ -19,41 +19,33 @@ def peaks():
 
 
 def measure_ae_train(args, dev, rank, world, dist):
-    """BASELINE.json configs[3], generator step of the warm-up phase (training/autoencoders.py:436-497 with `warmed_up` False: the
-    discriminator is not evaluated): Oobleck encode -> VAE -> decode, MRSTFT sum/difference + left + right + KL, backward, AdamW.
-    16 clips x 65536 samples per GPU (the config's 32 per GPU exceeds nothing but halves the steps timed; both fit)."""
+    """BASELINE.json configs[3], generator step of the warm-up phase (training/autoencoders.py:436-497 without a discriminator): Oobleck
+    encode -> VAE -> decode, MRSTFT sum/difference + left + right + KL, backward, fused AdamW + EMA (AutoencoderTrainingStep).
+    16 clips x 65536 samples per GPU."""
+    from b200sat.ae_training import AutoencoderTrainingStep
     from b200sat.autoencoder_train import OobleckTrainModel
-    from b200sat.stft_loss import SumAndDifferenceSTFTLoss, autoencoder_mrstft_terms
     B, T = 16, 65536
     g = torch.Generator(device=dev).manual_seed(11)
     model = OobleckTrainModel(_oobleck_state_dict(dev, g), device=dev)
-    opt = torch.optim.AdamW(model.parameters(), lr=1.5e-4, betas=(0.8, 0.99), fused=True)
     fft, hop = [2048, 1024, 512, 256, 128, 64, 32], [512, 256, 128, 64, 32, 16, 8]
-    loss_sd = SumAndDifferenceSTFTLoss(fft_sizes=fft, hop_sizes=hop, win_lengths=fft, perceptual_weighting=True, sample_rate=44100)
+    loss_config = {"spectral": {"type": "mrstft", "config": {"fft_sizes": fft, "hop_sizes": hop, "win_lengths": fft, "perceptual_weighting": True},
+                                "weights": {"mrstft": 1.0}},
+                   "time": {"type": "l1", "weights": {"l1": 0.0}}, "bottleneck": {"type": "kl", "weights": {"kl": 1e-4}}}
+    opt = {"autoencoder": {"optimizer": {"type": "AdamW", "config": {"betas": [0.8, 0.99], "lr": 1.5e-4, "weight_decay": 1e-3}}}}
+    allred = (lambda flat: dist.all_reduce(flat)) if world > 1 else None
+    step = AutoencoderTrainingStep(model, None, loss_config=loss_config, optimizer_configs=opt, sample_rate=44100, use_ema=True,
+                                   world_size=world, all_reduce=allred)
     gh = torch.Generator().manual_seed(42 + rank)
     h_audio = (torch.randn(B, 2, T, generator=gh).clamp(-1, 1) * 0.5).pin_memory()
     h_loss = torch.zeros(1).pin_memory()
-    params = list(model.parameters())
 
-    def step():
+    def one():
         reals = h_audio.to(dev, non_blocking=True)
-        noise = torch.randn(B, 64, T // 2048, device=dev, generator=g)
-        decoded, kl, _ = model(reals, noise)
-        sd_, l_, r_ = autoencoder_mrstft_terms(loss_sd, decoded, reals)
-        loss = sd_ + 0.5 * l_ + 0.5 * r_ + 1e-4 * kl
-        opt.zero_grad(set_to_none=True)
-        (loss / world).backward()
-        if world > 1:   # one flat bucket: 156 M fp32 gradients
-            flat = torch.cat([p.grad.view(-1) for p in params])
-            dist.all_reduce(flat)
-            off = 0
-            for p in params:
-                p.grad.copy_(flat[off:off + p.numel()].view_as(p)); off += p.numel()
-        opt.step()
-        h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+        loss, _ = step.training_step(reals, vae_noise=torch.randn(B, 64, T // 2048, device=dev, generator=g))
+        h_loss.copy_(loss.reshape(1), non_blocking=True)
 
     for _ in range(3):
-        step()
+        one()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -61,7 +53,7 @@ def measure_ae_train(args, dev, rank, world, dist):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(k):
-        step()
+        one()
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -72,92 +64,68 @@ def measure_ae_train(args, dev, rank, world, dist):
     pk = peaks()
     out = {"metric": "oobleck_generator_step_items_per_sec", "value": B * world / (ms_step * 1e-3), "unit": "clips/s", "ms_per_step": ms_step,
            "batch_per_gpu": B, "samples_per_clip": T, "loss": float(h_loss.item()),
-           "includes": "H2D audio, encoder+VAE+decoder fwd, 4-term MRSTFT + KL, full backward, (all-reduce), AdamW(fused), D2H loss",
+           "includes": "H2D audio, encoder+VAE+decoder fwd, 4-term MRSTFT + KL, full backward, (all-reduce), fused AdamW + EMA, D2H loss",
            "excludes": "adversarial / feature-matching terms (warm-up phase; see ae_adversarial for the post-warm-up steps)",
            "tflops_per_gpu": flop / (ms_step * 1e-3) / 1e12, "frac_of_sustained_peak": flop / (ms_step * 1e-3) / 1e12 / pk["bf16_sustained"]}
-    del model, opt
+    del model, step
     torch.cuda.empty_cache()
     return out
 
 
-def measure_ae_adversarial(args, dev, rank, world, dist):
+def measure_ae_adversarial(args, dev, rank, world, dist, B=32):
     """BASELINE.json configs[3] after warm-up (training/autoencoders.py:436-515): alternating discriminator / generator steps of the Oobleck
-    autoencoder with the EncodecDiscriminator (hinge + feature matching, weights 0.1 / 5.0), MRSTFT sum/difference + L/R and KL.
-    Minimal graphs: D step = AE forward (no grad) + D forward/backward on reals and fakes; G step = AE forward/backward + D forward on
-    both + D data-gradient through the fake path.  8 clips x 65536 samples per GPU; two consecutive steps (one D, one G) are timed."""
+    autoencoder with the EncodecDiscriminator (hinge + feature matching, weights 0.1 / 5.0), MRSTFT sum/difference + L/R and KL, through
+    b200sat.ae_training.AutoencoderTrainingStep (the reference's training_step semantics; fused AdamW + EMA per parameter group).
+    32 clips x 65536 samples per GPU; two consecutive D/G rounds are timed after two warm-up rounds."""
+    from b200sat.ae_training import AutoencoderTrainingStep
     from b200sat.autoencoder_train import OobleckTrainModel
     from b200sat.discriminator import EncodecDiscriminatorTrain
     from b200sat.init import encodec_disc_state_dict
-    from b200sat.stft_loss import SumAndDifferenceSTFTLoss, autoencoder_mrstft_terms
-    B, T = 8, 65536
+    T = 65536
     g = torch.Generator(device=dev).manual_seed(21)
     ae = OobleckTrainModel(_oobleck_state_dict(dev, g), device=dev)
     disc = EncodecDiscriminatorTrain(encodec_disc_state_dict(dev, g), device=dev)
-    opt_g = torch.optim.AdamW(ae.parameters(), lr=1.5e-4, betas=(0.8, 0.99), fused=True)
-    opt_d = torch.optim.AdamW(disc.parameters(), lr=3e-4, betas=(0.8, 0.99), fused=True)
     fft, hop = [2048, 1024, 512, 256, 128, 64, 32], [512, 256, 128, 64, 32, 16, 8]
-    loss_sd = SumAndDifferenceSTFTLoss(fft_sizes=fft, hop_sizes=hop, win_lengths=fft, perceptual_weighting=True, sample_rate=44100)
-    reals = (torch.randn(B, 2, T, device=dev, generator=g).clamp(-1, 1) * 0.5)
+    loss_config = {"discriminator": {"type": "encodec", "config": {"filters": 64, "n_ffts": fft[:5], "hop_lengths": hop[:5], "win_lengths": fft[:5]},
+                                     "weights": {"adversarial": 0.1, "feature_matching": 5.0}},
+                   "spectral": {"type": "mrstft", "config": {"fft_sizes": fft, "hop_sizes": hop, "win_lengths": fft, "perceptual_weighting": True},
+                                "weights": {"mrstft": 1.0}},
+                   "time": {"type": "l1", "weights": {"l1": 0.0}}, "bottleneck": {"type": "kl", "weights": {"kl": 1e-4}}}
+    opt = {"autoencoder": {"optimizer": {"type": "AdamW", "config": {"betas": [0.8, 0.99], "lr": 1.5e-4, "weight_decay": 1e-3}}},
+           "discriminator": {"optimizer": {"type": "AdamW", "config": {"betas": [0.8, 0.99], "lr": 3e-4, "weight_decay": 1e-3}}}}
+    allred = (lambda flat: dist.all_reduce(flat)) if world > 1 else None
+    step = AutoencoderTrainingStep(ae, disc, loss_config=loss_config, optimizer_configs=opt, sample_rate=44100, warmup_steps=0, use_ema=True,
+                                   world_size=world, all_reduce=allred)
+    gh = torch.Generator().manual_seed(42 + rank)
+    reals = (torch.randn(B, 2, T, generator=gh).clamp(-1, 1) * 0.5).to(dev)
 
-    def allreduce(params):
-        if world > 1:
-            flat = torch.cat([p.grad.view(-1) for p in params])
-            dist.all_reduce(flat)
-            off = 0
-            for p in params:
-                p.grad.copy_(flat[off:off + p.numel()].view_as(p)); off += p.numel()
+    def one():
+        return step.training_step(reals, vae_noise=torch.randn(B, 64, T // 2048, device=dev, generator=g))
 
-    def d_step():
-        noise = torch.randn(B, 64, T // 2048, device=dev, generator=g)
-        with torch.no_grad():
-            decoded = ae(reals, noise)[0]
-        dis = disc.discriminator_loss(reals, decoded)
-        opt_d.zero_grad(set_to_none=True)
-        (dis / world).backward()
-        allreduce(list(disc.parameters()))
-        opt_d.step()
-        return dis
-
-    def g_step():
-        noise = torch.randn(B, 64, T // 2048, device=dev, generator=g)
-        decoded, kl, _ = ae(reals, noise)
-        sd_, l_, r_ = autoencoder_mrstft_terms(loss_sd, decoded, reals)
-        adv, fm = disc.generator_terms(reals, decoded)
-        loss = sd_ + 0.5 * l_ + 0.5 * r_ + 1e-4 * kl + 0.1 * adv + 5.0 * fm
-        opt_g.zero_grad(set_to_none=True)
-        (loss / world).backward()
-        allreduce(list(ae.parameters()))
-        opt_g.step()
-        return loss
-
-    for _ in range(2):      # two warm-up rounds: the caching allocator sees both steps' buffer sizes in both orders
-        d_step(); g_step()
+    for _ in range(4):      # two warm-up rounds (G, D, G, D): the caching allocator sees both steps' buffer sizes in both orders
+        one()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    logs = []
     ev[0].record()
-    d = d_step()
-    ev[1].record()
-    l = g_step()
-    ev[2].record()
-    d = d_step()
-    ev[3].record()
-    l = g_step()
-    ev[4].record()
+    for i in range(4):
+        logs.append(one())
+        ev[i + 1].record()
     torch.cuda.synchronize()
-    t_d = 0.5 * (ev[0].elapsed_time(ev[1]) + ev[2].elapsed_time(ev[3]))
-    t_g = 0.5 * (ev[1].elapsed_time(ev[2]) + ev[3].elapsed_time(ev[4]))
+    t_g = 0.5 * (ev[0].elapsed_time(ev[1]) + ev[2].elapsed_time(ev[3]))     # global_step even: generator
+    t_d = 0.5 * (ev[1].elapsed_time(ev[2]) + ev[3].elapsed_time(ev[4]))
     ms = torch.tensor([(t_d + t_g) / 2], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = ms.item()
     flop = B * 2.86e12      # SURVEY 8d: mean of the G step (2.44 TFLOP/item) and the D step (3.27 TFLOP/item), minimal graphs
     out = {"metric": "oobleck_adversarial_step_items_per_sec", "value": B * world / (ms_step * 1e-3), "unit": "clips/s", "ms_per_step": ms_step,
-           "d_step_ms": t_d, "g_step_ms": t_g, "batch_per_gpu": B, "samples_per_clip": T, "dis_loss": float(d.detach()), "gen_loss": float(l.detach()),
-           "includes": "one discriminator step and one generator step (mean), AdamW(fused) on each parameter group, (all-reduce)",
+           "d_step_ms": t_d, "g_step_ms": t_g, "batch_per_gpu": B, "samples_per_clip": T, "gen_loss": float(logs[2][0]), "dis_loss": float(logs[3][0]),
+           "includes": "one generator step and one discriminator step (mean) through AutoencoderTrainingStep: fused AdamW (+ EMA on the generator) per group, (all-reduce)",
            "tflops_per_gpu": flop / (ms_step * 1e-3) / 1e12, "frac_of_sustained_peak": flop / (ms_step * 1e-3) / 1e12 / peaks()["bf16_sustained"]}
-    del ae, disc, opt_g, opt_d
+    del ae, disc, step
     torch.cuda.empty_cache()
     return out
 
@@ -263,12 +231,13 @@ def other_kernels(dev, pk):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
     gf = 0.55 * 8  # ~0.55 GFLOP fp32 per item per generator step
-    out.append({"kernel": "MRSTFT (FIR + 7-resolution Stockham STFT + loss sums), 8 x 2 x 65536, all four generator-loss terms", "bound": "hbm",
-                "achieved": 8 * 2 * 2 * 65536 * 4 / ms / 1e6, "peak": pk["hbm"], "unit": "GB/s", "frac": 8 * 2 * 2 * 65536 * 4 / ms / 1e6 / pk["hbm"], "ms": ms,
-                "gflops_fp32": gf / ms, "reference_materialised_traffic_gbs": 8 * 120e6 / ms / 1e6,
-                "note": "fused: 8.4 MB of waveforms in, 84 scalars out; bound by fp32 SIMT/shared memory, not HBM (frac is vs the HBM peak only "
-                        "because the contract wants one; the reference moves ~120 MB per item through HBM for the same result, "
-                        "reference_materialised_traffic_gbs is that traffic divided by our time)"})
+    fp32_peak_tflops = 148 * 128 * 2 * 1.9e9 / 1e12      # 148 SMs x 128 FMA lanes x 2 flop x ~1.9 GHz
+    out.append({"kernel": "MRSTFT (FIR + 7-resolution Stockham STFT + loss sums), 8 x 2 x 65536, all four generator-loss terms", "bound": "fp32 SIMT / shared memory",
+                "achieved": gf / ms, "peak": fp32_peak_tflops, "unit": "TFLOP/s (fp32, algorithmic 0.55 GFLOP per item)", "frac": gf / ms / fp32_peak_tflops, "ms": ms,
+                "hbm_GBps_algorithmic": 8 * 2 * 2 * 65536 * 4 / ms / 1e6, "reference_materialised_traffic_gbs": 8 * 120e6 / ms / 1e6,
+                "note": "fused: 8.4 MB of waveforms in, 84 scalars out: the algorithmic HBM traffic is negligible, so the row is stated against the fp32 "
+                        "FMA peak (nominal, 148 SMs x 128 lanes x 2 x 1.9 GHz); the reference moves ~120 MB per item through HBM for the same result "
+                        "(reference_materialised_traffic_gbs = that traffic divided by our time)"})
     return out
 
 
