@@ -75,6 +75,26 @@ def main():
     out = {"reals": reals.numpy()}
     for k, v in disc_sd.items():
         out["disc_init." + k] = v.numpy()
+    # diagnostics for the generator loss terms on a FIXED decoded signal (the step-0 reconstruction): value and gradient w.r.t. the
+    # decoded audio of every term, computed with the wrapper's own loss modules (AuralossLoss order: module(reals, decoded))
+    with torch.no_grad():
+        torch.manual_seed(100)
+        lat0, _ = ae.encode(reals, return_info=True)
+        dec0 = ae.decode(lat0)
+    out["diag.decoded"] = dec0.numpy().copy()
+    terms = {
+        "mrstft": lambda d: wrap.sdstft(reals, d),
+        "left": lambda d: wrap.lrstft(reals[:, 0:1], d[:, 0:1]),
+        "right": lambda d: wrap.lrstft(reals[:, 1:2], d[:, 1:2]),
+        "adv": lambda d: disc.loss(reals=reals, fakes=d)[1],
+        "fm": lambda d: disc.loss(reals=reals, fakes=d)[2],
+    }
+    for name, fn in terms.items():
+        leaf = dec0.clone().requires_grad_(True)
+        val = fn(leaf)
+        (g_,) = torch.autograd.grad(val, leaf)
+        out[f"diag.value.{name}"] = np.float64(val.detach())
+        out[f"diag.grad.{name}"] = g_.numpy().copy()
     for step in range(4):
         wrap.global_step = step
         torch.manual_seed(100 + step)

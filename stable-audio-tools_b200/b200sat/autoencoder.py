@@ -151,7 +151,10 @@ class OobleckEngine:
         """Three ResidualUnits (autoencoders.py:58-83).  x_raw: input planes; x_act = snake_{ru0.s0}(x_raw).
         Returns (raw, act) of the last unit where act = next_snake(raw) (or None)."""
         B, T, C = x_raw.B, x_raw.T, x_raw.C
-        fused = self.passes == 1 and C == 128 and os.environ.get("B200SAT_FUSED_RU", "1") != "0"
+        # B200SAT_FUSED_RU=1: one launch per unit (csrc/residual_unit.cu).  Measured on B200 (tools/ru_bench.py, T = 2 097 152): fused 983 us
+        # vs 386 + 447 us for the two launches - both are EPILOGUE-bound (SnakeBeta: ~10 instructions per element), so serialising the
+        # two epilogues on the same warps costs more than the 1.1 GB of HBM traffic it saves.  Off by default.
+        fused = self.passes == 1 and C == 128 and os.environ.get("B200SAT_FUSED_RU", "0") == "1"
         for j, ru in enumerate(rus):
             dil = (1, 3, 9)[j]
             if fused:

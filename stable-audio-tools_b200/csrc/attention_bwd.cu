@@ -147,9 +147,15 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
 // (S, dP) DOUBLE-BUFFERED in TMEM so the MMA thread runs two tiles ahead, operand tiles (P^T / dS^T / dS) double-buffered in
 // shared memory so the accumulate MMAs of tile j overlap the softmax math of tile j+1.  Accumulators never leave TMEM.
 constexpr int BW_HT = 64 * 64 * 2;  // a 64 x 64 bf16 tile = 8 KB
-constexpr int BW_STAGES = 4;    // inner-tile ring: the scores of tile j+3 are issued while tiles j+1, j+2 still wait for their accumulate MMAs
+// Inner-tile TMA rings.  A stage is held from the issue of a tile's score MMAs until its accumulate MMAs retire, i.e. for BW_NB = 3
+// iterations, so a ring of S stages gives the NEXT load only S - 3 iterations of lead.  Round 2 (ncu source view: the softmax warps'
+// top stall was the spin on s_full, the MMA warp's the spin on the ring's full barrier): with 4 stages the lead was one iteration
+// ~ 1 us ~ the L2 -> shared-memory latency of a TMA tile, so every iteration waited for its load.  Now 6 (dK/dV kernel, 224 KB of
+// shared memory) and 8 (dQ kernel) stages.
+constexpr int DKV_STAGES = 6;
+constexpr int DQ_STAGES = 8;
 constexpr int BW_NB = 3;       // score-tile buffers in TMEM and operand-tile buffers in shared memory (MMA thread runs BW_NB tiles ahead)
-constexpr int DKV_SMEM = 2 * BW_T /*K,V*/ + BW_STAGES * 2 * BW_HT /*(Q,dO) ring*/ + BW_NB * BW_T /*P^T*/ + BW_NB * BW_T /*dS^T*/ + 2 * BW_NB * 64 * 4 + 256;
+constexpr int DKV_SMEM = 2 * BW_T /*K,V*/ + DKV_STAGES * 2 * BW_HT /*(Q,dO) ring*/ + BW_NB * BW_T /*P^T*/ + BW_NB * BW_T /*dS^T*/ + 2 * BW_NB * 64 * 4 + 256;
 
 // SW = number of softmax warps: 8 (two threads per score row, 32 columns each) or 16 (four threads per row, 16 columns each).
 // Round 2: the kernels hold ONE CTA per SM (192 KB of tiles, all 512 TMEM columns), so 8 warps = 2 per scheduler could not hide the
@@ -162,18 +168,18 @@ __global__ void __launch_bounds__(64 + SW * 32, 1) attention_bwd_dkv_tcgen05(con
   uint8_t* sK = smem;
   uint8_t* sV = smem + BW_T;
   uint8_t* sRing = smem + 2 * BW_T;                         // stage s: Q tile (64 rows) at + s*2*BW_HT, dO tile at + BW_HT
-  uint8_t* sPT = sRing + BW_STAGES * 2 * BW_HT;             // BW_NB buffers of [128 keys x 64 queries]
+  uint8_t* sPT = sRing + DKV_STAGES * 2 * BW_HT;             // BW_NB buffers of [128 keys x 64 queries]
   uint8_t* sdST = sPT + BW_NB * BW_T;
   float* s_lse = reinterpret_cast<float*>(sdST + BW_NB * BW_T); // [BW_NB][64] (pre-multiplied by log2 e)
   float* s_delta = s_lse + BW_NB * 64;                          // [BW_NB][64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + BW_NB * 64);
   uint64_t* kv_full = bars + 0;
-  uint64_t* qdo_full = bars + 1;    // [BW_STAGES]
-  uint64_t* qdo_empty = bars + 5;   // [BW_STAGES]
-  uint64_t* s_full = bars + 9;      // [BW_NB]
-  uint64_t* p_full = bars + 12;     // [BW_NB]
-  uint64_t* acc_free = bars + 15;   // [BW_NB] accumulate MMAs of a tile retired: its P^T / dS^T buffer is reusable
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* qdo_full = bars + 1;                      // [DKV_STAGES]
+  uint64_t* qdo_empty = qdo_full + DKV_STAGES;        // [DKV_STAGES]
+  uint64_t* s_full = qdo_empty + DKV_STAGES;          // [BW_NB]
+  uint64_t* p_full = s_full + BW_NB;                  // [BW_NB]
+  uint64_t* acc_free = p_full + BW_NB;                // [BW_NB] accumulate MMAs of a tile retired: its P^T / dS^T buffer is reusable
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_free + BW_NB);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * 128;
@@ -186,7 +192,7 @@ __global__ void __launch_bounds__(64 + SW * 32, 1) attention_bwd_dkv_tcgen05(con
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
     mbar_init(kv_full, 1);
-    for (int i = 0; i < BW_STAGES; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+    for (int i = 0; i < DKV_STAGES; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
     for (int i = 0; i < BW_NB; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], NT); mbar_init(&acc_free[i], 1); }
     fence_barrier_init();
   }
@@ -206,9 +212,9 @@ __global__ void __launch_bounds__(64 + SW * 32, 1) attention_bwd_dkv_tcgen05(con
       tma_load_4d(sK, &p.tmK, kv_full, 0, hk, k0, b);
       tma_load_4d(sV, &p.tmV, kv_full, 0, hk, k0, b);
       for (int it = 0; it < iters; ++it) {
-        const int s = it % BW_STAGES;
+        const int s = it % DKV_STAGES;
         const int h = hk * G + it / nq, qt = it % nq;
-        mbar_wait(&qdo_empty[s], ((it / BW_STAGES) & 1) ^ 1);
+        mbar_wait(&qdo_empty[s], ((it / DKV_STAGES) & 1) ^ 1);
         mbar_arrive_expect_tx(&qdo_full[s], 2 * BW_HT);
         tma_load_4d(sRing + s * 2 * BW_HT, &p.tmQ, &qdo_full[s], 0, h, qt * 64, b);
         tma_load_4d(sRing + s * 2 * BW_HT + BW_HT, &p.tmdO, &qdo_full[s], 0, h, qt * 64, b);
@@ -226,8 +232,8 @@ __global__ void __launch_bounds__(64 + SW * 32, 1) attention_bwd_dkv_tcgen05(con
     const uint32_t loPT0 = desc_lo_kmajor(smem_u32(sPT)), lodST0 = desc_lo_kmajor(smem_u32(sdST));
     constexpr uint32_t kStageStep = (2 * BW_HT) >> 4, kBufStep = BW_T >> 4;
     auto issue_scores = [&](int it) {
-      const int s = it % BW_STAGES;
-      mbar_wait(&qdo_full[s], (it / BW_STAGES) & 1);
+      const int s = it % DKV_STAGES;
+      mbar_wait(&qdo_full[s], (it / DKV_STAGES) & 1);
       tc_fence_after();
       const uint32_t loQ = loQ0 + s * kStageStep, lodO = lodO0 + s * kStageStep;
       const uint32_t tS = tmem_base + (it % BW_NB) * 64, tP = tmem_base + 192 + (it % BW_NB) * 64;
@@ -240,7 +246,7 @@ __global__ void __launch_bounds__(64 + SW * 32, 1) attention_bwd_dkv_tcgen05(con
     mbar_wait(kv_full, 0);
     for (int i = 0; i < BW_NB && i < iters; ++i) issue_scores(i);
     for (int it = 0; it < iters; ++it) {
-      const int s = it % BW_STAGES;
+      const int s = it % DKV_STAGES;
       mbar_wait(&p_full[it % BW_NB], (it / BW_NB) & 1);
       tc_fence_after();
       const uint32_t loQm = loQm0 + s * kStageStep, lodOm = lodOm0 + s * kStageStep;
@@ -344,7 +350,7 @@ __global__ void __launch_bounds__(64 + SW * 32, 1) attention_bwd_dkv_tcgen05(con
 }
 
 // ------------------------------------------------------------------------------------------------------------
-constexpr int DQ_SMEM = 2 * BW_T /*Q,dO*/ + BW_STAGES * 2 * BW_HT /*(K,V) ring*/ + BW_NB * BW_T /*dS*/ + 256;
+constexpr int DQ_SMEM = 2 * BW_T /*Q,dO*/ + DQ_STAGES * 2 * BW_HT /*(K,V) ring*/ + BW_NB * BW_T /*dS*/ + 256;
 
 template <int SW>
 __global__ void __launch_bounds__(64 + SW * 32, 1) attention_bwd_dq_tcgen05(const __grid_constant__ AttnBwdParams p) {
@@ -354,15 +360,15 @@ __global__ void __launch_bounds__(64 + SW * 32, 1) attention_bwd_dq_tcgen05(cons
   uint8_t* sQ = smem;
   uint8_t* sdO = smem + BW_T;
   uint8_t* sRing = smem + 2 * BW_T;                       // stage s: K tile (64 keys) at + s*2*BW_HT, V tile at + BW_HT
-  uint8_t* sdS = sRing + BW_STAGES * 2 * BW_HT;           // 2 buffers of [128 queries x 64 keys]
+  uint8_t* sdS = sRing + DQ_STAGES * 2 * BW_HT;           // 2 buffers of [128 queries x 64 keys]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + BW_NB * BW_T);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;    // [BW_STAGES]
-  uint64_t* kv_empty = bars + 5;   // [BW_STAGES]
-  uint64_t* s_full = bars + 9;     // [BW_NB]
-  uint64_t* p_full = bars + 12;    // [BW_NB]
-  uint64_t* acc_free = bars + 15;  // [BW_NB]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* kv_full = bars + 1;                       // [DQ_STAGES]
+  uint64_t* kv_empty = kv_full + DQ_STAGES;           // [DQ_STAGES]
+  uint64_t* s_full = kv_empty + DQ_STAGES;            // [BW_NB]
+  uint64_t* p_full = s_full + BW_NB;                  // [BW_NB]
+  uint64_t* acc_free = p_full + BW_NB;                // [BW_NB]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_free + BW_NB);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128;
@@ -374,7 +380,7 @@ __global__ void __launch_bounds__(64 + SW * 32, 1) attention_bwd_dq_tcgen05(cons
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
     mbar_init(q_full, 1);
-    for (int i = 0; i < BW_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < DQ_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < BW_NB; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], NT); mbar_init(&acc_free[i], 1); }
     fence_barrier_init();
   }
@@ -394,8 +400,8 @@ __global__ void __launch_bounds__(64 + SW * 32, 1) attention_bwd_dq_tcgen05(cons
       tma_load_4d(sQ, &p.tmQ, q_full, 0, h, q0, b);
       tma_load_4d(sdO, &p.tmdO, q_full, 0, h, q0, b);
       for (int j = 0; j < nkv; ++j) {
-        const int s = j % BW_STAGES;
-        mbar_wait(&kv_empty[s], ((j / BW_STAGES) & 1) ^ 1);
+        const int s = j % DQ_STAGES;
+        mbar_wait(&kv_empty[s], ((j / DQ_STAGES) & 1) ^ 1);
         mbar_arrive_expect_tx(&kv_full[s], 2 * BW_HT);
         tma_load_4d(sRing + s * 2 * BW_HT, &p.tmK, &kv_full[s], 0, hk, j * 64, b);
         tma_load_4d(sRing + s * 2 * BW_HT + BW_HT, &p.tmV, &kv_full[s], 0, hk, j * 64, b);
@@ -411,8 +417,8 @@ __global__ void __launch_bounds__(64 + SW * 32, 1) attention_bwd_dq_tcgen05(cons
     const uint32_t lodS0 = desc_lo_kmajor(smem_u32(sdS));
     constexpr uint32_t kStageStep = (2 * BW_HT) >> 4, kBufStep = BW_T >> 4;
     auto issue_scores = [&](int j) {
-      const int s = j % BW_STAGES;
-      mbar_wait(&kv_full[s], (j / BW_STAGES) & 1);
+      const int s = j % DQ_STAGES;
+      mbar_wait(&kv_full[s], (j / DQ_STAGES) & 1);
       tc_fence_after();
       const uint32_t loK = loK0 + s * kStageStep, loV = loV0 + s * kStageStep;
       const uint32_t tS = tmem_base + (j % BW_NB) * 64, tP = tmem_base + 192 + (j % BW_NB) * 64;
@@ -425,7 +431,7 @@ __global__ void __launch_bounds__(64 + SW * 32, 1) attention_bwd_dq_tcgen05(cons
     mbar_wait(q_full, 0);
     for (int i = 0; i < BW_NB && i < nkv; ++i) issue_scores(i);
     for (int j = 0; j < nkv; ++j) {
-      const int s = j % BW_STAGES;
+      const int s = j % DQ_STAGES;
       mbar_wait(&p_full[j % BW_NB], (j / BW_NB) & 1);
       tc_fence_after();
       const uint32_t loKm = loKm0 + s * kStageStep;

@@ -74,7 +74,7 @@ __device__ __forceinline__ void ru_snake32(float* v, const float* a, const float
     const float aa[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float sn = fast_sin(v[4 * i + e] * aa[e]);
+      const float sn = __sinf(v[4 * i + e] * aa[e]);   // bf16 output: the SFU sine's own range handling is accurate enough
       v[4 * i + e] += bb[e] * sn * sn;
     }
   }

@@ -22,6 +22,42 @@ def _cos(a, b):
     return float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-30))
 
 
+def test_generator_loss_terms_on_a_fixed_reconstruction():
+    """Every term of the generator loss, value and gradient w.r.t. the decoded audio, on the golden step-0 reconstruction (the
+    wrapper's own loss modules produced the reference): isolates the loss kernels from the autoencoder backward."""
+    from b200sat.discriminator import EncodecDiscriminatorTrain
+    from b200sat.stft_loss import SumAndDifferenceSTFTLoss, autoencoder_mrstft_terms
+    G = np.load(GOLD, allow_pickle=False)
+    meta = json.loads(str(G["meta"]))
+    dev = "cuda"
+    reals = torch.from_numpy(G["reals"]).to(dev)
+    dec0 = torch.from_numpy(G["diag.decoded"]).to(dev)
+    stft = SumAndDifferenceSTFTLoss(sample_rate=44100, **meta["loss_config"]["spectral"]["config"])
+    dsd = {k[len("disc_init."):]: torch.from_numpy(G[k]) for k in G.files if k.startswith("disc_init.")}
+    disc = EncodecDiscriminatorTrain(dsd, n_ffts=tuple(meta["disc_fft"]), hop_lengths=tuple(meta["disc_hop"]), device=dev)
+
+    def grad_of(fn):
+        leaf = dec0.clone().requires_grad_(True)
+        val = fn(leaf)
+        (g,) = torch.autograd.grad(val, leaf)
+        return float(val), g
+
+    results = {}
+    for i, name in enumerate(("mrstft", "left", "right")):
+        results[name] = grad_of(lambda d, i=i: autoencoder_mrstft_terms(stft, d, reals)[i])
+    results["adv"] = grad_of(lambda d: disc.generator_terms(reals, d)[0])
+    results["fm"] = grad_of(lambda d: disc.generator_terms(reals, d)[1])
+    bad = []
+    for name, (val, g) in results.items():
+        ref_v, ref_g = float(G[f"diag.value.{name}"]), torch.from_numpy(G[f"diag.grad.{name}"]).to(dev)
+        c = _cos(g, ref_g)
+        nr = float(g.norm() / ref_g.norm())
+        print(f"\n[T2 term {name:7s}] value ours {val:+.6f} reference {ref_v:+.6f} | grad cos {c:.5f} norm ratio {nr:.4f}")
+        if abs(val - ref_v) > 2e-3 * abs(ref_v) + 1e-4 or c < 0.999 or abs(nr - 1) > 2e-2:
+            bad.append(name)
+    assert not bad, bad
+
+
 def test_four_steps_match_the_reference_wrapper():
     from oracle import oobleck as oo
     from b200sat.ae_training import AutoencoderTrainingStep
