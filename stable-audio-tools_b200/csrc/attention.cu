@@ -55,13 +55,18 @@ __global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_con
   uint8_t* sKV = smem + AT_QT;                                   // stage s: K at + s*2*AT_KT, V at + AT_KT
   uint8_t* sP = sKV + AT_KV_STAGES * 2 * AT_KT;                  // 2 x [128 rows x 64 keys]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * AT_QT);
+  // K and V tiles travel through SEPARATE rings (round 2): a K stage is free again as soon as its S = Q K^T MMAs retire, a V stage
+  // only after P V - with one shared ring every stage was held for ~3 iterations, the next load got a lead of less than one
+  // iteration (~1 us ~ the L2 -> shared-memory latency of a TMA tile), and each CTA's iteration time sat at that latency.
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;    // [3]
-  uint64_t* kv_empty = bars + 4;   // [3]
-  uint64_t* s_full = bars + 7;     // [2]
-  uint64_t* p_full = bars + 9;     // [2]
-  uint64_t* pv_done = bars + 11;   // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* k_full = bars + 1;                       // [AT_KV_STAGES]
+  uint64_t* k_empty = k_full + AT_KV_STAGES;
+  uint64_t* v_full = k_empty + AT_KV_STAGES;
+  uint64_t* v_empty = v_full + AT_KV_STAGES;
+  uint64_t* s_full = v_empty + AT_KV_STAGES;         // [2]
+  uint64_t* p_full = s_full + 2;                     // [2]
+  uint64_t* pv_done = p_full + 2;                    // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pv_done + 2);
   __nv_bfloat16* s_max = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5;
@@ -78,7 +83,7 @@ __global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_con
     tma_prefetch_desc(&p.tmK);
     tma_prefetch_desc(&p.tmV);
     mbar_init(q_full, 1);
-    for (int i = 0; i < AT_KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < AT_KV_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 256); mbar_init(&pv_done[i], 1); }
     fence_barrier_init();
   }
@@ -95,16 +100,21 @@ __global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_con
   const uint32_t tmem_O = tmem_base + 128;   // 64 fp32 columns; S buffers at +0 and +64
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (lane == 0) {          // Q, then the K tiles
       mbar_arrive_expect_tx(q_full, AT_QT);
       tma_load_4d(sQ, &p.tmQ, q_full, 0, h, q0, b);
       for (int j = 0; j < num_kv; ++j) {
         const int s = j % AT_KV_STAGES;
-        const uint32_t ph = (j / AT_KV_STAGES) & 1;
-        mbar_wait(&kv_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], 2 * AT_KT);
-        tma_load_4d(sKV + s * 2 * AT_KT, &p.tmK, &kv_full[s], 0, hkv, j * AT_BN, b);
-        tma_load_4d(sKV + s * 2 * AT_KT + AT_KT, &p.tmV, &kv_full[s], 0, hkv, j * AT_BN, b);
+        mbar_wait(&k_empty[s], ((j / AT_KV_STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[s], AT_KT);
+        tma_load_4d(sKV + s * 2 * AT_KT, &p.tmK, &k_full[s], 0, hkv, j * AT_BN, b);
+      }
+    } else if (lane == 1) {   // the V tiles, on their own ring so they never hold a K stage back
+      for (int j = 0; j < num_kv; ++j) {
+        const int s = j % AT_KV_STAGES;
+        mbar_wait(&v_empty[s], ((j / AT_KV_STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[s], AT_KT);
+        tma_load_4d(sKV + s * 2 * AT_KT + AT_KT, &p.tmV, &v_full[s], 0, hkv, j * AT_BN, b);
       }
     }
   } else if (warp == 1) {
@@ -118,13 +128,14 @@ __global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_con
     const uint32_t loP0 = desc_lo_kmajor(smem_u32(sP));
     auto issue_s = [&](int j) {
       const int s = j % AT_KV_STAGES;
-      mbar_wait(&kv_full[s], (j / AT_KV_STAGES) & 1);
+      mbar_wait(&k_full[s], (j / AT_KV_STAGES) & 1);
       tc_fence_after();
       const uint32_t loK = loK0 + s * ((2 * AT_KT) >> 4);
       const uint32_t tS = tmem_base + (j & 1) * 64;
 #pragma unroll
       for (int k = 0; k < AT_D / 16; ++k) umma_bf16_lo(tS, loQ + 2 * k, loK + 2 * k, idesc_s, k != 0, leader);
       umma_commit_if(&s_full[j & 1], leader);
+      umma_commit_if(&k_empty[s], leader);       // the K stage is reusable as soon as these MMAs retire
     };
     mbar_wait(q_full, 0);
     issue_s(0);
@@ -132,13 +143,14 @@ __global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_con
     for (int j = 0; j < num_kv; ++j) {
       const int s = j % AT_KV_STAGES;
       mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+      mbar_wait(&v_full[s], (j / AT_KV_STAGES) & 1);
       tc_fence_after();
       const uint32_t loP = loP0 + (j & 1) * (AT_QT >> 4);
       const uint32_t loV = loV0 + s * ((2 * AT_KT) >> 4);
 #pragma unroll
       for (int k = 0; k < AT_BN / 16; ++k) umma_bf16_lo(tmem_O, loP + 2 * k, loV + 128 * k, idesc_o, (j | k) != 0, leader);
       umma_commit_if(&pv_done[j & 1], leader);
-      umma_commit_if(&kv_empty[s], leader);
+      umma_commit_if(&v_empty[s], leader);
       if (j + 2 < num_kv) issue_s(j + 2);   // its S buffer was consumed before p_full(j) completed
     }
   } else {
