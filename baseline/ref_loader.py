@@ -142,6 +142,7 @@ def install_stubs():
     _kdiffusion_standin()
     _stub("einops_exts", rearrange_many=lambda *a, **k: None)
     _stub("wandb")
+    _stub("webdataset")      # data/dataset.py imports it at module top; only the S3/WebDataset loaders use it
     _stub("audiotools")      # training/losses/semantic.py imports it at module top; only HubertLoss/PESQ-style metrics use it
     _stub("auraloss")
     # pytorch_lightning: the training wrappers subclass pl.LightningModule and use .device / .log_dict / .trainer / .all_gather

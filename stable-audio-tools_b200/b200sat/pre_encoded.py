@@ -3,14 +3,12 @@
 Writer  = `pre_encode.py:39-125` (`PreEncodedLatentsInferenceWrapper.validation_step`): one `{rank:03d}{batch:06d}{i:04d}.npy` ([C, N]
           fp32 latents) + `.json` (metadata with the padding mask nearest-interpolated to the latent length) per clip under
           `<output>/<rank>/`, plus `<output>/details.json`.
-Reader  = `data/dataset.py:265-360` (`PreEncodedDataset`): crop to `latent_crop_length` (random start inside the un-padded part when
-          `random_crop`), min/max length filtering, `info["audio"] = latents`.
-The on-disk format is the reference's, byte-compatible in both directions, so a dataset pre-encoded by either side trains the other
+Reader  = the reference's own `PreEncodedDataset` (`data/dataset.py:265-360`), imported unchanged (`reference_dataset()` below).
+The on-disk format is the reference's, so a dataset pre-encoded here trains the unmodified reference and vice versa
 (`pre_encoded: true`, training/diffusion.py:344, 376-379).  Encoding runs on `OobleckEngine.encode_audio` (8 ms per 47 s clip on B200).
 """
 import json
 import os
-import random
 
 import numpy as np
 import torch
@@ -58,62 +56,12 @@ def write_pre_encoded(encode_fn, audio, metadata, output_path, rank=0, batch_idx
     return paths
 
 
-def _latent_files(path, ext):
-    out = []
-    for root, _, files in os.walk(path):
-        for fn in files:
-            if fn.endswith("." + ext) and not fn.startswith("."):
-                out.append(os.path.join(root, fn))
-    return sorted(out)
-
-
-class PreEncodedDataset(torch.utils.data.Dataset):
-    """`stable_audio_tools.data.dataset.PreEncodedDataset` semantics over plain directory paths."""
-
-    def __init__(self, paths, latent_crop_length=None, min_length_sec=None, max_length_sec=None, random_crop=False, latent_extension="npy",
-                 custom_metadata_fns=None):
-        super().__init__()
-        if isinstance(paths, (str, os.PathLike)):
-            paths = [paths]
-        self.latent_extension = latent_extension
-        self.filenames = []
-        for p in paths:
-            self.filenames.extend(_latent_files(str(p), latent_extension))
-        self.custom_metadata_fns = dict(custom_metadata_fns or {})
-        self.latent_crop_length = latent_crop_length
-        self.random_crop = random_crop
-        self.min_length_sec, self.max_length_sec = min_length_sec, max_length_sec
-
-    def __len__(self):
-        return len(self.filenames)
-
-    def __getitem__(self, idx):
-        fn = self.filenames[idx]
-        latents = torch.from_numpy(np.load(fn))   # [C, N]
-        with open(fn[: -len(self.latent_extension) - 1] + ".json") as f:
-            info = json.load(f)
-        info["latent_filename"] = fn
-        if self.latent_crop_length is not None:
-            pm = info["padding_mask"]
-            last_ix = len(pm) - 1 - pm[::-1].index(1)
-            start = random.randint(0, last_ix - self.latent_crop_length) if (self.random_crop and last_ix > self.latent_crop_length) else 0
-            latents = latents[:, start:start + self.latent_crop_length]
-            info["padding_mask"] = pm[start:start + self.latent_crop_length]
-            info["latent_crop_length"] = self.latent_crop_length
-            info["latent_crop_start"] = start
-        info["padding_mask"] = [torch.tensor(info["padding_mask"])]
-        seconds_total = info.get("seconds_total")
-        if seconds_total is not None:
-            if self.min_length_sec is not None and seconds_total < self.min_length_sec:
-                return self[random.randrange(len(self))]
-            if self.max_length_sec is not None and seconds_total > self.max_length_sec:
-                return self[random.randrange(len(self))]
-        for root, fn_ in self.custom_metadata_fns.items():
-            if root in fn:
-                info.update(fn_(info, None))
-            if info.get("__reject__"):
-                return self[random.randrange(len(self))]
-            if info.get("__replace__") is not None:
-                latents = info["__replace__"]
-        info["audio"] = latents
-        return latents, info
+def reference_dataset(paths, **kw):
+    """The READER is the reference's own class (`stable_audio_tools.data.dataset.PreEncodedDataset`, data/dataset.py:265-360) — the data
+    layer is out of the hot path's scope and is reused as-is; this helper only builds its `LocalDatasetConfig` list from plain paths.
+    Needs the reference package importable (and its `webdataset` dependency, or a stand-in module of that name)."""
+    from stable_audio_tools.data.dataset import LocalDatasetConfig, PreEncodedDataset
+    if isinstance(paths, (str, os.PathLike)):
+        paths = [paths]
+    cfgs = [LocalDatasetConfig(id=f"pre_encoded_{i}", path=str(p)) for i, p in enumerate(paths)]
+    return PreEncodedDataset(cfgs, **kw)

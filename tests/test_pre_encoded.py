@@ -42,13 +42,19 @@ def test_write_then_read_reference_layout(tmp_path):
     assert np.load(paths[1]).shape == (64, 64) and np.load(paths[1]).dtype == np.float32
     j = json.load(open(paths[2][:-4] + ".json"))
     assert len(j["padding_mask"]) == 64 and sum(j["padding_mask"]) == 64 - 16 and j["prompt"] == "clip 2"
-    ds = pe.PreEncodedDataset(str(tmp_path), latent_crop_length=32, random_crop=True)
+    # the reader is the REFERENCE's PreEncodedDataset, unmodified (baseline/_ref): our files must satisfy it
+    from baseline import ref_loader
+    if not ref_loader.available():
+        return
+    ref_loader.load(force_sdpa=True)
+    ds = pe.reference_dataset(str(tmp_path), latent_crop_length=32, random_crop=True)
     assert len(ds) == 3
     lat, info = ds[1]
     assert lat.shape == (64, 32) and info["audio"] is lat and info["padding_mask"][0].shape == (32,)
-    assert 0 <= info["latent_crop_start"] <= 64 - 8 - 1 - 32 + 32 and info["seconds_total"] == 11.0
-    full = torch.from_numpy(np.load(paths[1]))
+    k = paths.index(info["latent_filename"])                      # the reference does not sort its file list
+    assert info["seconds_total"] == 10.0 + k and 0 <= info["latent_crop_start"] <= 64
+    full = torch.from_numpy(np.load(paths[k]))
     assert torch.equal(lat, full[:, info["latent_crop_start"]:info["latent_crop_start"] + 32])
-    ds2 = pe.PreEncodedDataset([str(tmp_path)], min_length_sec=11.5)
+    ds2 = pe.reference_dataset([str(tmp_path)], min_length_sec=11.5)
     for i in range(3):
         assert ds2[i][1]["seconds_total"] >= 11.5
