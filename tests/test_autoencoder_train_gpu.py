@@ -141,6 +141,39 @@ def _oracle_step(sd, x, noise, wy, kl_w, strides, bf16_emulation=False):
     return y.detach(), kl.detach(), {k: v.grad for k, v in leaves.items()}
 
 
+@pytest.mark.parametrize("flat", [False, True])
+def test_oobleck_training_gradients_three_block_config(flat):
+    """Same check on the 3-block configuration of the assembled-step golden (channels 64, c_mults 1/2/4, strides 2/4/4, 128-step latent),
+    with and without the parameters re-homed into one flat buffer (b200sat.optim.FlatParameters)."""
+    from oracle import oobleck as oo
+    from b200sat.autoencoder_train import OobleckTrainModel
+    from b200sat.optim import FlatParameters
+    strides = (2, 4, 4)
+    sd = oo.make_state_dict(channels=64, c_mults=(1, 2, 4), strides=strides, enc_latent=128, dec_latent=64, seed=61)
+    g = torch.Generator().manual_seed(7)
+    B, T = 2, 4096
+    x = torch.randn(B, 2, T, generator=g).clamp(-1, 1) * 0.5
+    noise = torch.randn(B, 64, T // 32, generator=g)
+    wy = torch.randn(B, 2, T, generator=g) / math.sqrt(T)
+    kl_w = 1e-4
+    y_ref, kl_ref, g_ref = _oracle_step(sd, x, noise, wy, kl_w, strides)
+    y_emu, _, g_emu = _oracle_step(sd, x, noise, wy, kl_w, strides, bf16_emulation=True)
+    model = OobleckTrainModel(sd, strides=strides)
+    if flat:
+        fp = FlatParameters(list(model.parameters()))
+        fp.zero_grad()
+    y, kl, _ = model(x.cuda(), noise.cuda())
+    ((y * wy.cuda()).sum() + kl_w * kl).backward()
+    torch.cuda.synchronize()
+    allg = torch.cat([getattr(model, n.replace(".", "__")).grad.cpu().view(-1) for n in model.names])
+    allr = torch.cat([g_ref[n].view(-1) for n in model.names])
+    alle = torch.cat([g_emu[n].view(-1) for n in model.names])
+    worst = sorted(((_cos(getattr(model, n.replace(".", "__")).grad.cpu().view(-1), g_ref[n].view(-1)), n) for n in model.names))[:5]
+    print(f"\n[3-block AE grads flat={flat}] output rel {_rel(y.detach().cpu(), y_ref):.3e} | global cos {_cos(allg, allr):.4f} rel {_rel(allg, allr):.3f} "
+          f"| bf16-emulated oracle rel {_rel(alle, allr):.3f} | worst per-tensor cos {worst}")
+    assert _rel(allg, allr) <= 1.5 * _rel(alle, allr) + 2e-2
+
+
 def test_oobleck_training_gradients_match_oracle_autograd():
     """Every parameter gradient vs fp32 autograd through the oracle.  Bar: the error may not exceed 1.5x what the same network has
     when only its conv boundaries are rounded to bf16 (the oracle with a rounding shim) plus 2 % - i.e. the engine adds no error of
