@@ -7,11 +7,12 @@ asynchronous all-reduce per finished layer on a side stream, so the exchange of 
 layers i-1 ... 0; buckets are layer-sized (>= 64 MB: NVSwitch cost is launch-latency, not link-count, bound).  The mean is
 obtained by scaling the loss by 1/world_size before backward (no extra pass over 4.2 GB of gradients).
 
-SM sharing (round-2 finding): the persistent GEMM kernels launch one CTA per SM.  An NCCL kernel that occupies 16-32 SMs while a
-GEMM launches forces the GEMM's last CTAs into a second wave behind the collective (the +7 ms / step measured at N = 2 in round 1).
-So (a) the gradient all-reduce runs on its own communicator limited to `nccl_ctas` CTAs (NVSwitch needs few CTAs for the
-bandwidth this exchange requires: 4.2 GB per ~50 ms of backward), and (b) while reductions are in flight the library sizes its
-persistent grids for `num_sms - sm_reserve` SMs (`b200sat_set_sm_limit`), restored in `finish()`.
+SM sharing (round-2 experiment, tools/ddp2_ab.sh, 2 x B200): the persistent GEMM kernels launch one CTA per SM, so an NCCL kernel
+that holds SMs while a GEMM launches could push the GEMM's last CTAs into a second wave.  Two knobs exist for that: a dedicated
+communicator limited to `nccl_ctas` CTAs (B200SAT_DDP_NCCL_CTAS) and a reduced persistent-grid size while reductions are in flight
+(`b200sat_set_sm_limit`, B200SAT_DDP_SM_RESERVE).  Measured step times: defaults off 152.8 ms, 8 CTAs / 16 SMs 154.6 ms, 4 / 8 160.2 ms,
+16 / 32 156.0 ms (single-GPU step on the same pool: ~150 ms) - no gain, so both default to OFF; the exposed cost of the exchange at
+N = 2 is ~2-3 ms (the last layer's bucket and the optimizer step waiting for it), not SM contention.
 """
 import os
 
@@ -40,9 +41,9 @@ class GradAllReducer:
         self.cuda = model.flat_grad.is_cuda
         self.stream = torch.cuda.Stream() if self.cuda else None
         if nccl_ctas is None:
-            nccl_ctas = int(os.environ.get("B200SAT_DDP_NCCL_CTAS", "8"))
+            nccl_ctas = int(os.environ.get("B200SAT_DDP_NCCL_CTAS", "0"))
         if sm_reserve is None:
-            sm_reserve = int(os.environ.get("B200SAT_DDP_SM_RESERVE", "16"))
+            sm_reserve = int(os.environ.get("B200SAT_DDP_SM_RESERVE", "0"))
         self.sm_reserve = sm_reserve if (self.cuda and self.world > 1) else 0
         self.group = group
         self.nccl_ctas = 0
