@@ -30,6 +30,27 @@ def main():
         glob = torch.randn(1, 1536, device=dev, generator=g)
         fn = lambda: sampling.sample_k_dpmpp_3m_sde(eng, noise, 3, 0.03, 1000.0, 1.0, cross, glob, 7.0, 0.0, use_graph=False)
         warm = 1
+    elif what == "ae_train":
+        # one generator + one discriminator step of the assembled autoencoder training step, 4 clips x 65536 samples
+        from b200sat.ae_training import AutoencoderTrainingStep
+        from b200sat.autoencoder_train import OobleckTrainModel
+        from b200sat.discriminator import EncodecDiscriminatorTrain
+        from b200sat.init import encodec_disc_state_dict
+        g = torch.Generator(device=dev).manual_seed(21)
+        ae = OobleckTrainModel(bench._oobleck_state_dict(dev, g), device=dev)
+        disc = EncodecDiscriminatorTrain(encodec_disc_state_dict(dev, g), device=dev)
+        fft, hop = [2048, 1024, 512, 256, 128, 64, 32], [512, 256, 128, 64, 32, 16, 8]
+        lc = {"discriminator": {"type": "encodec", "config": {}, "weights": {"adversarial": 0.1, "feature_matching": 5.0}},
+              "spectral": {"type": "mrstft", "config": {"fft_sizes": fft, "hop_sizes": hop, "win_lengths": fft, "perceptual_weighting": True}, "weights": {"mrstft": 1.0}},
+              "time": {"type": "l1", "weights": {"l1": 0.0}}, "bottleneck": {"type": "kl", "weights": {"kl": 1e-4}}}
+        oc = {"autoencoder": {"optimizer": {"type": "AdamW", "config": {"betas": [0.8, 0.99], "lr": 1.5e-4, "weight_decay": 1e-3}}},
+              "discriminator": {"optimizer": {"type": "AdamW", "config": {"betas": [0.8, 0.99], "lr": 3e-4, "weight_decay": 1e-3}}}}
+        st = AutoencoderTrainingStep(ae, disc, loss_config=lc, optimizer_configs=oc, use_ema=True)
+        reals = torch.randn(4, 2, 65536, device=dev, generator=g).clamp(-1, 1) * 0.5
+
+        def fn():
+            st.training_step(reals); st.training_step(reals)
+        warm = 1
     elif what == "ae":
         from b200sat.autoencoder import OobleckEngine
         ae = OobleckEngine(bench._oobleck_state_dict(dev, torch.Generator(device=dev).manual_seed(3)), precision="bf16", device=dev)
