@@ -52,6 +52,10 @@ struct ConvParams {
   float leaky;       // > 0: LeakyReLU slope applied to the raw output (nn.LeakyReLU(0.2), encodec.py:68)
   int window;        // 1: stride-1 conv whose taps share one (128 + (taps-1)*dil)-row A window per channel block
   int win_rows;      // rows of one A item: 128 + (taps-1)*dil in window mode, 128 otherwise
+  // shared-memory layout chosen per launch (launch_conv): A items of exactly the window's size and one 2 KB transposition buffer per
+  // epilogue warp when only one bf16 plane is written leave room for a deeper weight ring (round 2: a ring stage covers ~512 MMA
+  // cycles, so 4 stages gave the weight loads ~1.5k cycles of lead - less than a TMA tile's L2 latency; the tensor pipe sat at 55-60 %)
+  int a_item_bytes, b_stages, stg_warp_bytes;
 };
 
 constexpr int CV_BM = 128;
@@ -68,10 +72,12 @@ struct ConvCfg {
   static constexpr int kAItemBytes = 24 * 1024;            // up to 192 rows x 128 B
   static constexpr int kAItems = (MSUB == 2) ? 4 : ((BN == 256) ? 2 : 3);
   static constexpr int kBBytes = BN * CV_BK * 2;
-  static constexpr int kBStages = (MSUB == 2) ? 4 : ((BN == 256) ? 3 : 5);
+  static constexpr int kBStagesMin = (MSUB == 2) ? 4 : ((BN == 256) ? 3 : 5);
+  static constexpr int kBStagesMax = 8;
   static constexpr int kTmemCols = 2 * MSUB * BN;
   static constexpr int kStagingBytes = 16 * 4096;  // two 32-row x 64-byte transposition buffers (raw, activated) per epilogue warp
-  static constexpr int kSmemBytes = kAItems * kAItemBytes + kBStages * kBBytes + kStagingBytes + 1024 + 512;
+  static constexpr int kSmemMax = 227 * 1024;
+  static constexpr int kFixedBytes = 1024 /*align slack*/ + 512 /*barriers*/;
   static_assert(kTmemCols <= 512, "TMEM has 512 columns");
 };
 
@@ -134,14 +140,15 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + Cfg::kAItems * Cfg::kAItemBytes;
-  uint8_t* stage_base = smem_b + Cfg::kBStages * Cfg::kBBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + Cfg::kStagingBytes);
+  const int a_item_bytes = p.a_item_bytes, nb = p.b_stages;
+  uint8_t* smem_b = smem + Cfg::kAItems * a_item_bytes;
+  uint8_t* stage_base = smem_b + nb * Cfg::kBBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + CV_EPI_WARPS * p.stg_warp_bytes);
   uint64_t* full_a = bars;
   uint64_t* empty_a = full_a + Cfg::kAItems;
   uint64_t* full_b = empty_a + Cfg::kAItems;
-  uint64_t* empty_b = full_b + Cfg::kBStages;
-  uint64_t* tmem_full = empty_b + Cfg::kBStages;
+  uint64_t* empty_b = full_b + nb;
+  uint64_t* tmem_full = empty_b + nb;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* res_bar = tmem_empty + 2;                       // one per epilogue warp (TMA residual loads)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + CV_EPI_WARPS);
@@ -163,7 +170,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::kAItems; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
-    for (int i = 0; i < Cfg::kBStages; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
+    for (int i = 0; i < nb; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CV_EPI_WARPS * 32); }
     for (int i = 0; i < CV_EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
@@ -207,7 +214,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
             mbar_wait(&empty_b[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full_b[stage], Cfg::kBBytes);
             tma_load_2d(smem_b + stage * Cfg::kBBytes, &p.tmB[b_plane], &full_b[stage], tap * p.Cin + cib * CV_BK, ph * p.Cout + n_blk * BN);
-            if (++stage == Cfg::kBStages) { stage = 0; phase ^= 1; }
+            if (++stage == nb) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -241,7 +248,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
           for (int sub = 0; sub < MSUB; ++sub) {
             mbar_wait(&empty_a[slot], phase ^ 1);
             mbar_arrive_expect_tx(&full_a[slot], item_bytes);
-            tma_load_4d(smem_a + slot * Cfg::kAItemBytes, &p.tmA[a_plane], &full_a[slot], cib * CV_BK, r, m0 + sub * 128 + row_off, b);
+            tma_load_4d(smem_a + slot * a_item_bytes, &p.tmA[a_plane], &full_a[slot], cib * CV_BK, r, m0 + sub * 128 + row_off, b);
             if (++slot == Cfg::kAItems) { slot = 0; phase ^= 1; }
           }
         }
@@ -262,7 +269,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
 #pragma unroll
           for (int sub = 0; sub < MSUB; ++sub) {
             mbar_wait(&full_a[slot], sphase);
-            la0[sub] = desc_lo_kmajor(smem_u32(smem_a + slot * Cfg::kAItemBytes));
+            la0[sub] = desc_lo_kmajor(smem_u32(smem_a + slot * a_item_bytes));
             slots[sub] = slot;
             if (++slot == Cfg::kAItems) { slot = 0; sphase ^= 1; }
           }
@@ -281,7 +288,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
                 umma_bf16_lo(tmem_d + sub * BN, la0[sub] + shift + 2 * k, lb + 2 * k, idesc, (it | tt | k) != 0, leader);
             }
             umma_commit_if(&empty_b[stage], leader);
-            if (++stage == Cfg::kBStages) { stage = 0; phase ^= 1; }
+            if (++stage == nb) { stage = 0; phase ^= 1; }
           }
 #pragma unroll
           for (int sub = 0; sub < MSUB; ++sub) umma_commit_if(&empty_a[slots[sub]], leader);
@@ -295,8 +302,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
     const int q = ew & 3;                  // TMEM lane quarter = 32 rows of the tile
     const int cg = ew >> 2;                // column group: BN/4 consecutive columns
     constexpr int NB = BN / 128;           // 32-column blocks per warp per tile
-    const uint32_t stg_o = smem_u32(stage_base) + ew * 4096;   // raw values (the residual is staged here first, overwritten in place)
-    const uint32_t stg_a = stg_o + 2048;                       // activated values
+    uint8_t* stg_ptr = stage_base + ew * p.stg_warp_bytes;
+    const uint32_t stg_o = smem_u32(stg_ptr);                  // raw values (the residual is staged here first, overwritten in place)
+    const uint32_t stg_a = stg_o + (p.stg_warp_bytes - 2048);  // activated values (the same 2 KB when only one plane is produced)
     const int lrow = lane >> 2, lchunk = lane & 3;             // line side: 8 rows x 4 chunks per instruction
     const int swz = (lane >> 1) & 3;
     const uint32_t my_o = stg_o + lane * 64, my_a = stg_a + lane * 64;
@@ -356,7 +364,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
             tma_store_wait_read<0>();                   // the previous block's stores have read the buffers
             if (p.res_hi) {
               mbar_arrive_expect_tx(&res_bar[ew], 2048);
-              tma_load_4d(stage_base + ew * 4096, &p.tmRes, &res_bar[ew], col, tph, trow, b);
+              tma_load_4d(stg_ptr, &p.tmRes, &res_bar[ew], col, tph, trow, b);
             }
           }
           __syncwarp();
@@ -436,8 +444,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv1d_tcgen05(const __grid_con
           fence_proxy_async_smem();                     // generic-proxy writes of the buffers -> visible to the TMA engine
           __syncwarp();
           if (lane == 0) {
-            if (p.out_hi) tma_store_4d(&p.tmOut, stage_base + ew * 4096, col, tph, trow, b);
-            if (p.act_hi) tma_store_4d(&p.tmAct, stage_base + ew * 4096 + 2048, col, tph, trow, b);
+            if (p.out_hi) tma_store_4d(&p.tmOut, stg_ptr, col, tph, trow, b);
+            if (p.act_hi) tma_store_4d(&p.tmAct, stg_ptr + (p.stg_warp_bytes - 2048), col, tph, trow, b);
             tma_store_commit();
           }
         } else {
@@ -471,14 +479,29 @@ static int launch_conv(ConvParams& p, cudaStream_t stream) {
   using Cfg = ConvCfg<BN, MSUB>;
   static bool attr_set = false;
   if (!attr_set) {
-    B200SAT_CHECK_CUDA(cudaFuncSetAttribute(conv1d_tcgen05<BN, LO, MSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    B200SAT_CHECK_CUDA(cudaFuncSetAttribute(conv1d_tcgen05<BN, LO, MSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemMax));
     attr_set = true;
   }
+  // shared-memory layout: A items sized to the rows they hold, one transposition buffer per epilogue warp unless both a raw and an
+  // activated plane (or a staged residual next to an activated plane) are needed, the rest goes to the weight ring (<= 8 stages)
+  p.a_item_bytes = ((p.win_rows * 128 + 1023) / 1024) * 1024;
+  const bool two_bufs = p.act_hi && (p.out_hi || p.res_hi);
+  p.stg_warp_bytes = two_bufs ? 4096 : 2048;
+  {
+    static const int ring_env = [] { const char* e = getenv("B200SAT_CONV_BSTAGES"); return e ? atoi(e) : 0; }();   // A/B measurement
+    const int room = Cfg::kSmemMax - Cfg::kFixedBytes - Cfg::kAItems * p.a_item_bytes - CV_EPI_WARPS * p.stg_warp_bytes;
+    int nb = room / Cfg::kBBytes;
+    if (nb > Cfg::kBStagesMax) nb = Cfg::kBStagesMax;
+    if (ring_env > 0 && ring_env < nb) nb = ring_env;
+    if (nb < 2) { set_last_error("conv1d: shared memory does not fit two weight stages"); return B200SAT_EUNSUPPORTED; }
+    p.b_stages = nb;
+  }
+  const int smem_bytes = Cfg::kFixedBytes + Cfg::kAItems * p.a_item_bytes + p.b_stages * Cfg::kBBytes + CV_EPI_WARPS * p.stg_warp_bytes;
   p.m_tiles = (p.m_rows + CV_BM * MSUB - 1) / (CV_BM * MSUB);
   p.n_tiles = (p.Cout + BN - 1) / BN;
   const long tiles = static_cast<long>(p.m_tiles) * p.B * p.n_tiles * p.phases;
   const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-  conv1d_tcgen05<BN, LO, MSUB><<<grid, CV_THREADS, Cfg::kSmemBytes, stream>>>(p);
+  conv1d_tcgen05<BN, LO, MSUB><<<grid, CV_THREADS, smem_bytes, stream>>>(p);
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }

@@ -78,7 +78,9 @@ struct GemmCfg {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = (BN / CTAS) * BLOCK_K * 2;   // per CTA
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (192 * 1024) / kStageBytes > 8 ? 8 : (192 * 1024) / kStageBytes;
+  // ring depth: as many stages as 224 KB hold (<= 8).  A stage feeds 4 MMAs = 384-512 tensor-pipe cycles, so the previous 192 KB budget
+  // (6 stages at BN = 192 / 256) gave a load ~2k cycles of lead - about one L2 -> shared-memory TMA latency
+  static constexpr int kStages = (224 * 1024) / kStageBytes > 8 ? 8 : (224 * 1024) / kStageBytes;
   static constexpr int kAccStride = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns per accumulator stage
   static constexpr int kTmemCols = 2 * kAccStride;                            // two stages, power of two
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
