@@ -265,9 +265,11 @@ def load(force_sdpa=None):
     return ns
 
 
-def load_training():
-    """The Lightning training wrappers (training/diffusion.py, training/autoencoders.py) on the stand-ins above."""
-    load()
+def load_training(force_sdpa="keep"):
+    """The Lightning training wrappers (training/diffusion.py, training/autoencoders.py) on the stand-ins above.
+    force_sdpa="keep": leave the attention backend as the last load() decided."""
+    if force_sdpa != "keep" or "stable_audio_tools.models.transformer" not in sys.modules:
+        load(None if force_sdpa == "keep" else force_sdpa)
     # demo-time visualisation helpers (matplotlib, PIL, ...) are only called from the demo callbacks
     viz = lambda *a, **k: None
     if not _have("matplotlib"):
