@@ -315,16 +315,20 @@ class _DiscLossFn(torch.autograd.Function):
         ctx.eng, ctx.saved, ctx.meta, ctx.names = eng, saved, (n_logit, n_feat, shape), names
         ctx.need_fakes = fakes.requires_grad
         ctx.need_params = any(p.requires_grad for p in params)
+        ctx.set_materialize_grads(False)      # an output that took no part in the loss arrives as None, not as a zero tensor
         return dis, adv, fm
 
     @staticmethod
     def backward(ctx, d_dis, d_adv, d_fm):
         n_logit, n_feat, shape = ctx.meta
+        # Which side runs is decided by which outputs actually received a gradient: the reference's generator step back-propagates only
+        # adv / fm (-> fakes), its discriminator step only dis (-> parameters); running both every time doubled the backward.
         g_fakes = None
-        if ctx.need_fakes:
-            g_fakes = ctx.eng._generator_backward(ctx.saved, n_logit, n_feat, shape, float(d_adv), float(d_fm))
+        if ctx.need_fakes and (d_adv is not None or d_fm is not None):
+            g_fakes = ctx.eng._generator_backward(ctx.saved, n_logit, n_feat, shape, 0.0 if d_adv is None else float(d_adv),
+                                                  0.0 if d_fm is None else float(d_fm))
         g_params = (None,) * len(ctx.names)
-        if ctx.need_params:
+        if ctx.need_params and d_dis is not None:
             grads = _discriminator_backward(ctx.eng, ctx.saved, n_logit, shape[0])
             g_params = tuple(grads[n] * d_dis for n in ctx.names)
         ctx.saved = None

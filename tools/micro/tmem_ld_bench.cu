@@ -78,16 +78,24 @@ void run(int nwarps) {
   uint32_t* out; long long* clk;
   cudaMalloc(&out, grid * 576 * 4); cudaMalloc(&clk, grid * 8);
   bench<X, DEPTH><<<grid, 576>>>(out, clk, 16, nwarps);
+  cudaError_t e0 = cudaDeviceSynchronize();
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  cudaEventRecord(a);
   bench<X, DEPTH><<<grid, 576>>>(out, clk, reps, nwarps);
-  cudaDeviceSynchronize();
+  cudaEventRecord(b);
+  cudaError_t e1 = cudaDeviceSynchronize();
+  float ms = 0;
+  cudaEventElapsedTime(&ms, a, b);
   long long h[148];
-  cudaMemcpy(h, clk, grid * 8, cudaMemcpyDeviceToHost);
+  cudaError_t e2 = cudaMemcpy(h, clk, grid * 8, cudaMemcpyDeviceToHost);
   double avg = 0;
   for (int i = 0; i < grid; ++i) avg += h[i];
   avg /= grid;
   const double bytes = double(nwarps) * reps * X * DEPTH * 32 * 4;
-  printf("32x32b.x%-3d loads-in-flight %d  warps %2d : %7.1f B/clk/SM  (%.0f clk per 4 KB warp-load)  err=%s\n", X, DEPTH, nwarps, bytes / avg,
-         avg / (double(nwarps) * reps * X * DEPTH / 32.0) , cudaGetErrorString(cudaGetLastError()));
+  printf("32x32b.x%-3d loads-in-flight %d  warps %2d : %7.1f B/clk/SM  (%.0f clk per 4 KB warp-load; %.0f clk, %.3f ms => %.2f GHz)  err=%s/%s/%s\n", X, DEPTH,
+         nwarps, bytes / avg, avg / (double(nwarps) * reps * X * DEPTH / 32.0), avg, ms, avg / (ms * 1e6), cudaGetErrorString(e0), cudaGetErrorString(e1),
+         cudaGetErrorString(e2));
   cudaFree(out); cudaFree(clk);
 }
 
