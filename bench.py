@@ -262,7 +262,7 @@ class OurTrainer:
         self.model = DiTTrainModel(sd, device=dev)
         del sd
         self.opt = FusedAdamWEMA(self.model, lr=5e-5, betas=(0.9, 0.999), weight_decay=1e-3, ema=True)   # stable_audio_2_0.json:95-102
-        self.red = GradAllReducer(self.model)
+        self.red = GradAllReducer(self.model, optimizer=self.opt)     # optimizer-in-backward: slices updated behind the all-reduce
         self.ae = OobleckEngine(_oobleck_state_dict(dev, torch.Generator(device=dev).manual_seed(3)), precision="bf16", device=dev)
         B = TRAIN_BATCH
         g = torch.Generator().manual_seed(42 + rank)                      # train.py:30-33: seed + rank
@@ -287,6 +287,7 @@ class OurTrainer:
         t = self.sobol.draw(B)[:, 0].to(self.dev, non_blocking=True)
         self.model.zero_grad()
         loss = v_objective_loss(self.model, lat, noise, t, cross, glob, cfg_dropout_prob=0.1)
+        self.red.begin_step()
         (loss * self.red.loss_scale).backward()
         self.red.finish()
         self.opt.step()
@@ -555,7 +556,7 @@ def run_ours(args):
     pk = peaks()
     flop_dit = 3 * GFLOP_PER_TOKEN * 1e9 * TRAIN_BATCH * (T_LAT + 1)
     flop_step = flop_dit + TRAIN_BATCH * ENC_TFLOP_PER_CLIP * 1e12
-    nccl_cfg = {"nccl_ctas": tr.red.nccl_ctas, "sm_reserve": tr.red.sm_reserve} if world > 1 else None
+    nccl_cfg = {"optimizer_in_backward": tr.red.opt is not None, "nccl_ctas": tr.red.nccl_ctas, "sm_reserve": tr.red.sm_reserve}
     ff1 = [(tr.model._w(i, "ff.ff.0.proj.weight").clone(), tr.model._f32(i, "ff.ff.0.proj.bias").clone()) for i in range(DEPTH)] if rank == 0 and not args.quick else None
     tr.free()
     del tr

@@ -248,6 +248,8 @@ int b200sat_vae_sample_bwd(const void* dz, const void* ms, const float* noise, c
  * g' = g*grad_scale; m, v updated; p = p(1 - lr wd) - lr/(1-b1^t) * m / (sqrt(v/(1-b2^t)) + eps); ema = ema*ema_decay + p*(1-ema_decay)
  * (ema NULL = off); the first n_bf16 elements of p are also written as bf16 to w_bf16 (NULL = off).  One HBM pass for
  * torch.optim.AdamW + ema_pytorch.EMA.update (training/diffusion.py:239-247, 489-491; training/utils.py:60-79) + the weight cast.
+ * step | (1 << 24): "slice" launch - the call covers one layer's slice of the flat buffers and runs next to the backward pass on a side
+ * stream (b200sat/ddp.py): many short blocks instead of a grid-stride loop, so SM resources return to the backward's kernels quickly.
  * ema_before_step != 0: the EMA averages the weights as they were BEFORE this update — AutoencoderTrainingWrapper.training_step calls
  * autoencoder_ema.update() ahead of opt_gen.step() (training/autoencoders.py:499-506); 0 = after it (DiffusionCondTrainingWrapper). */
 int b200sat_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, void* w_bf16, long n, long n_bf16, float lr, float beta1,

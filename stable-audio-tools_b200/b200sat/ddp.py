@@ -34,8 +34,12 @@ def _grad_group(nccl_ctas):
 
 
 class GradAllReducer:
-    def __init__(self, model, group=None, nccl_ctas=None, sm_reserve=None):
+    def __init__(self, model, group=None, nccl_ctas=None, sm_reserve=None, optimizer=None):
+        """optimizer: a FusedAdamWEMA over `model` -> optimizer-in-backward: each finished layer's slice is all-reduced (N > 1) and then
+        updated on the side stream while the backward of the earlier layers is still running (works at N = 1 too: the 40 GB optimizer
+        pass hides behind the backward instead of following it).  Call `begin_step()` before backward, `finish()` + `optimizer.step()` after."""
         self.model = model
+        self.opt = optimizer if (optimizer is not None and model.flat_grad.is_cuda and os.environ.get("B200SAT_OPT_IN_BACKWARD", "1") != "0") else None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.works = []
         self.cuda = model.flat_grad.is_cuda
@@ -52,7 +56,7 @@ class GradAllReducer:
             if g is not None:
                 self.group, self.nccl_ctas = g, nccl_ctas
         self._limited = False
-        model.grad_ready_hook = self._on_layer if self.world > 1 else None
+        model.grad_ready_hook = self._on_layer if (self.world > 1 or self.opt is not None) else None
 
     @property
     def loss_scale(self):
@@ -70,23 +74,37 @@ class GradAllReducer:
             L.b200sat_set_sm_limit(0)
         self._limited = on
 
-    def _launch(self, t):
+    def begin_step(self):
+        if self.opt is not None:
+            self.opt.begin_step()
+
+    def _launch(self, t, off=None):
+        """All-reduce `t` (N > 1) and, in optimizer-in-backward mode, update elements [off, off + t.numel()) right behind it."""
         if self.cuda:
             self.stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.stream):
-                self.works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+                if self.world > 1:
+                    w = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                    if self.opt is not None:
+                        w.wait()                      # stream-side wait: the side stream continues after the collective, the host does not block
+                    else:
+                        self.works.append(w)
+                if self.opt is not None:
+                    self.opt.step_slice(off, t.numel(), self.stream.cuda_stream)
         else:
             self.works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def _on_layer(self, layer_index, grad_slice):
-        self._launch(grad_slice)
-        self._limit(True)      # every persistent kernel launched from here on leaves room for the collective
+        self._launch(grad_slice, layer_index * grad_slice.numel())
+        if self.world > 1:
+            self._limit(True)      # every persistent kernel launched from here on leaves room for the collective
 
     def finish(self):
-        """Call after loss.backward(): reduces the non-stack parameters and joins the side stream."""
-        if self.world == 1:
+        """Call after loss.backward(): handles the non-stack parameters and joins the side stream."""
+        if self.world == 1 and self.opt is None:
             return
-        self._launch(self.model.misc_grad_slice())
+        misc = self.model.misc_grad_slice()
+        self._launch(misc, self.model.flat_grad.numel() - misc.numel())
         for w in self.works:
             w.wait()
         self.works.clear()

@@ -79,8 +79,45 @@ class FusedAdamWEMA:
     def param_groups(self):
         return [{"lr": self.lr}]
 
+    # ---- optimizer-in-backward (b200sat.ddp.GradAllReducer(optimizer=...)): the update of a finished layer's slice runs on the
+    # reducer's side stream right after that layer's gradients are final (and all-reduced), overlapping the rest of the backward;
+    # `step()` then only closes the step.  A layer's weights are not read again in the step once its backward has run.
+    def begin_step(self):
+        self.t += 1
+        self._decay = ema_decay_at(self.t, **self.ema_cfg) if self.ema is not None else 0.0
+        self._sliced = 0
+
+    def step_slice(self, off, n, stream, grad_scale=1.0):
+        """AdamW (+ EMA, + bf16 refresh where the slice lies inside the working copy) on elements [off, off + n) of the flat buffers."""
+        mdl = self.model
+        w16 = getattr(mdl, "_bf", None)
+        n16 = 0
+        w16_ptr = 0
+        if w16 is not None and off < w16.numel():
+            n16 = min(n, w16.numel() - off) // 4 * 4
+            w16_ptr = w16.data_ptr() + 2 * off
+        f = lambda t: t.data_ptr() + 4 * off
+        rc = lib().b200sat_adamw_ema_step(f(mdl.flat), f(mdl.flat_grad), f(self.m), f(self.v), 0 if self.ema is None else f(self.ema), w16_ptr,
+                                          n, n16, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.t | (1 << 24), self._decay,
+                                          grad_scale, int(self.ema_before_step), stream)
+        ops.LAUNCHES[0] += 1
+        check(rc, "adamw_ema_step (slice)")
+        self._sliced += n
+
+    def end_step(self):
+        """All slices of this step have been issued: the bf16 working copy is fresh if it was covered."""
+        mdl = self.model
+        if self._sliced != self.n:
+            raise RuntimeError(f"optimizer-in-backward covered {self._sliced} of {self.n} elements")
+        if getattr(mdl, "_bf", None) is not None:
+            mdl._bf_fresh = True
+
     def step(self, grad_scale=1.0):
         mdl = self.model
+        if getattr(self, "_sliced", 0):       # the reducer already applied this step slice by slice
+            self.end_step()
+            self._sliced = 0
+            return
         self.t += 1
         decay = ema_decay_at(self.t, **self.ema_cfg) if self.ema is not None else 0.0
         w16 = getattr(mdl, "_bf", None)

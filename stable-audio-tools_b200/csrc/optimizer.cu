@@ -60,6 +60,10 @@ extern "C" int b200sat_adamw_ema_step(float* p, const float* g, float* m, float*
                                       int ema_before_step, void* stream) {
   if (!p || !g || !m || !v || n <= 0 || step < 1) { set_last_error("adamw_ema_step: bad arguments"); return B200SAT_EINVAL; }
   if ((n & 3) || (n_bf16 & 3) || n_bf16 > n) { set_last_error("adamw_ema_step: element counts must be multiples of 4 (pad the flat buffer)"); return B200SAT_EINVAL; }
+  // step >= (1 << 24) marks a per-layer slice launched on a side stream NEXT TO the backward pass (b200sat/ddp.py): many short blocks
+  // that leave the SM quickly instead of a grid-stride loop that would hold registers the persistent GEMM CTAs are waiting for
+  const bool slice = step >= (1 << 24);
+  if (slice) step -= (1 << 24);
   AdamArgs a;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
   a.bc1 = 1.f - powf(beta1, static_cast<float>(step));
@@ -68,7 +72,7 @@ extern "C" int b200sat_adamw_ema_step(float* p, const float* g, float* m, float*
   const long n4 = n >> 2;
   long blocks = (n4 + 255) / 256;
   const long cap = static_cast<long>(num_sms()) * 16;
-  if (blocks > cap) blocks = cap;
+  if (!slice && blocks > cap) blocks = cap;
   adamw_ema_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, ema, static_cast<__nv_bfloat16*>(w_bf16), n,
                                                                                              w_bf16 ? n_bf16 : 0, a);
   B200SAT_CHECK_CUDA(cudaGetLastError());

@@ -60,3 +60,37 @@ def test_dit_train_model_steps_with_fused_optimizer():
     assert losses[-1] < losses[0], losses
     assert torch.equal(model._bf, model.flat[: model.stack_numel].bfloat16())
     assert set(opt.ema_state_dict()) == set(model._p)
+
+
+def test_optimizer_in_backward_matches_the_monolithic_step():
+    """GradAllReducer(optimizer=...): per-layer AdamW slices issued on the side stream during the backward give bit-identical masters,
+    moments, EMA and bf16 working copy to one whole-buffer step after the backward (same kernel, same element-wise arithmetic)."""
+    from oracle import dit as odit
+    from b200sat.ddp import GradAllReducer
+    from b200sat.dit_train import DiTTrainModel, v_objective_loss
+    from b200sat.optim import FusedAdamWEMA
+    kw = dict(embed_dim=256, depth=3, num_heads=4, io_channels=64, cond_token_dim=128, global_cond_dim=256)
+    sd = odit.make_state_dict(seed=4, **kw)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x0 = torch.randn(2, 64, 128, device="cuda", generator=g); nz = torch.randn(2, 64, 128, device="cuda", generator=g)
+    t = torch.rand(2, device="cuda", generator=g); c = torch.randn(2, 9, 128, device="cuda", generator=g); ge = torch.randn(2, 256, device="cuda", generator=g)
+    runs = []
+    for in_backward in (False, True):
+        model = DiTTrainModel(sd)
+        opt = FusedAdamWEMA(model, lr=2e-3, weight_decay=1e-2, ema=True)
+        red = GradAllReducer(model, optimizer=opt if in_backward else None)
+        assert (red.opt is not None) == in_backward
+        for _ in range(3):
+            model.zero_grad()
+            loss = v_objective_loss(model, x0, nz, t, c, ge)
+            red.begin_step()
+            loss.backward()
+            red.finish()
+            opt.step()
+        torch.cuda.synchronize()
+        runs.append((model.flat.clone(), opt.m.clone(), opt.v.clone(), opt.ema.clone(), model._bf.clone(), float(loss)))
+    for a, b in zip(runs[0], runs[1]):
+        if torch.is_tensor(a):
+            assert torch.equal(a, b)
+        else:
+            assert a == b
