@@ -19,9 +19,31 @@
 namespace b200sat {
 
 __device__ __forceinline__ float fast_exp2(float x) {
+#if defined(AT_VARIANT) && (AT_VARIANT & 1)
+  return x * 0.001f + 1.0f;
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
+}
+
+// packed fp32 pairs (sm_100: FFMA2 / FADD2 issue two lanes per slot)
+__device__ __forceinline__ uint64_t pack_f32x2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
 }
 
 struct AttnParams {
@@ -39,8 +61,18 @@ constexpr int AT_D = 64;
 constexpr int AT_QT = AT_BM * AT_D * 2;   // 16 KB: Q tile, P tile (128 x 64 bf16)
 constexpr int AT_KT = AT_BN * AT_D * 2;   //  8 KB: K tile, V tile
 constexpr int AT_KV_STAGES = 3;
-constexpr int AT_SMEM = AT_QT /*Q*/ + AT_KV_STAGES * 2 * AT_KT /*K,V ring*/ + 2 * AT_QT /*P x2*/ + 256 /*barriers*/ + 512 /*row-max exchange*/;
-constexpr float AT_RESCALE_THRESHOLD = 8.0f;  // log2 units: O/l are only rescaled when the row max grows by more than 2^8
+constexpr int AT_SMEM = AT_QT /*Q*/ + AT_KV_STAGES * 2 * AT_KT /*K,V ring*/ + 2 * AT_QT /*P x2*/ + 256 /*barriers*/ + 1024 /*row-max exchange, two parities*/;
+constexpr float AT_RESCALE_THRESHOLD = 8.0f;
+// AT_VARIANT bit 7: per-tile timeline of one early and one late CTA (SM clock, low 32 bits) written over the start of p.lse:
+// region r (CTA (0,0,0) -> 0, CTA (4,12,4) -> 1), record [r][j][16]: slots 0-7 softmax warp 2, 8-12 MMA warp, 13-15 CTA entry / loop start / end.
+#define AT_TRACE(j, slot)                                                                                                     \
+  do {                                                                                                                        \
+    if ((AT_VARIANT & 128) && trace_region >= 0 && lane == 0)                                                                 \
+      reinterpret_cast<uint32_t*>(p.lse)[(trace_region * 64 + (j)) * 16 + (slot)] = static_cast<uint32_t>(clock64());         \
+  } while (0)
+#ifndef AT_VARIANT
+#define AT_VARIANT 0   // timing experiments only (tools/attn_variants.py): bit 0 no MUFU, 1 no pair exchange, 2 no max, 3 no P store, 4 no TMEM load
+#endif  // log2 units: O/l are only rescaled when the row max grows by more than 2^8
 
 // Pipeline (round-1 redesign after the ncu capture of the first version: tensor pipe 17 %, issue slots 31 %, every tile paid
 // four serial barrier hops S -> softmax -> P -> PV -> O read):
@@ -76,6 +108,8 @@ __global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_con
   const int b = blockIdx.z;
   const int hkv = h / (p.Hq / p.Hkv);
   const int num_kv = (p.Nk + AT_BN - 1) / AT_BN;
+  const int trace_region = (AT_VARIANT & 128) ? ((blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? 0 : (blockIdx.x == 4 && blockIdx.y == 12 && blockIdx.z == 4) ? 1 : -1) : -1;
+  if (warp == 2) AT_TRACE(0, 13);
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();  // the swizzled layouts need a 1024-byte aligned base
@@ -84,7 +118,7 @@ __global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_con
     tma_prefetch_desc(&p.tmV);
     mbar_init(q_full, 1);
     for (int i = 0; i < AT_KV_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 256); mbar_init(&pv_done[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], (AT_VARIANT & 256) ? 8 : 256); mbar_init(&pv_done[i], 1); }
     fence_barrier_init();
   }
   griddep_launch();
@@ -142,8 +176,11 @@ __global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_con
     if (num_kv > 1) issue_s(1);
     for (int j = 0; j < num_kv; ++j) {
       const int s = j % AT_KV_STAGES;
+      AT_TRACE(j, 8);
       mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+      AT_TRACE(j, 9);
       mbar_wait(&v_full[s], (j / AT_KV_STAGES) & 1);
+      AT_TRACE(j, 10);
       tc_fence_after();
       const uint32_t loP = loP0 + (j & 1) * (AT_QT >> 4);
       const uint32_t loV = loV0 + s * ((2 * AT_KT) >> 4);
@@ -151,7 +188,9 @@ __global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_con
       for (int k = 0; k < AT_BN / 16; ++k) umma_bf16_lo(tmem_O, loP + 2 * k, loV + 128 * k, idesc_o, (j | k) != 0, leader);
       umma_commit_if(&pv_done[j & 1], leader);
       umma_commit_if(&v_empty[s], leader);
+      AT_TRACE(j, 11);
       if (j + 2 < num_kv) issue_s(j + 2);   // its S buffer was consumed before p_full(j) completed
+      AT_TRACE(j, 12);
     }
   } else {
     // ===================== softmax / output warps: two threads per query row, 32 keys each per tile =====================
@@ -161,19 +200,30 @@ __global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_con
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     float m_run = -INFINITY, l_run = 0.f;
     const int sw = r & 7;
+    if (warp == 2) AT_TRACE(0, 14);
     __nv_bfloat16* my_max = s_max + half * 128 + r;
     const __nv_bfloat16* other_max = s_max + (half ^ 1) * 128 + r;
 
     for (int j = 0; j < num_kv; ++j) {
       const int buf = j & 1;
+      if (warp == 2) AT_TRACE(j, 0);
       mbar_wait(&s_full[buf], (j >> 1) & 1);
+      if (warp == 2) AT_TRACE(j, 1);
       tc_fence_after();
       const int nvalid = p.Nk - j * AT_BN - half * 32;   // valid keys among this thread's 32 columns (may be <= 0)
       uint32_t raw[32];
-      tmem_ld_32x32(tmem_base + lane_off + buf * 64 + half * 32, raw);
-      tmem_ld_wait();
+      if (AT_VARIANT & 16) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(static_cast<float>((lane + i + j) & 7));
+      } else {
+        tmem_ld_32x32(tmem_base + lane_off + buf * 64 + half * 32, raw);
+        tmem_ld_wait();
+      }
+      if (warp == 2) AT_TRACE(j, 2);
       float mx = -INFINITY;
-      if (nvalid >= 32) {
+      if (AT_VARIANT & 4) {
+        mx = 8.0f / p.scale_log2;
+      } else if (nvalid >= 32) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
       } else {
@@ -181,13 +231,22 @@ __global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_con
         for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (i < nvalid) ? __uint_as_float(raw[i]) : -INFINITY);
       }
       // the two threads of a row agree on a shift: max of the two half-row maxima, rounded UP to bf16
+#if AT_VARIANT & 32
+      my_max[(j & 1) * 256] = __float2bfloat16_ru(mx * p.scale_log2);
+      asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
+      const float m_pair = fmaxf(__bfloat162float(__float2bfloat16_ru(mx * p.scale_log2)), __bfloat162float(other_max[(j & 1) * 256]));
+#elif AT_VARIANT & 2
+      const float m_pair = __bfloat162float(__float2bfloat16_ru(mx * p.scale_log2));
+#else
       *my_max = __float2bfloat16_ru(mx * p.scale_log2);
       asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
       const float m_pair = fmaxf(__bfloat162float(*my_max), __bfloat162float(*other_max));
       asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");   // partner has read my slot before I overwrite it next tile
+#endif
       // rare path: move the shift.  l and the TMEM-resident O row are rescaled; all earlier PV MMAs must have retired.
       // tcgen05.ld/st are warp-collective, so the branch is taken by the whole warp when ANY of its rows needs it (rows
       // that do not move use alpha = 1); the partner warp owns the same rows and takes the same decision.
+      if (warp == 2) AT_TRACE(j, 3);
       const bool need = m_pair > m_run + AT_RESCALE_THRESHOLD;
       if (__any_sync(0xffffffffu, need)) {
         const float alpha = need ? fast_exp2(m_run - m_pair) : 1.0f;
@@ -208,7 +267,24 @@ __global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_con
       // p = exp2(s*scale - m), partial row sum, bf16 P -> swizzled smem (A operand of the PV MMA)
       float lsum = 0.f;
       uint32_t pk[16];
-      if (nvalid >= 32) {
+      if (nvalid >= 32 && (AT_VARIANT & 64)) {
+        const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2), nm2 = pack_f32x2(-m_run, -m_run);
+        uint64_t acc0 = pack_f32x2(0.f, 0.f), acc1 = acc0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float a0, a1, b0, b1;
+          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1])), sc2, nm2), a0, a1);
+          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(raw[i + 2]), __uint_as_float(raw[i + 3])), sc2, nm2), b0, b1);
+          a0 = fast_exp2(a0); a1 = fast_exp2(a1); b0 = fast_exp2(b0); b1 = fast_exp2(b1);
+          acc0 = add_f32x2(acc0, pack_f32x2(a0, a1));
+          acc1 = add_f32x2(acc1, pack_f32x2(b0, b1));
+          pk[i >> 1] = pack_bf16(a0, a1);
+          pk[(i >> 1) + 1] = pack_bf16(b0, b1);
+        }
+        float s0, s1;
+        unpack_f32x2(add_f32x2(acc0, acc1), s0, s1);
+        lsum = s0 + s1;
+      } else if (nvalid >= 32) {
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           const float p0 = fast_exp2(fmaf(__uint_as_float(raw[i]), p.scale_log2, -m_run));
@@ -226,16 +302,25 @@ __global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_con
         }
       }
       l_run += lsum;
+      if (warp == 2) AT_TRACE(j, 4);
       if (j >= 2) mbar_wait(&pv_done[buf], ((j >> 1) - 1) & 1);   // PV(j-2) has finished reading this P buffer
+      if (warp == 2) AT_TRACE(j, 5);
       uint8_t* prow = sP + buf * AT_QT + r * 128;
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
+      for (int t = 0; t < ((AT_VARIANT & 8) ? 0 : 4); ++t) {
         const int ch = half * 4 + t;              // 16-byte chunk index along the 64 keys
         *reinterpret_cast<uint4*>(prow + ((ch ^ sw) << 4)) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(&p_full[buf]);
+      if (warp == 2) AT_TRACE(j, 6);
+      if (AT_VARIANT & 256) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[buf]);
+      } else {
+        mbar_arrive(&p_full[buf]);
+      }
+      if (warp == 2) AT_TRACE(j, 7);
     }
     // epilogue: all PV MMAs retired -> read this thread's 32 output dims, combine the two partial row sums, normalise
     mbar_wait(&pv_done[(num_kv - 1) & 1], ((num_kv - 1) >> 1) & 1);
@@ -261,9 +346,10 @@ __global__ void __launch_bounds__(320, 2) attention_fwd_tcgen05(const __grid_con
         u.w = pack_bf16(__uint_as_float(ov[8 * i + 6]) * inv, __uint_as_float(ov[8 * i + 7]) * inv);
         d4[i] = u;
       }
-      if (p.lse && half == 0) p.lse[(static_cast<long>(b) * p.Hq + h) * p.Nq + qrow] = m_run * 0.6931471805599453f + logf(l_tot);
+      if (p.lse && half == 0 && !(AT_VARIANT & 128)) p.lse[(static_cast<long>(b) * p.Hq + h) * p.Nq + qrow] = m_run * 0.6931471805599453f + logf(l_tot);
     }
     tc_fence_before();
+    if (warp == 2) AT_TRACE(0, 15);
   }
 
   tc_fence_before();

@@ -52,8 +52,9 @@ __global__ void __launch_bounds__(576, 1) bench(uint32_t* out, long long* clk, i
   const uint32_t base = tptr;
   uint32_t acc = 0;
   __syncthreads();
-  const long long t0 = clock64();
+  long long t0 = 0, t1 = 0;
   if (warp >= 2 && warp < 2 + nwarps) {
+    t0 = clock64();
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const int span = X * DEPTH;
     for (int r = 0; r < reps; ++r) {
@@ -62,10 +63,10 @@ __global__ void __launch_bounds__(576, 1) bench(uint32_t* out, long long* clk, i
       for (int d = 0; d < DEPTH; ++d) acc ^= ld<X>(base + lane_off + ((col + d * X) & 511 & ~(X - 1)));
       wait_ld();
     }
+    t1 = clock64();
+    if (threadIdx.x == 64) clk[blockIdx.x] = t1 - t0 + (acc == 0x12345u);   // warp 2 lane 0: cycles for its own `reps` loads (acc keeps the loads live)
   }
   __syncthreads();
-  const long long t1 = clock64();
-  if (threadIdx.x == 0) clk[blockIdx.x] = t1 - t0;
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -93,8 +94,9 @@ void run(int nwarps) {
   for (int i = 0; i < grid; ++i) avg += h[i];
   avg /= grid;
   const double bytes = double(nwarps) * reps * X * DEPTH * 32 * 4;
-  printf("32x32b.x%-3d loads-in-flight %d  warps %2d : %7.1f B/clk/SM  (%.0f clk per 4 KB warp-load; %.0f clk, %.3f ms => %.2f GHz)  err=%s/%s/%s\n", X, DEPTH,
-         nwarps, bytes / avg, avg / (double(nwarps) * reps * X * DEPTH / 32.0), avg, ms, avg / (ms * 1e6), cudaGetErrorString(e0), cudaGetErrorString(e1),
+  // avg = cycles warp 2 spent in its loop (clock64 inside the reading warp); ms = the whole launch by CUDA events (cross-check)
+  printf("32x32b.x%-3d loads-in-flight %d  warps %2d : %7.1f B/clk/SM  (%.0f clk per warp iteration of %d B; kernel %.3f ms => %.1f B/ns/SM)  err=%s/%s/%s\n", X,
+         DEPTH, nwarps, bytes / avg, avg / reps, X * DEPTH * 128, ms, bytes / (ms * 1e6), cudaGetErrorString(e0), cudaGetErrorString(e1),
          cudaGetErrorString(e2));
   cudaFree(out); cudaFree(clk);
 }
