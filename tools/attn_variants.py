@@ -91,7 +91,7 @@ def trace(k=128):
         ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], out=o, lse=lse)
     torch.cuda.synchronize()
     t = lse.view(torch.int32).flatten()[: 2 * 64 * 16].view(2, 64, 16).cpu().to(torch.int64) & 0xFFFFFFFF
-    names = ["sm:pre-S", "S-ready", "ld-done", "max+xchg", "exp-done", "pv(j-2)", "P-stored", "arrived", "mma:pre-P", "P-ready", "V-ready", "PV-issued", "S(j+2)-iss"]
+    names = ["sm:pre-S", "S-ready", "ld+free", "max", "pv(j-1)", "exp+store", "fenced", "arrived", "mma:top", "S(j+1)-iss", "P-ready", "V-ready", "PV-issued"]
     for r in range(2):
         t0 = int(t[r, 0, 13])
         rel = lambda v: (int(v) - t0) & 0xFFFFFFFF
