@@ -150,7 +150,9 @@ int b200sat_vae_sample(const void* hi, const void* lo, const float* noise, float
 
 /* Flash-attention backward (tcgen05): dQ, dK, dV from dO with the forward's O and LSE; optional inverse RoPE on dQ/dK rows
  * (rope_cos/sin [N,16], position = sequence index) so gradients land in the pre-rotation layout of the qkv projection.
- * strides: HOST array of 8 x (batch, seq, head) element strides for q, k, v, o, dO, dQ, dK, dV.  delta_scratch: fp32 [B,Hq,Nq].
+ * strides: HOST array of 8 x (batch, seq, head) element strides for q, k, v, o, dO, dQ, dK, dV.  delta_scratch: fp32 workspace of B*Hq*(Nq + 2*roundup(Nq,64)) elements
+ * (-lse*log2(e) and -delta padded to [2][B,Hq,roundup(Nq,64)] for the aligned broadcast loads of the dK/dV kernel, then delta [B,Hq,Nq];
+ * the pointer must be 16-byte aligned).
  * Backward of models/transformer.py:406-441 (+ :154-174). */
 int b200sat_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                           float* delta_scratch, void* dq, void* dk, void* dv, int B, int Hq, int Hkv, int Nq, int Nk,

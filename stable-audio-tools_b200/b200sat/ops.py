@@ -215,7 +215,8 @@ def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, scale=None, rope=None):
         _chk_bf16(t, "attention_bwd operand")
         st += [t.stride(0), t.stride(1), t.stride(2)]
     arr = (ctypes.c_long * 24)(*st)
-    delta = torch.empty(B, Hq, Nq, device=q.device, dtype=torch.float32)
+    npad = (Nq + 63) // 64 * 64
+    delta = torch.empty(B * Hq * (Nq + 2 * npad), device=q.device, dtype=torch.float32)   # padded -lse*log2e and -delta rows, then delta
     rc = lib().b200sat_attention_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr(), lse.data_ptr(),
                                      delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, Hq, Hkv, Nq, Nk, arr, D,
                                      float(scale), _p(rope[0]) if rope else 0, _p(rope[1]) if rope else 0, _stream())

@@ -360,6 +360,62 @@ __device__ __forceinline__ void fast_sincos(float x, float* s, float* c) {
 }
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
+// ---- softmax arithmetic shared by the attention kernels
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// packed fp32 pairs (sm_100: FFMA2 / FADD2 issue two lanes per slot)
+__device__ __forceinline__ uint64_t pack_f32x2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// exp2 on the FMA pipe for a share of the score tile (the MUFU, 16 ex2 / clk / SM, is the binding unit of this kernel at head_dim 64):
+// x = n + f with n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 minimax polynomial (max relative error 7.5e-5, far below the bf16
+// rounding of P); 2^n by adding n to the exponent field.  The magic-number add leaves n in the low mantissa bits of t, so the result
+// is bits(p) + (bits(t) << 23).  x is clamped at -126 (masked keys arrive as -inf) so the exponent never wraps.
+__device__ __forceinline__ void poly_exp2_x2(uint64_t x2, float& ea, float& eb) {
+  constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23
+  float xa, xb;
+  unpack_f32x2(x2, xa, xb);
+  const uint64_t xc = pack_f32x2(fmaxf(xa, -126.0f), fmaxf(xb, -126.0f));
+  const uint64_t t2 = add_f32x2(xc, pack_f32x2(kMagic, kMagic));
+  const uint64_t n2 = add_f32x2(t2, pack_f32x2(-kMagic, -kMagic));
+  const uint64_t f2 = fma_f32x2(n2, pack_f32x2(-1.0f, -1.0f), xc);
+  uint64_t p2 = fma_f32x2(pack_f32x2(0.055171460f, 0.055171460f), f2, pack_f32x2(0.24261086f, 0.24261086f));
+  p2 = fma_f32x2(p2, f2, pack_f32x2(0.69326097f, 0.69326097f));
+  p2 = fma_f32x2(p2, f2, pack_f32x2(0.99992812f, 0.99992812f));
+  float pa, pb, ta, tb;
+  unpack_f32x2(p2, pa, pb);
+  unpack_f32x2(t2, ta, tb);
+  ea = __uint_as_float(__float_as_uint(pa) + (__float_as_uint(ta) << 23));
+  eb = __uint_as_float(__float_as_uint(pb) + (__float_as_uint(tb) << 23));
+}
+__device__ __forceinline__ void mbar_arrive_if(uint64_t* bar, uint32_t pred) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %1, 0;\n@p mbarrier.arrive.shared::cta.b64 _, [%0];\n}" ::"r"(smem_u32(bar)), "r"(pred) : "memory");
+}
+
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+
 }  // namespace b200sat
 
 // ----------------------------------------------------------------------------------------------

@@ -31,10 +31,10 @@ def _attn_ref(q, k, v, do, rope=None):
 
 @pytest.mark.parametrize("B,Nq,Nk,H,Hkv,use_rope", [(1, 128, 128, 1, 1, False), (2, 1025, 1025, 6, 6, True), (2, 1025, 130, 8, 4, False),
                                                      (1, 300, 77, 4, 2, False), (1, 513, 513, 3, 3, True)])
-@pytest.mark.parametrize("softmax_warps", ["16", "8"])
-def test_attention_bwd(B, Nq, Nk, H, Hkv, use_rope, softmax_warps, monkeypatch):
+@pytest.mark.parametrize("v3_mask", ["3", "0"])      # 3: round-2 kernels (default); 0: the round-1 kernels kept for comparison
+def test_attention_bwd(B, Nq, Nk, H, Hkv, use_rope, v3_mask, monkeypatch):
     from b200sat import ops
-    monkeypatch.setenv("B200SAT_ATTN_BWD_WARPS", softmax_warps)     # read by the library at every call
+    monkeypatch.setenv("B200SAT_ATTN_BWD_V3", v3_mask)     # read by the library at every call
     torch.manual_seed(0)
     q = torch.randn(B, Nq, H, 64, device="cuda").bfloat16()
     k = torch.randn(B, Nk, Hkv, 64, device="cuda").bfloat16()

@@ -1,5 +1,5 @@
 """Attention backward at the training shapes (B = 8, N = 1025 self-attention; 130-key GQA cross-attention): CUDA-event timing of
-the 8- and 16-softmax-warp variants (B200SAT_ATTN_BWD_WARPS) and the forward kernel."""
+the round-2 (v3) and round-1 (v2) kernels per half (B200SAT_ATTN_BWD_V3 bit 0 = dK/dV, bit 1 = dQ) and the forward kernel."""
 import os
 import sys
 
@@ -38,12 +38,12 @@ def main():
     o2 = torch.empty_like(q2); lse2 = torch.empty(B, H, N, device=dev)
     dq2 = torch.empty_like(q2); dkv = torch.empty_like(kv)
     ops.attention(q2, kv[:, :, 0], kv[:, :, 1], out=o2, lse=lse2)
-    for w in ("8", "16"):
-        os.environ["B200SAT_ATTN_BWD_WARPS"] = w
+    for w in ("0", "1", "2", "3"):
+        os.environ["B200SAT_ATTN_BWD_V3"] = w
         us = timeit(lambda: ops.attention_bwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], o, do, lse, dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2]))
-        print(f"self bwd  warps={w:2s} {us:8.1f} us  {2.5 * fl / us / 1e6:7.1f} TFLOP/s (algorithmic 2.5x fwd)")
+        print(f"self bwd  v3mask={w:2s} {us:8.1f} us  {2.5 * fl / us / 1e6:7.1f} TFLOP/s (algorithmic 2.5x fwd)")
         us = timeit(lambda: ops.attention_bwd(q2, kv[:, :, 0], kv[:, :, 1], o2, do, lse2, dq2, dkv[:, :, 0], dkv[:, :, 1]))
-        print(f"cross bwd warps={w:2s} {us:8.1f} us")
+        print(f"cross bwd v3mask={w:2s} {us:8.1f} us")
 
 
 if __name__ == "__main__":
