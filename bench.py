@@ -454,6 +454,20 @@ def gpu_reference(args, dev, rank, world, dist, barrier, do_train=True, do_sampl
     return out
 
 
+def _ncu_dram_bytes(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full summary (profiles/)."""
+    path = os.path.join(ROOT, "profiles", name)
+    try:
+        vals = {}
+        for ln in open(path):
+            f = ln.split()
+            if len(f) >= 2 and f[0] in ("dram_read_MB", "dram_write_MB"):
+                vals[f[0]] = float(f[1])
+        return (vals["dram_read_MB"] + vals["dram_write_MB"]) * 1e6, "profiles/" + name
+    except Exception:
+        return None, None
+
+
 def roofline_rows(dev, eng_w, pk):
     """Live microbenchmarks (CUDA events, inputs > L2) of the two kernels that dominate the headline step."""
     from b200sat import ops
@@ -476,8 +490,10 @@ def roofline_rows(dev, eng_w, pk):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     fl = 2.0 * T_AUDIO * 128 * 128 * 7
+    traffic, traffic_src = _ncu_dram_bytes("r2_ncu_conv_k7_summary.txt")
     rows.append({"kernel": "conv1d_tcgen05<128,0,2> (ResidualUnit k7 conv + SnakeBeta epilogue, C=128, T=2097152, bf16)", "bound": "tensor", "achieved": fl / ms / 1e9,
-                 "peak": pk["bf16"], "unit": "TFLOP/s", "frac": fl / ms / 1e9 / pk["bf16"], "avg_launch_ms": ms, "traffic": None,
+                 "peak": pk["bf16"], "unit": "TFLOP/s", "frac": fl / ms / 1e9 / pk["bf16"], "avg_launch_ms": ms, "traffic": traffic,
+                 "traffic_unit": "bytes per launch (dram read + write, ncu --set full capture of the same launch: %s); algorithmic bytes = %d" % (traffic_src, 2 * T_AUDIO * 128 * 2),
                  "peak_source": pk["src"] + " burst", "share_of_step": "conv1d_tcgen05 = the frozen-encoder part of the step (see profiles/r2_*)",
                  "hbm_GBps_algorithmic": 2.0 * T_AUDIO * 128 * 2 / ms / 1e6})
     del ae, x, h

@@ -217,6 +217,11 @@ int b200sat_conv_wgrad(const void* a_plane, int Ca, int Ta, int sA, int rA, int 
 int b200sat_conv_wgrad_taps(const void* a_plane, int Ca, const void* b_plane, int Cb, int T, const int* tap_off, int ntaps, float* dW, int B,
                             void* stream);
 
+/* The same weight gradient for 64 -> 64 channel convs in ONE launch: a 128 x 256 accumulator tile covers four taps (column block -> tap row
+ * shift), so both planes stream from HBM ceil(ntaps/4) times instead of ntaps times.  Output layout dWc[Ca=64][ntaps][Cb=64] (fp32, +=);
+ * ntaps <= 32.  Backward of the Conv2d stacks of models/encodec.py:94-138 (dW = dY (*) X). */
+int b200sat_conv_wgrad_taps_cat(const void* a_plane, const void* b_plane, int T, const int* tap_off, int ntaps, float* dWc, int B, void* stream);
+
 /* SnakeBeta backward fused with the skip-connection add and the parameter reductions (models/blocks.py:291-329 under autograd):
  * d_raw = d_skip + d_act * (1 + invb*a*sin(2 a x)); dalpha/dbeta [C] (log-scale parameters) and dbias [C] (= column sums of d_raw, the
  * bias gradient of the conv that produced x; optional) are accumulated with fp32 atomics.  Planes are bf16 [rows, C]. */
@@ -267,6 +272,12 @@ int b200sat_adamw_ema_step(float* p, const float* g, float* m, float* v, float* 
  * (row % fp) is outside [f0, f1) are written as zeros, optional LeakyReLU (encodec.py:80-87, :102-103). */
 int b200sat_conv2d_flat(const void* in, const void* w, const float* bias, void* out, int B, int P, int Cin, int Cout, int ntaps,
                         const int* tap_off, int fp, int f0, int f1, float leaky, void* stream);
+
+/* First conv (4 -> 64 channels, 3 x 9; encodec.py:77-79) on the tensor cores: the nine frequency taps are folded into channels,
+ * S9[row][ci*9 + df] = spec[row + df - 4][ci] (bf16 [B, P, 64], 36 channels used), which makes the layer a 3-tap (row shifts -Fp, 0, +Fp)
+ * 64 -> 64 flattened conv served by b200sat_conv2d_flat / b200sat_conv_wgrad_taps_cat / b200sat_wn_pack / b200sat_wn_bwd.
+ * backward == 0: s9 = pack(spec fp32 [B, P, 4]);  backward != 0: spec (d spec) = pack^T(s9 (d S9)). */
+int b200sat_disc_spec_pack(float* spec, void* s9, int B, int frames, int F, int backward, void* stream);
 
 /* Complex STFT front end (torchaudio Spectrogram normalized=True, center=False, power=None, hann, win = n_fft; encodec.py:72-74, :96-99):
  * x fp32 [B,2,T] -> spec fp32 [B,P,4] = (re ch0, re ch1, im ch0, im ch1); pad columns are NOT written (pre-zero the buffer).

@@ -68,9 +68,11 @@ SIGNATURES = {
     "b200sat_disc_l1_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_void_p]),
     "b200sat_disc_logit_grad": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "b200sat_disc_act_bwd": (c_int, [c_void_p, c_fp, c_fp, c_void_p, c_void_p, c_float, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "b200sat_disc_spec_pack": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200sat_disc_conv0_wgrad": (c_int, [c_void_p, c_fp, c_fp, c_int, c_int, c_int, c_void_p]),
     "b200sat_disc_convpost_wgrad": (c_int, [c_fp, c_void_p, c_fp, c_fp, c_int, c_int, c_int, c_void_p]),
     "b200sat_conv_wgrad_taps": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_fp, c_int, c_void_p]),
+    "b200sat_conv_wgrad_taps_cat": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_fp, c_int, c_void_p]),
     "b200sat_snake_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_fp, c_fp, c_void_p, c_fp, c_fp, c_fp, c_long, c_int, c_void_p]),
     "b200sat_wn_pack_dgrad": (c_int, [c_fp, c_fp, c_fp, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200sat_wn_bwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_void_p]),

@@ -13,6 +13,7 @@ weight-normed parameters) is `EncodecDiscriminatorTrain.discriminator_loss`: wei
 """
 import ctypes
 import math
+import os
 
 import torch
 from torch import nn
@@ -22,6 +23,8 @@ from . import ops
 
 LEAKY = 0.2
 DILATIONS = (1, 2, 4)
+# first conv on the tensor cores (default); B200SAT_DISC_CONV0=simt keeps the round-1 fp32 SIMT kernels
+CONV0_TC = os.environ.get("B200SAT_DISC_CONV0", "tc") != "simt"
 
 
 def _s():
@@ -54,11 +57,18 @@ class _Scale:
         self.b0 = sd[pre + "convs.0.conv.bias"].float().to(dev).contiguous()
         self.wp = _wn_dense(sd, pre + "conv_post.conv.").to(dev).reshape(64, 9).contiguous()      # [1,64,3,3] -> [c][tap]
         self.bp = sd[pre + "conv_post.conv.bias"].float().to(dev).contiguous()
-        # the four 64 -> 64 convs: packed bf16 weights (forward and data-gradient layouts) + per-tap row shifts
+        # the four 64 -> 64 convs: packed bf16 weights (forward and data-gradient layouts) + per-tap row shifts.  Entry 0 of the list
+        # built here is the FIRST conv in its tensor-core form (CONV0_TC): frequency taps folded into channels (b200sat_disc_spec_pack),
+        # v9[co][ci*9 + df][dt] = v[co][ci][dt][df], three taps = row shifts (-Fp, 0, +Fp); its zero rows leave the weight norm unchanged.
         self.convs = []
-        for j in range(1, 5):
+        self.cv0 = None
+        for j in (range(0, 5) if CONV0_TC else range(1, 5)):
             q = f"{pre}convs.{j}.conv."
             v = sd[q + "weight_v"].float().to(dev)
+            if j == 0:
+                v9 = torch.zeros(64, 64, 3, device=dev)
+                v9[:, :36] = v.reshape(64, 4, 3, 9).permute(0, 1, 3, 2).reshape(64, 36, 3)
+                v = v9.view(64, 64, 3, 1)
             K = v.shape[2] * v.shape[3]
             v3 = v.reshape(64, 64, K).contiguous()
             g = sd[q + "weight_g"].float().to(dev).reshape(-1).contiguous()
@@ -67,14 +77,20 @@ class _Scale:
             check(lib().b200sat_wn_pack(v3.data_ptr(), g.data_ptr(), inv.data_ptr(), w_f.data_ptr(), 0, 64, 64, K, 0, 1, _s()), "wn_pack")
             w_d = torch.empty(64, K * 64, device=dev, dtype=torch.bfloat16)
             check(lib().b200sat_wn_pack_dgrad(v3.data_ptr(), g.data_ptr(), inv.data_ptr(), w_d.data_ptr(), 64, 64, K, 0, 1, _s()), "wn_pack_dgrad")
-            if j <= 3:
+            if j == 0:
+                offs = [-self.Fp, 0, self.Fp]
+            elif j <= 3:
                 d = DILATIONS[j - 1]
                 offs = [(k_ // 9 - 1) * d * self.Fp + (k_ % 9 - 4) for k_ in range(27)]
             else:
                 offs = [(k_ // 3 - 1) * self.Fp + (k_ % 3 - 1) for k_ in range(9)]
-            self.convs.append(dict(w=w_f, wd=w_d, bias=sd[q + "bias"].float().to(dev).contiguous(), K=K, offs=(ctypes.c_int * K)(*offs),
-                                   offs_py=offs, v3=v3, g=g, inv=inv, name=f"convs.{j}.conv."))
-        ops.LAUNCHES[0] += 12
+            cv = dict(w=w_f, wd=w_d, bias=sd[q + "bias"].float().to(dev).contiguous(), K=K, offs=(ctypes.c_int * K)(*offs),
+                      offs_py=offs, v3=v3, g=g, inv=inv, name=f"convs.{j}.conv.")
+            if j == 0:
+                self.cv0 = cv
+            else:
+                self.convs.append(cv)
+        ops.LAUNCHES[0] += 12 + (3 if CONV0_TC else 0)
 
     def frames(self, T):
         return (T - self.n) // self.hop + 1
@@ -105,7 +121,13 @@ class EncodecDiscriminatorEngine:
         spec = torch.zeros(B, P, 4, device=self.dev)
         check(lib().b200sat_disc_stft(x.data_ptr(), spec.data_ptr(), sc.window.data_ptr(), sc.twiddle.data_ptr(), B, T, sc.n, sc.hop, 0, _s()), "disc_stft")
         f0 = torch.empty(B, P, 64, device=self.dev, dtype=torch.bfloat16)
-        check(lib().b200sat_disc_conv0(spec.data_ptr(), sc.w0.data_ptr(), sc.b0.data_ptr(), f0.data_ptr(), 0, 0, B, fr, sc.F, LEAKY, _s()), "disc_conv0")
+        if sc.cv0 is not None:
+            s9 = torch.empty(B, P, 64, device=self.dev, dtype=torch.bfloat16)
+            check(lib().b200sat_disc_spec_pack(spec.data_ptr(), s9.data_ptr(), B, fr, sc.F, 0, _s()), "disc_spec_pack")
+            self._flat_conv(sc, s9, sc.cv0, f0, sc.cv0["bias"], sc.cv0["w"])
+            spec = s9                 # what the weight gradient of the first conv reads
+        else:
+            check(lib().b200sat_disc_conv0(spec.data_ptr(), sc.w0.data_ptr(), sc.b0.data_ptr(), f0.data_ptr(), 0, 0, B, fr, sc.F, LEAKY, _s()), "disc_conv0")
         fmaps = [f0]
         for cv in sc.convs:
             fmaps.append(self._flat_conv(sc, fmaps[-1], cv, torch.empty_like(f0), cv["bias"], cv["w"]))
@@ -192,7 +214,11 @@ class EncodecDiscriminatorEngine:
                                                  sc.F, st), "disc_act_bwd")
                 ops.LAUNCHES[0] += 1
             dspec = torch.empty(B, P, 4, device=self.dev)
-            check(lib().b200sat_disc_conv0(0, sc.w0.data_ptr(), 0, 0, d_pre.data_ptr(), dspec.data_ptr(), B, fr, sc.F, LEAKY, st), "disc_conv0 dgrad")
+            if sc.cv0 is not None:
+                ds9 = self._flat_conv(sc, d_pre, sc.cv0, torch.empty_like(d_pre), None, sc.cv0["wd"])
+                check(lib().b200sat_disc_spec_pack(dspec.data_ptr(), ds9.data_ptr(), B, fr, sc.F, 1, st), "disc_spec_pack backward")
+            else:
+                check(lib().b200sat_disc_conv0(0, sc.w0.data_ptr(), 0, 0, d_pre.data_ptr(), dspec.data_ptr(), B, fr, sc.F, LEAKY, st), "disc_conv0 dgrad")
             check(lib().b200sat_disc_stft(d_audio.data_ptr(), dspec.data_ptr(), sc.window.data_ptr(), sc.twiddle.data_ptr(), B, T, sc.n, sc.hop, 1, st),
                   "disc_stft backward")
             ops.LAUNCHES[0] += 2
@@ -234,10 +260,13 @@ def _discriminator_backward(eng, saved, n_logit, B):
         ft, ff, lf, fr, lt, spec_r, spec_f = saved[i]
         P = fr * sc.Fp
         dW0 = torch.zeros(64, 4, 27, device=dev)
+        dW0c = torch.zeros(64, 3, 64, device=dev)     # tensor-core form of the first conv: [co][dt][ci*9 + df]
         db0 = torch.zeros(64, device=dev)
         dWp = torch.zeros(64, 9, device=dev)
         dbp = torch.zeros(1, device=dev)
-        dwps = [torch.zeros(cv["K"], 64, 64, device=dev) for cv in sc.convs]
+        # batched taps (default): one launch per layer writes dWc[ca][tap][cb]; B200SAT_DISC_WGRAD_CAT=0 = one launch per tap, dW[tap][ca][cb]
+        cat = os.environ.get("B200SAT_DISC_WGRAD_CAT", "1") != "0"
+        dwps = [torch.zeros(64, cv["K"], 64, device=dev) if cat else torch.zeros(cv["K"], 64, 64, device=dev) for cv in sc.convs]
         dbs = [torch.zeros(64, device=dev) for _ in sc.convs]
         for lg, fm, spec, mode in ((lt, ft, spec_r, 1), (lf, ff, spec_f, 2)):
             g = torch.empty(B, P, device=dev)
@@ -248,20 +277,30 @@ def _discriminator_backward(eng, saved, n_logit, B):
             ops.LAUNCHES[0] += 3
             for l in range(4, 0, -1):
                 cv = sc.convs[l - 1]
-                check(lib().b200sat_conv_wgrad_taps(d_pre.data_ptr(), 64, fm[l - 1].data_ptr(), 64, P, cv["offs"], cv["K"], dwps[l - 1].data_ptr(), B, st),
-                      "conv_wgrad_taps")
-                ops.LAUNCHES[0] += cv["K"]
+                if cat:
+                    check(lib().b200sat_conv_wgrad_taps_cat(d_pre.data_ptr(), fm[l - 1].data_ptr(), P, cv["offs"], cv["K"], dwps[l - 1].data_ptr(), B, st),
+                          "conv_wgrad_taps_cat")
+                    ops.LAUNCHES[0] += 1
+                else:
+                    check(lib().b200sat_conv_wgrad_taps(d_pre.data_ptr(), 64, fm[l - 1].data_ptr(), 64, P, cv["offs"], cv["K"], dwps[l - 1].data_ptr(), B, st),
+                          "conv_wgrad_taps")
+                    ops.LAUNCHES[0] += cv["K"]
                 ops.colsum(d_pre.view(-1, 64), dbs[l - 1])
                 d_in = eng._flat_conv(sc, d_pre, cv, torch.empty_like(d_pre), None, cv["wd"])
                 d_pre = torch.empty_like(d_in)
                 check(lib().b200sat_disc_act_bwd(d_in.data_ptr(), 0, 0, fm[l - 1].data_ptr(), 0, 0.0, LEAKY, d_pre.data_ptr(), B, fr, sc.F, st), "disc_act_bwd")
                 ops.LAUNCHES[0] += 1
-            check(lib().b200sat_disc_conv0_wgrad(d_pre.data_ptr(), spec.data_ptr(), dW0.data_ptr(), B, fr, sc.F, st), "disc_conv0_wgrad")
+            if sc.cv0 is not None:     # `spec` is the packed S9 plane: a 3-tap 64 -> 64 weight gradient
+                check(lib().b200sat_conv_wgrad_taps_cat(d_pre.data_ptr(), spec.data_ptr(), P, sc.cv0["offs"], 3, dW0c.data_ptr(), B, st), "conv_wgrad_taps_cat")
+            else:
+                check(lib().b200sat_disc_conv0_wgrad(d_pre.data_ptr(), spec.data_ptr(), dW0.data_ptr(), B, fr, sc.F, st), "disc_conv0_wgrad")
             ops.colsum(d_pre.view(-1, 64), db0)
             ops.LAUNCHES[0] += 1
         # weight-norm backward
         pre = sc.pre
         for l, cv in enumerate(sc.convs):
+            if cat:
+                dwps[l] = dwps[l].permute(1, 0, 2).contiguous()      # [ca][tap][cb] -> [tap][ca][cb] (110 K floats)
             dv = torch.empty_like(cv["v3"])
             dg = torch.empty_like(cv["g"])
             check(lib().b200sat_wn_bwd(dwps[l].data_ptr(), cv["v3"].data_ptr(), cv["g"].data_ptr(), cv["inv"].data_ptr(), dv.data_ptr(), dg.data_ptr(), 64, 64,
@@ -271,7 +310,17 @@ def _discriminator_backward(eng, saved, n_logit, B):
             grads[pre + cv["name"] + "weight_g"] = dg.view_as(sc.raw[cv["name"] + "weight_g"])
             grads[pre + cv["name"] + "bias"] = dbs[l]
         v0, g0 = sc.raw["convs.0.conv.weight_v"], sc.raw["convs.0.conv.weight_g"]
-        dv0, dg0 = _wn_small_bwd(v0, g0, dW0.view_as(v0))
+        if sc.cv0 is not None:
+            cv = sc.cv0
+            dv9 = torch.empty_like(cv["v3"])
+            dg0 = torch.empty_like(cv["g"])
+            check(lib().b200sat_wn_bwd(dW0c.permute(1, 0, 2).contiguous().data_ptr(), cv["v3"].data_ptr(), cv["g"].data_ptr(), cv["inv"].data_ptr(),
+                                       dv9.data_ptr(), dg0.data_ptr(), 64, 64, 3, st), "wn_bwd")
+            ops.LAUNCHES[0] += 1
+            dv0 = dv9[:, :36].reshape(64, 4, 9, 3).permute(0, 1, 3, 2).reshape(v0.shape).contiguous()     # [co][ci*9+df][dt] -> [co][ci][dt][df]
+            dg0 = dg0.view_as(g0)
+        else:
+            dv0, dg0 = _wn_small_bwd(v0, g0, dW0.view_as(v0))
         grads[pre + "convs.0.conv.weight_v"], grads[pre + "convs.0.conv.weight_g"], grads[pre + "convs.0.conv.bias"] = dv0, dg0, db0
         vp, gp = sc.raw["conv_post.conv.weight_v"], sc.raw["conv_post.conv.weight_g"]
         dvp, dgp = _wn_small_bwd(vp, gp, dWp.view(1, 64, 3, 3))

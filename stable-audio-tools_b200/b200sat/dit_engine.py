@@ -120,10 +120,29 @@ class DiTEngine:
         return ws
 
     # ------------------------------------------------------------------ forward
+    def precompute_conditioning(self, ctx_in, global_in, Bx, T):
+        """The step-invariant part of the forward (dit.py:140-168, transformer.py:469-472): conditioning-token embedding, the cross-attention
+        K/V of every layer and the global-embedding MLP depend only on the prompt, not on x or t, so a sampler computes them ONCE per run and
+        replays its step with `cond_cached=True`.  Returns False (nothing cached) when the per-layer K/V weights are not stacked."""
+        w = self.w
+        if ctx_in is not None and "_all_to_kv.weight" not in w:
+            return False
+        L = 0 if ctx_in is None else ctx_in.shape[0] // Bx
+        ws = self.workspace(Bx, T, L)
+        if ctx_in is not None:
+            ops.linear(ctx_in, w["to_cond_embed.0.weight"], silu=True, out=ws["ctx1"])
+            ctx = ops.linear(ws["ctx1"], w["to_cond_embed.2.weight"], out=ws["ctx"])
+            ops.linear(ctx, w["_all_to_kv.weight"], out=ws["kv_all"])
+        if global_in is not None:
+            self._lin_small(global_in, w["to_global_embed.0.weight"], None, ws["ge1"], silu=True)
+            self._lin_small(ws["ge1"], w["to_global_embed.2.weight"], None, ws["ge"])
+        return True
+
     def forward_into(self, out, x, t, ctx_in, global_in, Bx, reps, cfg, cfg_scale, scale_phi,
-                     cin_table=None, t_table_step=None, step=None):
+                     cin_table=None, t_table_step=None, step=None, cond_cached=False):
         """out fp32 [B,C,T];  x fp32 [B,C,T];  t fp32 [Bx] (or a [steps, Bx] table walked by *step);
-        ctx_in bf16 [Bx*L, cond_token_dim] or None;  global_in bf16 [Bx, global_cond_dim] or None."""
+        ctx_in bf16 [Bx*L, cond_token_dim] or None;  global_in bf16 [Bx, global_cond_dim] or None.
+        cond_cached: `precompute_conditioning` already filled this signature's ctx / kv_all / ge buffers for the same ctx_in / global_in."""
         c, w = self.cfg, self.w
         d, H = c.embed_dim, c.num_heads
         B, C, T = x.shape
@@ -133,7 +152,9 @@ class DiTEngine:
         h = ws["h"]
         # --- conditioning (dit.py:140-168)
         ctx = None
-        if ctx_in is not None:
+        if ctx_in is not None and cond_cached:
+            ctx = ws["ctx"]
+        elif ctx_in is not None:
             ops.linear(ctx_in, w["to_cond_embed.0.weight"], silu=True, out=ws["ctx1"])
             ctx = ops.linear(ws["ctx1"], w["to_cond_embed.2.weight"], out=ws["ctx"])
             if "_all_to_kv.weight" in w:   # K/V of the conditioning tokens for every layer (transformer.py:469-472), one launch
@@ -148,8 +169,9 @@ class DiTEngine:
             st.zero_()
         st0 = dict(stats=st[0], stats_stride=2 * N) if fuse else {}
         if global_in is not None:
-            self._lin_small(global_in, w["to_global_embed.0.weight"], None, ws["ge1"], silu=True)
-            self._lin_small(ws["ge1"], w["to_global_embed.2.weight"], None, ws["ge"])
+            if not cond_cached:
+                self._lin_small(global_in, w["to_global_embed.0.weight"], None, ws["ge1"], silu=True)
+                self._lin_small(ws["ge1"], w["to_global_embed.2.weight"], None, ws["ge"])
             self._lin_small(ws["te1"], w["to_timestep_embed.2.weight"], w["to_timestep_embed.2.bias"], gdst, add=ws["ge"], **st0)
         else:
             self._lin_small(ws["te1"], w["to_timestep_embed.2.weight"], w["to_timestep_embed.2.bias"], gdst, **st0)

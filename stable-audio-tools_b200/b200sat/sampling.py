@@ -101,6 +101,8 @@ class GraphSampler:
         self.ctx = torch.zeros(self.Bx * L, engine.cfg.cond_token_dim, device=dev, dtype=torch.bfloat16) if L > 0 else None
         self.glob = torch.zeros(self.Bx, engine.cfg.global_cond_dim, device=dev, dtype=torch.bfloat16) if has_global else None
         self.use_graph = use_graph
+        # prompt-only work (conditioning embedding, every layer's cross-attention K/V, global-embedding MLP) runs once per run(), not per step
+        self.cond_cached = L == 0 or "_all_to_kv.weight" in engine.w
         self.graph = None
         self.max_steps = 0
         self.coef = self.cin = self.tt = self.noise = None
@@ -118,7 +120,7 @@ class GraphSampler:
 
     def _one_step(self):
         self.e.forward_into(self.v, self.x, self.tt, self.ctx, self.glob, self.Bx, self.reps, self.cfg, self.cfg_scale,
-                            self.scale_phi, cin_table=self.cin, step=self.step)
+                            self.scale_phi, cin_table=self.cin, step=self.step, cond_cached=self.cond_cached)
         ops.sampler_update(self.x, self.v, self.hist, self.noise, self.coef, self.step, advance=True)
 
     def _ensure_graph(self):
@@ -163,6 +165,8 @@ class GraphSampler:
             self.glob[: self.B].copy_(gg)
             if self.cfg:
                 self.glob[self.B:].copy_(gg)
+        if self.cond_cached:
+            self.e.precompute_conditioning(self.ctx, self.glob, self.Bx, self.T)
         self.x.copy_(noise.to(dev, torch.float32, non_blocking=True))
         if init_scale != 1.0:
             self.x.mul_(init_scale)

@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(128) disc_conv0_dgrad_kernel(const __nv_bfloat
 }
 
 // Last conv (64 -> 1, 3 x 3, no activation; encodec.py:88-90): logits[p] = b + sum_{tap, c} act[p + off][c] * w[c][tap].
-__global__ void __launch_bounds__(128) disc_convpost_fwd_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ w /*[1][64][9]*/,
+__global__ void __launch_bounds__(128) disc_convpost_fwd_v1_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ w /*[1][64][9]*/,
                                                                 const float* __restrict__ bias, float* __restrict__ logits, int B, int frames,
                                                                 int Fp, int F) {
   __shared__ float sw[9 * 64];   // [tap][c]
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(256) disc_conv0_wgrad_kernel(const __nv_bfloat
 }
 
 // conv_post: dW[c][tap] += sum_p g[p] * act[p + off(tap)][c];  dbias += sum_p g[p].   thread = (c, tap group of 3)
-__global__ void __launch_bounds__(256) disc_convpost_wgrad_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ act,
+__global__ void __launch_bounds__(256) disc_convpost_wgrad_v1_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ act,
                                                                   float* __restrict__ dW /*[64][9]*/, float* __restrict__ dbias, int B, int frames,
                                                                   int Fp, int F) {
   const int c = threadIdx.x & 63, tg = threadIdx.x >> 6;
@@ -465,6 +465,160 @@ __global__ void __launch_bounds__(256) disc_convpost_wgrad_kernel(const float* _
     if (tap < 9) atomicAdd(dW + c * 9 + tap, acc[i]);
   }
   if (threadIdx.x == 0 && dbias) atomicAdd(dbias, gsum);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Round 2: row-coalesced versions of the two conv_post kernels.  The v1 kernels above give one thread a whole 128-byte activation row
+// (32 different cache lines per warp load: 72 such loads per output position made the forward L1-wavefront bound at 1.2 ms per scale
+// and batch 32) or one channel (2-byte loads).  Here EIGHT lanes share a row (one 16-byte chunk each, so a warp load touches four
+// full lines) and the per-row dot products are finished with three shuffles.
+__global__ void __launch_bounds__(256) disc_convpost_fwd_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ w /*[1][64][9]*/,
+                                                                const float* __restrict__ bias, float* __restrict__ logits, int B, int frames,
+                                                                int Fp, int F) {
+  const int lane = threadIdx.x & 31, l8 = lane & 7, sub = lane >> 3;
+  float wr[9][8];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[tap][j] = __ldg(w + (l8 * 8 + j) * 9 + tap);
+  const long P = static_cast<long>(frames) * Fp;
+  const long total = static_cast<long>(B) * P;
+  const float bv = bias ? bias[0] : 0.f;
+  const long stride = static_cast<long>(gridDim.x) * (blockDim.x >> 3);
+  for (long base = (static_cast<long>(blockIdx.x) * blockDim.x + (threadIdx.x & ~31)) >> 3; base < total; base += stride) {   // warp-uniform
+    const long idx = base + sub;
+    const bool in = idx < total;
+    const long p = in ? idx % P : 0;
+    const bool ok = in && col_valid(static_cast<int>(p % Fp), Fp, F);
+    float acc = 0.f;
+    if (ok) {
+      const __nv_bfloat16* rowbase = act + (idx - p) * 64 + l8 * 8;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const long q = p + (tap / 3 - 1) * Fp + (tap % 3 - 1);
+        if (q < 0 || q >= P) continue;
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(rowbase + q * 64));
+        const float2 d0 = unpack_bf16(u.x), d1 = unpack_bf16(u.y), d2 = unpack_bf16(u.z), d3 = unpack_bf16(u.w);
+        acc += d0.x * wr[tap][0] + d0.y * wr[tap][1] + d1.x * wr[tap][2] + d1.y * wr[tap][3] + d2.x * wr[tap][4] + d2.y * wr[tap][5] +
+               d3.x * wr[tap][6] + d3.y * wr[tap][7];
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (in && l8 == 0) logits[idx] = ok ? acc + bv : 0.f;
+  }
+}
+
+// conv_post weight gradient, gather form: the activation row r is read ONCE and meets the nine logit gradients g[r - off(tap)]:
+//   dW[c][tap] += sum_r act[r][c] * g[r - off(tap)]          dbias += sum_p g[p]
+// lane = 8 channels of one row (72 fp32 partial sums per thread), four rows per warp step; partial sums meet in shared memory once.
+__global__ void __launch_bounds__(256) disc_convpost_wgrad_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ act,
+                                                                  float* __restrict__ dW /*[64][9]*/, float* __restrict__ dbias, int B, int frames,
+                                                                  int Fp, int F) {
+  __shared__ float red[9 * 64];
+  __shared__ float red_g;
+  const int lane = threadIdx.x & 31, l8 = lane & 7, sub = lane >> 3;
+  for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) red[i] = 0.f;
+  if (threadIdx.x == 0) red_g = 0.f;
+  __syncthreads();
+  float acc[9][8];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[tap][j] = 0.f;
+  float gsum = 0.f;
+  const long P = static_cast<long>(frames) * Fp;
+  const long total = static_cast<long>(B) * P;
+  const long stride = static_cast<long>(gridDim.x) * (blockDim.x >> 3);
+  for (long idx = ((static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3); idx < total; idx += stride) {
+    const long p = idx % P;
+    if (!col_valid(static_cast<int>(p % Fp), Fp, F)) continue;     // activation rows and logit gradients are zero in the pad columns
+    const float* gb = g + (idx - p);
+    if (l8 == 0) gsum += __ldg(gb + p);
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(act + idx * 64 + l8 * 8));
+    const float2 d0 = unpack_bf16(u.x), d1 = unpack_bf16(u.y), d2 = unpack_bf16(u.z), d3 = unpack_bf16(u.w);
+    const float a[8] = {d0.x, d0.y, d1.x, d1.y, d2.x, d2.y, d3.x, d3.y};
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const long q = p - ((tap / 3 - 1) * Fp + (tap % 3 - 1));
+      if (q < 0 || q >= P) continue;
+      const float gv = __ldg(gb + q);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[tap][j] += gv * a[j];
+    }
+  }
+  // the four row groups of a warp hold the same channels: fold them, then one shared-memory add per (warp, tap, channel)
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = acc[tap][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (sub == 0) atomicAdd(&red[tap * 64 + l8 * 8 + j], v);
+    }
+  gsum += __shfl_xor_sync(0xffffffffu, gsum, 8);
+  gsum += __shfl_xor_sync(0xffffffffu, gsum, 16);
+  if (lane == 0) atomicAdd(&red_g, gsum);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) atomicAdd(dW + (i % 64) * 9 + i / 64, red[i]);
+  if (threadIdx.x == 0 && dbias) atomicAdd(dbias, red_g);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Round 2: the first conv (4 -> 64 channels, 3 x 9; encodec.py:77-79) on the tensor cores.  Its nine frequency taps are folded into
+// channels once per spectrogram:   S9[row][ci*9 + df] = spec[row + df - 4][ci]   (36 of 64 bf16 channels, the rest zero)
+// which turns the layer into a 3-tap (dt = -1, 0, 1 -> row shifts -Fp, 0, Fp) 64 -> 64 channel flattened conv: forward and data gradient
+// run on b200sat_conv2d_flat, the weight gradient on b200sat_conv_wgrad_taps_cat, weight-norm on b200sat_wn_pack / b200sat_wn_bwd - the
+// same entries as the other four layers.  (The fp32 SIMT kernels above took 2.6 / 5 / 10 ms per scale at batch 32: forward / data /
+// weight gradient.)  The spectrogram is rounded to bf16 here - what the reference's Conv2d does under bf16 autocast.
+__global__ void __launch_bounds__(256) disc_spec_pack_kernel(const float* __restrict__ spec, __nv_bfloat16* __restrict__ s9, long total, long P,
+                                                             int Fp, int F) {
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total * 8; idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long pos = idx >> 3;
+    const int ch8 = static_cast<int>(idx & 7);
+    const long p = pos % P;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (ch8 < 5 && col_valid(static_cast<int>(p % Fp), Fp, F)) {
+      const float* sb = spec + (pos - p) * 4;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = ch8 * 8 + j;
+        const int ci = c / 9, df = c % 9;
+        const long q = p + df - 4;
+        v[j] = (c < 36 && q >= 0 && q < P) ? __ldg(sb + q * 4 + ci) : 0.f;
+      }
+      o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    }
+    reinterpret_cast<uint4*>(s9)[idx] = o;
+  }
+}
+
+// d spec[q][ci] = sum_df dS9[q - df + 4][ci*9 + df]   (the transpose of the packing above); block = 128 consecutive rows of one item
+__global__ void __launch_bounds__(128) disc_spec_unpack_kernel(const __nv_bfloat16* __restrict__ ds9, float* __restrict__ dspec, long P, int Fp, int F) {
+  __shared__ __align__(16) __nv_bfloat16 sm[136][40];
+  const long r0 = static_cast<long>(blockIdx.x) * 128;
+  const __nv_bfloat16* base = ds9 + static_cast<long>(blockIdx.y) * P * 64;
+  for (int i = threadIdx.x; i < 136 * 5; i += 128) {
+    const int rr = i / 5, ck = i % 5;
+    const long q = r0 - 4 + rr;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (q >= 0 && q < P) u = __ldg(reinterpret_cast<const uint4*>(base + q * 64 + ck * 8));
+    *reinterpret_cast<uint4*>(&sm[rr][ck * 8]) = u;
+  }
+  __syncthreads();
+  const long q = r0 + threadIdx.x;
+  if (q >= P) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (col_valid(static_cast<int>(q % Fp), Fp, F)) {
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+      for (int df = 0; df < 9; ++df) acc[ci] += __bfloat162float(sm[threadIdx.x + 8 - df][ci * 9 + df]);
+  }
+  reinterpret_cast<float4*>(dspec)[static_cast<long>(blockIdx.y) * P + q] = make_float4(acc[0], acc[1], acc[2], acc[3]);
 }
 
 static int fft_launch_cfg(int n_fft, int* log2n, int* warps, int* smem) {
@@ -527,12 +681,39 @@ extern "C" int b200sat_disc_conv0(const float* spec, const float* w, const float
   return B200SAT_OK;
 }
 
+static bool disc_post_v1() {
+  static const bool v = [] { const char* e = getenv("B200SAT_DISC_POST_V1"); return e && atoi(e) != 0; }();
+  return v;
+}
+
 extern "C" int b200sat_disc_convpost(const void* act, const float* w, const float* bias, float* logits, int B, int frames, int F, void* stream) {
   if (!act || !w || !logits || B <= 0 || frames <= 0 || F <= 0) { set_last_error("disc_convpost: bad arguments"); return B200SAT_EINVAL; }
   const int Fp = F + 8;
   const long total = static_cast<long>(B) * frames * Fp;
-  disc_convpost_fwd_kernel<<<grid_for(total, 128, 8), 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(act), w, bias, logits, B,
-                                                                                                  frames, Fp, F);
+  if (disc_post_v1())
+    disc_convpost_fwd_v1_kernel<<<grid_for(total, 128, 8), 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(act), w, bias, logits,
+                                                                                                       B, frames, Fp, F);
+  else
+    disc_convpost_fwd_kernel<<<grid_for(total * 8, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(act), w, bias, logits,
+                                                                                                        B, frames, Fp, F);
+  B200SAT_CHECK_CUDA(cudaGetLastError());
+  return B200SAT_OK;
+}
+
+/* spec fp32 [B, P, 4] <-> S9 bf16 [B, P, 64] (frequency taps of the first conv folded into channels; see disc_spec_pack_kernel):
+ * backward == 0: s9 = pack(spec);  backward != 0: spec (= d spec) = pack^T(s9 (= d S9)). */
+extern "C" int b200sat_disc_spec_pack(float* spec, void* s9, int B, int frames, int F, int backward, void* stream) {
+  if (!spec || !s9 || B <= 0 || frames <= 0 || F <= 0) { set_last_error("disc_spec_pack: bad arguments"); return B200SAT_EINVAL; }
+  const int Fp = F + 8;
+  const long P = static_cast<long>(frames) * Fp;
+  const long total = static_cast<long>(B) * P;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!backward) {
+    disc_spec_pack_kernel<<<grid_for(total * 8, 256, 8), 256, 0, s>>>(spec, static_cast<__nv_bfloat16*>(s9), total, P, Fp, F);
+  } else {
+    dim3 grid(static_cast<unsigned>((P + 127) / 128), B);
+    disc_spec_unpack_kernel<<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(s9), spec, P, Fp, F);
+  }
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }
@@ -587,9 +768,14 @@ extern "C" int b200sat_disc_conv0_wgrad(const void* dpre, const float* spec, flo
 extern "C" int b200sat_disc_convpost_wgrad(const float* g, const void* act, float* dW, float* dbias, int B, int frames, int F, void* stream) {
   if (!g || !act || !dW || B <= 0 || frames <= 0 || F <= 0) { set_last_error("disc_convpost_wgrad: bad arguments"); return B200SAT_EINVAL; }
   const long total = static_cast<long>(B) * frames * (F + 8);
-  const long cap = static_cast<long>(num_sms()) * 8;
-  disc_convpost_wgrad_kernel<<<static_cast<int>((total + 7) / 8 < cap ? (total + 7) / 8 : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      g, static_cast<const __nv_bfloat16*>(act), dW, dbias, B, frames, F + 8, F);
+  if (disc_post_v1()) {
+    const long cap = static_cast<long>(num_sms()) * 8;
+    disc_convpost_wgrad_v1_kernel<<<static_cast<int>((total + 7) / 8 < cap ? (total + 7) / 8 : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        g, static_cast<const __nv_bfloat16*>(act), dW, dbias, B, frames, F + 8, F);
+  } else {
+    disc_convpost_wgrad_kernel<<<grid_for(total * 8, 256, 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, static_cast<const __nv_bfloat16*>(act), dW, dbias,
+                                                                                                          B, frames, F + 8, F);
+  }
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }

@@ -64,6 +64,10 @@ struct GemmParams {
   // conv weight-gradient addressing (both operands are time-major activation planes behind 4-D maps {C, s, T/s, B}): the K loop walks
   // (item, 64-step time block); each operand is read at its own (phase r, row offset) = one tap of the convolution
   int wg_kb_per_item, wg_rA, wg_offA, wg_rB, wg_offB;
+  // all taps of a flattened 2-D conv weight gradient in ONE launch: the N extent is (tap, 64 channels) and every 64-column block of a B
+  // tile is the same 64-channel plane read at that tap's row shift, so the dY tile is staged once per BN/64 taps instead of once per tap
+  int wg_ntaps;
+  int wg_tap_off[32];
 };
 
 constexpr int BLOCK_M = 128;
@@ -192,8 +196,13 @@ __global__ void __launch_bounds__(384, 1) gemm_bf16_tcgen05(const __grid_constan
             }
 #pragma unroll
             for (int i = 0; i < BN / CTAS / 64; ++i) {
-              if (CTAS == 2) tma_load_4d_pair(sb + i * 8192, &p.tmB, &full_bar[stage], nb0 + 64 * i, p.wg_rB, t0 + p.wg_offB, item);
-              else tma_load_4d(sb + i * 8192, &p.tmB, &full_bar[stage], nb0 + 64 * i, p.wg_rB, t0 + p.wg_offB, item);
+              int chan = nb0 + 64 * i, offB = p.wg_offB;
+              if (p.wg_ntaps > 0) {   // column block -> tap (blocks past the last tap re-read it; the epilogue never stores them)
+                offB = p.wg_tap_off[min(chan >> 6, p.wg_ntaps - 1)];
+                chan = 0;
+              }
+              if (CTAS == 2) tma_load_4d_pair(sb + i * 8192, &p.tmB, &full_bar[stage], chan, p.wg_rB, t0 + offB, item);
+              else tma_load_4d(sb + i * 8192, &p.tmB, &full_bar[stage], chan, p.wg_rB, t0 + offB, item);
             }
           } else if (a_mn || b_mn) {
             // MN-major operands: 64(mn) x 64(k) boxes, one per 64-wide block of the M / N extent (8 KB each)
@@ -672,6 +681,35 @@ extern "C" int b200sat_conv_wgrad(const void* a_plane, int Ca, int Ta, int sA, i
   if (Ca > 128 && Cb > 128) return launch_gemm<256, 2>(p, s);
   if (Cb > 128) return launch_gemm<256, 1>(p, s);
   return launch_gemm<128, 1>(p, s);
+}
+
+// All taps of a 64 -> 64 channel flattened 2-D conv weight gradient in ONE launch (see GemmParams::wg_ntaps):
+//     dWc[ca][tap][cb] += sum_{b,t} A[b,t,ca] * B[b,t + tap_off[tap],cb]          (note the [Ca][ntaps][Cb] output layout)
+// The per-tap entry below reads both planes from HBM once per tap (27 x for a 3x9 kernel; the planes are far larger than L2); here a
+// 128 x 256 tile covers four taps, so the planes stream 7 x instead of 27 x and the zero-padded upper half of the M = 64 accumulator is
+// amortised over four taps.  Backward (dW = dY (*) X) of the Conv2d stacks of models/encodec.py:94-138.
+extern "C" int b200sat_conv_wgrad_taps_cat(const void* a_plane, const void* b_plane, int T, const int* tap_off, int ntaps, float* dWc, int B,
+                                           void* stream) {
+  if (!a_plane || !b_plane || !dWc || !tap_off || ntaps <= 0 || ntaps > 32 || B <= 0 || T <= 0) { set_last_error("conv_wgrad_taps_cat: bad arguments"); return B200SAT_EINVAL; }
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  auto plane_map = [](CUtensorMap* tm, const void* base, int Bn, int Tn) {
+    uint64_t dims[4] = {64, 1, static_cast<uint64_t>(Tn), static_cast<uint64_t>(Bn)};
+    uint64_t strides[3] = {128, 128, static_cast<uint64_t>(Tn) * 128};
+    uint32_t box[4] = {64, 1, 64, 1};
+    return encode_tmap_bf16(tm, base, 4, dims, strides, box, 1);
+  };
+  int rc;
+  if ((rc = plane_map(&p.tmA, a_plane, B, T))) return rc;
+  if ((rc = plane_map(&p.tmB, b_plane, B, T))) return rc;
+  p.D = dWc; p.M = 64; p.N = ntaps * 64; p.ldd = ntaps * 64;
+  p.wg_kb_per_item = (T + BLOCK_K - 1) / BLOCK_K;
+  p.K = B * p.wg_kb_per_item * BLOCK_K;
+  p.wg_ntaps = ntaps;
+  for (int k = 0; k < ntaps; ++k) p.wg_tap_off[k] = tap_off[k];
+  p.flags = GEMM_A_MN | GEMM_B_MN | GEMM_OUT_F32 | GEMM_ACCUM;
+  p.seg_in = 1; p.rope_seq = 1; p.rope_dmodel = 1; p.rope_dh = 64;
+  return launch_gemm<256, 1>(p, static_cast<cudaStream_t>(stream));
 }
 
 // All taps of one conv weight gradient with a per-tap row shift table on the B operand (flattened 2-D convs): dW[tap][Ca][Cb] +=

@@ -1,6 +1,7 @@
 """GPU parity of the Encodec multi-scale STFT discriminator (row G1) against the CPU oracle and the reference-generated golden vectors.
-Tolerances: the STFT front end and the first conv are fp32 (<= 1e-4); the 64-channel convs run bf16 with fp32 accumulation, so logits,
-feature maps and the generator-side gradient are compared at the bf16 level (stated per assertion)."""
+Tolerances: the STFT front end is fp32 (<= 1e-4); all convs run bf16 operands with fp32 accumulation on the tensor cores (the first conv
+through its packed-spectrogram form), so logits, feature maps and the generator-side gradient are compared at the bf16 level (stated per
+assertion)."""
 import json
 import os
 
@@ -55,7 +56,10 @@ def test_discriminator_forward_matches_oracle():
         # reference layout is [B, C, frames, freq] as well (encodec.py:100: 'b c w t -> b c t w')
         assert logits[i].shape == ref_logits[i].shape, (i, logits[i].shape, ref_logits[i].shape)
         e0 = _rel(fmaps[i][0].cpu(), ref_fmaps[i][0])
-        assert e0 <= 6e-3, (i, e0)                                   # fp32 conv, bf16 storage
+        print("scale", i, "first conv rel err", e0)
+        # first conv: bf16 spectrogram x bf16 weights on the tensor cores, fp32 accumulation, bf16 storage (what the reference's Conv2d does
+        # under bf16 autocast); the fp32 SIMT kernels of round 1 (B200SAT_DISC_CONV0=simt) measure <= 6e-3 (storage rounding only)
+        assert e0 <= 1.2e-2, (i, e0)
         for l in range(1, 5):
             e = _rel(fmaps[i][l].cpu(), ref_fmaps[i][l])
             assert e <= 2.5e-2, (i, l, e)
@@ -174,3 +178,38 @@ def test_reference_module_drop_in_loss_is_consistent_with_the_two_step_functions
     for n, p in m.discriminators.named_parameters():
         want = getattr(ref, ("discriminators." + n).replace(".", "__")).grad
         assert (p.grad - want).norm().item() <= 2e-3 * want.norm().item() + 1e-5, n
+
+
+@pytest.mark.parametrize("ntaps,B,T", [(27, 2, 3000), (9, 3, 1111), (5, 1, 64)])
+def test_batched_tap_weight_gradient_matches_fp32_and_the_per_tap_entry(ntaps, B, T):
+    """b200sat_conv_wgrad_taps_cat (all taps of a 64 -> 64 conv weight gradient in one launch, output [ca][tap][cb]) against an fp32 torch
+    evaluation of dW[tap][ca][cb] = sum_{b,t} A[b,t,ca] B[b,t+off,cb] on the same bf16 planes (fp32 accumulation: <= 1e-5 relative to the
+    gradient norm, split-K summation order only) and against the one-launch-per-tap entry (same arithmetic: <= 1e-5)."""
+    import ctypes
+    from b200sat._lib import lib, check
+    g = torch.Generator().manual_seed(ntaps * 100 + T)
+    a = (torch.randn(B, T, 64, generator=g) * 0.5).bfloat16()
+    b = (torch.randn(B, T, 64, generator=g) * 0.5).bfloat16()
+    offs = [int(v) for v in torch.randint(-T // 3 if T > 64 else -20, T // 3 if T > 64 else 20, (ntaps,), generator=g)]
+    offs[0] = 0
+    want = torch.zeros(ntaps, 64, 64, dtype=torch.float64)
+    af, bf = a.double(), b.double()
+    for k, o in enumerate(offs):
+        lo, hi = max(0, -o), min(T, T - o)                         # rows t with 0 <= t + o < T (others are zero padding)
+        if hi > lo:
+            want[k] = torch.einsum("bti,btj->ij", af[:, lo:hi], bf[:, lo + o:hi + o])
+    ad, bd = a.cuda(), b.cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    c_offs = (ctypes.c_int * ntaps)(*offs)
+    cat = torch.zeros(64, ntaps, 64, device="cuda")
+    check(lib().b200sat_conv_wgrad_taps_cat(ad.data_ptr(), bd.data_ptr(), T, c_offs, ntaps, cat.data_ptr(), B, st), "conv_wgrad_taps_cat")
+    per = torch.zeros(ntaps, 64, 64, device="cuda")
+    check(lib().b200sat_conv_wgrad_taps(ad.data_ptr(), 64, bd.data_ptr(), 64, T, c_offs, ntaps, per.data_ptr(), B, st), "conv_wgrad_taps")
+    torch.cuda.synchronize()
+    got = cat.permute(1, 0, 2).cpu().double()
+    assert _rel(got, want) <= 1e-5
+    assert _rel(got, per.cpu().double()) <= 1e-5
+    # accumulation semantics (+=): a second call doubles the result
+    check(lib().b200sat_conv_wgrad_taps_cat(ad.data_ptr(), bd.data_ptr(), T, c_offs, ntaps, cat.data_ptr(), B, st), "conv_wgrad_taps_cat")
+    torch.cuda.synchronize()
+    assert _rel(cat.permute(1, 0, 2).cpu().double(), 2 * want) <= 1e-5

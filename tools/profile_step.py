@@ -31,7 +31,7 @@ def main():
         fn = lambda: sampling.sample_k_dpmpp_3m_sde(eng, noise, 3, 0.03, 1000.0, 1.0, cross, glob, 7.0, 0.0, use_graph=False)
         warm = 1
     elif what == "ae_train":
-        # one generator + one discriminator step of the assembled autoencoder training step, 4 clips x 65536 samples
+        # one generator + one discriminator step of the assembled autoencoder training step, argv[2] (default 4) clips x 65536 samples
         from b200sat.ae_training import AutoencoderTrainingStep
         from b200sat.autoencoder_train import OobleckTrainModel
         from b200sat.discriminator import EncodecDiscriminatorTrain
@@ -46,7 +46,7 @@ def main():
         oc = {"autoencoder": {"optimizer": {"type": "AdamW", "config": {"betas": [0.8, 0.99], "lr": 1.5e-4, "weight_decay": 1e-3}}},
               "discriminator": {"optimizer": {"type": "AdamW", "config": {"betas": [0.8, 0.99], "lr": 3e-4, "weight_decay": 1e-3}}}}
         st = AutoencoderTrainingStep(ae, disc, loss_config=lc, optimizer_configs=oc, use_ema=True)
-        reals = torch.randn(4, 2, 65536, device=dev, generator=g).clamp(-1, 1) * 0.5
+        reals = torch.randn(int(sys.argv[2]) if len(sys.argv) > 2 else 4, 2, 65536, device=dev, generator=g).clamp(-1, 1) * 0.5
 
         def fn():
             st.training_step(reals); st.training_step(reals)
