@@ -84,6 +84,12 @@ int b200sat_fourier_features(const float* t, const void* w, void* out, int B, in
 int b200sat_dit_pre(const float* x, const void* wconv, void* out, int B, int C, int T, int reps, const float* cin_table,
                     const int* step, void* stream);
 
+/* DiT input stage with channel-concatenated conditioning (inpainting; dit.py:160-165 `torch.cat([x, input_concat_cond], dim=1)`, CFG duplication
+ * :336-337): out rows [(rep*B+b)*T + t][Cp] bf16 = (x[b,:,t]*c_in | cond[b,:,t] | 0).  x fp32 [B,C,T], cond fp32 [B,Dc,T]; the 1x1
+ * preprocess_conv + residual (dit.py:193) then run as b200sat_gemm_bf16 with the residual epilogue on a [Cp,Cp] zero-padded weight. */
+int b200sat_dit_concat(const float* x, const float* cond, void* out, int B, int C, int Dc, int Cp, int T, int reps, const float* cin_table,
+                       const int* step, void* stream);
+
 /* DiT output stage: drop `prepend` tokens, transpose to [B,C,T], 1x1 conv + residual, optional classifier-free guidance
  * over the (cond|uncond) batch halves with std-rescale.  Replaces models/dit.py:219-224 and :398-408.  out fp32 [B,C,T]. */
 int b200sat_dit_post(const void* h, long ld_batch, int prepend, const void* wconv, float* out, int B, int C, int T, int cfg,
@@ -221,6 +227,12 @@ int b200sat_conv_wgrad_taps(const void* a_plane, int Ca, const void* b_plane, in
  * shift), so both planes stream from HBM ceil(ntaps/4) times instead of ntaps times.  Output layout dWc[Ca=64][ntaps][Cb=64] (fp32, +=);
  * ntaps <= 32.  Backward of the Conv2d stacks of models/encodec.py:94-138 (dW = dY (*) X). */
 int b200sat_conv_wgrad_taps_cat(const void* a_plane, const void* b_plane, int T, const int* tap_off, int ntaps, float* dWc, int B, void* stream);
+
+/* The same weight gradient in ONE pass over the planes (csrc/disc_wgrad.cu): per 64 time steps one dY tile and, per band of consecutive row
+ * shifts (the frequency taps of one time offset), one 72-row window of X in shared memory; every tap is a row-shifted MN-major descriptor
+ * into its window, two taps share a 128 x 64 MMA.  dW[ntaps][64][64] (fp32, +=).  tap_off must ascend and form at most three bands of at
+ * most nine consecutive shifts (else B200SAT_EUNSUPPORTED: use the _cat entry); ntaps in [2, 28]. */
+int b200sat_conv_wgrad_taps_win(const void* a_plane, const void* b_plane, int T, const int* tap_off, int ntaps, float* dW, int B, void* stream);
 
 /* SnakeBeta backward fused with the skip-connection add and the parameter reductions (models/blocks.py:291-329 under autograd):
  * d_raw = d_skip + d_act * (1 + invb*a*sin(2 a x)); dalpha/dbeta [C] (log-scale parameters) and dbias [C] (= column sums of d_raw, the

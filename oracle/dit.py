@@ -150,8 +150,13 @@ def fourier_features(t, weight):
     return torch.cat([f.cos(), f.sin()], dim=-1)
 
 
-def dit_inner(x, t, sd, depth, cross_attn_cond=None, global_embed=None, global_cond_type="prepend", dim_heads=64):
-    """DiffusionTransformer._forward — dit.py:125-229.  x [B,C,T], t [B]."""
+def dit_inner(x, t, sd, depth, cross_attn_cond=None, global_embed=None, global_cond_type="prepend", dim_heads=64, input_concat_cond=None):
+    """DiffusionTransformer._forward — dit.py:125-229.  x [B,C,T], t [B]; input_concat_cond [B, Dc, T'] is resized (nearest) and
+    concatenated on the channel axis before the preprocess conv (dit.py:160-165)."""
+    if input_concat_cond is not None:
+        if input_concat_cond.shape[2] != x.shape[2]:
+            input_concat_cond = F.interpolate(input_concat_cond, (x.shape[2],), mode="nearest")
+        x = torch.cat([x, input_concat_cond], dim=1)
     if cross_attn_cond is not None:
         c = F.linear(cross_attn_cond, sd["to_cond_embed.0.weight"])
         cross_attn_cond = F.linear(F.silu(c), sd["to_cond_embed.2.weight"])
@@ -178,10 +183,13 @@ def dit_inner(x, t, sd, depth, cross_attn_cond=None, global_embed=None, global_c
 
 
 def dit_forward(x, t, sd, depth, cross_attn_cond=None, global_embed=None, cfg_scale=1.0, scale_phi=0.0,
-                global_cond_type="prepend", dim_heads=64, negative_cross_attn_cond=None):
-    """DiffusionTransformer.forward, inference branch — dit.py:231-431 (CFG :324-410)."""
+                global_cond_type="prepend", dim_heads=64, negative_cross_attn_cond=None, input_concat_cond=None):
+    """DiffusionTransformer.forward, inference branch — dit.py:231-431 (CFG :324-410; the concatenated conditioning is the same for
+    both halves of the CFG batch, :336-337)."""
     dt = sd["preprocess_conv.weight"].dtype
     x, t = x.to(dt), t.to(dt)
+    if input_concat_cond is not None:
+        input_concat_cond = input_concat_cond.to(dt)
     if cross_attn_cond is not None:
         cross_attn_cond = cross_attn_cond.to(dt)
     if global_embed is not None:
@@ -192,7 +200,8 @@ def dit_forward(x, t, sd, depth, cross_attn_cond=None, global_embed=None, cfg_sc
         bg = None if global_embed is None else torch.cat([global_embed, global_embed], 0)
         null = torch.zeros_like(cross_attn_cond) if negative_cross_attn_cond is None else negative_cross_attn_cond.to(dt)
         bc = torch.cat([cross_attn_cond, null], 0)
-        out = dit_inner(bx, bt, sd, depth, bc, bg, global_cond_type, dim_heads)
+        bi = None if input_concat_cond is None else torch.cat([input_concat_cond, input_concat_cond], 0)
+        out = dit_inner(bx, bt, sd, depth, bc, bg, global_cond_type, dim_heads, input_concat_cond=bi)
         cond, uncond = out.chunk(2, 0)
         cfg = uncond + (cond - uncond) * cfg_scale
         if scale_phi != 0.0:
@@ -200,7 +209,7 @@ def dit_forward(x, t, sd, depth, cross_attn_cond=None, global_embed=None, cfg_sc
             os_ = cfg.std(dim=1, keepdim=True)
             return scale_phi * (cfg * (cs / os_)) + (1 - scale_phi) * cfg
         return cfg
-    return dit_inner(x, t, sd, depth, cross_attn_cond, global_embed, global_cond_type, dim_heads)
+    return dit_inner(x, t, sd, depth, cross_attn_cond, global_embed, global_cond_type, dim_heads, input_concat_cond=input_concat_cond)
 
 
 # ---------------------------------------------------------------------------
@@ -215,7 +224,7 @@ def v_objective_loss(model_fn, x0, noise, t):
 
 
 def make_state_dict(embed_dim=1536, depth=24, num_heads=24, io_channels=64, cond_token_dim=768,
-                    global_cond_dim=1536, global_cond_type="prepend", seed=0, std=0.02, dtype=torch.float32):
+                    global_cond_dim=1536, global_cond_type="prepend", seed=0, std=0.02, dtype=torch.float32, input_concat_dim=0):
     """Seeded random DiT weights with the reference's names/shapes (dit.py:12-123, transformer.py).
     Zero-initialised reference weights (to_out, ff out, pre/post conv) are re-randomised so parity is
     not vacuous."""
@@ -227,9 +236,9 @@ def make_state_dict(embed_dim=1536, depth=24, num_heads=24, io_channels=64, cond
         "timestep_features.weight": r(128, 1, sc=1.0),
         "to_timestep_embed.0.weight": r(d, 256), "to_timestep_embed.0.bias": r(d),
         "to_timestep_embed.2.weight": r(d, d), "to_timestep_embed.2.bias": r(d),
-        "preprocess_conv.weight": r(io_channels, io_channels, 1, sc=0.05),
+        "preprocess_conv.weight": r(io_channels + input_concat_dim, io_channels + input_concat_dim, 1, sc=0.05),      # dit.py:88, :115
         "postprocess_conv.weight": r(io_channels, io_channels, 1, sc=0.05),
-        "transformer.project_in.weight": r(d, io_channels, sc=0.1),
+        "transformer.project_in.weight": r(d, io_channels + input_concat_dim, sc=0.1),
         "transformer.project_out.weight": r(io_channels, d),
     }
     rot = max(dh // 2, 32)

@@ -30,6 +30,7 @@ SIGNATURES = {
     "b200sat_small_linear": (c_int, [c_void_p, c_long, c_void_p, c_long, c_fp, c_void_p, c_long, c_void_p, c_long,
                                      c_int, c_int, c_int, c_int, c_int, c_int, c_fp, c_long, c_void_p]),
     "b200sat_fourier_features": (c_int, [c_fp, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "b200sat_dit_concat": (c_int, [c_fp, c_fp, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_fp, c_void_p, c_void_p]),
     "b200sat_dit_pre": (c_int, [c_fp, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_fp, c_void_p, c_void_p]),
     "b200sat_dit_post": (c_int, [c_void_p, c_long, c_int, c_void_p, c_fp, c_int, c_int, c_int, c_int, c_float, c_float,
                                  c_void_p]),
@@ -72,6 +73,7 @@ SIGNATURES = {
     "b200sat_disc_conv0_wgrad": (c_int, [c_void_p, c_fp, c_fp, c_int, c_int, c_int, c_void_p]),
     "b200sat_disc_convpost_wgrad": (c_int, [c_fp, c_void_p, c_fp, c_fp, c_int, c_int, c_int, c_void_p]),
     "b200sat_conv_wgrad_taps": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_fp, c_int, c_void_p]),
+    "b200sat_conv_wgrad_taps_win": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_fp, c_int, c_void_p]),
     "b200sat_conv_wgrad_taps_cat": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_fp, c_int, c_void_p]),
     "b200sat_snake_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_fp, c_fp, c_void_p, c_fp, c_fp, c_fp, c_long, c_int, c_void_p]),
     "b200sat_wn_pack_dgrad": (c_int, [c_fp, c_fp, c_fp, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -25,6 +25,7 @@ LEAKY = 0.2
 DILATIONS = (1, 2, 4)
 # first conv on the tensor cores (default); B200SAT_DISC_CONV0=simt keeps the round-1 fp32 SIMT kernels
 CONV0_TC = os.environ.get("B200SAT_DISC_CONV0", "tc") != "simt"
+WGRAD_MODE = os.environ.get("B200SAT_DISC_WGRAD", "cat")
 
 
 def _s():
@@ -260,12 +261,15 @@ def _discriminator_backward(eng, saved, n_logit, B):
         ft, ff, lf, fr, lt, spec_r, spec_f = saved[i]
         P = fr * sc.Fp
         dW0 = torch.zeros(64, 4, 27, device=dev)
-        dW0c = torch.zeros(64, 3, 64, device=dev)     # tensor-core form of the first conv: [co][dt][ci*9 + df]
+        dW0c = torch.zeros(64, 3, 64, device=dev)     # tensor-core form of the first conv: [co][dt][ci*9 + df] (cat entry)
+        dW0t = torch.zeros(3, 64, 64, device=dev)     # ... [dt][co][ci*9 + df] (win entry)
         db0 = torch.zeros(64, device=dev)
         dWp = torch.zeros(64, 9, device=dev)
         dbp = torch.zeros(1, device=dev)
-        # batched taps (default): one launch per layer writes dWc[ca][tap][cb]; B200SAT_DISC_WGRAD_CAT=0 = one launch per tap, dW[tap][ca][cb]
-        cat = os.environ.get("B200SAT_DISC_WGRAD_CAT", "1") != "0"
+        # weight gradients of the 64 -> 64 convs, B200SAT_DISC_WGRAD = win (default: one pass over the planes, csrc/disc_wgrad.cu, dW[tap][ca][cb])
+        # | cat (four taps per tile, dWc[ca][tap][cb]) | tap (one launch per tap)
+        wmode = WGRAD_MODE
+        cat = wmode == "cat"
         dwps = [torch.zeros(64, cv["K"], 64, device=dev) if cat else torch.zeros(cv["K"], 64, 64, device=dev) for cv in sc.convs]
         dbs = [torch.zeros(64, device=dev) for _ in sc.convs]
         for lg, fm, spec, mode in ((lt, ft, spec_r, 1), (lf, ff, spec_f, 2)):
@@ -277,7 +281,11 @@ def _discriminator_backward(eng, saved, n_logit, B):
             ops.LAUNCHES[0] += 3
             for l in range(4, 0, -1):
                 cv = sc.convs[l - 1]
-                if cat:
+                if wmode == "win":
+                    check(lib().b200sat_conv_wgrad_taps_win(d_pre.data_ptr(), fm[l - 1].data_ptr(), P, cv["offs"], cv["K"], dwps[l - 1].data_ptr(), B, st),
+                          "conv_wgrad_taps_win")
+                    ops.LAUNCHES[0] += 1
+                elif cat:
                     check(lib().b200sat_conv_wgrad_taps_cat(d_pre.data_ptr(), fm[l - 1].data_ptr(), P, cv["offs"], cv["K"], dwps[l - 1].data_ptr(), B, st),
                           "conv_wgrad_taps_cat")
                     ops.LAUNCHES[0] += 1
@@ -290,7 +298,9 @@ def _discriminator_backward(eng, saved, n_logit, B):
                 d_pre = torch.empty_like(d_in)
                 check(lib().b200sat_disc_act_bwd(d_in.data_ptr(), 0, 0, fm[l - 1].data_ptr(), 0, 0.0, LEAKY, d_pre.data_ptr(), B, fr, sc.F, st), "disc_act_bwd")
                 ops.LAUNCHES[0] += 1
-            if sc.cv0 is not None:     # `spec` is the packed S9 plane: a 3-tap 64 -> 64 weight gradient
+            if sc.cv0 is not None and wmode == "win":     # `spec` is the packed S9 plane: a 3-tap 64 -> 64 weight gradient
+                check(lib().b200sat_conv_wgrad_taps_win(d_pre.data_ptr(), spec.data_ptr(), P, sc.cv0["offs"], 3, dW0t.data_ptr(), B, st), "conv_wgrad_taps_win")
+            elif sc.cv0 is not None:
                 check(lib().b200sat_conv_wgrad_taps_cat(d_pre.data_ptr(), spec.data_ptr(), P, sc.cv0["offs"], 3, dW0c.data_ptr(), B, st), "conv_wgrad_taps_cat")
             else:
                 check(lib().b200sat_disc_conv0_wgrad(d_pre.data_ptr(), spec.data_ptr(), dW0.data_ptr(), B, fr, sc.F, st), "disc_conv0_wgrad")
@@ -314,7 +324,8 @@ def _discriminator_backward(eng, saved, n_logit, B):
             cv = sc.cv0
             dv9 = torch.empty_like(cv["v3"])
             dg0 = torch.empty_like(cv["g"])
-            check(lib().b200sat_wn_bwd(dW0c.permute(1, 0, 2).contiguous().data_ptr(), cv["v3"].data_ptr(), cv["g"].data_ptr(), cv["inv"].data_ptr(),
+            dw0 = dW0t if wmode == "win" else dW0c.permute(1, 0, 2).contiguous()
+            check(lib().b200sat_wn_bwd(dw0.data_ptr(), cv["v3"].data_ptr(), cv["g"].data_ptr(), cv["inv"].data_ptr(),
                                        dv9.data_ptr(), dg0.data_ptr(), 64, 64, 3, st), "wn_bwd")
             ops.LAUNCHES[0] += 1
             dv0 = dv9[:, :36].reshape(64, 4, 9, 3).permute(0, 1, 3, 2).reshape(v0.shape).contiguous()     # [co][ci*9+df][dt] -> [co][ci][dt][df]

@@ -13,8 +13,13 @@ from . import ops
 
 class DiTConfig:
     def __init__(self, io_channels=64, embed_dim=1536, depth=24, num_heads=24, cond_token_dim=768, global_cond_dim=1536,
-                 global_cond_type="prepend", project_cond_tokens=False, project_global_cond=True):
+                 global_cond_type="prepend", project_cond_tokens=False, project_global_cond=True, input_concat_dim=0):
         self.io_channels, self.embed_dim, self.depth, self.num_heads = io_channels, embed_dim, depth, num_heads
+        # channels concatenated to the input (inpainting: mask + masked latents, dit.py:86-88); rows are padded to a multiple of 8 channels
+        self.input_concat_dim = int(input_concat_dim)
+        self.dim_in_pad = (io_channels + self.input_concat_dim + 7) // 8 * 8
+        if self.input_concat_dim < 0 or self.dim_in_pad > 256:
+            raise NotImplementedError("b200sat DiT engine: input_concat_dim must keep io_channels + input_concat_dim <= 256")
         self.cond_token_dim, self.global_cond_dim, self.global_cond_type = cond_token_dim, global_cond_dim, global_cond_type
         self.dim_heads = embed_dim // num_heads
         self.cond_embed_dim = cond_token_dim if not project_cond_tokens else embed_dim
@@ -26,13 +31,14 @@ class DiTConfig:
     @staticmethod
     def from_state_dict(sd, num_heads=None):
         d = sd["transformer.project_in.weight"].shape[0]
-        io = sd["transformer.project_in.weight"].shape[1]
+        io = sd["transformer.project_out.weight"].shape[0]
+        icd = sd["transformer.project_in.weight"].shape[1] - io
         depth = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("transformer.layers."))
         ctd = sd["to_cond_embed.0.weight"].shape[1] if "to_cond_embed.0.weight" in sd else 0
         gcd = sd["to_global_embed.0.weight"].shape[1] if "to_global_embed.0.weight" in sd else 0
         gct = "adaLN" if "transformer.global_cond_embedder.0.weight" in sd else "prepend"
         pct = ("to_cond_embed.0.weight" in sd) and sd["to_cond_embed.0.weight"].shape[0] != ctd
-        return DiTConfig(io, d, depth, num_heads or d // 64, ctd, gcd, gct, project_cond_tokens=pct)
+        return DiTConfig(io, d, depth, num_heads or d // 64, ctd, gcd, gct, project_cond_tokens=pct, input_concat_dim=icd)
 
 
 class DiTEngine:
@@ -71,6 +77,14 @@ class DiTEngine:
         kvs = [w[f"transformer.layers.{i}.cross_attn.to_kv.weight"] for i in range(self.cfg.depth) if f"transformer.layers.{i}.cross_attn.to_kv.weight" in w]
         if len(kvs) == self.cfg.depth and self.cfg.depth > 0:
             w["_all_to_kv.weight"] = torch.cat(kvs, dim=0).contiguous()
+        if self.cfg.input_concat_dim > 0:
+            # preprocess_conv [dim_in, dim_in] and project_in [d, dim_in] zero-padded to the row pitch of the concatenated input
+            cp, di = self.cfg.dim_in_pad, self.cfg.io_channels + self.cfg.input_concat_dim
+            wp = torch.zeros(cp, cp, device=dev, dtype=torch.bfloat16)
+            wp[:di, :di] = w["preprocess_conv.weight"]
+            wi = torch.zeros(self.cfg.embed_dim, cp, device=dev, dtype=torch.bfloat16)
+            wi[:, :di] = w["transformer.project_in.weight"]
+            w["_preprocess_pad.weight"], w["_project_in_pad.weight"] = wp, wi
         self.ln_fold = {}
         if getattr(self, "fuse_ln", False):
             for i in range(self.cfg.depth):
@@ -109,6 +123,8 @@ class DiTEngine:
             xin=bf(Bx * T, c.io_channels), o=bf(M, c.io_channels),
             ff_feat=bf(Bx, 256), te1=bf(Bx, d), ge1=bf(Bx, d), ge=bf(Bx, d), gl=bf(Bx, d),
         )
+        if c.input_concat_dim > 0:
+            ws.update(xcat=bf(Bx * T, c.dim_in_pad), xin_cat=bf(Bx * T, c.dim_in_pad))
         if L > 0:
             ws.update(ctx_in=bf(Bx * L, c.cond_token_dim), ctx1=bf(Bx * L, c.cond_embed_dim), ctx=bf(Bx * L, c.cond_embed_dim),
                       kv=bf(Bx * L, 2 * c.cond_embed_dim), kv_all=bf(Bx * L, c.depth * 2 * c.cond_embed_dim))
@@ -139,10 +155,11 @@ class DiTEngine:
         return True
 
     def forward_into(self, out, x, t, ctx_in, global_in, Bx, reps, cfg, cfg_scale, scale_phi,
-                     cin_table=None, t_table_step=None, step=None, cond_cached=False):
+                     cin_table=None, t_table_step=None, step=None, cond_cached=False, concat_in=None):
         """out fp32 [B,C,T];  x fp32 [B,C,T];  t fp32 [Bx] (or a [steps, Bx] table walked by *step);
         ctx_in bf16 [Bx*L, cond_token_dim] or None;  global_in bf16 [Bx, global_cond_dim] or None.
-        cond_cached: `precompute_conditioning` already filled this signature's ctx / kv_all / ge buffers for the same ctx_in / global_in."""
+        cond_cached: `precompute_conditioning` already filled this signature's ctx / kv_all / ge buffers for the same ctx_in / global_in.
+        concat_in: fp32 [B, input_concat_dim, T] (models with input_concat_dim > 0; the same tensor serves both CFG halves, dit.py:336-337)."""
         c, w = self.cfg, self.w
         d, H = c.embed_dim, c.num_heads
         B, C, T = x.shape
@@ -176,8 +193,17 @@ class DiTEngine:
         else:
             self._lin_small(ws["te1"], w["to_timestep_embed.2.weight"], w["to_timestep_embed.2.bias"], gdst, **st0)
         # --- input stage (dit.py:193-195, transformer.py:811-819)
-        ops.dit_pre(x, w["preprocess_conv.weight"], ws["xin"], reps=reps, cin_table=cin_table, step=step)
-        ops.linear(ws["xin"], w["transformer.project_in.weight"], out=h, row_remap=(T, N, P), out_stats=st[0] if fuse else None)
+        if c.input_concat_dim > 0:
+            if concat_in is None:
+                raise ValueError("this DiT was built with input_concat_dim > 0: input_concat_cond is required (dit.py:160-165)")
+            ops.dit_concat(x, concat_in, ws["xcat"], reps=reps, cin_table=cin_table, step=step)
+            ops.linear(ws["xcat"], w["_preprocess_pad.weight"], residual=ws["xcat"], out=ws["xin_cat"])      # preprocess_conv(x) + x, dit.py:193
+            ops.linear(ws["xin_cat"], w["_project_in_pad.weight"], out=h, row_remap=(T, N, P), out_stats=st[0] if fuse else None)
+        else:
+            if concat_in is not None:
+                raise ValueError("input_concat_cond given to a DiT without input_concat_dim")
+            ops.dit_pre(x, w["preprocess_conv.weight"], ws["xin"], reps=reps, cin_table=cin_table, step=step)
+            ops.linear(ws["xin"], w["transformer.project_in.weight"], out=h, row_remap=(T, N, P), out_stats=st[0] if fuse else None)
         cos, sin = self.rope_tables(N)
         # --- adaLN modulation tables (transformer.py:836-837, :677)
         mods = None
@@ -259,7 +285,7 @@ class DiTEngine:
 
     @torch.no_grad()
     def forward(self, x, t, cross_attn_cond=None, global_embed=None, cfg_scale=1.0, scale_phi=0.0,
-                negative_cross_attn_cond=None, out=None):
+                negative_cross_attn_cond=None, out=None, input_concat_cond=None):
         """Mirror of DiffusionTransformer.forward's inference branch (dit.py:231-431)."""
         B, C, T = x.shape
         dev = self.device
@@ -286,4 +312,14 @@ class DiTEngine:
         t = t.contiguous()
         if out is None:
             out = torch.empty(B, C, T, device=dev, dtype=torch.float32)
-        return self.forward_into(out, x, t, ctx_in, g_in, Bx, reps, cfg, float(cfg_scale), float(scale_phi))
+        concat = None
+        if input_concat_cond is not None:
+            concat = self.prepare_concat(input_concat_cond, T)
+        return self.forward_into(out, x, t, ctx_in, g_in, Bx, reps, cfg, float(cfg_scale), float(scale_phi), concat_in=concat)
+
+    def prepare_concat(self, input_concat_cond, T):
+        """dit.py:160-163 + :268-269: nearest-neighbour resize to the input length, cast to the model dtype (bf16), kept as fp32 values."""
+        cc = input_concat_cond.to(self.device, torch.float32)
+        if cc.shape[2] != T:
+            cc = torch.nn.functional.interpolate(cc, (T,), mode="nearest")
+        return cc.bfloat16().float().contiguous()

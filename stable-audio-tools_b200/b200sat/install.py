@@ -86,7 +86,10 @@ def _dit_supported(m, kwargs):
     bad = []
     if getattr(m, "transformer_type", "continuous_transformer") != "continuous_transformer": bad.append("transformer_type")
     if getattr(m, "patch_size", 1) != 1: bad.append("patch_size != 1")
-    if getattr(m, "input_concat_dim", 0) != 0: bad.append("input_concat_cond")
+    icd = int(getattr(m, "input_concat_dim", 0) or 0)
+    if icd < 0 or 64 + icd > 256: bad.append("input_concat_dim")
+    if (icd > 0) != (kwargs.get("input_concat_cond") is not None):
+        bad.append("input_concat_cond missing / unexpected for this input_concat_dim")
     if getattr(m, "timestep_cond_type", "global") != "global": bad.append("timestep_cond_type")
     if getattr(m, "global_cond_type", "prepend") not in ("prepend", "adaLN"): bad.append("global_cond_type")
     if getattr(m, "diffusion_objective", "v") not in ("v",): bad.append("diffusion_objective")
@@ -96,7 +99,7 @@ def _dit_supported(m, kwargs):
     if getattr(t, "sliding_window", None) is not None: bad.append("sliding window")
     if getattr(t, "rotary_pos_emb", None) is None: bad.append("no rotary embedding")
     pin = getattr(t, "project_in", None)
-    if not isinstance(pin, torch.nn.Linear) or pin.in_features != 64: bad.append("io_channels != 64")
+    if not isinstance(pin, torch.nn.Linear) or pin.in_features != 64 + icd: bad.append("io_channels != 64")
     if getattr(m, "to_cond_embed", None) is None: bad.append("no cross-attention conditioning")
     blk = t.layers[0] if len(t.layers) else None
     if blk is None:
@@ -117,7 +120,7 @@ def _dit_supported(m, kwargs):
         if not all(getattr(b_, "cross_attend", False) for b_ in t.layers): bad.append("layers without cross-attention (final_cross_attn_ix)")
         ff0 = blk.ff.ff[0]
         if not hasattr(ff0, "proj") or getattr(blk.ff.ff[2], "bias", None) is None: bad.append("feed-forward variant (needs SwiGLU + biases)")
-    for k in ("prepend_cond", "input_concat_cond", "mask", "exit_layer_ix", "negative_global_embed"):
+    for k in ("prepend_cond", "mask", "exit_layer_ix", "negative_global_embed"):
         if kwargs.get(k) is not None: bad.append(k)
     if kwargs.get("return_info"): bad.append("return_info")
     if kwargs.get("causal"): bad.append("causal")
@@ -202,6 +205,8 @@ def install(strict=False, engine_factories=None, fp32_models=None, training=True
             bad.append("cross_attn_cond is None")
         if grad and (cfg_scale != 1.0 or negative_cross_attn_cond is not None):
             bad.append("classifier-free guidance inside an autograd-tracked call")
+        if grad and getattr(self, "input_concat_dim", 0):
+            bad.append("input_concat_cond in the training path")
         if not bad and not _half_compute(self, fp32_models):
             bad.append("fp32 model outside autocast (reference computes in fp32; pass fp32_models=True to opt in to bf16)")
             if not strict:
@@ -228,8 +233,9 @@ def install(strict=False, engine_factories=None, fp32_models=None, training=True
         if eng is None:
             return reference()
         STATS["dit_fast"] += 1
+        extra = {"input_concat_cond": kw["input_concat_cond"]} if kw.get("input_concat_cond") is not None else {}
         out = eng.forward(x, t, cross_attn_cond=cross_attn_cond, global_embed=global_embed, cfg_scale=cfg_scale, scale_phi=scale_phi,
-                          negative_cross_attn_cond=negative_cross_attn_cond)
+                          negative_cross_attn_cond=negative_cross_attn_cond, **extra)
         return out.to(out_dtype)
 
     dit_mod.DiffusionTransformer.forward = dit_forward
@@ -265,7 +271,8 @@ def install(strict=False, engine_factories=None, fp32_models=None, training=True
     orig_sample_k = samp_mod.sample_k
     # negative_global_cond is accepted and dropped by DiTWrapper.forward itself (models/diffusion.py:507-557)
     _SAMPLER_KW = {"cross_attn_cond", "cross_attn_mask", "global_cond", "cfg_scale", "batch_cfg", "rescale_cfg", "scale_phi",
-                   "negative_cross_attn_cond", "negative_cross_attn_mask", "negative_global_cond", "cfg_interval"}
+                   "negative_cross_attn_cond", "negative_cross_attn_mask", "negative_global_cond", "cfg_interval",
+                   "input_concat_cond", "negative_input_concat_cond"}     # the negative copy is never read by DiTWrapper / the DiT (models/diffusion.py:204)
 
     @functools.wraps(orig_sample_k)
     def sample_k(model_fn, noise, init_data=None, steps=100, sampler_type="dpmpp-2m-sde", sigma_min=0.01, sigma_max=100, rho=1.0,
@@ -282,7 +289,8 @@ def install(strict=False, engine_factories=None, fp32_models=None, training=True
               and sampler_type in ("dpmpp-3m-sde", "v-ddim") and isinstance(inner, dit_mod.DiffusionTransformer)
               and live <= _SAMPLER_KW and extra_args.get("cross_attn_cond") is not None
               and (ci is None or tuple(float(v) for v in ci) == (0.0, 1.0))
-              and extra_args.get("batch_cfg", True) and not _dit_supported(inner, {}) and _half_compute(inner, fp32_models))
+              and extra_args.get("batch_cfg", True) and not _dit_supported(inner, {"input_concat_cond": extra_args.get("input_concat_cond")})
+              and _half_compute(inner, fp32_models))
         eng = guarded(dit_cache, inner, "DiT") if ok else None
         if eng is None:
             STATS["sample_k_ref"] += 1
@@ -295,6 +303,8 @@ def install(strict=False, engine_factories=None, fp32_models=None, training=True
             neg = _apply_negative_mask(neg, extra_args["negative_cross_attn_mask"])
         kw = dict(cross_attn_cond=extra_args.get("cross_attn_cond"), global_embed=extra_args.get("global_cond"),
                   cfg_scale=extra_args.get("cfg_scale", 1.0), scale_phi=extra_args.get("scale_phi", 0.0), negative_cross_attn_cond=neg)
+        if extra_args.get("input_concat_cond") is not None:
+            kw["input_concat_cond"] = extra_args["input_concat_cond"]
         run = ef.get("sampler")
         if run is not None:
             return run(eng, noise, steps, sampler_type, sigma_min, sigma_max, rho, **kw).to(noise.dtype)

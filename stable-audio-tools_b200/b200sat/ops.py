@@ -180,6 +180,18 @@ def dit_pre(x, wconv, out, reps=1, cin_table=None, step=None):
     return out
 
 
+def dit_concat(x, cond, out, reps=1, cin_table=None, step=None):
+    """out rows [(rep*B+b)*T + t][Cp] bf16 = (x[b,:,t]*c_in | cond[b,:,t] | 0): dit.py:160-165 (`torch.cat([x, input_concat_cond], dim=1)`)."""
+    B, C, T = x.shape
+    Dc, Cp = cond.shape[1], out.shape[1]
+    assert x.dtype == torch.float32 and x.is_contiguous() and cond.dtype == torch.float32 and cond.is_contiguous()
+    assert cond.shape[0] == B and cond.shape[2] == T and out.dtype == torch.bfloat16 and out.is_contiguous()
+    rc = lib().b200sat_dit_concat(x.data_ptr(), cond.data_ptr(), out.data_ptr(), B, C, Dc, Cp, T, reps, _p(cin_table), _p(step), _stream())
+    LAUNCHES[0] += 1
+    check(rc, "dit_concat")
+    return out
+
+
 def dit_post(h, ld_batch, prepend, wconv, out, cfg=False, cfg_scale=1.0, scale_phi=0.0):
     B, C, T = out.shape
     rc = lib().b200sat_dit_post(h.data_ptr(), ld_batch, prepend, wconv.data_ptr(), out.data_ptr(), B, C, T, int(cfg),

@@ -100,6 +100,9 @@ class GraphSampler:
         self.step = torch.zeros(1, dtype=torch.int32, device=dev)
         self.ctx = torch.zeros(self.Bx * L, engine.cfg.cond_token_dim, device=dev, dtype=torch.bfloat16) if L > 0 else None
         self.glob = torch.zeros(self.Bx, engine.cfg.global_cond_dim, device=dev, dtype=torch.bfloat16) if has_global else None
+        # channel-concatenated conditioning (inpainting mask + masked latents): constant over the run, same for both CFG halves
+        dc = engine.cfg.input_concat_dim
+        self.concat = torch.zeros(B, dc, T, device=dev) if dc > 0 else None
         self.use_graph = use_graph
         # prompt-only work (conditioning embedding, every layer's cross-attention K/V, global-embedding MLP) runs once per run(), not per step
         self.cond_cached = L == 0 or "_all_to_kv.weight" in engine.w
@@ -120,7 +123,7 @@ class GraphSampler:
 
     def _one_step(self):
         self.e.forward_into(self.v, self.x, self.tt, self.ctx, self.glob, self.Bx, self.reps, self.cfg, self.cfg_scale,
-                            self.scale_phi, cin_table=self.cin, step=self.step, cond_cached=self.cond_cached)
+                            self.scale_phi, cin_table=self.cin, step=self.step, cond_cached=self.cond_cached, concat_in=self.concat)
         ops.sampler_update(self.x, self.v, self.hist, self.noise, self.coef, self.step, advance=True)
 
     def _ensure_graph(self):
@@ -142,9 +145,11 @@ class GraphSampler:
 
     @torch.no_grad()
     def run(self, noise, coef, cin, tt, cross_attn_cond=None, global_embed=None, step_noise=None, init_scale=1.0,
-            negative_cross_attn_cond=None):
+            negative_cross_attn_cond=None, input_concat_cond=None, init_data=None, init_data_scale=1.0):
         """noise [B,C,T] (unit variance), tables from *_tables(); step_noise [steps,B,C,T] or None (drawn with torch.randn).
-        Host tensors are accepted (copied with non_blocking=True from pinned memory)."""
+        Host tensors are accepted (copied with non_blocking=True from pinned memory).
+        input_concat_cond [B, input_concat_dim, T'] for models built with input_concat_dim (resized like dit.py:160-163);
+        init_data: start from init_data*init_data_scale + noise*init_scale (sampling.py:360-366 / :396-399: variations)."""
         steps = coef.shape[0]
         dev = self.e.device
         self._alloc_tables(steps)
@@ -167,9 +172,17 @@ class GraphSampler:
                 self.glob[self.B:].copy_(gg)
         if self.cond_cached:
             self.e.precompute_conditioning(self.ctx, self.glob, self.Bx, self.T)
+        if self.concat is not None:
+            if input_concat_cond is None:
+                raise ValueError("this DiT was built with input_concat_dim > 0: input_concat_cond is required")
+            self.concat.copy_(self.e.prepare_concat(input_concat_cond, self.T))
+        elif input_concat_cond is not None:
+            raise ValueError("input_concat_cond given to a DiT without input_concat_dim")
         self.x.copy_(noise.to(dev, torch.float32, non_blocking=True))
         if init_scale != 1.0:
             self.x.mul_(init_scale)
+        if init_data is not None:
+            self.x.add_(init_data.to(dev, torch.float32), alpha=float(init_data_scale))
         if step_noise is None:
             if bool((coef[:, 6] != 0).any()):
                 torch.randn(self.noise[:steps].shape, out=self.noise[:steps])
@@ -189,7 +202,7 @@ class GraphSampler:
 
 def sample_k_dpmpp_3m_sde(engine, noise, steps=100, sigma_min=0.03, sigma_max=1000.0, rho=1.0, cross_attn_cond=None,
                           global_embed=None, cfg_scale=1.0, scale_phi=0.0, eta=1.0, s_noise=1.0, step_noise=None,
-                          sampler=None, use_graph=True, negative_cross_attn_cond=None):
+                          sampler=None, use_graph=True, negative_cross_attn_cond=None, input_concat_cond=None, init_data=None):
     """`sample_k(model_fn, noise, steps=..., sampler_type='dpmpp-3m-sde', ...)` for a DiTEngine (inference/sampling.py:331-387)."""
     B, C, T = noise.shape
     L = 0 if cross_attn_cond is None else cross_attn_cond.shape[1]
@@ -198,15 +211,18 @@ def sample_k_dpmpp_3m_sde(engine, noise, steps=100, sigma_min=0.03, sigma_max=10
     if sampler is None:
         sampler = GraphSampler(engine, B, C, T, L, global_embed is not None, cfg_scale, scale_phi, use_graph)
     return sampler.run(noise, coef, cin, tt, cross_attn_cond, global_embed, step_noise, init_scale=float(sig[0]),
-                       negative_cross_attn_cond=negative_cross_attn_cond).clone()
+                       negative_cross_attn_cond=negative_cross_attn_cond, input_concat_cond=input_concat_cond, init_data=init_data).clone()
 
 
 def sample_v_ddim(engine, noise, steps=100, sigma_max=1.0, cross_attn_cond=None, global_embed=None, cfg_scale=1.0,
-                  scale_phi=0.0, sampler=None, use_graph=True, negative_cross_attn_cond=None):
+                  scale_phi=0.0, sampler=None, use_graph=True, negative_cross_attn_cond=None, input_concat_cond=None, init_data=None):
     """`sample_k(..., sampler_type='v-ddim')` -> in-repo `sample(model, x, steps, eta=0)` (inference/sampling.py:253-307,:405-407)."""
     B, C, T = noise.shape
     L = 0 if cross_attn_cond is None else cross_attn_cond.shape[1]
     coef, cin, tt = v_ddim_tables(steps, min(sigma_max, 1.0))
     if sampler is None:
         sampler = GraphSampler(engine, B, C, T, L, global_embed is not None, cfg_scale, scale_phi, use_graph)
-    return sampler.run(noise, coef, cin, tt, cross_attn_cond, global_embed, None, negative_cross_attn_cond=negative_cross_attn_cond).clone()
+    sm = min(sigma_max, 1.0)
+    a0, s0 = (math.cos(sm * math.pi / 2), math.sin(sm * math.pi / 2)) if init_data is not None else (1.0, 1.0)   # sampling.py:394-399
+    return sampler.run(noise, coef, cin, tt, cross_attn_cond, global_embed, None, negative_cross_attn_cond=negative_cross_attn_cond,
+                       input_concat_cond=input_concat_cond, init_scale=s0, init_data=init_data, init_data_scale=a0).clone()

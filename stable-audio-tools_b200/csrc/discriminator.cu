@@ -475,12 +475,10 @@ __global__ void __launch_bounds__(256) disc_convpost_wgrad_v1_kernel(const float
 __global__ void __launch_bounds__(256) disc_convpost_fwd_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ w /*[1][64][9]*/,
                                                                 const float* __restrict__ bias, float* __restrict__ logits, int B, int frames,
                                                                 int Fp, int F) {
+  __shared__ __align__(16) float sw[9 * 64];   // [tap][c]
+  for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) sw[i] = w[(i % 64) * 9 + i / 64];
+  __syncthreads();
   const int lane = threadIdx.x & 31, l8 = lane & 7, sub = lane >> 3;
-  float wr[9][8];
-#pragma unroll
-  for (int tap = 0; tap < 9; ++tap)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) wr[tap][j] = __ldg(w + (l8 * 8 + j) * 9 + tap);
   const long P = static_cast<long>(frames) * Fp;
   const long total = static_cast<long>(B) * P;
   const float bv = bias ? bias[0] : 0.f;
@@ -493,14 +491,22 @@ __global__ void __launch_bounds__(256) disc_convpost_fwd_kernel(const __nv_bfloa
     float acc = 0.f;
     if (ok) {
       const __nv_bfloat16* rowbase = act + (idx - p) * 64 + l8 * 8;
+      // nine independent loads (row index clamped, contribution masked): a bounds branch per tap would serialise them behind each other
+      uint4 u[9];
+      float m[9];
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
         const long q = p + (tap / 3 - 1) * Fp + (tap % 3 - 1);
-        if (q < 0 || q >= P) continue;
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(rowbase + q * 64));
-        const float2 d0 = unpack_bf16(u.x), d1 = unpack_bf16(u.y), d2 = unpack_bf16(u.z), d3 = unpack_bf16(u.w);
-        acc += d0.x * wr[tap][0] + d0.y * wr[tap][1] + d1.x * wr[tap][2] + d1.y * wr[tap][3] + d2.x * wr[tap][4] + d2.y * wr[tap][5] +
-               d3.x * wr[tap][6] + d3.y * wr[tap][7];
+        const long qc = q < 0 ? 0 : (q >= P ? P - 1 : q);
+        m[tap] = (q == qc) ? 1.f : 0.f;
+        u[tap] = __ldg(reinterpret_cast<const uint4*>(rowbase + qc * 64));
+      }
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&sw[tap * 64 + l8 * 8]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&sw[tap * 64 + l8 * 8 + 4]);
+        const float2 d0 = unpack_bf16(u[tap].x), d1 = unpack_bf16(u[tap].y), d2 = unpack_bf16(u[tap].z), d3 = unpack_bf16(u[tap].w);
+        acc += m[tap] * (d0.x * w0.x + d0.y * w0.y + d1.x * w0.z + d1.y * w0.w + d2.x * w1.x + d2.y * w1.y + d3.x * w1.z + d3.y * w1.w);
       }
     }
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
@@ -539,14 +545,18 @@ __global__ void __launch_bounds__(256) disc_convpost_wgrad_kernel(const float* _
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(act + idx * 64 + l8 * 8));
     const float2 d0 = unpack_bf16(u.x), d1 = unpack_bf16(u.y), d2 = unpack_bf16(u.z), d3 = unpack_bf16(u.w);
     const float a[8] = {d0.x, d0.y, d1.x, d1.y, d2.x, d2.y, d3.x, d3.y};
+    float gv[9];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
+    for (int tap = 0; tap < 9; ++tap) {     // independent loads: clamp the row, mask the value
       const long q = p - ((tap / 3 - 1) * Fp + (tap % 3 - 1));
-      if (q < 0 || q >= P) continue;
-      const float gv = __ldg(gb + q);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[tap][j] += gv * a[j];
+      const long qc = q < 0 ? 0 : (q >= P ? P - 1 : q);
+      const float t = __ldg(gb + qc);
+      gv[tap] = (q == qc) ? t : 0.f;
     }
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[tap][j] += gv[tap] * a[j];
   }
   // the four row groups of a warp hold the same channels: fold them, then one shared-memory add per (warp, tap, channel)
 #pragma unroll
@@ -588,7 +598,9 @@ __global__ void __launch_bounds__(256) disc_spec_pack_kernel(const float* __rest
         const int c = ch8 * 8 + j;
         const int ci = c / 9, df = c % 9;
         const long q = p + df - 4;
-        v[j] = (c < 36 && q >= 0 && q < P) ? __ldg(sb + q * 4 + ci) : 0.f;
+        const long qc = q < 0 ? 0 : (q >= P ? P - 1 : q);
+        const float t = __ldg(sb + qc * 4 + (c < 36 ? ci : 0));          // unconditional load, masked: the eight loads stay independent
+        v[j] = (c < 36 && q == qc) ? t : 0.f;
       }
       o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
     }

@@ -210,6 +210,43 @@ __global__ void __launch_bounds__(256) dit_pre_kernel(const float* __restrict__ 
   }
 }
 
+// DiT input with channel-concatenated conditioning (inpainting: dit.py:160-165, `x = torch.cat([x, input_concat_cond], dim=1)`):
+//   out[(rep*B + b)*T + t][c] = bf16(x[b][c][t] * c_in)        c <  C            (the sampler's state, rescaled per step)
+//                               bf16(cond[b][c - C][t])         C <= c < C + Dc   (the same conditioning for both CFG halves, dit.py:336-337)
+//                               0                               C + Dc <= c < Cp  (Cp = row pitch, a multiple of 8 for the GEMM's K)
+// The 1x1 preprocess_conv + residual then run as ONE tcgen05 GEMM with the residual epilogue on these rows (its weight zero-padded to
+// [Cp, Cp]); this kernel is only the transposition.  block = 32 time steps x all channels.
+__global__ void __launch_bounds__(256) dit_concat_kernel(const float* __restrict__ x, const float* __restrict__ cond, __nv_bfloat16* __restrict__ out,
+                                                         int B, int C, int Dc, int Cp, int T, int reps, const float* __restrict__ cin_table,
+                                                         const int* __restrict__ step) {
+  extern __shared__ float sx[];   // [Cp][33]
+  griddep_launch();
+  griddep_wait();
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * 32;
+  const float c_in = cin_table ? cin_table[step ? *step : 0] : 1.0f;
+  for (int i = threadIdx.x; i < Cp * 32; i += 256) {
+    const int c = i >> 5, tt = i & 31;
+    const int t = t0 + tt;
+    float v = 0.f;
+    if (t < T) {
+      if (c < C) v = x[(static_cast<long>(b) * C + c) * T + t] * c_in;
+      else if (c < C + Dc) v = cond[(static_cast<long>(b) * Dc + (c - C)) * T + t];
+    }
+    sx[c * 33 + tt] = v;
+  }
+  __syncthreads();
+  const int pairs = Cp >> 1;
+  for (int i = threadIdx.x; i < 32 * pairs; i += 256) {
+    const int tt = i / pairs, cp = i % pairs;
+    const int t = t0 + tt;
+    if (t >= T) continue;
+    const uint32_t v = pack_bf16(sx[(2 * cp) * 33 + tt], sx[(2 * cp + 1) * 33 + tt]);
+    for (int rep = 0; rep < reps; ++rep)
+      *reinterpret_cast<uint32_t*>(out + (static_cast<long>(rep * B + b) * T + t) * Cp + 2 * cp) = v;
+  }
+}
+
 // DiT output: rows [bb, P + t, C] bf16 -> o[bb, c, t]; y = bf16(conv1x1(o)) + o  (dit.py:219-224), then classifier-free
 // guidance over the (cond | uncond) batch halves: cfg = u + (c - u)*s, optional std rescale (dit.py:398-408).
 // Writes fp32 v[B, C, T].
@@ -386,6 +423,17 @@ extern "C" int b200sat_dit_pre(const float* x, const void* wconv, void* out, int
   B200SAT_CHECK_CUDA(launch_k(dit_pre_kernel<64>, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, x, static_cast<const __nv_bfloat16*>(wconv),
                                                                          static_cast<__nv_bfloat16*>(out), B, T, reps,
                                                                          cin_table, step));
+  B200SAT_CHECK_CUDA(cudaGetLastError());
+  return B200SAT_OK;
+}
+
+extern "C" int b200sat_dit_concat(const float* x, const float* cond, void* out, int B, int C, int Dc, int Cp, int T, int reps, const float* cin_table,
+                                  const int* step, void* stream) {
+  if (!x || !cond || !out || B <= 0 || T <= 0 || reps <= 0 || C <= 0 || Dc <= 0) { set_last_error("dit_concat: bad arguments"); return B200SAT_EINVAL; }
+  if (Cp < C + Dc || (Cp & 7) || Cp > 256) { set_last_error("dit_concat: Cp must be a multiple of 8 in [C + Dc, 256]"); return B200SAT_EINVAL; }
+  dim3 grid((T + 31) / 32, B);
+  B200SAT_CHECK_CUDA(launch_k(dit_concat_kernel, dim3(grid), dim3(256), static_cast<size_t>(Cp) * 33 * sizeof(float), static_cast<cudaStream_t>(stream), 1, x,
+                              cond, static_cast<__nv_bfloat16*>(out), B, C, Dc, Cp, T, reps, cin_table, step));
   B200SAT_CHECK_CUDA(cudaGetLastError());
   return B200SAT_OK;
 }

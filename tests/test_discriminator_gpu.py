@@ -213,3 +213,45 @@ def test_batched_tap_weight_gradient_matches_fp32_and_the_per_tap_entry(ntaps, B
     check(lib().b200sat_conv_wgrad_taps_cat(ad.data_ptr(), bd.data_ptr(), T, c_offs, ntaps, cat.data_ptr(), B, st), "conv_wgrad_taps_cat")
     torch.cuda.synchronize()
     assert _rel(cat.permute(1, 0, 2).cpu().double(), 2 * want) <= 1e-5
+
+
+def _disc_offsets(kind, Fp):
+    if kind == "3x9d2":
+        return [(k // 9 - 1) * 2 * Fp + (k % 9 - 4) for k in range(27)]
+    if kind == "3x3":
+        return [(k // 3 - 1) * Fp + (k % 3 - 1) for k in range(9)]
+    return [-Fp, 0, Fp]
+
+
+@pytest.mark.parametrize("kind,B,T", [("3x9d2", 2, 73 * 31), ("3x3", 3, 41 * 27), ("3x1", 1, 137 * 5), ("3x9d2", 1, 64)])
+def test_window_weight_gradient_one_pass_over_the_planes(kind, B, T):
+    """b200sat_conv_wgrad_taps_win (csrc/disc_wgrad.cu: row-shifted MN-major descriptors into one shared-memory window per band, two taps per
+    MMA, dW[tap][ca][cb]) on the discriminator's own tap tables against fp64 on the same bf16 planes: <= 1e-5 of the gradient norm (fp32
+    accumulation, split-K order only); accumulation semantics (+=) checked with a second call."""
+    import ctypes
+    from b200sat._lib import lib, check
+    Fp = 73 if kind == "3x9d2" else (41 if kind == "3x3" else 137)
+    offs = _disc_offsets(kind, Fp)
+    ntaps = len(offs)
+    g = torch.Generator().manual_seed(ntaps * 1000 + T)
+    a = (torch.randn(B, T, 64, generator=g) * 0.5).bfloat16()
+    b = (torch.randn(B, T, 64, generator=g) * 0.5).bfloat16()
+    want = torch.zeros(ntaps, 64, 64, dtype=torch.float64)
+    af, bf = a.double(), b.double()
+    for k, o in enumerate(offs):
+        lo, hi = max(0, -o), min(T, T - o)
+        if hi > lo:
+            want[k] = torch.einsum("bti,btj->ij", af[:, lo:hi], bf[:, lo + o:hi + o])
+    ad, bd = a.cuda(), b.cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    c_offs = (ctypes.c_int * ntaps)(*offs)
+    dw = torch.zeros(ntaps, 64, 64, device="cuda")
+    check(lib().b200sat_conv_wgrad_taps_win(ad.data_ptr(), bd.data_ptr(), T, c_offs, ntaps, dw.data_ptr(), B, st), "conv_wgrad_taps_win")
+    torch.cuda.synchronize()
+    got = dw.cpu().double()
+    worst = max(_rel(got[k], want[k]) for k in range(ntaps) if want[k].norm() > 0)
+    print(kind, "window wgrad rel err", _rel(got, want), "worst tap", worst)
+    assert _rel(got, want) <= 1e-5 and worst <= 1e-4
+    check(lib().b200sat_conv_wgrad_taps_win(ad.data_ptr(), bd.data_ptr(), T, c_offs, ntaps, dw.data_ptr(), B, st), "conv_wgrad_taps_win")
+    torch.cuda.synchronize()
+    assert _rel(dw.cpu().double(), 2 * want) <= 1e-5

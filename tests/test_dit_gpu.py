@@ -84,3 +84,64 @@ def test_dit_sampler_graph_matches_eager_and_oracle():
     e = _rel(outs[0], ref)
     print("sampler rel err vs fp32 oracle", e)
     assert e <= 5e-2, e
+
+
+def test_dit_input_concat_forward_and_inpaint_driver_vs_reference_golden():
+    """Row f4 (inpainting).  (1) DiTEngine with input_concat_dim = 65 (mask + masked latents concatenated to the input, dit.py:160-165; the
+    1x1 preprocess conv + residual run as one GEMM on the zero-padded 136-channel rows) against the REFERENCE module's fp32 outputs
+    (tests/golden/dit_inpaint.npz), plain / CFG / shorter conditioning (nearest resize) — bf16 budget as in the file header.
+    (2) b200sat.generation.generate_diffusion_cond_inpaint against the latents of the reference's own generate_diffusion_cond_inpaint
+    (v-ddim, 6 steps, CFG 4; with a mask, with a mask + init_audio at noise level 0.7, without a mask), CUDA-graph loop == eager loop."""
+    import json
+    import math
+    import os
+    import numpy as np
+    from oracle import dit as odit, sampling as osamp
+    from b200sat.dit_engine import DiTEngine
+    from b200sat.generation import DiffusionCondModel, generate_diffusion_cond_inpaint
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "dit_inpaint.npz"))
+    f = {k: torch.from_numpy(z[k]) for k in z.files if k != "meta"}
+    meta = json.loads(str(z["meta"]))
+    cfg, dc, gen = meta["cfg"], meta["input_concat_dim"], meta["gen"]
+    sd = odit.make_state_dict(seed=meta["weights_seed"], input_concat_dim=dc, **cfg)
+    sd16 = {k: v.bfloat16() for k, v in sd.items()}
+    eng = DiTEngine(sd)
+    assert eng.cfg.input_concat_dim == dc and eng.cfg.dim_in_pad == 136
+    cases = (("y_plain", dict(input_concat_cond=f["concat"])), ("y_cfg", dict(cfg_scale=5.0, input_concat_cond=f["concat"])),
+             ("y_cfg_short", dict(cfg_scale=5.0, scale_phi=0.5, input_concat_cond=f["concat_short"])))
+    for key, kw in cases:
+        with torch.no_grad():
+            ref16 = odit.dit_forward(f["x"], f["t"], sd16, cfg["depth"], f["cross"], f["glob"], **kw).float()
+        out = eng.forward(f["x"].cuda(), f["t"].cuda(), f["cross"].cuda(), f["glob"].cuda(),
+                          **{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in kw.items()}).cpu()
+        e_ours, e_ref16 = _rel(out, f[key]), _rel(ref16, f[key])
+        print(f"inpaint forward {key}: rel err ours {e_ours:.3e}  reference-bf16 {e_ref16:.3e}")
+        assert e_ours <= 1.5 * e_ref16 + 2e-3, (key, e_ours, e_ref16)
+    with pytest.raises(ValueError):
+        eng.forward(f["x"].cuda(), f["t"].cuda(), f["cross"].cuda(), f["glob"].cuda())          # the concatenated input is not optional
+    # ---- the driver
+    model = DiffusionCondModel(eng, pretransform=None, io_channels=64, downsampling_ratio=0)
+    ct = {"cross_attn_cond": f["gen_cross"], "global_cond": f["gen_glob"]}
+    B, T = f["gen_noise"].shape[0], f["gen_noise"].shape[2]
+    mask = f["gen_mask"].unsqueeze(1)
+    concat = torch.cat([mask, f["gen_audio"].unsqueeze(0).repeat(B, 1, 1) * mask], dim=1)
+    sm = gen["init_noise_level"]
+    runs = (("gen_lat", dict(inpaint_audio=f["gen_audio"], inpaint_mask=f["gen_mask"]), concat, None),
+            ("gen_lat_init", dict(inpaint_audio=f["gen_audio"], inpaint_mask=f["gen_mask"], init_audio=f["gen_init"], init_noise_level=sm), concat, sm),
+            ("gen_lat_nomask", dict(), torch.zeros_like(concat), None))
+    for key, kw, cc, s_init in runs:
+        fn16 = lambda x, t: odit.dit_forward(x, t, sd16, cfg["depth"], f["gen_cross"], f["gen_glob"], cfg_scale=gen["cfg_scale"], input_concat_cond=cc).float()
+        with torch.no_grad():
+            if s_init is None:
+                ref16 = osamp.sample_v_ddim(fn16, f["gen_noise"], gen["steps"])
+            else:
+                a0, s0 = math.cos(s_init * math.pi / 2), math.sin(s_init * math.pi / 2)
+                ref16 = osamp.sample_v_ddim(fn16, f["gen_init"].unsqueeze(0) * a0 + f["gen_noise"] * s0, gen["steps"], sigma_max=s_init)
+        common = dict(steps=gen["steps"], cfg_scale=gen["cfg_scale"], conditioning_tensors=ct, batch_size=B, sample_size=T, sampler_type="v-ddim",
+                      noise=f["gen_noise"], return_latents=True)
+        lat = generate_diffusion_cond_inpaint(model, use_graph=True, **common, **kw).cpu()
+        lat_eager = generate_diffusion_cond_inpaint(model, use_graph=False, **common, **kw).cpu()
+        assert torch.equal(lat, lat_eager), key
+        e_ours, e_ref16 = _rel(lat, f[key]), _rel(ref16, f[key])
+        print(f"inpaint driver {key}: rel err vs the reference driver ours {e_ours:.3e}  oracle-bf16 {e_ref16:.3e}")
+        assert e_ours <= 1.5 * e_ref16 + 2e-3, (key, e_ours, e_ref16)

@@ -240,6 +240,10 @@ def test_unsupported_architectures_fall_back_instead_of_approximating():
     ok = R.dit.DiffusionTransformer(**kw)
     assert inst._dit_supported(ok, {}) == []
     assert inst._dit_supported(ok, {"cfg_interval": (0.1, 1.0)}) == ["cfg_interval"]
+    # inpainting models (input_concat_dim = mask + masked latents): routed only together with their concatenated conditioning
+    inp = R.dit.DiffusionTransformer(input_concat_dim=65, **kw)
+    assert inst._dit_supported(inp, {"input_concat_cond": torch.zeros(1, 65, 8)}) == []
+    assert inst._dit_supported(inp, {}) != [] and inst._dit_supported(ok, {"input_concat_cond": torch.zeros(1, 65, 8)}) != []
 
 
 def test_engine_cache_is_weak_and_tracks_dtype_and_storage():

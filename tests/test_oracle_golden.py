@@ -1,5 +1,6 @@
 """CPU: the oracle restatements reproduce the committed reference outputs (tests/golden, made by oracle/gen_golden.py)."""
 import json
+import math
 import os
 
 import numpy as np
@@ -109,3 +110,36 @@ def test_encodec_discriminator_oracle_matches_reference_golden():
     l4 = torch.from_numpy(z["logits4"])
     assert logits[4].shape == l4.shape and ((logits[4] - l4).norm() / l4.norm()).item() <= 1e-5
     assert [tuple(f.shape[1:3]) for f in fmaps[0]] == [(64, 13)] * 5 and fmaps[0][0].shape[-1] == 1025
+
+
+def _inpaint_concat(f):
+    mask = f["gen_mask"].unsqueeze(1)
+    return torch.cat([mask, f["gen_audio"].unsqueeze(0).repeat(mask.shape[0], 1, 1) * mask], dim=1)
+
+
+def test_dit_input_concat_and_inpaint_driver_match_reference():
+    """Row f4: the oracle's input_concat_cond path against the reference module (dit.py:160-165, CFG duplication :336-337, nearest resize
+    :162-163), and the oracle v-DDIM loop driven like `generate_diffusion_cond_inpaint` (inference/generation.py:222-405: mask + masked
+    input concatenated, optional init_audio start at init_noise_level) against the reference driver's own latents."""
+    f = _load("dit_inpaint.npz")
+    cfg, dc = f["meta"]["cfg"], f["meta"]["input_concat_dim"]
+    sd = odit.make_state_dict(seed=f["meta"]["weights_seed"], input_concat_dim=dc, **cfg)
+    with torch.no_grad():
+        y = odit.dit_forward(f["x"], f["t"], sd, cfg["depth"], f["cross"], f["glob"], input_concat_cond=f["concat"])
+        yc = odit.dit_forward(f["x"], f["t"], sd, cfg["depth"], f["cross"], f["glob"], cfg_scale=5.0, input_concat_cond=f["concat"])
+        ys = odit.dit_forward(f["x"], f["t"], sd, cfg["depth"], f["cross"], f["glob"], cfg_scale=5.0, scale_phi=0.5, input_concat_cond=f["concat_short"])
+    for got, key in ((y, "y_plain"), (yc, "y_cfg"), (ys, "y_cfg_short")):
+        assert (got - f[key]).abs().max() <= 2e-5 * max(1.0, f[key].abs().max()), key
+    gen = f["meta"]["gen"]
+    concat = _inpaint_concat(f)
+    fn = lambda x, t: odit.dit_forward(x, t, sd, cfg["depth"], f["gen_cross"], f["gen_glob"], cfg_scale=gen["cfg_scale"], input_concat_cond=concat)
+    with torch.no_grad():
+        lat = osamp.sample_v_ddim(fn, f["gen_noise"], gen["steps"])
+        sm = gen["init_noise_level"]
+        a0, s0 = math.cos(sm * math.pi / 2), math.sin(sm * math.pi / 2)
+        lat_init = osamp.sample_v_ddim(fn, f["gen_init"].unsqueeze(0) * a0 + f["gen_noise"] * s0, gen["steps"], sigma_max=sm)
+        zero = torch.zeros_like(concat)
+        fn0 = lambda x, t: odit.dit_forward(x, t, sd, cfg["depth"], f["gen_cross"], f["gen_glob"], cfg_scale=gen["cfg_scale"], input_concat_cond=zero)
+        lat0 = osamp.sample_v_ddim(fn0, f["gen_noise"], gen["steps"])
+    for got, key in ((lat, "gen_lat"), (lat_init, "gen_lat_init"), (lat0, "gen_lat_nomask")):
+        assert (got - f[key]).abs().max() <= 5e-5 * max(1.0, f[key].abs().max()), key
