@@ -25,7 +25,7 @@ LEAKY = 0.2
 DILATIONS = (1, 2, 4)
 # first conv on the tensor cores (default); B200SAT_DISC_CONV0=simt keeps the round-1 fp32 SIMT kernels
 CONV0_TC = os.environ.get("B200SAT_DISC_CONV0", "tc") != "simt"
-WGRAD_MODE = os.environ.get("B200SAT_DISC_WGRAD", "cat")
+WGRAD_MODE = os.environ.get("B200SAT_DISC_WGRAD", "win")
 
 
 def _s():

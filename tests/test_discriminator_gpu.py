@@ -58,8 +58,8 @@ def test_discriminator_forward_matches_oracle():
         e0 = _rel(fmaps[i][0].cpu(), ref_fmaps[i][0])
         print("scale", i, "first conv rel err", e0)
         # first conv: bf16 spectrogram x bf16 weights on the tensor cores, fp32 accumulation, bf16 storage (what the reference's Conv2d does
-        # under bf16 autocast); the fp32 SIMT kernels of round 1 (B200SAT_DISC_CONV0=simt) measure <= 6e-3 (storage rounding only)
-        assert e0 <= 1.2e-2, (i, e0)
+        # under bf16 autocast); same bar as the fp32 SIMT kernels of round 1 (B200SAT_DISC_CONV0=simt): bf16 storage rounding dominates
+        assert e0 <= 6e-3, (i, e0)                                   # measured 2.8e-3
         for l in range(1, 5):
             e = _rel(fmaps[i][l].cpu(), ref_fmaps[i][l])
             assert e <= 2.5e-2, (i, l, e)

@@ -91,7 +91,7 @@ def test_dit_input_concat_forward_and_inpaint_driver_vs_reference_golden():
     1x1 preprocess conv + residual run as one GEMM on the zero-padded 136-channel rows) against the REFERENCE module's fp32 outputs
     (tests/golden/dit_inpaint.npz), plain / CFG / shorter conditioning (nearest resize) — bf16 budget as in the file header.
     (2) b200sat.generation.generate_diffusion_cond_inpaint against the latents of the reference's own generate_diffusion_cond_inpaint
-    (v-ddim, 6 steps, CFG 4; with a mask, with a mask + init_audio at noise level 0.7, without a mask), CUDA-graph loop == eager loop."""
+    (v-ddim, 6 steps, CFG 4; with a mask, with a mask + init_audio at noise level 0.7, without a mask), CUDA-graph loop vs eager loop."""
     import json
     import math
     import os
@@ -141,7 +141,9 @@ def test_dit_input_concat_forward_and_inpaint_driver_vs_reference_golden():
                       noise=f["gen_noise"], return_latents=True)
         lat = generate_diffusion_cond_inpaint(model, use_graph=True, **common, **kw).cpu()
         lat_eager = generate_diffusion_cond_inpaint(model, use_graph=False, **common, **kw).cpu()
-        assert torch.equal(lat, lat_eager), key
+        # graph replay and eager launches run the same kernels; the LayerNorm row statistics of this 128-wide model are fp32 atomics from four
+        # (tile, column-half) contributions per row, so the two runs may differ in the last bits (bf16 rounding flips downstream)
+        assert _rel(lat, lat_eager) <= 5e-3, (key, _rel(lat, lat_eager))
         e_ours, e_ref16 = _rel(lat, f[key]), _rel(ref16, f[key])
         print(f"inpaint driver {key}: rel err vs the reference driver ours {e_ours:.3e}  oracle-bf16 {e_ref16:.3e}")
         assert e_ours <= 1.5 * e_ref16 + 2e-3, (key, e_ours, e_ref16)
