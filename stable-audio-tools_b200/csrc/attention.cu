@@ -6,13 +6,12 @@
 // from the projection outputs ([B, N, heads, 64] views with arbitrary strides), so the 'b n (h d) -> b h n d' rearranges
 // and the repeat_interleave of K/V never touch HBM.
 //
-// One CTA = one 128-query tile of one (batch, head); two CTAs are resident per SM so one CTA's softmax overlaps the
-// other's MMAs.  320 threads:
-//   warp 0 lane 0 : TMA producer (Q once; K,V tiles of 128 keys through a 2-stage ring; 4-D tensor maps, 128B swizzle)
-//   warp 1        : TMEM allocation; lane 0 issues S = Q K^T (128x128x64) and O_j = P V (128x64x128) on tcgen05
-//   warps 2..9    : online softmax — two threads per query row (64 keys each; tcgen05.ld 32x32b), P written to smem as the
-//                   bf16 A operand, O (32 dims per thread) accumulated in registers with the running-max rescale.
-//                   (ncu r1: with 4 softmax warps the kernel was latency-bound: issue-active 31 %, tensor pipe 17 %.)
+// One CTA = one 128-query tile of one (batch, head); THREE CTAs are resident per SM so one CTA's softmax runs under the others' MMAs and
+// latencies.  192 threads (the round-2 redesign and what its in-kernel timeline showed are described above the kernel):
+//   warp 0 lane 0 : TMA producer (Q once; K and V tiles of 64 keys through separate rings; 4-D tensor maps, 128B swizzle)
+//   warp 1        : TMEM allocation; one elected lane issues S = Q K^T (128x64x64) and O += P V (128x64x64) on tcgen05
+//   warps 2..5    : online softmax, ONE thread per query row (64 keys per tile in registers from one tcgen05.ld pair), P written to smem
+//                   as the bf16 A operand, O accumulated in TMEM with a lazy rescale; a quarter of the exp2 on the FMA pipe.
 #include "common.cuh"
 #include <cstring>
 

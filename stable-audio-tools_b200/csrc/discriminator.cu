@@ -331,15 +331,16 @@ __global__ void __launch_bounds__(256) disc_act_bwd_kernel(const __nv_bfloat16* 
     for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) sw[i] = w_post[(i % 64) * 9 + i / 64];
   }
   __syncthreads();
-  const long P = static_cast<long>(frames) * Fp;
-  const long total = static_cast<long>(B) * P * 8;
-  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long>(gridDim.x) * blockDim.x) {
-    const long pos = idx >> 3;
-    const int ch = static_cast<int>(idx & 7);
+  // 32-bit position arithmetic (entry point: B * P < 2^27); the 64-bit `/` and `%` of round 1 dominated this kernel's instruction count
+  const int P = frames * Fp;
+  const int total = B * P * 8;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int pos = idx >> 3;
+    const int ch = idx & 7;
     const int b = pos / P;
-    const long p = pos % P;
+    const int p = pos - b * P;
     uint4 o = make_uint4(0, 0, 0, 0);
-    if (col_valid(static_cast<int>(p % Fp), Fp, F)) {
+    if (col_valid(p, Fp, F)) {
       float d[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) d[j] = 0.f;
@@ -350,12 +351,13 @@ __global__ void __launch_bounds__(256) disc_act_bwd_kernel(const __nv_bfloat16* 
         for (int e = 0; e < 4; ++e) { const float2 f = unpack_bf16(uw[e]); d[2 * e] = f.x; d[2 * e + 1] = f.y; }
       }
       if (d_logit) {
-        const float* gl = d_logit + static_cast<long>(b) * P;
-#pragma unroll 1
+        const float* gl = d_logit + static_cast<size_t>(b) * P;
+#pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-          const long q = p - ((tap / 3 - 1) * Fp + (tap % 3 - 1));
-          if (q < 0 || q >= P) continue;
-          const float g = __ldg(gl + q);
+          const int q = p - ((tap / 3 - 1) * Fp + (tap % 3 - 1));
+          const int qc = min(max(q, 0), P - 1);
+          const float gt = __ldg(gl + qc);
+          const float g = (q == qc) ? gt : 0.f;
 #pragma unroll
           for (int j = 0; j < 8; ++j) d[j] += g * sw[tap * 64 + ch * 8 + j];
         }
@@ -479,27 +481,29 @@ __global__ void __launch_bounds__(256) disc_convpost_fwd_kernel(const __nv_bfloa
   for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) sw[i] = w[(i % 64) * 9 + i / 64];
   __syncthreads();
   const int lane = threadIdx.x & 31, l8 = lane & 7, sub = lane >> 3;
-  const long P = static_cast<long>(frames) * Fp;
-  const long total = static_cast<long>(B) * P;
+  // 32-bit position arithmetic (the entry point checks B * P < 2^27): the 64-bit `%` of the first version cost more instructions than the
+  // nine taps (ncu: 508 M warp instructions for 4.1 M rows, issue-bound at 63 %)
+  const int P = frames * Fp;
+  const int total = B * P;
   const float bv = bias ? bias[0] : 0.f;
-  const long stride = static_cast<long>(gridDim.x) * (blockDim.x >> 3);
-  for (long base = (static_cast<long>(blockIdx.x) * blockDim.x + (threadIdx.x & ~31)) >> 3; base < total; base += stride) {   // warp-uniform
-    const long idx = base + sub;
+  const int stride = gridDim.x * (blockDim.x >> 3);
+  for (int base = (blockIdx.x * blockDim.x + (threadIdx.x & ~31)) >> 3; base < total; base += stride) {   // warp-uniform
+    const int idx = base + sub;
     const bool in = idx < total;
-    const long p = in ? idx % P : 0;
-    const bool ok = in && col_valid(static_cast<int>(p % Fp), Fp, F);
+    const int p = in ? idx % P : 0;
+    const bool ok = in && col_valid(p, Fp, F);
     float acc = 0.f;
     if (ok) {
-      const __nv_bfloat16* rowbase = act + (idx - p) * 64 + l8 * 8;
+      const __nv_bfloat16* rowbase = act + static_cast<size_t>(idx - p) * 64 + l8 * 8;
       // nine independent loads (row index clamped, contribution masked): a bounds branch per tap would serialise them behind each other
       uint4 u[9];
       float m[9];
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
-        const long q = p + (tap / 3 - 1) * Fp + (tap % 3 - 1);
-        const long qc = q < 0 ? 0 : (q >= P ? P - 1 : q);
+        const int q = p + (tap / 3 - 1) * Fp + (tap % 3 - 1);
+        const int qc = min(max(q, 0), P - 1);
         m[tap] = (q == qc) ? 1.f : 0.f;
-        u[tap] = __ldg(reinterpret_cast<const uint4*>(rowbase + qc * 64));
+        u[tap] = __ldg(reinterpret_cast<const uint4*>(rowbase + static_cast<size_t>(qc) * 64));
       }
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
@@ -534,22 +538,22 @@ __global__ void __launch_bounds__(256) disc_convpost_wgrad_kernel(const float* _
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[tap][j] = 0.f;
   float gsum = 0.f;
-  const long P = static_cast<long>(frames) * Fp;
-  const long total = static_cast<long>(B) * P;
-  const long stride = static_cast<long>(gridDim.x) * (blockDim.x >> 3);
-  for (long idx = ((static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3); idx < total; idx += stride) {
-    const long p = idx % P;
-    if (!col_valid(static_cast<int>(p % Fp), Fp, F)) continue;     // activation rows and logit gradients are zero in the pad columns
+  const int P = frames * Fp;          // 32-bit position arithmetic (entry point: B * P < 2^27)
+  const int total = B * P;
+  const int stride = gridDim.x * (blockDim.x >> 3);
+  for (int idx = ((blockIdx.x * blockDim.x + threadIdx.x) >> 3); idx < total; idx += stride) {
+    const int p = idx % P;
+    if (!col_valid(p, Fp, F)) continue;     // activation rows and logit gradients are zero in the pad columns
     const float* gb = g + (idx - p);
     if (l8 == 0) gsum += __ldg(gb + p);
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(act + idx * 64 + l8 * 8));
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(act + static_cast<size_t>(idx) * 64 + l8 * 8));
     const float2 d0 = unpack_bf16(u.x), d1 = unpack_bf16(u.y), d2 = unpack_bf16(u.z), d3 = unpack_bf16(u.w);
     const float a[8] = {d0.x, d0.y, d1.x, d1.y, d2.x, d2.y, d3.x, d3.y};
     float gv[9];
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {     // independent loads: clamp the row, mask the value
-      const long q = p - ((tap / 3 - 1) * Fp + (tap % 3 - 1));
-      const long qc = q < 0 ? 0 : (q >= P ? P - 1 : q);
+      const int q = p - ((tap / 3 - 1) * Fp + (tap % 3 - 1));
+      const int qc = min(max(q, 0), P - 1);
       const float t = __ldg(gb + qc);
       gv[tap] = (q == qc) ? t : 0.f;
     }
@@ -583,22 +587,23 @@ __global__ void __launch_bounds__(256) disc_convpost_wgrad_kernel(const float* _
 // run on b200sat_conv2d_flat, the weight gradient on b200sat_conv_wgrad_taps_cat, weight-norm on b200sat_wn_pack / b200sat_wn_bwd - the
 // same entries as the other four layers.  (The fp32 SIMT kernels above took 2.6 / 5 / 10 ms per scale at batch 32: forward / data /
 // weight gradient.)  The spectrogram is rounded to bf16 here - what the reference's Conv2d does under bf16 autocast.
-__global__ void __launch_bounds__(256) disc_spec_pack_kernel(const float* __restrict__ spec, __nv_bfloat16* __restrict__ s9, long total, long P,
+__global__ void __launch_bounds__(256) disc_spec_pack_kernel(const float* __restrict__ spec, __nv_bfloat16* __restrict__ s9, int total, int P,
                                                              int Fp, int F) {
-  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total * 8; idx += static_cast<long>(gridDim.x) * blockDim.x) {
-    const long pos = idx >> 3;
-    const int ch8 = static_cast<int>(idx & 7);
-    const long p = pos % P;
+  // thread = 8 channels of one position; 32-bit position arithmetic (entry point: B * P < 2^27)
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total * 8; idx += gridDim.x * blockDim.x) {
+    const int pos = idx >> 3;
+    const int ch8 = idx & 7;
+    const int p = pos % P;
     uint4 o = make_uint4(0, 0, 0, 0);
-    if (ch8 < 5 && col_valid(static_cast<int>(p % Fp), Fp, F)) {
-      const float* sb = spec + (pos - p) * 4;
+    if (ch8 < 5 && col_valid(p, Fp, F)) {
+      const float* sb = spec + static_cast<size_t>(pos - p) * 4;
       float v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int c = ch8 * 8 + j;
-        const int ci = c / 9, df = c % 9;
-        const long q = p + df - 4;
-        const long qc = q < 0 ? 0 : (q >= P ? P - 1 : q);
+        const int ci = c / 9, df = c - 9 * ci;
+        const int q = p + df - 4;
+        const int qc = min(max(q, 0), P - 1);
         const float t = __ldg(sb + qc * 4 + (c < 36 ? ci : 0));          // unconditional load, masked: the eight loads stay independent
         v[j] = (c < 36 && q == qc) ? t : 0.f;
       }
@@ -702,7 +707,7 @@ extern "C" int b200sat_disc_convpost(const void* act, const float* w, const floa
   if (!act || !w || !logits || B <= 0 || frames <= 0 || F <= 0) { set_last_error("disc_convpost: bad arguments"); return B200SAT_EINVAL; }
   const int Fp = F + 8;
   const long total = static_cast<long>(B) * frames * Fp;
-  if (disc_post_v1())
+  if (disc_post_v1() || total >= (1L << 27))
     disc_convpost_fwd_v1_kernel<<<grid_for(total, 128, 8), 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(act), w, bias, logits,
                                                                                                        B, frames, Fp, F);
   else
@@ -721,7 +726,8 @@ extern "C" int b200sat_disc_spec_pack(float* spec, void* s9, int B, int frames, 
   const long total = static_cast<long>(B) * P;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!backward) {
-    disc_spec_pack_kernel<<<grid_for(total * 8, 256, 8), 256, 0, s>>>(spec, static_cast<__nv_bfloat16*>(s9), total, P, Fp, F);
+    if (total >= (1L << 27)) { set_last_error("disc_spec_pack: more than 2^27 positions"); return B200SAT_EUNSUPPORTED; }
+    disc_spec_pack_kernel<<<grid_for(total * 8, 256, 8), 256, 0, s>>>(spec, static_cast<__nv_bfloat16*>(s9), static_cast<int>(total), static_cast<int>(P), Fp, F);
   } else {
     dim3 grid(static_cast<unsigned>((P + 127) / 128), B);
     disc_spec_unpack_kernel<<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(s9), spec, P, Fp, F);
@@ -760,6 +766,7 @@ extern "C" int b200sat_disc_act_bwd(const void* d_in, const float* d_logit, cons
     set_last_error("disc_act_bwd: bad arguments"); return B200SAT_EINVAL;
   }
   const long total = static_cast<long>(B) * frames * (F + 8) * 8;
+  if (total >= (1L << 30)) { set_last_error("disc_act_bwd: more than 2^27 positions"); return B200SAT_EUNSUPPORTED; }
   disc_act_bwd_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(d_in), d_logit, w_post, static_cast<const __nv_bfloat16*>(post), static_cast<const __nv_bfloat16*>(other), fm_coef,
       leaky, static_cast<__nv_bfloat16*>(d_pre), B, frames, F + 8, F);
@@ -780,7 +787,7 @@ extern "C" int b200sat_disc_conv0_wgrad(const void* dpre, const float* spec, flo
 extern "C" int b200sat_disc_convpost_wgrad(const float* g, const void* act, float* dW, float* dbias, int B, int frames, int F, void* stream) {
   if (!g || !act || !dW || B <= 0 || frames <= 0 || F <= 0) { set_last_error("disc_convpost_wgrad: bad arguments"); return B200SAT_EINVAL; }
   const long total = static_cast<long>(B) * frames * (F + 8);
-  if (disc_post_v1()) {
+  if (disc_post_v1() || total >= (1L << 27)) {
     const long cap = static_cast<long>(num_sms()) * 8;
     disc_convpost_wgrad_v1_kernel<<<static_cast<int>((total + 7) / 8 < cap ? (total + 7) / 8 : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         g, static_cast<const __nv_bfloat16*>(act), dW, dbias, B, frames, F + 8, F);

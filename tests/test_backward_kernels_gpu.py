@@ -78,3 +78,17 @@ def test_layernorm_bwd_and_colsum():
         ops.colsum(dy, cs)
         r = dy.float().sum(0)
         assert (cs - r).abs().max().item() <= 1e-3 * r.abs().max().item() + 1e-2
+
+
+@pytest.mark.parametrize("rows,N", [(300001, 64), (4097, 128), (33, 64), (1000, 32)])
+def test_colsum_narrow_planes(rows, N):
+    """Bias gradients of the 64 / 128-channel planes (discriminator feature maps, Oobleck blocks): the narrow-plane kernel (N/8 lanes per row,
+    16-byte loads) against an fp64 column sum of the same bf16 values; accumulates (+=) into `out`."""
+    from b200sat import ops
+    g = torch.Generator(device="cuda").manual_seed(rows + N)
+    dy = torch.randn(rows, N, device="cuda", generator=g).bfloat16()
+    out = torch.full((N,), 0.5, device="cuda")
+    ops.colsum(dy, out)
+    torch.cuda.synchronize()
+    want = dy.double().sum(0) + 0.5
+    assert (out.double() - want).abs().max().item() <= 1e-5 * dy.double().abs().sum(0).max().item() + 1e-4
