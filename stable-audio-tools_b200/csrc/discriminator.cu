@@ -474,15 +474,18 @@ __global__ void __launch_bounds__(256) disc_convpost_wgrad_v1_kernel(const float
 // (32 different cache lines per warp load: 72 such loads per output position made the forward L1-wavefront bound at 1.2 ms per scale
 // and batch 32) or one channel (2-byte loads).  Here EIGHT lanes share a row (one 16-byte chunk each, so a warp load touches four
 // full lines) and the per-row dot products are finished with three shuffles.
-__global__ void __launch_bounds__(256) disc_convpost_fwd_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ w /*[1][64][9]*/,
-                                                                const float* __restrict__ bias, float* __restrict__ logits, int B, int frames,
-                                                                int Fp, int F) {
-  __shared__ __align__(16) float sw[9 * 64];   // [tap][c]
-  for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) sw[i] = w[(i % 64) * 9 + i / 64];
-  __syncthreads();
+__global__ void __launch_bounds__(256, 2) disc_convpost_fwd_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ w /*[1][64][9]*/,
+                                                                   const float* __restrict__ bias, float* __restrict__ logits, int B, int frames,
+                                                                   int Fp, int F) {
   const int lane = threadIdx.x & 31, l8 = lane & 7, sub = lane >> 3;
-  // 32-bit position arithmetic (the entry point checks B * P < 2^27): the 64-bit `%` of the first version cost more instructions than the
-  // nine taps (ncu: 508 M warp instructions for 4.1 M rows, issue-bound at 63 %)
+  // this lane's 9 x 8 weights stay in registers: reading them from shared memory per row made the kernel shared-memory bound
+  // (ncu: 152 M shared wavefronts for 4.1 M rows, 0.75 ms); taps are loaded three at a time so the register budget allows two blocks per SM
+  float wr[9][8];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[tap][j] = __ldg(w + (l8 * 8 + j) * 9 + tap);
+  // 32-bit position arithmetic (the entry point checks B * P < 2^27)
   const int P = frames * Fp;
   const int total = B * P;
   const float bv = bias ? bias[0] : 0.f;
@@ -495,22 +498,25 @@ __global__ void __launch_bounds__(256) disc_convpost_fwd_kernel(const __nv_bfloa
     float acc = 0.f;
     if (ok) {
       const __nv_bfloat16* rowbase = act + static_cast<size_t>(idx - p) * 64 + l8 * 8;
-      // nine independent loads (row index clamped, contribution masked): a bounds branch per tap would serialise them behind each other
-      uint4 u[9];
-      float m[9];
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const int q = p + (tap / 3 - 1) * Fp + (tap % 3 - 1);
-        const int qc = min(max(q, 0), P - 1);
-        m[tap] = (q == qc) ? 1.f : 0.f;
-        u[tap] = __ldg(reinterpret_cast<const uint4*>(rowbase + static_cast<size_t>(qc) * 64));
-      }
+      for (int g3 = 0; g3 < 3; ++g3) {
+        // three independent loads (row index clamped, contribution masked): a bounds branch per tap would serialise them behind each other
+        uint4 u[3];
+        float m[3];
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const float4 w0 = *reinterpret_cast<const float4*>(&sw[tap * 64 + l8 * 8]);
-        const float4 w1 = *reinterpret_cast<const float4*>(&sw[tap * 64 + l8 * 8 + 4]);
-        const float2 d0 = unpack_bf16(u[tap].x), d1 = unpack_bf16(u[tap].y), d2 = unpack_bf16(u[tap].z), d3 = unpack_bf16(u[tap].w);
-        acc += m[tap] * (d0.x * w0.x + d0.y * w0.y + d1.x * w0.z + d1.y * w0.w + d2.x * w1.x + d2.y * w1.y + d3.x * w1.z + d3.y * w1.w);
+        for (int t = 0; t < 3; ++t) {
+          const int q = p + (g3 - 1) * Fp + (t - 1);
+          const int qc = min(max(q, 0), P - 1);
+          m[t] = (q == qc) ? 1.f : 0.f;
+          u[t] = __ldg(reinterpret_cast<const uint4*>(rowbase + static_cast<size_t>(qc) * 64));
+        }
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          const int tap = g3 * 3 + t;
+          const float2 d0 = unpack_bf16(u[t].x), d1 = unpack_bf16(u[t].y), d2 = unpack_bf16(u[t].z), d3 = unpack_bf16(u[t].w);
+          acc += m[t] * (d0.x * wr[tap][0] + d0.y * wr[tap][1] + d1.x * wr[tap][2] + d1.y * wr[tap][3] + d2.x * wr[tap][4] + d2.y * wr[tap][5] +
+                         d3.x * wr[tap][6] + d3.y * wr[tap][7]);
+        }
       }
     }
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);

@@ -20,9 +20,11 @@ class _FakeDiT:
         self.gct = module.global_cond_type
         self.odit = odit
 
-    def forward(self, x, t, cross_attn_cond=None, global_embed=None, cfg_scale=1.0, scale_phi=0.0, negative_cross_attn_cond=None):
+    def forward(self, x, t, cross_attn_cond=None, global_embed=None, cfg_scale=1.0, scale_phi=0.0, negative_cross_attn_cond=None,
+                input_concat_cond=None):
         return self.odit.dit_forward(x, t, self.sd, self.depth, cross_attn_cond, global_embed, cfg_scale=cfg_scale, scale_phi=scale_phi,
-                                     global_cond_type=self.gct, negative_cross_attn_cond=negative_cross_attn_cond)
+                                     global_cond_type=self.gct, negative_cross_attn_cond=negative_cross_attn_cond,
+                                     input_concat_cond=input_concat_cond)
 
 
 class _FakeTrainer:
@@ -167,7 +169,7 @@ def test_discriminator_loss_routing_and_fallbacks(installed):
 
 
 def _oracle_sampler(eng, noise, steps, sampler_type, sigma_min, sigma_max, rho, cross_attn_cond=None, global_embed=None, cfg_scale=1.0,
-                    scale_phi=0.0, negative_cross_attn_cond=None):
+                    scale_phi=0.0, negative_cross_attn_cond=None, input_concat_cond=None):
     """engine_factories['sampler'] hook: the v-DDIM loop of b200sat.sampling's tables driven by the fake engine (CPU)."""
     from b200sat import sampling
     assert sampler_type == "v-ddim"
@@ -175,8 +177,9 @@ def _oracle_sampler(eng, noise, steps, sampler_type, sigma_min, sigma_max, rho, 
     x = noise.float()
     for i in range(steps):
         t = torch.full((x.shape[0],), float(tt[i]))
+        extra = {} if input_concat_cond is None else {"input_concat_cond": input_concat_cond}
         v = eng.forward(x * cin[i], t, cross_attn_cond=cross_attn_cond, global_embed=global_embed, cfg_scale=cfg_scale, scale_phi=scale_phi,
-                        negative_cross_attn_cond=negative_cross_attn_cond)
+                        negative_cross_attn_cond=negative_cross_attn_cond, **extra)
         den = v * coef[i, 0] + x * coef[i, 1]
         x = coef[i, 2] * x + coef[i, 3] * den
     return x
@@ -219,6 +222,44 @@ def test_generate_diffusion_cond_takes_the_fast_sampler_route():
         inst.uninstall()
         ref_ci = R.generation.generate_diffusion_cond(model, conditioning_tensors=ct, cfg_interval=(0.2, 0.8), **kw)
         assert torch.allclose(got_ci, ref_ci, atol=2e-4)
+    finally:
+        inst._TEST_TREAT_CPU_AS_DEVICE = False
+        inst.uninstall()
+
+
+def test_generate_diffusion_cond_inpaint_reaches_the_engines():
+    """Row f4: the reference's OWN generate_diffusion_cond_inpaint (inference/generation.py:222-405) on a model built with
+    input_concat_ids = [inpaint_mask, inpaint_masked_input]: the mask / masked-input tensors it concatenates reach the sampler route as
+    `input_concat_cond`; with init_audio (variation start) the reference's loop runs and only its model calls are routed.  Same latents
+    as without install() in both cases."""
+    import b200sat.install as inst
+    from baseline import ref_models
+    R = ref_harness.load(force_sdpa=True)
+    inst.uninstall()
+    cfg = ref_models.sao_config(depth=2, embed_dim=128, num_heads=2, cond_token_dim=64, global_cond_dim=128, sample_size=48)
+    cfg["model"]["diffusion"]["config"]["input_concat_dim"] = 65
+    cfg["model"]["diffusion"]["input_concat_ids"] = ["inpaint_mask", "inpaint_masked_input"]
+    model = ref_models.build_diffusion_cond(R, cfg, seed=6)
+    B, T = 2, 48
+    ct = ref_models.conditioning_tensors(model, B, prompt_tokens=5, seed=1)
+    g = torch.Generator().manual_seed(3)
+    audio, init = torch.randn(64, T, generator=g), torch.randn(64, T, generator=g)
+    mask = (torch.arange(T) >= 20).float().unsqueeze(0).repeat(B, 1)
+    kw = dict(steps=4, cfg_scale=3.0, batch_size=B, sample_size=T, seed=9, device="cpu", sampler_type="v-ddim", return_latents=True,
+              inpaint_audio=(44100, audio), inpaint_mask=mask)
+    ref = R.generation.generate_diffusion_cond_inpaint(model, conditioning_tensors=dict(ct), **kw)
+    ref_init = R.generation.generate_diffusion_cond_inpaint(model, conditioning_tensors=dict(ct), init_audio=(44100, init), init_noise_level=0.6, **kw)
+    inst._TEST_TREAT_CPU_AS_DEVICE = True
+    try:
+        inst.install(strict=True, engine_factories={"dit": _FakeDiT, "oobleck": _FakeAE, "dit_train": _FakeTrainer, "sampler": _oracle_sampler})
+        n0 = dict(inst.STATS)
+        got = R.generation.generate_diffusion_cond_inpaint(model, conditioning_tensors=dict(ct), **kw)
+        assert inst.STATS["sample_k_fast"] == n0["sample_k_fast"] + 1 and inst.STATS["sample_k_ref"] == n0["sample_k_ref"]
+        assert torch.allclose(got, ref, atol=2e-4), float((got - ref).abs().max())
+        n1 = dict(inst.STATS)
+        got_init = R.generation.generate_diffusion_cond_inpaint(model, conditioning_tensors=dict(ct), init_audio=(44100, init), init_noise_level=0.6, **kw)
+        assert inst.STATS["sample_k_ref"] == n1["sample_k_ref"] + 1 and inst.STATS["dit_fast"] == n1["dit_fast"] + 4   # reference loop, routed model
+        assert torch.allclose(got_init, ref_init, atol=2e-4), float((got_init - ref_init).abs().max())
     finally:
         inst._TEST_TREAT_CPU_AS_DEVICE = False
         inst.uninstall()
