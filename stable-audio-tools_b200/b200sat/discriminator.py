@@ -152,8 +152,9 @@ class EncodecDiscriminatorEngine:
         return logits, feats
 
     # ------------------------------------------------------------------ losses
-    def _loss_forward(self, reals, fakes, keep_all=False):
-        """keep_all: also keep the real-path logits and both spectrograms (needed by the discriminator-side backward)."""
+    def _loss_forward(self, reals, fakes, keep_all=False, need_fm=True):
+        """keep_all: also keep the real-path logits and both spectrograms (needed by the discriminator-side backward).
+        need_fm=False skips the 25 feature-matching L1 reductions (the discriminator step only uses the hinge loss; fm is returned as 0)."""
         reals = reals.to(self.dev, torch.float32).contiguous()
         fakes = fakes.to(self.dev, torch.float32).contiguous()
         B = reals.shape[0]
@@ -168,9 +169,9 @@ class EncodecDiscriminatorEngine:
             lf, ff, _ = self._scale_forward(sc, fakes)
             spec_f = self._last_spec
             check(lib().b200sat_disc_hinge_sums(lt.data_ptr(), lf.data_ptr(), hs[i].data_ptr(), B, fr, sc.F, _s()), "disc_hinge_sums")
-            for l in range(5):
+            for l in range(5 if need_fm else 0):
                 check(lib().b200sat_disc_l1_sum(ft[l].data_ptr(), ff[l].data_ptr(), l1[i, l:].data_ptr(), ft[l].numel(), _s()), "disc_l1_sum")
-            ops.LAUNCHES[0] += 6
+            ops.LAUNCHES[0] += 6 if need_fm else 1
             n_logit.append(B * fr * sc.F)
             n_feat.append(B * 64 * fr * sc.F)
             saved.append((ft, ff, lf, fr, lt, spec_r, spec_f) if keep_all else (ft, ff, lf, fr))
@@ -341,7 +342,7 @@ def _discriminator_backward(eng, saved, n_logit, B):
 
 def _discriminator_forward_backward(eng, reals, fakes):
     """Hinge discriminator loss and the gradients of every discriminator parameter: returns (dis, {reference name: grad})."""
-    dis, _, _, saved, n_logit, _, shape = eng._loss_forward(reals, fakes, keep_all=True)
+    dis, _, _, saved, n_logit, _, shape = eng._loss_forward(reals, fakes, keep_all=True, need_fm=False)
     return dis, _discriminator_backward(eng, saved, n_logit, shape[0])
 
 
