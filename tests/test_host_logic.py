@@ -45,3 +45,54 @@ def test_hann_window_power_used_by_the_stft_front_end():
     for n in (128, 512, 2048):
         w = torch.hann_window(n, periodic=True, dtype=torch.float64)
         assert abs(w.pow(2).sum().item() - 0.375 * n) < 1e-9 * n
+
+
+def test_inpaint_driver_host_logic_against_the_reference_driver(monkeypatch):
+    """Row f4, CPU: what `b200sat.generation.generate_diffusion_cond_inpaint` hands to the sampler (mask resized / repeated, masked latents,
+    concatenation order, the init_audio start with sigma_max = init_noise_level) reproduces the latents of the reference's own
+    `generate_diffusion_cond_inpaint` (tests/golden/dit_inpaint.npz) when the sampler is the fp32 oracle loop instead of the CUDA-graph one."""
+    import json
+    import math
+    import os
+    import types
+    import numpy as np
+    import torch
+    from oracle import dit as odit, sampling as osamp
+    from b200sat import generation as gen
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "dit_inpaint.npz"))
+    f = {k: torch.from_numpy(z[k]) for k in z.files if k != "meta"}
+    meta = json.loads(str(z["meta"]))
+    cfg, dc, g = meta["cfg"], meta["input_concat_dim"], meta["gen"]
+    sd = odit.make_state_dict(seed=meta["weights_seed"], input_concat_dim=dc, **cfg)
+    seen = []
+
+    def oracle_v_ddim(engine, noise, steps, sigma_max, cross, glob, cfg_scale, scale_phi, sampler=None, input_concat_cond=None, init_data=None):
+        seen.append((tuple(input_concat_cond.shape), init_data is not None, float(sigma_max)))
+        fn = lambda x, t: odit.dit_forward(x, t, sd, cfg["depth"], cross, glob, cfg_scale=cfg_scale, scale_phi=scale_phi,
+                                           input_concat_cond=input_concat_cond)
+        sm = min(float(sigma_max), 1.0)
+        x = noise
+        if init_data is not None:                                   # inference/sampling.py:394-399
+            x = init_data * math.cos(sm * math.pi / 2) + noise * math.sin(sm * math.pi / 2)
+        with torch.no_grad():
+            return osamp.sample_v_ddim(fn, x, steps, sigma_max=sm)
+
+    monkeypatch.setattr(gen.sampling, "sample_v_ddim", oracle_v_ddim)
+    engine = types.SimpleNamespace(cfg=types.SimpleNamespace(input_concat_dim=dc))
+    model = types.SimpleNamespace(engine=engine, pretransform=None, io_channels=64, downsampling_ratio=0, sampler=lambda *a, **k: None)
+    B, T = f["gen_noise"].shape[0], f["gen_noise"].shape[2]
+    common = dict(steps=g["steps"], cfg_scale=g["cfg_scale"], conditioning_tensors={"cross_attn_cond": f["gen_cross"], "global_cond": f["gen_glob"]},
+                  batch_size=B, sample_size=T, sampler_type="v-ddim", noise=f["gen_noise"], return_latents=True, device="cpu")
+    lat = gen.generate_diffusion_cond_inpaint(model, inpaint_audio=f["gen_audio"], inpaint_mask=f["gen_mask"], **common)
+    lat_one_mask = gen.generate_diffusion_cond_inpaint(model, inpaint_audio=f["gen_audio"], inpaint_mask=f["gen_mask"][:1], **common)   # [1, T] mask
+    lat_init = gen.generate_diffusion_cond_inpaint(model, inpaint_audio=f["gen_audio"], inpaint_mask=f["gen_mask"], init_audio=f["gen_init"],
+                                                   init_noise_level=g["init_noise_level"], **common)
+    lat0 = gen.generate_diffusion_cond_inpaint(model, **common)
+    for got, key in ((lat, "gen_lat"), (lat_one_mask, "gen_lat"), (lat_init, "gen_lat_init"), (lat0, "gen_lat_nomask")):
+        assert (got - f[key]).abs().max() <= 5e-5 * max(1.0, float(f[key].abs().max())), key
+    assert seen[0] == ((B, dc, T), False, 1000.0) and seen[2] == ((B, dc, T), True, g["init_noise_level"])
+    bad = types.SimpleNamespace(engine=types.SimpleNamespace(cfg=types.SimpleNamespace(input_concat_dim=0)), pretransform=None, io_channels=64,
+                                downsampling_ratio=0, sampler=lambda *a, **k: None)
+    import pytest
+    with pytest.raises(ValueError):
+        gen.generate_diffusion_cond_inpaint(bad, **common)
